@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric on configs[1]: batched Driving-v1 model.step
+random-action rollout sweep (16M particles per GPU, depth 50), env-steps/s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+One "step" = one depth-50 sweep over the particle batch through the step-API kernel
+(50 launches; every launch reads the packed state and writes state, packed obs, float64
+rewards, flags and the sampled joint action: 51 B per env-step, HBM-bound).  Prints ONE
+JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "driving_v1_model_env_steps_per_s"
+UNIT = "env-steps/s"
+BYTES_PER_ENV_STEP = 51  # 8 B state in; 8 state + 16 obs + 16 rewards + 1 flags + 2 actions out
+DEPTH = 50
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                mx = max(mx, float(parts[1]))
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(parts[0]))
+                    for nm, v in zip(names, parts[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU reference arm: the oracle port of the posggym Driving-v1 model (pure Python,
+    like the reference), one process per host core, same random-action sweep."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+
+    cores = os.cpu_count() or 1
+    budget = max(1.0, min(8.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_bench.driving_sweep(budget_s=1.0, depth=DEPTH, procs=cores, seed=1)
+    vals, secs = [], 0.0
+    for k in range(args.steps):
+        r = cpu_bench.driving_sweep(budget_s=budget, depth=DEPTH, procs=cores, seed=100 + k)
+        vals.append(r["env_steps_per_s"])
+        secs += r["seconds"]
+    v = sum(vals) / len(vals)
+    sample = f"{budget:.1f} s of Driving-v1 random-action depth-{DEPTH} episodes per step on each of {cores} processes (Python oracle port)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "Driving-v1 14x14RoundAbout 2 agents random-action sweep depth 50 (bounded CPU sample)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=1 << 24, help="particles per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from posggym_baselines_b200.envs.driving import BatchedDriving, StepOut
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, seed = args.particles, 2026
+    env = BatchedDriving(device=dev)
+    offset = rank * n  # Philox counters are global particle indices: results independent of N
+    st0 = env.sample_initial_state(n, seed=seed, particle_offset=offset)
+    mk = lambda: StepOut(  # noqa: E731
+        torch.empty((n, 2), dtype=torch.int32, device=dev), torch.empty((n, 2), dtype=torch.int64, device=dev),
+        torch.empty((n, 2), dtype=torch.float64, device=dev), torch.empty((n,), dtype=torch.uint8, device=dev),
+        torch.empty((n, 2), dtype=torch.uint8, device=dev))
+    bufs = [mk(), mk()]
+    live = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def sweep():
+        cur = st0
+        for k in range(DEPTH):
+            out = bufs[k & 1]
+            env.step(cur, seed=seed, step_idx=k, particle_offset=offset, out=out, live_count=live)
+            cur = out.state
+
+    for _ in range(max(3, args.warmup)):
+        sweep()
+    barrier()
+    live.zero_()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        sweep()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    live_total = live.clone()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(live_total, op=dist.ReduceOp.SUM)
+    ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    executed = int(live_total.item())
+    padded = n * DEPTH * args.steps * world
+    value = executed / (ms / 1e3)
+    launches = args.steps * DEPTH
+    launch_ms = ms / launches
+    peak, peak_src = load_peaks()
+    achieved = BYTES_PER_ENV_STEP * n / (launch_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_per_launch"] * (n / tj["particles"])
+        except Exception:
+            traffic = None
+
+    # ---- fused rollout kernel (not HBM-bound; reported beside the step sweep) ----
+    rl = None
+    r_live = torch.zeros(1, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        env.rollout(st0, 0, DEPTH, 0.95, seed=seed, particle_offset=offset)
+    barrier()
+    r_live.zero_()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(args.steps):
+        env.rollout(st0, 0, DEPTH, 0.95, seed=seed, particle_offset=offset, live_count=r_live)
+    r1.record()
+    barrier()
+    rms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+    rl_live = r_live.clone()
+    if world > 1:
+        dist.all_reduce(rms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rl_live, op=dist.ReduceOp.SUM)
+    rl = {"rollouts_per_s": n * world * args.steps / (rms.item() / 1e3),
+          "env_steps_per_s": int(rl_live.item()) / (rms.item() / 1e3),
+          "ms_per_batch": rms.item() / args.steps, "depth": DEPTH, "ego_agent": 0,
+          "note": "fused MCTS._rollout kernel: stops at ego termination; issue-bound, ~16 B of HBM per rollout"}
+
+    # ---- e2e: C-ABI with pinned HOST buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((n, 2), dtype=torch.int32).pin_memory()
+        h_in.copy_(st0.cpu())
+        outs = (torch.empty((n, 2), dtype=torch.int32).pin_memory().numpy(),
+                torch.empty((n, 2), dtype=torch.int64).pin_memory().numpy(),
+                torch.empty((n, 2), dtype=torch.float64).pin_memory().numpy(),
+                torch.empty((n,), dtype=torch.uint8).pin_memory().numpy())
+        h_np = h_in.numpy()
+        e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            env.sweep_host(h_np, DEPTH, seed=seed, particle_offset=offset, outs=outs)
+        barrier()
+        w0 = time.perf_counter()
+        e_live = 0
+        for _ in range(e_steps):
+            _, lv = env.sweep_host(h_np, DEPTH, seed=seed, particle_offset=offset, outs=outs)
+            e_live += lv
+        torch.cuda.synchronize()
+        w = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        lv_t = torch.tensor([e_live], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lv_t, op=dist.ReduceOp.SUM)
+        e2e = {"value": int(lv_t.item()) / w.item(), "unit": UNIT,
+               "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (8 + 16 + 16 + 1) + 8,
+               "ms_per_step": 1e3 * w.item() / e_steps, "steps": e_steps,
+               "api": "posg_driving_sweep_host (pinned host state in; last step's state/obs/rewards/flags out)"}
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu_bench
+
+        cores = os.cpu_count() or 1
+        r = cpu_bench.driving_sweep(budget_s=args.cpu_seconds, depth=DEPTH, procs=cores, seed=0)
+        cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{r['env_steps']} env-steps of the same random-action depth-{DEPTH} Driving-v1 sweep in "
+                         f"{r['seconds']:.1f} s, one Python process per core (the reference's model is pure Python)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"Driving-v1 14x14RoundAbout, 2 agents, obs_dim (3,1,1): random-action model.step sweep, "
+                                   f"{n} particles per GPU x depth {DEPTH} (BASELINE.json configs[1])",
+                       "particles_per_gpu": n, "depth": DEPTH, "seed": seed,
+                       "l2": f"per-launch working set {n * BYTES_PER_ENV_STEP / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)",
+                       "counted": "env-steps executed on not-yet-all-done particles", "padded_env_steps_per_s": padded / (ms / 1e3)},
+            "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "posg::driving::step_kernel<2>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "launch_ms": launch_ms, "peak_source": peak_src},
+            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+/*
+ * posg_b200.h -- C-ABI of libposg_b200.so: batched posggym grid-world models on B200.
+ *
+ * The reference (RDLLab/posggym-baselines) has no FFI: its hot path calls the Python
+ * methods of a posggym.model.POSGModel one state at a time.  Each entry point below is
+ * the batched replacement of one of those call sites (cited per function, paths
+ * relative to /root/reference).  Conventions:
+ *
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the
+ *     function name ends in _host (then every data pointer is a HOST pointer and the
+ *     call does its own H2D/D2H copies and synchronises before returning);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - return value: 0 = ok, negative = POSG_E_* below; no exceptions cross the ABI;
+ *     posg_last_error() returns a thread-local message for the last failure;
+ *   - no ownership transfer: the caller (PyTorch) owns all buffers; the library owns
+ *     only the immutable per-model map blob created by *_create / freed by *_destroy;
+ *   - thread-compatible: handles are immutable after creation.
+ *
+ * Packed layouts (SoA, one element per env / particle; see DESIGN.md "Data layout"):
+ *
+ *   Driving state   : uint32 per vehicle, vehicles of one env adjacent
+ *                     (n_agents == 2 -> one uint64 per env, vehicle 0 in the low word)
+ *       bits  0-3 x | 4-7 y | 8-9 facing (N,E,S,W) | 10-11 speed (REV,STOP,SLOW,FAST)
+ *       12-14 destination index | 15 dest_reached | 16 crashed
+ *       17-23 min_dest_dist | 24-30 init_dest_dist
+ *   Driving obs     : uint64 per agent, agents of one env adjacent
+ *       bits 0-29 fifteen 2-bit cells (row-major 5x3 window, VEHICLE=0 WALL=1 EMPTY=2
+ *       DESTINATION=3) | 30-31 speed | 32-35 x | 36-39 y | 40-43 dest x | 44-47 dest y
+ *       48 dest_reached | 49 crashed
+ *   rewards         : double per agent, agents of one env adjacent
+ *   flags           : uint8 per env: bit a = terminated[a] (a < 4); bits 4-6 reserved (0:
+ *                     truncation belongs to the TimeLimit wrapper, not the model);
+ *                     bit 7 = all_done (POSG_FLAG_ALL_DONE)
+ *   actions         : uint8 per agent, agents of one env adjacent
+ */
+#ifndef POSG_B200_H
+#define POSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POSG_OK 0
+#define POSG_E_INVALID (-1)   /* bad argument */
+#define POSG_E_UNSUPPORTED (-2)
+#define POSG_E_CUDA (-3)      /* a CUDA runtime call failed */
+#define POSG_E_NOGPU (-4)     /* no CUDA device: there is no CPU fallback */
+
+#define POSG_FLAG_ALL_DONE 0x80u
+
+typedef struct posg_model* posg_model_t;
+
+const char* posg_last_error(void);
+int posg_version(void);
+/* number of CUDA devices visible, or POSG_E_NOGPU */
+int posg_device_count(void);
+
+/* ------------------------------------------------------------------ Driving-v1 */
+
+/* posggym DrivingModel.__init__ (called through posggym.make("Driving-v1", ...),
+ * README.md:52, tests/planning/test_pomcp.py:52-58).  `grid_rows` is the
+ * newline-separated ASCII layout ('.', '#', '+', '-', digits, 'a'-'j').  Builds the
+ * padded wall bitmaps, destination/start tables and all shortest-path distances on
+ * the host and uploads one immutable blob to the current device. */
+int posg_driving_create(const char* grid_rows, int num_agents, int obs_front, int obs_back,
+                        int obs_side, int obstacle_collisions, posg_model_t* out);
+int posg_model_destroy(posg_model_t m);
+/* bytes of the device blob (what each CTA stages into shared memory) */
+int posg_model_blob_bytes(posg_model_t m);
+int posg_model_num_agents(posg_model_t m);
+
+/* model.sample_initial_state() (planning/mcts.py:191, planning/intmcp.py:237) for n
+ * envs.  With picks == NULL the picks come from Philox4x32-10, key = seed, counter =
+ * (particle_offset + i, stream 0xB0); otherwise picks[i*2*n_agents + k] are the
+ * explicit noise words (start_pick, dest_pick per agent, see oracle/driving.py). */
+int posg_driving_sample_initial_state(posg_model_t m, int64_t n, const uint8_t* picks,
+                                      uint64_t seed, uint64_t particle_offset,
+                                      uint32_t* state_out, void* stream);
+
+/* model.sample_initial_obs(state) (planning/mcts.py:192, planning/intmcp.py:238). */
+int posg_driving_observe(posg_model_t m, int64_t n, const uint32_t* state, uint64_t* obs_out,
+                         void* stream);
+
+/* model.step(state, joint_action) (planning/mcts.py:333,418; planning/belief.py:165;
+ * planning/intmcp.py:468,562) for n envs.
+ *   actions_in : n*n_agents uint8, or NULL -> uniform actions from Philox (counter =
+ *                (particle_offset + i, step_idx, stream 0xA0)), written to actions_out
+ *                when that is non-NULL;
+ *   order_in   : n uint8 explicit processing-order noise (permutation index), or NULL
+ *                -> from the same Philox block;
+ *   live_count : optional device uint64 incremented by the number of envs whose input
+ *                state was not all-done (the "executed" env-steps of a sweep).
+ * state_out may alias state_in. */
+int posg_driving_step(posg_model_t m, int64_t n, const uint32_t* state_in,
+                      const uint8_t* actions_in, const uint8_t* order_in, uint64_t seed,
+                      uint32_t step_idx, uint64_t particle_offset, uint32_t* state_out,
+                      uint64_t* obs_out, double* rewards_out, uint8_t* flags_out,
+                      uint8_t* actions_out, unsigned long long* live_count, void* stream);
+
+/* MCTS._rollout (planning/mcts.py:405-452) with RandomSearchPolicy
+ * (planning/search_policy.py:176-177) for the ego agent and RandomOtherAgentPolicy
+ * (planning/other_policy.py:150-151) for the others, fused over `max_steps` model
+ * steps: returns_out[i] = sum_k discount^k * r_ego,k, stopping after the step on which
+ * terminated[ego] || all_done.  steps_out[i] (optional) = model steps executed,
+ * state_out (optional) = final state.  Randomness: Philox counter (particle_offset + i,
+ * step0 + k, stream 0xA0) -- identical to calling posg_driving_step k times with
+ * step_idx = step0 + k.  max_steps is min(depth_limit - depth + 1, step_limit - t + 1)
+ * evaluated by the caller (mcts.py:414). */
+int posg_driving_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, int ego_agent,
+                         int max_steps, double discount, uint64_t seed, uint32_t step0,
+                         uint64_t particle_offset, double* returns_out, uint8_t* steps_out,
+                         uint32_t* state_out, unsigned long long* live_count, void* stream);
+
+/* Host-buffer variants (the e2e path of bench.py): copy in, run, copy out, synchronise. */
+int posg_driving_rollout_host(posg_model_t m, int64_t n, const uint32_t* state_in_host,
+                              int ego_agent, int max_steps, double discount, uint64_t seed,
+                              uint32_t step0, uint64_t particle_offset, double* returns_out_host,
+                              uint8_t* steps_out_host, uint32_t* state_out_host,
+                              unsigned long long* live_count_host);
+/* depth `num_steps` sweep through posg_driving_step (every step writes state, obs,
+ * rewards, flags, actions to device scratch owned by the call); copies the LAST step's
+ * outputs back. */
+int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_host,
+                            int num_steps, uint64_t seed, uint64_t particle_offset,
+                            uint32_t* state_out_host, uint64_t* obs_out_host,
+                            double* rewards_out_host, uint8_t* flags_out_host,
+                            unsigned long long* live_count_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSG_B200_H */

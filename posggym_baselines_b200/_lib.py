@@ -1,0 +1,97 @@
+"""ctypes binding of libposg_b200.so (C-ABI declared in include/posg_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libposg_b200.so")
+
+
+class PosgB200Error(RuntimeError):
+    """Raised for every non-zero return of the C-ABI (and a missing library)."""
+
+
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+_i64 = C.c_int64
+_u64 = C.c_uint64
+_u32 = C.c_uint32
+_int = C.c_int
+_dbl = C.c_double
+
+# name -> (restype, argtypes); mirrors include/posg_b200.h one to one
+SIGNATURES = {
+    "posg_last_error": (C.c_char_p, []),
+    "posg_version": (_int, []),
+    "posg_device_count": (_int, []),
+    "posg_model_destroy": (_int, [_vp]),
+    "posg_model_blob_bytes": (_int, [_vp]),
+    "posg_model_num_agents": (_int, [_vp]),
+    "posg_driving_create": (_int, [C.c_char_p, _int, _int, _int, _int, _int, C.POINTER(_vp)]),
+    "posg_driving_sample_initial_state": (_int, [_vp, _i64, _vp, _u64, _u64, _vp, _vp]),
+    "posg_driving_observe": (_int, [_vp, _i64, _vp, _vp, _vp]),
+    "posg_driving_step": (
+        _int,
+        [_vp, _i64, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    ),
+    "posg_driving_rollout": (
+        _int,
+        [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp],
+    ),
+    "posg_driving_rollout_host": (
+        _int,
+        [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp],
+    ),
+    "posg_driving_sweep_host": (_int, [_vp, _i64, _vp, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the C-ABI library.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise PosgB200Error(
+                f"{_LIB_PATH} is missing: build it with `python -m posggym_baselines_b200.build` "
+                "(nvcc, sm_100a).  There is no CPU fallback."
+            )
+        handle = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the header and the .so diverge
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = lib().posg_last_error()
+        raise PosgB200Error(f"libposg_b200 error {rc}: {msg.decode() if msg else '?'}")
+    return rc
+
+
+def ptr(t) -> Optional[int]:
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        assert t.is_contiguous(), "libposg_b200 needs contiguous buffers"
+        return t.data_ptr()
+    assert t.flags["C_CONTIGUOUS"]
+    return t.ctypes.data
+
+
+def stream_ptr(stream=None) -> Optional[int]:
+    import torch
+
+    s = torch.cuda.current_stream() if stream is None else stream
+    return s.cuda_stream or None

@@ -1,0 +1,44 @@
+// Shared host-side helpers of libposg_b200 (error reporting, launch geometry).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/posg_b200.h"
+
+namespace posg {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define POSG_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t _e = (call);                              \
+    if (_e != cudaSuccess) return posg::cuda_fail(_e, #call); \
+  } while (0)
+
+#define POSG_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      posg::set_error(__VA_ARGS__);      \
+      return POSG_E_INVALID;             \
+    }                                    \
+  } while (0)
+
+// SM count of the current device (cached per device).
+int sm_count();
+
+enum ModelKind : int { KIND_DRIVING = 1, KIND_PREDATOR_PREY = 2, KIND_LBF = 3 };
+
+}  // namespace posg
+
+struct posg_model {
+  int kind;
+  int device;
+  int num_agents;
+  int blob_bytes;
+  void* d_blob;   // device copy of the immutable model blob
+  void* h_blob;   // host copy (for the *_host entry points / introspection)
+};

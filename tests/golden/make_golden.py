@@ -1,0 +1,126 @@
+"""Generate the committed golden vectors from the CPU oracle (run in the build
+container: `python tests/golden/make_golden.py`).  Representation-independent: raw
+field arrays, not the kernels' packed words."""
+from __future__ import annotations
+
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import shims  # noqa: E402
+
+shims.install()
+from oracle import rollout as R  # noqa: E402
+from oracle.driving import DrivingModel, VehicleState  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def vs_fields(vs):
+    return [vs.coord[0], vs.coord[1], vs.facing_dir, vs.speed, vs.dest_coord[0], vs.dest_coord[1],
+            vs.dest_reached, vs.crashed, vs.min_dest_dist, vs.init_dest_dist]
+
+
+def obs_fields(o):
+    cells, speed, coord, dest, reached, crashed = o
+    return [*cells, speed, coord[0], coord[1], dest[0], dest[1], reached, crashed]
+
+
+def synthetic_state(m, rng):
+    """Two vehicles on distinct road cells with random heading / speed (dense in
+    near-collision configurations, which random play reaches rarely)."""
+    g = m.grid
+    road = g.unblocked_coords
+    dests = g.dest_coords[0]
+    c0 = rng.choice(road)
+    near = [c for c in road if c != c0 and g.manhattan_dist(c, c0) <= 3]
+    c1 = rng.choice(near) if near and rng.random() < 0.7 else rng.choice([c for c in road if c != c0])
+    d = rng.sample(dests, 2)
+    out = []
+    for c, dest in zip((c0, c1), d):
+        dist = g.get_shortest_path_distance(c, dest)
+        mind = max(0, dist - rng.randrange(3))
+        d0 = min(63, max(1, mind + rng.randrange(8)))
+        crashed = int(rng.random() < 0.05)
+        out.append(VehicleState(c, rng.randrange(4), rng.randrange(4), dest, int(c == dest), crashed, mind, d0))
+    return tuple(out)
+
+
+def driving_step_cases(n_play=2500, n_syn=2500, seed=20261018):
+    m = DrivingModel()
+    m.seed(seed)
+    rng = random.Random(seed)
+    states, actions, orders = [], [], []
+    while len(states) < n_play:
+        s = m.sample_initial_state()
+        for _ in range(51):  # one step past the horizon: stepping a terminal state is legal
+            a = [rng.randrange(5), rng.randrange(5)]
+            o = rng.randrange(2)
+            states.append(s); actions.append(a); orders.append(o)
+            ts = m.step_with_noise(s, {"0": a[0], "1": a[1]}, o)
+            s = ts.state
+            if ts.all_done and rng.random() < 0.7:
+                break
+    for _ in range(n_syn):
+        states.append(synthetic_state(m, rng))
+        actions.append([rng.randrange(5), rng.randrange(5)])
+        orders.append(rng.randrange(2))
+    S, S2, O, RW, T, AD = [], [], [], [], [], []
+    for s, a, o in zip(states, actions, orders):
+        ts = m.step_with_noise(s, {"0": a[0], "1": a[1]}, o)
+        S.append([vs_fields(v) for v in s])
+        S2.append([vs_fields(v) for v in ts.state])
+        O.append([obs_fields(ts.observations[i]) for i in m.possible_agents])
+        RW.append([ts.rewards[i] for i in m.possible_agents])
+        T.append([ts.terminations[i] for i in m.possible_agents])
+        AD.append(ts.all_done)
+    return dict(
+        state=np.array(S, np.int16), action=np.array(actions, np.uint8), order=np.array(orders, np.uint8),
+        next_state=np.array(S2, np.int16), obs=np.array(O, np.int8), reward=np.array(RW, np.float64),
+        terminated=np.array(T, np.bool_), all_done=np.array(AD, np.bool_),
+    )
+
+
+def driving_init_cases():
+    """Every legal pick combination of sample_initial_state + its initial obs."""
+    m = DrivingModel()
+    picks, S, O = [], [], []
+    for a in range(4):
+        for b in range(4):
+            for c in range(3):
+                for d in range(3):
+                    p = [a, b, c, d]
+                    s = m.initial_state_from_noise(p)
+                    o = m.sample_initial_obs(s)
+                    picks.append(p); S.append([vs_fields(v) for v in s])
+                    O.append([obs_fields(o[i]) for i in m.possible_agents])
+    return dict(picks=np.array(picks, np.uint8), state=np.array(S, np.int16), obs=np.array(O, np.int8))
+
+
+def driving_rollout_cases(n=512, seed=7, discount=0.95, max_steps=50):
+    """Philox-driven rollouts: initial state from (seed, particle), random joint actions."""
+    m = DrivingModel()
+    particles = np.arange(n, dtype=np.uint64) + np.uint64(1000)
+    picks = R.driving_initial_picks(m, seed, particles)
+    rets, steps, finals, inits = [], [], [], []
+    for p, pk in zip(particles, picks):
+        s0 = m.initial_state_from_noise(pk)
+        ret, k, s = R.rollout(m, s0, "0", max_steps, discount, seed, int(p))
+        rets.append(ret); steps.append(k)
+        inits.append([vs_fields(v) for v in s0]); finals.append([vs_fields(v) for v in s])
+    return dict(seed=np.array(seed), particle=particles, discount=np.array(discount), max_steps=np.array(max_steps),
+                init_state=np.array(inits, np.int16), ret=np.array(rets, np.float64),
+                steps=np.array(steps, np.uint8), final_state=np.array(finals, np.int16))
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "driving_step.npz"), **driving_step_cases())
+    np.savez_compressed(os.path.join(HERE, "driving_init.npz"), **driving_init_cases())
+    np.savez_compressed(os.path.join(HERE, "driving_rollout.npz"), **driving_rollout_cases())
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,166 @@
+"""Parity of the Driving-v1 CUDA path (through the C-ABI) against the CPU oracle and
+the committed golden vectors.  Integer state / observations / flags and the float64
+rewards and returns must be BIT-EXACT."""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from posggym_baselines_b200.envs.driving import BatchedDriving
+
+    return BatchedDriving()
+
+
+def to_vs(env, fields):
+    from posggym_baselines_b200.envs.driving import VehicleState
+
+    return [tuple(VehicleState((int(f[0]), int(f[1])), int(f[2]), int(f[3]), (int(f[4]), int(f[5])),
+                               int(f[6]), int(f[7]), int(f[8]), int(f[9])) for f in row) for row in fields]
+
+
+def obs_fields(o):
+    cells, speed, coord, dest, reached, crashed = o
+    return [*cells, speed, coord[0], coord[1], dest[0], dest[1], reached, crashed]
+
+
+def vs_fields(v):
+    return [v.coord[0], v.coord[1], v.facing_dir, v.speed, v.dest_coord[0], v.dest_coord[1],
+            v.dest_reached, v.crashed, v.min_dest_dist, v.init_dest_dist]
+
+
+def test_step_matches_golden(env):
+    g = golden("driving_step.npz")
+    dev = env.device
+    packed = torch.from_numpy(env.pack_state(to_vs(env, g["state"]))).to(dev)
+    out = env.step(packed, torch.from_numpy(g["action"]).to(dev), torch.from_numpy(g["order"]).to(dev))
+    torch.cuda.synchronize()
+    nxt = np.array([[vs_fields(v) for v in row] for row in env.unpack_state(out.state)], np.int16)
+    assert (nxt == g["next_state"]).all(), np.nonzero((nxt != g["next_state"]).any((1, 2)))[0][:10]
+    obs = np.array([[obs_fields(o) for o in row] for row in env.unpack_obs(out.obs)], np.int8)
+    assert (obs == g["obs"]).all(), np.nonzero((obs != g["obs"]).any((1, 2)))[0][:10]
+    rew = out.rewards.cpu().numpy()
+    assert (rew.view(np.uint64) == g["reward"].view(np.uint64)).all()      # bit-exact doubles
+    flags = out.flags.cpu().numpy()
+    assert ((flags & 1).astype(bool) == g["terminated"][:, 0]).all()
+    assert (((flags >> 1) & 1).astype(bool) == g["terminated"][:, 1]).all()
+    assert ((flags & 0x80).astype(bool) == g["all_done"]).all()
+    assert ((flags & 0x7C) == 0).all()
+
+
+def test_initial_state_and_obs_match_golden(env):
+    g = golden("driving_init.npz")
+    dev = env.device
+    st = env.sample_initial_state(len(g["picks"]), picks=torch.from_numpy(g["picks"]).to(dev))
+    got = np.array([[vs_fields(v) for v in row] for row in env.unpack_state(st)], np.int16)
+    assert (got == g["state"]).all()
+    obs = np.array([[obs_fields(o) for o in row] for row in env.unpack_obs(env.observe(st))], np.int8)
+    assert (obs == g["obs"]).all()
+
+
+def test_rollout_matches_golden(env):
+    g = golden("driving_rollout.npz")
+    seed, disc, max_steps = int(g["seed"]), float(g["discount"]), int(g["max_steps"])
+    n, off = len(g["particle"]), int(g["particle"][0])
+    st = env.sample_initial_state(n, seed=seed, particle_offset=off)
+    got0 = np.array([[vs_fields(v) for v in row] for row in env.unpack_state(st)], np.int16)
+    assert (got0 == g["init_state"]).all()
+    ret, steps, final = env.rollout(st, 0, max_steps, disc, seed=seed, particle_offset=off, want_state=True)
+    assert (ret.cpu().numpy().view(np.uint64) == g["ret"].view(np.uint64)).all()
+    assert (steps.cpu().numpy() == g["steps"]).all()
+    gotf = np.array([[vs_fields(v) for v in row] for row in env.unpack_state(final)], np.int16)
+    assert (gotf == g["final_state"]).all()
+
+
+def test_step_vs_oracle_live(env, oracle_env):
+    """Fresh random triples (not the committed ones), Philox actions included."""
+    from oracle import rollout as R
+    from oracle.driving import DrivingModel
+
+    m = DrivingModel()
+    n, seed, off = 3000, 99, 12345
+    st = env.sample_initial_state(n, seed=seed, particle_offset=off)
+    states = env.unpack_state(st)
+    picks = R.driving_initial_picks(m, seed, np.arange(n, dtype=np.uint64) + np.uint64(off))
+    for i in range(0, n, 37):
+        assert tuple(tuple(v) for v in states[i]) == tuple(tuple(v) for v in m.initial_state_from_noise(picks[i]))
+    cur = st
+    cpu_states = [m.initial_state_from_noise(p) for p in picks]
+    for step in range(12):
+        out = env.step(cur, seed=seed, step_idx=step, particle_offset=off)
+        acts, order = R.driving_step_noise(seed, np.arange(n, dtype=np.uint64) + np.uint64(off), step, 2)
+        assert (out.actions.cpu().numpy() == acts).all()
+        gs, go = env.unpack_state(out.state), env.unpack_obs(out.obs)
+        rew, flags = out.rewards.cpu().numpy(), out.flags.cpu().numpy()
+        for i in range(n):
+            ts = m.step_with_noise(cpu_states[i], {"0": int(acts[i, 0]), "1": int(acts[i, 1])}, int(order[i]))
+            cpu_states[i] = ts.state
+            assert tuple(tuple(v) for v in gs[i]) == tuple(tuple(v) for v in ts.state), (step, i)
+            assert go[i] == (ts.observations["0"], ts.observations["1"]), (step, i)
+            assert rew[i, 0] == ts.rewards["0"] and rew[i, 1] == ts.rewards["1"]
+            assert bool(flags[i] & 0x80) == ts.all_done
+        cur = out.state
+
+
+def test_edge_cases(env):
+    dev = env.device
+    # empty batch
+    e = torch.empty((0, 2), dtype=torch.int32, device=dev)
+    out = env.step(e, torch.empty((0, 2), dtype=torch.uint8, device=dev), torch.empty((0,), dtype=torch.uint8, device=dev))
+    assert out.state.shape == (0, 2)
+    r, s, _ = env.rollout(e, 0, 50, 0.95)
+    assert r.shape == (0,)
+    # ragged sizes around warp / CTA / grid boundaries: results independent of launch geometry
+    big = env.sample_initial_state(300_001, seed=5)
+    ref, refsteps, _ = env.rollout(big, 1, 50, 0.9, seed=5)
+    for n in (1, 31, 33, 255, 257, 4099):
+        r, s, _ = env.rollout(big[:n].contiguous(), 1, 50, 0.9, seed=5)
+        assert torch.equal(r, ref[:n]) and torch.equal(s, refsteps[:n])
+    # max_steps = 0 -> zero return, zero steps
+    r, s, _ = env.rollout(big[:100].contiguous(), 0, 0, 0.9)
+    assert (r == 0).all() and (s == 0).all()
+    # terminal states are absorbing: stepping them changes nothing and pays nothing
+    cur = big[:50_000].contiguous()
+    for k in range(60):
+        o = env.step(cur, seed=5, step_idx=k)
+        cur = o.state
+    done = (o.flags & 0x80) != 0
+    assert done.any()
+    o2 = env.step(cur, seed=5, step_idx=61)
+    assert torch.equal(o2.state[done], cur[done]) and (o2.rewards[done] == 0).all()
+
+
+def test_full_size_properties(env):
+    """BASELINE configs[1] at its largest size (16M particles, depth 50): size-independent
+    properties -- the fused rollout equals the 50-launch step sweep; offsets shard cleanly."""
+    n, depth, seed, disc = 1 << 24, 50, 2026, 0.95
+    st = env.sample_initial_state(n, seed=seed)
+    ret, steps, final = env.rollout(st, 0, depth, disc, seed=seed, want_state=True)
+    # (1) sweep through the step API with the same Philox counters
+    cur = st.clone()
+    acc = torch.zeros(n, dtype=torch.float64, device=env.device)
+    alive = torch.ones(n, dtype=torch.bool, device=env.device)
+    live = torch.zeros(1, dtype=torch.int64, device=env.device)
+    out = None
+    frozen = st.clone()
+    for k in range(depth):
+        out = env.step(cur, seed=seed, step_idx=k, out=out, want_actions=False)
+        acc = torch.where(alive, acc + (disc**k) * out.rewards[:, 0], acc)
+        frozen = torch.where(alive.unsqueeze(1), out.state, frozen)
+        alive = alive & ((out.flags & 0x81) == 0)   # ego terminated (bit 0) or all done (bit 7)
+        cur, out = out.state, out._replace(state=cur)
+    assert torch.equal(acc, ret)
+    assert torch.equal(frozen, final)
+    # (2) sharding by particle offset reproduces the monolithic result (multi-GPU partitioning)
+    h = n // 2
+    r2, s2, _ = env.rollout(st[h:].contiguous(), 0, depth, disc, seed=seed, particle_offset=h)
+    assert torch.equal(r2, ret[h:]) and torch.equal(s2, steps[h:])
+    # (3) statistics of uniform-random play agree with the reference's div_results.csv lattice
+    crashed = ((final[:, 0] >> 16) & 1).double().mean().item()
+    assert 0.10 < crashed < 0.30
+    assert steps.max().item() == depth and steps.min().item() >= 1
