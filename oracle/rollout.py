@@ -6,7 +6,7 @@ mcts.py:405-452) for ``state_belief_only=True`` with ``RandomSearchPolicy`` /
 ``RandomOtherAgentPolicy`` (search_policy.py:176-177, other_policy.py:150-151): the
 loop bound ``depth <= depth_limit and t <= step_limit`` is pre-evaluated by the caller
 into ``max_steps``; the uniform actions and the model's step noise come from the
-Philox block (seed; particle, step0 + k; stream 0xA0) instead of three host RNGs.
+Philox word (seed; particle, step0 + k; stream 0xA0; see driving_step_noise) instead of three host RNGs.
 """
 from __future__ import annotations
 
@@ -18,31 +18,31 @@ import numpy as np
 from oracle import philox as P
 
 
-def driving_step_noise(seed: int, particles, step: int, num_agents: int):
-    """(actions [n, A], order_idx [n]) exactly as the kernels derive them."""
-    w = P.philox_block(seed, particles, step, P.STREAM_STEP)
-    acts = [P.uniform_below(w[0], 5)]
-    if num_agents > 1:
-        acts.append(P.uniform_below(w[1], 5))
-    order = P.uniform_below(w[2], math.factorial(num_agents))
-    if num_agents > 2:
-        w2 = P.philox_block(seed, particles, step, P.STREAM_STEP2)
-        acts.append(P.uniform_below(w2[0], 5))
-        if num_agents > 3:
-            acts.append(P.uniform_below(w2[1], 5))
-    return np.stack(acts, axis=-1), order
+def driving_step_noise(seed: int, particles, step: int, num_agents: int = 2):
+    """(actions [n, 2], order_idx [n]) exactly as the kernels derive them: ONE 32-bit
+    Philox word per env-step -- block = counter (particle >> 2, step, stream 0xA0), word
+    = particle & 3; idx = floor(word * 50 / 2**32) enumerates the 50 (order, a0, a1)
+    combinations: order = idx % 2, a0 = (idx // 2) % 5, a1 = idx // 10."""
+    assert num_agents == 2
+    particles = np.asarray(particles, dtype=np.uint64)
+    w = P.philox_block(seed, particles >> np.uint64(2), step, P.STREAM_STEP)
+    which = (particles & np.uint64(3)).astype(np.int64)
+    word = np.choose(which, w)
+    idx = P.uniform_below(word, 50)
+    order = idx & 1
+    r = idx >> 1
+    a1 = r // 5
+    a0 = r - 5 * a1
+    return np.stack([a0, a1], axis=-1), order
 
 
 def driving_initial_picks(model, seed: int, particles: Sequence[int]):
     """Start/destination picks per particle as the kernels derive them from Philox."""
     na = len(model.possible_agents)
+    assert na == 2
     particles = np.asarray(particles, dtype=np.uint64)
     w = P.philox_block(seed, particles, 0, P.STREAM_INIT)
-    w2 = P.philox_block(seed, particles, 0, P.STREAM_INIT2) if na > 2 else w
-    words = []
-    for i in range(na):
-        src = w if i < 2 else w2
-        words.append((src[0 if i % 2 == 0 else 2], src[1 if i % 2 == 0 else 3]))
+    words = [(w[0], w[1]), (w[2], w[3])]  # agent 0: words x, y; agent 1: words z, w
     out = []
     for p in range(len(particles)):
         picks = []

@@ -1,6 +1,7 @@
-// Driving-v1 kernels + C-ABI.  One thread per env / particle; persistent CTAs
-// (grid = k x SM count) stage the model blob into shared memory once via TMA and
-// then grid-stride over the batch with coalesced 8/16-byte loads and stores.
+// Driving-v1 kernels + C-ABI.  Persistent CTAs (grid = k x SM count) stage the model
+// blob (wall bitmap, distance tables, observation base table, reward table; ~20 KB)
+// into shared memory once via one TMA bulk copy and then grid-stride over the batch
+// with coalesced 16-byte loads and stores.
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -18,131 +19,176 @@ namespace driving {
 constexpr int THREADS = 256;
 
 // ------------------------------------------------------------------ step (model.step)
-template <int NA>
-__global__ void __launch_bounds__(THREADS)
-step_kernel(const Blob* __restrict__ gblob, int64_t n, const uint32_t* __restrict__ state_in,
-            const uint8_t* __restrict__ actions_in, const uint8_t* __restrict__ order_in,
-            uint64_t seed, uint32_t step_idx, uint64_t particle_offset,
-            uint32_t* __restrict__ state_out, uint64_t* __restrict__ obs_out,
+// Each thread owns EPT = 4 consecutive envs (one Philox block serves the four), loads
+// their states with two 16-byte loads and writes every output with 16-byte stores
+// (obs, rewards: one 16-byte store per env; states: two per thread; flags: one 4-byte
+// store; actions: one 8-byte store) -- every warp-level access is fully coalesced.
+constexpr int EPT = 4;
+#ifndef STEP_MIN_CTAS
+#define STEP_MIN_CTAS 4
+#endif
+
+struct EnvOut { uint32_t v0, v1; uint64_t o0, o1; double r0, r1; uint32_t flags; };
+
+__device__ __forceinline__ EnvOut step_env(const Blob& B, uint32_t v0, uint32_t v1, int a0, int a1, int order_idx) {
+  const uint32_t b0 = v0, b1 = v1;
+  int c0, c1;
+  transition(B, v0, v1, a0, a1, order_idx, c0, c1);
+  EnvOut e;
+  e.v0 = v0; e.v1 = v1;
+  e.o0 = observe(B, v0, v1);
+  e.o1 = observe(B, v1, v0);
+  e.r0 = reward(B, b0, v0, c0);
+  e.r1 = reward(B, b1, v1, c1);
+  const uint32_t t0 = vdone(v0) ? 1u : 0u, t1 = vdone(v1) ? 1u : 0u;
+  e.flags = t0 | (t1 << 1) | ((t0 & t1) ? POSG_FLAG_ALL_DONE : 0u);
+  return e;
+}
+
+__global__ void __launch_bounds__(THREADS, STEP_MIN_CTAS)
+step_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+            const uint32_t* __restrict__ state_in, const uint8_t* __restrict__ actions_in,
+            const uint8_t* __restrict__ order_in, uint64_t seed, uint32_t step_idx,
+            uint64_t particle_offset, uint32_t* __restrict__ state_out, uint64_t* __restrict__ obs_out,
             double* __restrict__ rewards_out, uint8_t* __restrict__ flags_out,
             uint8_t* __restrict__ actions_out, unsigned long long* __restrict__ live_count) {
-  __shared__ Blob B;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
-  stage_blob(&B, gblob, (uint32_t)sizeof(Blob), &mbar);
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const Blob& B = *reinterpret_cast<const Blob*>(smem_raw);
 
   unsigned live = 0;
+  const int64_t ngroups = (n + EPT - 1) / EPT;
   const int64_t stride = (int64_t)gridDim.x * THREADS;
-  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
-    uint32_t veh[NA], before[NA];
-    if (NA == 2) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(state_in) + i);
-      veh[0] = v.x; veh[1] = v.y;
+  // the fast path needs 16-byte aligned group accesses: particle_offset only shifts the RNG
+  for (int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x; g < ngroups; g += stride) {
+    const int64_t i0 = g * EPT;
+    const bool full = (i0 + EPT <= n);
+    uint32_t sv[2 * EPT];
+    if (full) {
+      const uint4 s01 = __ldg(reinterpret_cast<const uint4*>(state_in) + 2 * g);
+      const uint4 s23 = __ldg(reinterpret_cast<const uint4*>(state_in) + 2 * g + 1);
+      sv[0] = s01.x; sv[1] = s01.y; sv[2] = s01.z; sv[3] = s01.w;
+      sv[4] = s23.x; sv[5] = s23.y; sv[6] = s23.z; sv[7] = s23.w;
     } else {
 #pragma unroll
-      for (int a = 0; a < NA; ++a) veh[a] = __ldg(state_in + i * NA + a);
+      for (int j = 0; j < EPT; ++j) {
+        const bool ok = i0 + j < n;
+        sv[2 * j] = ok ? __ldg(state_in + 2 * (i0 + j)) : 0u;
+        sv[2 * j + 1] = ok ? __ldg(state_in + 2 * (i0 + j) + 1) : 0u;
+      }
     }
-    bool all_done_before = true;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) { before[a] = veh[a]; all_done_before &= vdone(veh[a]); }
-    live += all_done_before ? 0u : 1u;
-
-    int act[NA], order_idx;
+    int act[2 * EPT], ord[EPT];
     if (actions_in == nullptr || order_in == nullptr) {
-      int ract[NA], rorder;
-      sample_step_noise<NA>(seed, particle_offset + (uint64_t)i, step_idx, ract, rorder);
+      // particle_offset + i0 is a multiple of 4 whenever particle_offset is; handle the general case
+      const uint64_t p0 = particle_offset + (uint64_t)i0;
+      uint4 blk = philox_block(seed, p0 >> 2, step_idx, STREAM_STEP);
+      uint4 blk2 = blk;
+      if (p0 & 3ULL) blk2 = philox_block(seed, (p0 >> 2) + 1, step_idx, STREAM_STEP);
 #pragma unroll
-      for (int a = 0; a < NA; ++a) act[a] = ract[a];
-      order_idx = rorder;
+      for (int j = 0; j < EPT; ++j) {
+        const uint64_t p = p0 + j;
+        const uint32_t w = pick_word(((p >> 2) == (p0 >> 2)) ? blk : blk2, (unsigned)(p & 3ULL));
+        decode_step_noise(w, act[2 * j], act[2 * j + 1], ord[j]);
+      }
     }
     if (actions_in != nullptr) {
-      if (NA == 2) {
-        const uint16_t aa = __ldg(reinterpret_cast<const uint16_t*>(actions_in) + i);
-        act[0] = aa & 255; act[1] = aa >> 8;
+      if (full) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(actions_in) + g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { act[j] = (a.x >> (8 * j)) & 255; act[4 + j] = (a.y >> (8 * j)) & 255; }
       } else {
 #pragma unroll
-        for (int a = 0; a < NA; ++a) act[a] = __ldg(actions_in + i * NA + a);
+        for (int j = 0; j < 2 * EPT; ++j) act[j] = (i0 + j / 2 < n) ? __ldg(actions_in + 2 * i0 + j) : 0;
       }
     }
-    if (order_in != nullptr) order_idx = __ldg(order_in + i);
-
-    int coll[NA];
-    transition<NA>(B, veh, act, order_idx, coll);
-
-    uint64_t obs[NA];
-    double rew[NA];
-    unsigned flags = 0;
-    bool all_done = true;
+    if (order_in != nullptr) {
+      if (full) {
+        const uint32_t o = __ldg(reinterpret_cast<const uint32_t*>(order_in) + g);
 #pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      obs[a] = observe<NA>(B, veh, a);
-      rew[a] = reward(B, before[a], veh[a], coll[a]);
-      const bool t = vdone(veh[a]);
-      flags |= (t ? 1u : 0u) << a;
-      all_done &= t;
+        for (int j = 0; j < EPT; ++j) ord[j] = (o >> (8 * j)) & 255;
+      } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) ord[j] = (i0 + j < n) ? __ldg(order_in + i0 + j) : 0;
+      }
     }
-    if (all_done) flags |= POSG_FLAG_ALL_DONE;
 
-    if (NA == 2) {
-      reinterpret_cast<uint2*>(state_out)[i] = make_uint2(veh[0], veh[1]);
-      reinterpret_cast<ulonglong2*>(obs_out)[i] = make_ulonglong2(obs[0], obs[1]);
-      reinterpret_cast<double2*>(rewards_out)[i] = make_double2(rew[0], rew[1]);
-      if (actions_out) reinterpret_cast<uint16_t*>(actions_out)[i] = (uint16_t)(act[0] | (act[1] << 8));
+    uint32_t so[2 * EPT], fl = 0, a_lo = 0, a_hi = 0;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const bool ok = full || (i0 + j < n);
+      live += (ok && !(vdone(sv[2 * j]) && vdone(sv[2 * j + 1]))) ? 1u : 0u;
+      const EnvOut e = step_env(B, sv[2 * j], sv[2 * j + 1], act[2 * j], act[2 * j + 1], ord[j]);
+      so[2 * j] = e.v0; so[2 * j + 1] = e.v1;
+      fl |= e.flags << (8 * j);
+      const uint32_t aa = (uint32_t)act[2 * j] | ((uint32_t)act[2 * j + 1] << 8);
+      if (j < 2) a_lo |= aa << (16 * j); else a_hi |= aa << (16 * (j - 2));
+      if (ok) {
+        reinterpret_cast<ulonglong2*>(obs_out)[i0 + j] = make_ulonglong2(e.o0, e.o1);
+        reinterpret_cast<double2*>(rewards_out)[i0 + j] = make_double2(e.r0, e.r1);
+      }
+    }
+    if (full) {
+      reinterpret_cast<uint4*>(state_out)[2 * g] = make_uint4(so[0], so[1], so[2], so[3]);
+      reinterpret_cast<uint4*>(state_out)[2 * g + 1] = make_uint4(so[4], so[5], so[6], so[7]);
+      reinterpret_cast<uint32_t*>(flags_out)[g] = fl;
+      if (actions_out) reinterpret_cast<uint2*>(actions_out)[g] = make_uint2(a_lo, a_hi);
     } else {
 #pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        state_out[i * NA + a] = veh[a];
-        obs_out[i * NA + a] = obs[a];
-        rewards_out[i * NA + a] = rew[a];
-        if (actions_out) actions_out[i * NA + a] = (uint8_t)act[a];
+      for (int j = 0; j < EPT; ++j) {
+        if (i0 + j < n) {
+          state_out[2 * (i0 + j)] = so[2 * j]; state_out[2 * (i0 + j) + 1] = so[2 * j + 1];
+          flags_out[i0 + j] = (uint8_t)(fl >> (8 * j));
+          if (actions_out) {
+            actions_out[2 * (i0 + j)] = (uint8_t)act[2 * j];
+            actions_out[2 * (i0 + j) + 1] = (uint8_t)act[2 * j + 1];
+          }
+        }
       }
     }
-    flags_out[i] = (uint8_t)flags;
   }
   if (live_count != nullptr) {
-    // warp-aggregated, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
     if ((threadIdx.x & 31) == 0 && live) atomicAdd(live_count, (unsigned long long)live);
   }
 }
 
 // ------------------------------------------------------------------ observe / initial state
-template <int NA>
 __global__ void __launch_bounds__(THREADS)
-observe_kernel(const Blob* __restrict__ gblob, int64_t n, const uint32_t* __restrict__ state,
-               uint64_t* __restrict__ obs_out) {
-  __shared__ Blob B;
+observe_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+               const uint32_t* __restrict__ state, uint64_t* __restrict__ obs_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
-  stage_blob(&B, gblob, (uint32_t)sizeof(Blob), &mbar);
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const Blob& B = *reinterpret_cast<const Blob*>(smem_raw);
   const int64_t stride = (int64_t)gridDim.x * THREADS;
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
-    uint32_t veh[NA];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) veh[a] = __ldg(state + i * NA + a);
-#pragma unroll
-    for (int a = 0; a < NA; ++a) obs_out[i * NA + a] = observe<NA>(B, veh, a);
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(state) + i);
+    reinterpret_cast<ulonglong2*>(obs_out)[i] = make_ulonglong2(observe(B, v.x, v.y), observe(B, v.y, v.x));
   }
 }
 
-template <int NA>
 __global__ void __launch_bounds__(THREADS)
-initial_state_kernel(const Blob* __restrict__ gblob, int64_t n, const uint8_t* __restrict__ picks,
-                     uint64_t seed, uint64_t particle_offset, uint32_t* __restrict__ state_out) {
-  __shared__ Blob B;
+initial_state_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+                     const uint8_t* __restrict__ picks, uint64_t seed, uint64_t particle_offset,
+                     uint32_t* __restrict__ state_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
-  stage_blob(&B, gblob, (uint32_t)sizeof(Blob), &mbar);
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const Blob& B = *reinterpret_cast<const Blob*>(smem_raw);
   const int64_t stride = (int64_t)gridDim.x * THREADS;
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
     uint32_t veh[NA];
     if (picks != nullptr) {
+      const uint32_t pk = __ldg(reinterpret_cast<const uint32_t*>(picks) + i);
       int p[2 * NA];
 #pragma unroll
-      for (int k = 0; k < 2 * NA; ++k) p[k] = __ldg(picks + i * 2 * NA + k);
-      initial_state<NA>(B, p, veh);
+      for (int k = 0; k < 2 * NA; ++k) p[k] = (pk >> (8 * k)) & 255;
+      initial_state(B, p, veh);
     } else {
-      initial_state_random<NA>(B, seed, particle_offset + (uint64_t)i, veh);
+      initial_state_random(B, seed, particle_offset + (uint64_t)i, veh);
     }
-#pragma unroll
-    for (int a = 0; a < NA; ++a) state_out[i * NA + a] = veh[a];
+    reinterpret_cast<uint2*>(state_out)[i] = make_uint2(veh[0], veh[1]);
   }
 }
 
@@ -156,22 +202,23 @@ initial_state_kernel(const Blob* __restrict__ gblob, int64_t n, const uint8_t* _
 // CPython's ``discount**rollout_t`` (mcts.py:421) calls -- so returns match bit for bit.
 struct DiscountTable { double v[256]; };
 
-template <int NA>
 __global__ void __launch_bounds__(THREADS)
-rollout_kernel(const Blob* __restrict__ gblob, int64_t n, const uint32_t* __restrict__ state_in,
-               int ego, int max_steps, const __grid_constant__ DiscountTable dtab, uint64_t seed, uint32_t step0,
+rollout_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+               const uint32_t* __restrict__ state_in, int ego, int max_steps,
+               const __grid_constant__ DiscountTable dtab, uint64_t seed, uint32_t step0,
                uint64_t particle_offset, double* __restrict__ returns_out,
                uint8_t* __restrict__ steps_out, uint32_t* __restrict__ state_out,
                unsigned long long* __restrict__ work_counter,
                unsigned long long* __restrict__ live_count) {
-  __shared__ Blob B;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   __shared__ double sdisc[256];
   for (int t = threadIdx.x; t < 256; t += THREADS) sdisc[t] = dtab.v[t];
-  stage_blob(&B, gblob, (uint32_t)sizeof(Blob), &mbar);  // contains a __syncthreads()
+  stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
+  const Blob& B = *reinterpret_cast<const Blob*>(smem_raw);
 
   const unsigned lane = threadIdx.x & 31u;
-  uint32_t veh[NA];
+  uint32_t v0 = 0, v1 = 0;
   int64_t item = -1;       // rollout owned by this lane (-1: none)
   int k = 0;               // steps taken
   double ret = 0.0;
@@ -184,19 +231,15 @@ rollout_kernel(const Blob* __restrict__ gblob, int64_t n, const uint32_t* __rest
     if (idle && !exhausted) {
       unsigned long long base = 0;
       const int cnt = __popc(idle);
-      if (lane == (unsigned)(__ffs(idle) - 1)) base = atomicAdd(work_counter, (unsigned long long)cnt);
-      base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+      const int leader = __ffs(idle) - 1;
+      if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)cnt);
+      base = __shfl_sync(0xffffffffu, base, leader);
       if (item < 0) {
         const int64_t mine = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
         if (mine < n) {
           item = mine;
-          if (NA == 2) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(state_in) + item);
-            veh[0] = v.x; veh[1] = v.y;
-          } else {
-#pragma unroll
-            for (int a = 0; a < NA; ++a) veh[a] = __ldg(state_in + item * NA + a);
-          }
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(state_in) + item);
+          v0 = v.x; v1 = v.y;
           k = 0; ret = 0.0;
         }
       }
@@ -208,30 +251,20 @@ rollout_kernel(const Blob* __restrict__ gblob, int64_t n, const uint32_t* __rest
     if (item >= 0) {
       bool finished = (k >= max_steps);
       if (!finished) {
-        int act[NA], order_idx, coll[NA];
-        sample_step_noise<NA>(seed, particle_offset + (uint64_t)item, step0 + (uint32_t)k, act, order_idx);
-        uint32_t before = 0;
-#pragma unroll
-        for (int a = 0; a < NA; ++a) if (a == ego) before = veh[a];
-        transition<NA>(B, veh, act, order_idx, coll);
-        uint32_t after = 0; int c = 0; bool all_done = true;
-#pragma unroll
-        for (int a = 0; a < NA; ++a) {
-          if (a == ego) { after = veh[a]; c = coll[a]; }
-          all_done &= vdone(veh[a]);
-        }
-        const double r = reward(B, before, after, c);
+        int a0, a1, order_idx, c0, c1;
+        sample_step_noise(seed, particle_offset + (uint64_t)item, step0 + (uint32_t)k, a0, a1, order_idx);
+        const uint32_t before = ego ? v1 : v0;
+        transition(B, v0, v1, a0, a1, order_idx, c0, c1);
+        const uint32_t after = ego ? v1 : v0;
+        const double r = reward(B, before, after, ego ? c1 : c0);
         ret = __dadd_rn(ret, __dmul_rn(sdisc[k], r));
         ++k; ++executed;
-        finished = vdone(after) || all_done || (k >= max_steps);
+        finished = vdone(after) || (vdone(v0) && vdone(v1)) || (k >= max_steps);
       }
       if (finished) {
         returns_out[item] = ret;
         if (steps_out) steps_out[item] = (uint8_t)k;
-        if (state_out) {
-#pragma unroll
-          for (int a = 0; a < NA; ++a) state_out[item * NA + a] = veh[a];
-        }
+        if (state_out) reinterpret_cast<uint2*>(state_out)[item] = make_uint2(v0, v1);
         item = -1;
       }
     }
@@ -243,8 +276,20 @@ rollout_kernel(const Blob* __restrict__ gblob, int64_t n, const uint32_t* __rest
 }
 
 // ------------------------------------------------------------------ host: model build
-static bool build_blob(const char* grid_rows, int num_agents, int obs_front, int obs_back,
-                       int obs_side, int obstacle_collisions, Blob* out) {
+// grid cell seen at window position (row r: 0 = farthest ahead, col c: 0 = left) by a
+// vehicle at (x, y) facing `dir`, for the (front, back, side) = (3, 1, 1) window
+static void window_to_grid(int x, int y, int dir, int r, int c, int* gx, int* gy) {
+  const int FRONT = 3, SIDE = 1;
+  switch (dir) {
+    case 0: *gy = y + r - FRONT; *gx = x + c - SIDE; break;   // NORTH
+    case 1: *gy = y + c - SIDE;  *gx = x - r + FRONT; break;  // EAST
+    case 2: *gy = y - r + FRONT; *gx = x - c + SIDE; break;   // SOUTH
+    default: *gy = y - c + SIDE; *gx = x + r - FRONT; break;  // WEST
+  }
+}
+
+static Blob* build_blob(const char* grid_rows, int num_agents, int obs_front, int obs_back,
+                        int obs_side, int obstacle_collisions, size_t* bytes_out) {
   std::vector<std::string> rows;
   {
     std::string cur;
@@ -255,41 +300,47 @@ static bool build_blob(const char* grid_rows, int num_agents, int obs_front, int
     if (!cur.empty()) rows.push_back(cur);
   }
   const int H = (int)rows.size();
-  if (H < 1 || H > 16) { set_error("grid height %d outside [1,16]", H); return false; }
+  if (H < 1 || H > 16) { set_error("grid height %d outside [1,16]", H); return nullptr; }
   const int W = (int)rows[0].size();
-  if (W < 1 || W > 16) { set_error("grid width %d outside [1,16]", W); return false; }
-  for (auto& r : rows) if ((int)r.size() != W) { set_error("ragged grid rows"); return false; }
-  if (num_agents < 1 || num_agents > MAX_AGENTS) { set_error("num_agents %d outside [1,%d]", num_agents, MAX_AGENTS); return false; }
+  if (W < 1 || W > 16) { set_error("grid width %d outside [1,16]", W); return nullptr; }
+  for (auto& r : rows) if ((int)r.size() != W) { set_error("ragged grid rows"); return nullptr; }
 
-  memset(out, 0, sizeof(Blob));
-  for (int l = 0; l < LINES; ++l) { out->rows[l] = 0xffffffffu; out->cols[l] = 0xffffffffu; }
+  // first pass: count destinations (sizes the blob)
+  int n_dest_total = 0;
+  for (auto& r : rows) for (char ch : r) n_dest_total += (ch == '-' || (ch >= 'a' && ch <= 'j'));
+  if (n_dest_total > MAX_CELLS) { set_error("more than %d destination cells", MAX_CELLS); return nullptr; }
+  const size_t bytes = blob_bytes(n_dest_total);
+  Blob* out = (Blob*)calloc(1, bytes);
+  for (int l = 0; l < LINES; ++l) out->rows[l] = 0xffffffffu;
   bool blk[16][16];
+  memset(blk, 1, sizeof(blk));
   int n_start = 0, n_dest = 0;
   for (int y = 0; y < H; ++y) {
     for (int x = 0; x < W; ++x) {
       const char ch = rows[y][x];
       blk[y][x] = (ch == '#');
-      if (!blk[y][x]) {
-        out->rows[y + PAD] &= ~(1u << (x + PAD));
-        out->cols[x + PAD] &= ~(1u << (y + PAD));
-      }
+      if (!blk[y][x]) out->rows[y + PAD] &= ~(1u << (x + PAD));
       uint8_t smask = 0, dmask = 0;
       if (ch == '+') smask = 0x0f;
-      else if (ch >= '0' && ch <= '9') smask = (ch - '0') < MAX_AGENTS ? (uint8_t)(1u << (ch - '0')) : 0;
+      else if (ch >= '0' && ch <= '9') smask = (uint8_t)(((ch - '0') < 4) ? (1u << (ch - '0')) : 0x80u);
       else if (ch == '-') dmask = 0x0f;
-      else if (ch >= 'a' && ch <= 'j') dmask = (ch - 'a') < MAX_AGENTS ? (uint8_t)(1u << (ch - 'a')) : 0;
-      else if (ch != '.' && ch != '#') { set_error("bad grid character '%c'", ch); return false; }
+      else if (ch >= 'a' && ch <= 'j') dmask = (uint8_t)(((ch - 'a') < 4) ? (1u << (ch - 'a')) : 0x80u);
+      else if (ch != '.' && ch != '#') { set_error("bad grid character '%c'", ch); free(out); return nullptr; }
       if (smask) {
-        if (n_start >= MAX_CELLS) { set_error("more than %d start cells", MAX_CELLS); return false; }
+        if (n_start >= MAX_CELLS) { set_error("more than %d start cells", MAX_CELLS); free(out); return nullptr; }
         out->start_xy[n_start] = (uint8_t)(x | (y << 4)); out->start_agents[n_start++] = smask;
       }
-      if (dmask) {
-        if (n_dest >= MAX_CELLS) { set_error("more than %d destination cells", MAX_CELLS); return false; }
-        out->dest_xy[n_dest] = (uint8_t)(x | (y << 4)); out->dest_agents[n_dest++] = dmask;
-      }
+      if (dmask) { out->dest_xy[n_dest] = (uint8_t)(x | (y << 4)); out->dest_agents[n_dest++] = dmask; }
     }
   }
-  if (n_start < num_agents || n_dest < num_agents) { set_error("grid supports fewer than %d agents", num_agents); return false; }
+  for (int i = 0; i < num_agents; ++i) {
+    int ns = 0, nd = 0;
+    for (int c = 0; c < n_start; ++c) ns += (out->start_agents[c] >> i) & 1;
+    for (int c = 0; c < n_dest; ++c) nd += (out->dest_agents[c] >> i) & 1;
+    if (ns < 1 || nd < 1 || n_start < num_agents || n_dest < num_agents) {
+      set_error("grid does not support %d agents", num_agents); free(out); return nullptr;
+    }
+  }
   out->n_start = (uint8_t)n_start; out->n_dest = (uint8_t)n_dest;
   out->width = (uint8_t)W; out->height = (uint8_t)H;
   out->n_agents = (uint8_t)num_agents;
@@ -310,7 +361,7 @@ static bool build_blob(const char* grid_rows, int num_agents, int obs_front, int
         if (nx < 0 || ny < 0 || nx >= W || ny >= H || blk[ny][nx]) continue;
         const int k = nx | (ny << 4);
         if (out->dist[d][k] != 255) continue;
-        if (out->dist[d][c] + 1 >= 127) { set_error("shortest path longer than 126"); return false; }
+        if (out->dist[d][c] + 1 >= 127) { set_error("shortest path longer than 126"); free(out); return nullptr; }
         out->dist[d][k] = (uint8_t)(out->dist[d][c] + 1); q.push(k);
       }
     }
@@ -318,12 +369,48 @@ static bool build_blob(const char* grid_rows, int num_agents, int obs_front, int
   for (int d0 = 0; d0 < MAX_D0; ++d0)
     for (int p = 0; p < 3; ++p)
       out->progress[d0 * 3 + p] = 0.5 * ((double)p / (double)(d0 < 1 ? 1 : d0));
-  return true;
+  // window lookup: where inside the 5x3 window does the grid offset (dx, dy) fall?
+  memset(out->win_lut, 15, sizeof(out->win_lut));
+  for (int dir = 0; dir < 4; ++dir)
+    for (int r = 0; r < 5; ++r)
+      for (int c = 0; c < 3; ++c) {
+        int gx, gy;
+        window_to_grid(0, 0, dir, r, c, &gx, &gy);
+        out->win_lut[dir][(gy + 3) * 8 + (gx + 3)] = (uint8_t)(r * 3 + c);
+      }
+  // local-cell codes of a lone vehicle: walls / own destination / ego cell
+  for (int d = 0; d < n_dest; ++d)
+    for (int dir = 0; dir < 4; ++dir)
+      for (int y = 0; y < 16; ++y)
+        for (int x = 0; x < 16; ++x) {
+          uint32_t cells = 0;
+          for (int r = 0; r < 5; ++r)
+            for (int c = 0; c < 3; ++c) {
+              int gx, gy;
+              window_to_grid(x, y, dir, r, c, &gx, &gy);
+              uint32_t code;
+              if (gx < 0 || gy < 0 || gx >= W || gy >= H || blk[gy][gx]) code = WALL;
+              else if (gx == x && gy == y) code = VEHICLE;
+              else if ((gx | (gy << 4)) == out->dest_xy[d]) code = DESTINATION;
+              else code = EMPTY;
+              cells |= code << (2 * (r * 3 + c));
+            }
+          out->obs_base[((d * 4 + dir) << 8) | (y << 4) | x] = cells;
+        }
+  *bytes_out = bytes;
+  return out;
 }
 
-static int grid_for(int64_t n, int ctas_per_sm) {
-  const int64_t need = (n + THREADS - 1) / THREADS;
-  const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+// persistent grid: every resident CTA slot of every SM gets exactly one CTA
+template <typename K>
+static int grid_for(K kernel, size_t smem, int64_t work_items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int64_t need = (work_items + THREADS - 1) / THREADS;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 
@@ -332,15 +419,6 @@ static int grid_for(int64_t n, int ctas_per_sm) {
 
 using namespace posg;
 using namespace posg::driving;
-
-#define DISPATCH_NA(m, ...)                                         \
-  switch ((m)->num_agents) {                                        \
-    case 1: { constexpr int NA = 1; __VA_ARGS__; } break;           \
-    case 2: { constexpr int NA = 2; __VA_ARGS__; } break;           \
-    case 3: { constexpr int NA = 3; __VA_ARGS__; } break;           \
-    case 4: { constexpr int NA = 4; __VA_ARGS__; } break;           \
-    default: set_error("unsupported num_agents"); return POSG_E_UNSUPPORTED; \
-  }
 
 static int check_driving(posg_model_t m) {
   if (!m || m->kind != KIND_DRIVING) { set_error("not a Driving model handle"); return POSG_E_INVALID; }
@@ -358,17 +436,19 @@ int posg_driving_create(const char* grid_rows, int num_agents, int obs_front, in
   }
   int ndev = posg_device_count();
   if (ndev < 0) return ndev;
-  Blob* h = (Blob*)malloc(sizeof(Blob));
-  if (!build_blob(grid_rows, num_agents, obs_front, obs_back, obs_side, obstacle_collisions, h)) {
-    free(h);
-    return POSG_E_INVALID;
+  if (num_agents != NA) {
+    set_error("num_agents %d unsupported: the sm_100a kernels are specialised for 2 vehicles", num_agents);
+    return POSG_E_UNSUPPORTED;
   }
+  size_t bytes = 0;
+  Blob* h = build_blob(grid_rows, num_agents, obs_front, obs_back, obs_side, obstacle_collisions, &bytes);
+  if (!h) return POSG_E_INVALID;
   posg_model* m = new posg_model();
-  m->kind = KIND_DRIVING; m->num_agents = num_agents; m->blob_bytes = (int)sizeof(Blob);
+  m->kind = KIND_DRIVING; m->num_agents = num_agents; m->blob_bytes = (int)bytes;
   m->h_blob = h; m->d_blob = nullptr;
   cudaError_t e = cudaGetDevice(&m->device);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, sizeof(Blob));
-  if (e == cudaSuccess) e = cudaMemcpy(m->d_blob, h, sizeof(Blob), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_blob, h, bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { int rc = cuda_fail(e, "model upload"); posg_model_destroy(m); return rc; }
   *out = m;
   return POSG_OK;
@@ -377,20 +457,20 @@ int posg_driving_create(const char* grid_rows, int num_agents, int obs_front, in
 int posg_driving_sample_initial_state(posg_model_t m, int64_t n, const uint8_t* picks, uint64_t seed,
                                       uint64_t particle_offset, uint32_t* state_out, void* stream) {
   int rc = check_driving(m); if (rc) return rc;
-  POSG_REQUIRE(n >= 0 && state_out, "bad arguments");
   if (n == 0) return POSG_OK;
-  DISPATCH_NA(m, initial_state_kernel<NA><<<grid_for(n, 4), THREADS, 0, (cudaStream_t)stream>>>(
-      (const Blob*)m->d_blob, n, picks, seed, particle_offset, state_out));
+  POSG_REQUIRE(n > 0 && state_out, "bad arguments");
+  initial_state_kernel<<<grid_for(initial_state_kernel, m->blob_bytes, n), THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, picks, seed, particle_offset, state_out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
 
 int posg_driving_observe(posg_model_t m, int64_t n, const uint32_t* state, uint64_t* obs_out, void* stream) {
   int rc = check_driving(m); if (rc) return rc;
-  POSG_REQUIRE(n >= 0 && state && obs_out, "bad arguments");
   if (n == 0) return POSG_OK;
-  DISPATCH_NA(m, observe_kernel<NA><<<grid_for(n, 4), THREADS, 0, (cudaStream_t)stream>>>(
-      (const Blob*)m->d_blob, n, state, obs_out));
+  POSG_REQUIRE(n > 0 && state && obs_out, "bad arguments");
+  observe_kernel<<<grid_for(observe_kernel, m->blob_bytes, n), THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, obs_out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
@@ -400,11 +480,11 @@ int posg_driving_step(posg_model_t m, int64_t n, const uint32_t* state_in, const
                       uint32_t* state_out, uint64_t* obs_out, double* rewards_out, uint8_t* flags_out,
                       uint8_t* actions_out, unsigned long long* live_count, void* stream) {
   int rc = check_driving(m); if (rc) return rc;
-  POSG_REQUIRE(n >= 0 && state_in && state_out && obs_out && rewards_out && flags_out, "bad arguments");
   if (n == 0) return POSG_OK;
-  DISPATCH_NA(m, step_kernel<NA><<<grid_for(n, 8), THREADS, 0, (cudaStream_t)stream>>>(
-      (const Blob*)m->d_blob, n, state_in, actions_in, order_in, seed, step_idx, particle_offset,
-      state_out, obs_out, rewards_out, flags_out, actions_out, live_count));
+  POSG_REQUIRE(n > 0 && state_in && state_out && obs_out && rewards_out && flags_out, "bad arguments");
+  step_kernel<<<grid_for(step_kernel, m->blob_bytes, (n + EPT - 1) / EPT), THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, actions_in, order_in, seed, step_idx,
+      particle_offset, state_out, obs_out, rewards_out, flags_out, actions_out, live_count);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
@@ -416,9 +496,9 @@ static int rollout_launch(posg_model_t m, int64_t n, const uint32_t* state_in, i
                           cudaStream_t stream) {
   DiscountTable dtab;
   for (int k = 0; k < 256; ++k) dtab.v[k] = pow(discount, (double)k);
-  DISPATCH_NA(m, rollout_kernel<NA><<<grid_for(n, 8), THREADS, 0, stream>>>(
-      (const Blob*)m->d_blob, n, state_in, ego, max_steps, dtab, seed, step0, particle_offset,
-      returns_out, steps_out, state_out, work_counter, live_count));
+  rollout_kernel<<<grid_for(rollout_kernel, m->blob_bytes, n), THREADS, m->blob_bytes, stream>>>(
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, ego, max_steps, dtab, seed, step0,
+      particle_offset, returns_out, steps_out, state_out, work_counter, live_count);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
@@ -428,10 +508,10 @@ int posg_driving_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, in
                          double* returns_out, uint8_t* steps_out, uint32_t* state_out,
                          unsigned long long* live_count, void* stream) {
   int rc = check_driving(m); if (rc) return rc;
-  POSG_REQUIRE(n >= 0 && state_in && returns_out, "bad arguments");
   POSG_REQUIRE(ego_agent >= 0 && ego_agent < m->num_agents, "ego_agent out of range");
   POSG_REQUIRE(max_steps >= 0 && max_steps <= 255, "max_steps outside [0,255]");
   if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && state_in && returns_out, "bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   // per-call work counter (stream-ordered allocation: no global mutable state)
   unsigned long long* counter = nullptr;
@@ -448,8 +528,8 @@ int posg_driving_rollout_host(posg_model_t m, int64_t n, const uint32_t* state_i
                               uint64_t particle_offset, double* returns_out_host, uint8_t* steps_out_host,
                               uint32_t* state_out_host, unsigned long long* live_count_host) {
   int rc = check_driving(m); if (rc) return rc;
-  POSG_REQUIRE(n >= 0 && state_in_host && returns_out_host, "bad arguments");
   if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && state_in_host && returns_out_host, "bad arguments");
   const size_t na = (size_t)m->num_agents;
   uint32_t *d_in = nullptr, *d_out = nullptr; double* d_ret = nullptr; uint8_t* d_steps = nullptr;
   unsigned long long* d_live = nullptr;
@@ -474,37 +554,62 @@ int posg_driving_rollout_host(posg_model_t m, int64_t n, const uint32_t* state_i
   return rc;
 }
 
+// Pipelined over CHUNKS slices of the batch on two streams so that, after the first
+// slice, the H2D copy of slice k+1, the 50 step launches of slice k and the D2H copy of
+// slice k-1 overlap (PCIe is full duplex; the copy engines run beside the SMs).
 int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_host, int num_steps,
                             uint64_t seed, uint64_t particle_offset, uint32_t* state_out_host,
                             uint64_t* obs_out_host, double* rewards_out_host, uint8_t* flags_out_host,
                             unsigned long long* live_count_host) {
   int rc = check_driving(m); if (rc) return rc;
-  POSG_REQUIRE(n >= 0 && state_in_host && num_steps >= 1, "bad arguments");
   if (n == 0) return POSG_OK;
-  const size_t na = (size_t)m->num_agents;
-  uint32_t* d_state = nullptr; uint64_t* d_obs = nullptr; double* d_rew = nullptr;
-  uint8_t *d_flags = nullptr, *d_act = nullptr; unsigned long long* d_live = nullptr;
-  cudaStream_t s = nullptr;
-  POSG_CUDA(cudaMalloc((void**)&d_state, n * na * 4));
-  POSG_CUDA(cudaMalloc((void**)&d_obs, n * na * 8));
-  POSG_CUDA(cudaMalloc((void**)&d_rew, n * na * 8));
-  POSG_CUDA(cudaMalloc((void**)&d_flags, n));
-  POSG_CUDA(cudaMalloc((void**)&d_act, n * na));
-  POSG_CUDA(cudaMalloc((void**)&d_live, 8));
-  POSG_CUDA(cudaMemcpyAsync(d_state, state_in_host, n * na * 4, cudaMemcpyHostToDevice, s));
-  POSG_CUDA(cudaMemsetAsync(d_live, 0, 8, s));
-  for (int k = 0; k < num_steps && rc == POSG_OK; ++k)
-    rc = posg_driving_step(m, n, d_state, nullptr, nullptr, seed, (uint32_t)k, particle_offset, d_state,
-                           d_obs, d_rew, d_flags, d_act, d_live, s);
-  if (rc == POSG_OK) {
-    if (state_out_host) POSG_CUDA(cudaMemcpyAsync(state_out_host, d_state, n * na * 4, cudaMemcpyDeviceToHost, s));
-    if (obs_out_host) POSG_CUDA(cudaMemcpyAsync(obs_out_host, d_obs, n * na * 8, cudaMemcpyDeviceToHost, s));
-    if (rewards_out_host) POSG_CUDA(cudaMemcpyAsync(rewards_out_host, d_rew, n * na * 8, cudaMemcpyDeviceToHost, s));
-    if (flags_out_host) POSG_CUDA(cudaMemcpyAsync(flags_out_host, d_flags, n, cudaMemcpyDeviceToHost, s));
-    if (live_count_host) POSG_CUDA(cudaMemcpyAsync(live_count_host, d_live, 8, cudaMemcpyDeviceToHost, s));
-    POSG_CUDA(cudaStreamSynchronize(s));
+  POSG_REQUIRE(n > 0 && state_in_host && num_steps >= 1, "bad arguments");
+  constexpr int NSTREAM = 2;
+  // slices are multiples of 4 envs so that every slice keeps the 16-byte fast path and
+  // the Philox word grouping (particle >> 2) of the monolithic call
+  int64_t chunk = ((n + 7) / 8 + 3) & ~(int64_t)3;
+  if (chunk < 1 << 16) chunk = (n + 3) & ~(int64_t)3;
+  const size_t per_env = 8 + 16 + 16 + 1 + 2;
+  unsigned char* d_base[NSTREAM] = {nullptr, nullptr};
+  cudaStream_t st[NSTREAM] = {nullptr, nullptr};
+  unsigned long long* d_live = nullptr;
+  auto cleanup = [&]() {
+    for (int i = 0; i < NSTREAM; ++i) { if (st[i]) cudaStreamDestroy(st[i]); cudaFree(d_base[i]); }
+    cudaFree(d_live);
+  };
+#define SWEEP_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
+  SWEEP_CUDA(cudaMalloc((void**)&d_live, 8));
+  SWEEP_CUDA(cudaMemset(d_live, 0, 8));
+  for (int i = 0; i < NSTREAM; ++i) {
+    SWEEP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    SWEEP_CUDA(cudaMalloc((void**)&d_base[i], (size_t)chunk * per_env + 256));
   }
-  cudaFree(d_state); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_flags); cudaFree(d_act); cudaFree(d_live);
+  int slot = 0;
+  for (int64_t off = 0; off < n && rc == POSG_OK; off += chunk, slot ^= 1) {
+    const int64_t c = (n - off < chunk) ? (n - off) : chunk;
+    cudaStream_t s = st[slot];
+    unsigned char* base = d_base[slot];
+    uint32_t* d_state = (uint32_t*)base;
+    uint64_t* d_obs = (uint64_t*)(base + (size_t)chunk * 8);
+    double* d_rew = (double*)(base + (size_t)chunk * 24);
+    uint8_t* d_flags = base + (size_t)chunk * 40;
+    uint8_t* d_act = base + (size_t)chunk * 41 + 64;
+    SWEEP_CUDA(cudaMemcpyAsync(d_state, state_in_host + 2 * off, (size_t)c * 8, cudaMemcpyHostToDevice, s));
+    for (int k = 0; k < num_steps && rc == POSG_OK; ++k)
+      rc = posg_driving_step(m, c, d_state, nullptr, nullptr, seed, (uint32_t)k, particle_offset + (uint64_t)off,
+                             d_state, d_obs, d_rew, d_flags, d_act, d_live, s);
+    if (rc != POSG_OK) break;
+    if (state_out_host) SWEEP_CUDA(cudaMemcpyAsync(state_out_host + 2 * off, d_state, (size_t)c * 8, cudaMemcpyDeviceToHost, s));
+    if (obs_out_host) SWEEP_CUDA(cudaMemcpyAsync(obs_out_host + 2 * off, d_obs, (size_t)c * 16, cudaMemcpyDeviceToHost, s));
+    if (rewards_out_host) SWEEP_CUDA(cudaMemcpyAsync(rewards_out_host + 2 * off, d_rew, (size_t)c * 16, cudaMemcpyDeviceToHost, s));
+    if (flags_out_host) SWEEP_CUDA(cudaMemcpyAsync(flags_out_host + off, d_flags, (size_t)c, cudaMemcpyDeviceToHost, s));
+  }
+  if (rc == POSG_OK) {
+    for (int i = 0; i < NSTREAM; ++i) SWEEP_CUDA(cudaStreamSynchronize(st[i]));
+    if (live_count_host) SWEEP_CUDA(cudaMemcpy(live_count_host, d_live, 8, cudaMemcpyDeviceToHost));
+  }
+#undef SWEEP_CUDA
+  cleanup();
   return rc;
 }
 

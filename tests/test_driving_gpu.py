@@ -164,3 +164,25 @@ def test_full_size_properties(env):
     crashed = ((final[:, 0] >> 16) & 1).double().mean().item()
     assert 0.10 < crashed < 0.30
     assert steps.max().item() == depth and steps.min().item() >= 1
+
+
+def test_host_entry_points_match_device_path(env):
+    """posg_driving_sweep_host / posg_driving_rollout_host (host buffers, chunked and
+    pipelined over two streams) give exactly what the device-pointer entry points give."""
+    n, seed, depth, off = 1_000_003, 77, 20, 4096
+    st = env.sample_initial_state(n, seed=seed, particle_offset=off)
+    cur, out = st, None
+    live = torch.zeros(1, dtype=torch.int64, device=env.device)
+    for k in range(depth):
+        out = env.step(cur, seed=seed, step_idx=k, particle_offset=off, live_count=live)
+        cur = out.state
+    (h_state, h_obs, h_rew, h_flags), h_live = env.sweep_host(st.cpu().numpy(), depth, seed=seed, particle_offset=off)
+    assert (h_state == out.state.cpu().numpy()).all()
+    assert (h_obs == out.obs.cpu().numpy()).all()
+    assert (h_rew.view(np.uint64) == out.rewards.cpu().numpy().view(np.uint64)).all()
+    assert (h_flags == out.flags.cpu().numpy()).all()
+    assert h_live == int(live.item())
+    ret, steps, _ = env.rollout(st, 1, depth, 0.95, seed=seed, particle_offset=off)
+    h_ret, h_steps, _ = env.rollout_host(st.cpu().numpy(), 1, depth, 0.95, seed=seed, particle_offset=off)
+    assert (h_ret.view(np.uint64) == ret.cpu().numpy().view(np.uint64)).all()
+    assert (h_steps == steps.cpu().numpy()).all()
