@@ -582,7 +582,7 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
   SWEEP_CUDA(cudaMemset(d_live, 0, 8));
   for (int i = 0; i < NSTREAM; ++i) {
     SWEEP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    SWEEP_CUDA(cudaMalloc((void**)&d_base[i], (size_t)chunk * per_env + 256));
+    SWEEP_CUDA(cudaMalloc((void**)&d_base[i], (size_t)chunk * per_env + 512));
   }
   int slot = 0;
   for (int64_t off = 0; off < n && rc == POSG_OK; off += chunk, slot ^= 1) {
@@ -593,7 +593,7 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
     uint64_t* d_obs = (uint64_t*)(base + (size_t)chunk * 8);
     double* d_rew = (double*)(base + (size_t)chunk * 24);
     uint8_t* d_flags = base + (size_t)chunk * 40;
-    uint8_t* d_act = base + (size_t)chunk * 41 + 64;
+    uint8_t* d_act = base + (((size_t)chunk * 41 + 255) & ~(size_t)255);
     SWEEP_CUDA(cudaMemcpyAsync(d_state, state_in_host + 2 * off, (size_t)c * 8, cudaMemcpyHostToDevice, s));
     for (int k = 0; k < num_steps && rc == POSG_OK; ++k)
       rc = posg_driving_step(m, c, d_state, nullptr, nullptr, seed, (uint32_t)k, particle_offset + (uint64_t)off,
