@@ -129,6 +129,63 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
                             double* rewards_out_host, uint8_t* flags_out_host,
                             unsigned long long* live_count_host);
 
+
+/* ------------------------------------------------------------------ POMCP search tree
+ * The tree (obs nodes, per-action statistics, child lists, particle log) lives in one
+ * caller-owned device arena; see posggym_baselines_b200/csrc/search.cuh for the layout.
+ * These entry points replace the reference's MCTS hot loops for RandomSearchPolicy /
+ * RandomOtherAgentPolicy and state_belief_only=True (the POMCP configuration,
+ * planning/pomcp.py:20-35). */
+
+typedef struct posg_search_params {
+  double discount;                  /* MCTSConfig.discount */
+  double c;                         /* MCTSConfig.c */
+  double known_min, known_max;      /* MCTSConfig.known_bounds; min > max = none */
+  double pucb_exploration_fraction; /* MCTSConfig.pucb_exploration_fraction */
+  int depth_limit;                  /* MCTSConfig.depth_limit (derived, config.py:50-55) */
+  int step_limit;                   /* MCTS.step_limit (mcts.py:53-58) */
+  int selection;                    /* 0 ucb, 1 pucb, 2 uniform (mcts.py:66-74) */
+  int ego_agent;
+  uint64_t seed;
+} posg_search_params;
+
+/* ego action count, 64-bit words per observation key, 32-bit words per packed state */
+int posg_model_info(posg_model_t m, int* n_actions, int* obs_words, int* state_words);
+int64_t posg_tree_arena_bytes(posg_model_t m, int64_t cap_nodes, int64_t cap_log);
+/* MCTS.reset (mcts.py:123-138): empty tree whose root is node 0 at time root_t. */
+int posg_tree_reset(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root_t,
+                    double known_min, double known_max, void* stream);
+/* n_sims simulations of MCTS.get_action's loop body (mcts.py:285-290 -> _simulate
+ * 308-382 -> _evaluate/_rollout 384-452) from the belief `particles` (n_particles packed
+ * states) of node `root`; simulation i uses Philox counter sim_id0 + i. */
+int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
+                const uint32_t* particles, int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
+                const posg_search_params* p, void* stream);
+/* Copies to HOST: visits[A], completed[A], total_value[A] of the node's action children
+ * (ActionNode.visits / total_value, node.py:138-140) then node visits, node count, log
+ * count, max search depth, min value, max value, overflow count, sims done, node flags. */
+int posg_tree_node_stats(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
+                         double* out_host, void* stream);
+/* MCTS._update re-rooting (mcts.py:229-263): child of (root, action) with observation
+ * obs (HOST words); out_host = {node or -1, created, flags, t}. */
+int posg_tree_advance(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root,
+                      int action, const uint64_t* obs_host, int create_if_missing, int* out_host,
+                      void* stream);
+/* obs_node.belief.particles: every particle logged at `node` -> states_out (device). */
+int posg_tree_gather_belief(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
+                            uint32_t* states_out, int64_t max_out, int64_t* count_host, void* stream);
+/* BeliefRejectionSampler._rejection_sample (planning/belief.py:145-194) with
+ * use_rejected_samples=True: result_host = {accepted, attempts, written}. */
+int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, int64_t n_parent,
+                             int ego_agent, int action, const uint64_t* target_obs_host,
+                             int64_t n_needed, int64_t max_attempts, uint64_t seed, uint64_t draw_id,
+                             uint32_t* out_states, uint32_t* reject_scratch, int64_t* result_host,
+                             void* stream);
+/* MCTS._initial_update rejection loop (mcts.py:186-194): result_host as above. */
+int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_obs_host,
+                        int64_t n_needed, int64_t max_attempts, uint64_t seed, uint64_t draw_id,
+                        uint32_t* out_states, int64_t* result_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

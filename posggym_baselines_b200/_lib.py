@@ -45,7 +45,27 @@ SIGNATURES = {
         [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp],
     ),
     "posg_driving_sweep_host": (_int, [_vp, _i64, _vp, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "posg_model_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "posg_tree_arena_bytes": (_i64, [_vp, _i64, _i64]),
+    "posg_tree_reset": (_int, [_vp, _vp, _i64, _i64, _int, _dbl, _dbl, _vp]),
+    "posg_search": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _u64, _vp, _vp]),
+    "posg_tree_node_stats": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
+    "posg_tree_advance": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _int, _vp, _vp]),
+    "posg_tree_gather_belief": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp, _vp]),
+    "posg_belief_reinvigorate": (
+        _int, [_vp, _vp, _i64, _int, _int, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
+    "posg_belief_initial": (_int, [_vp, _int, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp]),
 }
+
+
+class SearchParams(C.Structure):
+    """Mirror of posg_search_params (include/posg_b200.h)."""
+
+    _fields_ = [
+        ("discount", _dbl), ("c", _dbl), ("known_min", _dbl), ("known_max", _dbl),
+        ("pucb_exploration_fraction", _dbl), ("depth_limit", _int), ("step_limit", _int),
+        ("selection", _int), ("ego_agent", _int), ("seed", _u64),
+    ]
 
 _lib: Optional[C.CDLL] = None
 

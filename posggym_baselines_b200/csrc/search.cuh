@@ -1,0 +1,365 @@
+// POMCP search tree on the device (SoA arena owned by the caller) and the wave-parallel
+// simulation kernel.  Restates, for a batch of simulations per launch, the reference's
+//   MCTS.get_action / _simulate / _evaluate / _rollout / ucb_action_selection /
+//   pucb_action_selection / min_visit_action_selection
+// (planning/mcts.py:269-306, 308-382, 384-403, 405-452, 494-561) with
+// RandomSearchPolicy / RandomOtherAgentPolicy plugins and state_belief_only=True.
+//
+// One thread = one simulation (root-to-leaf descent, leaf rollout, backup).  Lanes of a
+// warp that sit at the same tree node choose their actions by "water-filling": lane with
+// rank r takes the action sequential UCB would take on the r-th of those visits with the
+// value estimates frozen, so a wave of 1 is exactly the reference's sequential search and
+// larger waves spread over the actions the way consecutive reference simulations would.
+#pragma once
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace posg {
+namespace search {
+
+constexpr int MAX_DEPTH = 64;      // path stack (the in-scope envs stop at 50 steps)
+constexpr int SEL_UCB = 0, SEL_PUCB = 1, SEL_UNIFORM = 2;
+
+struct Counters {               // first 64 bytes of the arena
+  unsigned long long node_count;
+  unsigned long long log_count;
+  unsigned long long min_key;   // order-preserving keys of the min / max action value
+  unsigned long long max_key;
+  unsigned int max_depth;
+  unsigned int overflow;        // simulations that could not expand (arena full)
+  unsigned long long sims_done;
+  unsigned long long pad_[2];
+};
+static_assert(sizeof(Counters) == 64, "counter block is 64 bytes");
+
+struct Params {
+  double discount;
+  double c;
+  double known_min, known_max;  // known_min > known_max: no known bounds
+  double pucb_exploration_fraction;
+  int depth_limit;
+  int step_limit;               // max_episode_steps (node.t may not exceed it)
+  int selection;                // SEL_*
+  int ego;
+  uint64_t seed;
+  double disc_pow[MAX_DEPTH];   // discount**k from libm pow (mcts.py:421)
+};
+
+// Arena view.  OW = 64-bit words per observation key, SW = 32-bit words per state.
+struct Tree {
+  Counters* ctr;
+  int* node_visits;
+  int* node_next;
+  unsigned char* node_flags;    // bit 0 expanded, bit 1 absorbing
+  unsigned char* node_t;
+  unsigned long long* node_obs;
+  int* an_first;
+  int* an_visits;               // selections, in-flight included (virtual visits)
+  int* an_done;                 // completed backups
+  double* an_total;
+  unsigned int* log_node;       // particle log: node id ...
+  unsigned int* log_state;      // ... and state words
+  long long cap_nodes, cap_log;
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Lays the arrays out inside `base` (may be null to only compute the size).
+__host__ __device__ inline size_t layout(Tree* t, unsigned char* base, long long cap_nodes, long long cap_log,
+                                         int n_actions, int obs_words, int state_words) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return base ? base + o : nullptr; };
+  unsigned char* p;
+  p = take(sizeof(Counters)); if (t) t->ctr = (Counters*)p;
+  p = take((size_t)cap_nodes * 4); if (t) t->node_visits = (int*)p;
+  p = take((size_t)cap_nodes * 4); if (t) t->node_next = (int*)p;
+  p = take((size_t)cap_nodes); if (t) t->node_flags = p;
+  p = take((size_t)cap_nodes); if (t) t->node_t = p;
+  p = take((size_t)cap_nodes * 8 * obs_words); if (t) t->node_obs = (unsigned long long*)p;
+  p = take((size_t)cap_nodes * n_actions * 4); if (t) t->an_first = (int*)p;
+  p = take((size_t)cap_nodes * n_actions * 4); if (t) t->an_visits = (int*)p;
+  p = take((size_t)cap_nodes * n_actions * 4); if (t) t->an_done = (int*)p;
+  p = take((size_t)cap_nodes * n_actions * 8); if (t) t->an_total = (double*)p;
+  p = take((size_t)cap_log * 4); if (t) t->log_node = (unsigned int*)p;
+  p = take((size_t)cap_log * 4 * state_words); if (t) t->log_state = (unsigned int*)p;
+  if (t) { t->cap_nodes = cap_nodes; t->cap_log = cap_log; }
+  return off;
+}
+
+// order-preserving map double -> uint64 (for atomicMin / atomicMax)
+__device__ __forceinline__ unsigned long long dkey(double d) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+constexpr unsigned long long KEY_POS_INF = 0xFFF0000000000000ULL;  // dkey(+inf)
+constexpr unsigned long long KEY_NEG_INF = 0x000FFFFFFFFFFFFFULL;  // dkey(-inf)
+
+template <int OW>
+__device__ __forceinline__ bool obs_eq(const unsigned long long* a, const unsigned long long (&b)[OW]) {
+  bool e = true;
+#pragma unroll
+  for (int w = 0; w < OW; ++w) e &= (a[w] == b[w]);
+  return e;
+}
+
+// Child obs node of action node `anode` with observation `obs`; created when missing
+// (action_node.has_child / _add_obs_node, mcts.py:358-369).  Lock-free prepend to the
+// action node's child list; returns -1 when the arena is full.
+template <int A, int OW>
+__device__ int find_or_insert(const Tree& T, int anode, const unsigned long long (&obs)[OW], int t, bool& created) {
+  created = false;
+  int head = *((volatile int*)&T.an_first[anode]);
+  int stop = -1, mine = -1;
+  while (true) {
+    for (int c = head; c >= 0 && c != stop; c = *((volatile int*)&T.node_next[c]))
+      if (obs_eq<OW>(T.node_obs + (size_t)c * OW, obs)) return c;  // (a spare `mine` stays unused)
+    if (mine < 0) {
+      const unsigned long long id = atomicAdd(&T.ctr->node_count, 1ULL);
+      if (id >= (unsigned long long)T.cap_nodes) { atomicAdd(&T.ctr->overflow, 1u); return -1; }
+      mine = (int)id;
+#pragma unroll
+      for (int w = 0; w < OW; ++w) T.node_obs[(size_t)mine * OW + w] = obs[w];
+      T.node_t[mine] = (unsigned char)t;
+      // visits / flags / action-node arrays were zeroed (an_first: -1) by posg_tree_reset
+    }
+    T.node_next[mine] = head;
+    __threadfence();
+    const int old = atomicCAS(&T.an_first[anode], head, mine);
+    if (old == head) { created = true; return mine; }
+    stop = head;
+    head = old;
+  }
+}
+
+__device__ __forceinline__ double normalize(double v, double mn, double mx) {
+  return (mx > mn) ? (v - mn) / (mx - mn) : v;
+}
+
+// Action for the lane with rank `rank` among the `gsize` lanes sharing `node` this level.
+// `grp` = mask of those lanes.  Every lane of a group runs the same arithmetic.
+template <int A>
+__device__ int select_action(const Tree& T, const Params& P, int node, bool is_root, unsigned grp, int rank,
+                             int max_gsize, int n_base, uint32_t rnd_word) {
+  float n[A], q[A];
+  const double mn = dunkey(*((volatile unsigned long long*)&T.ctr->min_key));
+  const double mx = dunkey(*((volatile unsigned long long*)&T.ctr->max_key));
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    const int an = node * A + a;
+    const int vis = *((volatile int*)&T.an_visits[an]);
+    const int done = *((volatile int*)&T.an_done[an]);
+    const double tot = *((volatile double*)&T.an_total[an]);
+    n[a] = (float)vis;
+    q[a] = done > 0 ? (float)normalize(tot / (double)done, mn, mx) : 0.0f;
+  }
+  const float c = (float)P.c;
+  const float prior = 1.0f / (float)A;  // RandomSearchPolicy.get_pi is uniform; so is the noise mix
+  int mine = 0;
+  for (int s = 0; s < max_gsize; ++s) {
+    const int N = n_base + s + (is_root ? 0 : 1);
+    int choice = 0;
+    if (N == 0) {
+      // obs_node.visits == 0: random action (mcts.py:496,531); derived from the node so the
+      // whole group agrees on it
+      choice = (int)uniform_below(rnd_word * 0x9E3779B1u + (uint32_t)s * 0x85EBCA77u, (uint32_t)A);
+    } else if (P.selection == SEL_UCB) {
+      const float logn = __logf((float)N);
+      float best = -3.0e38f;
+      bool unvisited = false;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        if (!unvisited) {
+          if (n[a] == 0.0f) { choice = a; unvisited = true; }
+          else {
+            const float v = q[a] + c * sqrtf(logn / n[a]);
+            if (v > best) { best = v; choice = a; }
+          }
+        }
+      }
+    } else if (P.selection == SEL_PUCB) {
+      const float sq = sqrtf((float)N);
+      float best = -3.0e38f;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        const float v = (n[a] > 0.0f ? q[a] : 0.0f) + c * prior * (sq / (1.0f + n[a]));
+        if (v > best) { best = v; choice = a; }
+      }
+    } else {
+      float best = (float)N + 1.0f;
+#pragma unroll
+      for (int a = 0; a < A; ++a)
+        if (n[a] < best) { best = n[a]; choice = a; }
+    }
+    if (s == rank) mine = choice;
+#pragma unroll
+    for (int a = 0; a < A; ++a) n[a] += (a == choice) ? 1.0f : 0.0f;
+  }
+  return mine;
+}
+
+// Model concept (see driving_sim.cuh):
+//   using Blob; static constexpr int A, OW, SW;
+//   struct State { uint32_t w[SW]; };
+//   static void step(const Blob&, State&, int ego, int ego_action, uint32_t word,
+//                    unsigned long long (&obs)[OW], double& reward, bool& done);
+//   static void rollout_step(const Blob&, State&, int ego, uint32_t word, double& reward, bool& done);
+template <class M>
+__device__ void simulate(const typename M::Blob& B, const Tree& T, const Params& P, int root, int root_t,
+                         const uint32_t* __restrict__ root_particles, long long n_particles,
+                         unsigned long long sim_id, bool active) {
+  constexpr int A = M::A, OW = M::OW, SW = M::SW;
+  const unsigned full = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  typename M::State st;
+  int path_an[MAX_DEPTH];
+  double path_r[MAX_DEPTH];
+  int depth = 0, node = root, t = root_t, npath = 0;
+  double leaf = 0.0;
+  bool descending = active;
+  if (active) {
+    const uint4 w = philox_block(P.seed, sim_id, 0xFFFFu, STREAM_BELIEF);
+    const long long pi = (long long)(((unsigned long long)w.x * (unsigned long long)n_particles) >> 32);
+#pragma unroll
+    for (int k = 0; k < SW; ++k) st.w[k] = __ldg(root_particles + pi * SW + k);
+  }
+
+  while (__any_sync(full, descending)) {
+    // ---- stop conditions / leaf expansion ------------------------------------------
+    bool expand = false;
+    if (descending) {
+      if (depth > P.depth_limit || t > P.step_limit || depth >= MAX_DEPTH - 1) {
+        descending = false;  // returns 0 (mcts.py:315-316)
+      } else {
+        const unsigned char old = T.node_flags[node];
+        if (!(old & 1u)) {
+          // first simulation to arrive expands the node and evaluates it by a rollout
+          const unsigned int word = atomicOr((unsigned int*)(T.node_flags + (node & ~3)), 1u << (8 * (node & 3)));
+          expand = !((word >> (8 * (node & 3))) & 1u);
+        }
+        if (expand) descending = false;
+      }
+    }
+    if (expand) {
+      // MCTS._rollout (mcts.py:405-452): uniform random joint actions until done / limits
+      int d = depth, tt = t, k = 0;
+      double ret = 0.0;
+      uint4 blk = make_uint4(0, 0, 0, 0);
+      while (d <= P.depth_limit && tt <= P.step_limit && k < MAX_DEPTH) {
+        if ((k & 3) == 0) blk = philox_block(P.seed, sim_id, 0x10000u + (uint32_t)(k >> 2), STREAM_TREE);
+        const uint32_t word = (k & 3) == 0 ? blk.x : (k & 3) == 1 ? blk.y : (k & 3) == 2 ? blk.z : blk.w;
+        double r; bool done;
+        M::rollout_step(B, st, P.ego, word, r, done);
+        ret = __dadd_rn(ret, __dmul_rn(P.disc_pow[k], r));
+        if (done) break;
+        ++d; ++tt; ++k;
+      }
+      leaf = ret;
+    }
+    if (!__any_sync(full, descending)) break;
+
+    // ---- action selection (water-filling among lanes sharing the node) ---------------
+    const unsigned grp = __match_any_sync(full, descending ? node : -1 - (int)lane);
+    const int rank = __popc(grp & ((1u << lane) - 1u));
+    const int gsize = descending ? __popc(grp) : 0;
+    const int max_g = __reduce_max_sync(full, gsize);
+    uint4 w = make_uint4(0, 0, 0, 0);
+    int action = 0, n_base = 0;
+    if (descending) {
+      w = philox_block(P.seed, sim_id, (uint32_t)depth, STREAM_TREE);
+      n_base = *((volatile int*)&T.node_visits[node]);
+      if (node != root) n_base -= gsize;  // the group's own entries were already counted
+      if (n_base < 0) n_base = 0;
+    }
+    // group-consistent random word: the group leader's
+    const uint32_t rnd = __shfl_sync(full, w.z, __ffs(grp) - 1);
+    if (descending) {
+      action = select_action<A>(T, P, node, node == root, grp, rank, max_g, n_base, rnd ^ (uint32_t)node);
+      atomicAdd(&T.an_visits[node * A + action], 1);
+    }
+    __syncwarp(full);
+
+    // ---- model step, child lookup, particle log ---------------------------------------
+    unsigned long long obs[OW];
+#pragma unroll
+    for (int k = 0; k < OW; ++k) obs[k] = 0ULL;
+    double r = 0.0;
+    bool done = false;
+    int anode = -1;
+    if (descending) {
+      M::step(B, st, P.ego, action, w.y, obs, r, done);
+      anode = node * A + action;
+    }
+    // lanes with the same (action node, observation) resolve the child once
+    unsigned same = __match_any_sync(full, descending ? anode : -1 - (int)lane);
+#pragma unroll
+    for (int k = 0; k < OW; ++k) same &= __match_any_sync(full, obs[k]);
+    const int leader = __ffs(same) - 1;
+    int child = -1;
+    if (descending && (int)lane == leader) {
+      bool created;
+      child = find_or_insert<A, OW>(T, anode, obs, t + 1, created);
+      if (child >= 0) {
+        atomicAdd(&T.node_visits[child], __popc(same));
+        // child_obs_node.is_absorbing = ego_done (mcts.py:370)
+        if (done) atomicOr((unsigned int*)(T.node_flags + (child & ~3)), 2u << (8 * (child & 3)));
+        else atomicAnd((unsigned int*)(T.node_flags + (child & ~3)), ~(2u << (8 * (child & 3))));
+      }
+    }
+    child = __shfl_sync(full, child, leader < 0 ? 0 : leader);
+    // child_obs_node.belief.add_particle(next_hps) (mcts.py:371): one counter bump per warp
+    const unsigned app = __ballot_sync(full, descending && child >= 0);
+    unsigned long long log_base = 0;
+    if (app) {
+      const int app_leader = __ffs(app) - 1;
+      if ((int)lane == app_leader) log_base = atomicAdd(&T.ctr->log_count, (unsigned long long)__popc(app));
+      log_base = __shfl_sync(full, log_base, app_leader);
+    }
+    if (descending) {
+      path_an[npath] = anode;
+      path_r[npath] = r;
+      ++npath;
+      if (child < 0) {
+        descending = false;  // arena full: evaluate nothing further (future return 0)
+      } else {
+        const unsigned long long li = log_base + (unsigned long long)__popc(app & ((1u << lane) - 1u));
+        if (li < (unsigned long long)T.cap_log) {
+          T.log_node[li] = (unsigned int)child;
+#pragma unroll
+          for (int k = 0; k < SW; ++k) T.log_state[li * SW + k] = st.w[k];
+        }
+        node = child; ++depth; ++t;
+        if (done) descending = false;  // future return not added (mcts.py:373-378)
+      }
+    }
+  }
+
+  // ---- backup (mcts.py:378-381; node.py:166-178) --------------------------------------
+  if (active) {
+    double G = leaf;
+    for (int i = npath - 1; i >= 0; --i) {
+      G = __dadd_rn(path_r[i], __dmul_rn(P.discount, G));
+      const int an = path_an[i];
+      const double old_tot = atomicAdd(&T.an_total[an], G);
+      const int old_done = atomicAdd(&T.an_done[an], 1);
+      const unsigned long long vk = dkey((old_tot + G) / (double)(old_done + 1));
+      // MinMaxStats.update (utils.py:29-32); the atomics fire only when the bound moves
+      if (vk < *((volatile unsigned long long*)&T.ctr->min_key)) atomicMin(&T.ctr->min_key, vk);
+      if (vk > *((volatile unsigned long long*)&T.ctr->max_key)) atomicMax(&T.ctr->max_key, vk);
+    }
+  }
+  const unsigned act = __ballot_sync(full, active);
+  const unsigned int dmax = __reduce_max_sync(full, active ? (unsigned int)depth : 0u);
+  if (act && (int)lane == __ffs(act) - 1) {
+    atomicAdd(&T.node_visits[root], __popc(act));  // self.root.visits += 1 per simulation (mcts.py:288)
+    atomicAdd(&T.ctr->sims_done, (unsigned long long)__popc(act));
+    if (dmax > *((volatile unsigned int*)&T.ctr->max_depth)) atomicMax(&T.ctr->max_depth, dmax);
+  }
+}
+
+}  // namespace search
+}  // namespace posg

@@ -1,0 +1,340 @@
+// Search-tree and particle-belief entry points of the C-ABI (model-generic; dispatched
+// on the model kind).  See search.cuh / belief.cuh for the algorithms.
+#include <cmath>
+#include <cstring>
+
+#include "belief.cuh"
+#include "common.h"
+#include "driving_sim.cuh"
+#include "search.cuh"
+#include "stage.cuh"
+
+namespace posg {
+
+constexpr int SEARCH_THREADS = 128;
+
+template <class M>
+__global__ void __launch_bounds__(SEARCH_THREADS)
+search_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, search::Tree T,
+              const __grid_constant__ search::Params P, int root, int root_t,
+              const uint32_t* __restrict__ particles, long long n_particles, long long n_sims,
+              unsigned long long sim_id0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  const long long i = (long long)blockIdx.x * SEARCH_THREADS + threadIdx.x;
+  // whole warps enter (warp collectives inside); lanes past n_sims are inactive
+  search::simulate<M>(B, T, P, root, root_t, particles, n_particles, sim_id0 + (unsigned long long)i, i < n_sims);
+}
+
+template <class M>
+__global__ void __launch_bounds__(belief::CTA)
+reinvigorate_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
+                    const uint32_t* __restrict__ parent, long long n_parent, int ego, int action,
+                    const unsigned long long* __restrict__ target_obs, long long n_needed, long long max_attempts,
+                    uint64_t seed, uint64_t draw_id, uint32_t* __restrict__ out, uint32_t* __restrict__ rej,
+                    long long* __restrict__ result) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  belief::reinvigorate<M>(B, parent, n_parent, ego, action, target_obs, n_needed, max_attempts, seed, draw_id, out,
+                          rej, result);
+}
+
+template <class M>
+__global__ void __launch_bounds__(belief::CTA)
+initial_belief_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int ego,
+                      const unsigned long long* __restrict__ target_obs, long long n_needed, long long max_attempts,
+                      uint64_t seed, uint64_t draw_id, uint32_t* __restrict__ out, long long* __restrict__ result) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  belief::initial_belief<M>(B, ego, target_obs, n_needed, max_attempts, seed, draw_id, out, result);
+}
+
+// arena initialisation: zero everything, an_first = -1, root node 0, min/max keys
+__global__ void tree_init_kernel(search::Tree T, int n_actions, int root_t, double known_min, double known_max) {
+  const long long n = T.cap_nodes * n_actions;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    T.an_first[i] = -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    T.ctr->node_count = 1;  // node 0 = root
+    T.ctr->log_count = 0;
+    const bool known = known_min <= known_max;
+    T.ctr->min_key = known ? search::dkey(known_min) : search::KEY_POS_INF;
+    T.ctr->max_key = known ? search::dkey(known_max) : search::KEY_NEG_INF;
+    T.ctr->max_depth = 0; T.ctr->overflow = 0; T.ctr->sims_done = 0;
+    T.node_t[0] = (unsigned char)root_t;
+  }
+}
+
+template <int OW>
+__global__ void tree_advance_kernel(search::Tree T, int n_actions, int root, int action,
+                                    const unsigned long long* __restrict__ obs_in, int create, int* __restrict__ out) {
+  unsigned long long obs[OW];
+#pragma unroll
+  for (int k = 0; k < OW; ++k) obs[k] = obs_in[k];
+  const int anode = root * n_actions + action;
+  int found = -1;
+  for (int c = T.an_first[anode]; c >= 0; c = T.node_next[c])
+    if (search::obs_eq<OW>(T.node_obs + (size_t)c * OW, obs)) { found = c; break; }
+  int created = 0;
+  if (found < 0 && create) {
+    const unsigned long long id = atomicAdd(&T.ctr->node_count, 1ULL);
+    if (id < (unsigned long long)T.cap_nodes) {
+      found = (int)id;
+#pragma unroll
+      for (int k = 0; k < OW; ++k) T.node_obs[(size_t)found * OW + k] = obs[k];
+      T.node_t[found] = (unsigned char)(T.node_t[root] + 1);
+      T.node_next[found] = T.an_first[anode];
+      T.an_first[anode] = found;
+      // obs_node.is_absorbing = self.root.is_absorbing (mcts.py:250)
+      if (T.node_flags[root] & 2u) T.node_flags[found] |= 2u;
+      created = 1;
+    }
+  }
+  out[0] = found;
+  out[1] = created;
+  out[2] = found >= 0 ? (int)T.node_flags[found] : 0;
+  out[3] = found >= 0 ? (int)T.node_t[found] : 0;
+}
+
+// belief of `node`: every logged particle that passed through it (order irrelevant)
+__global__ void gather_belief_kernel(search::Tree T, int state_words, int node, uint32_t* __restrict__ out,
+                                     long long max_out, unsigned long long* __restrict__ count) {
+  const unsigned long long n = T.ctr->log_count < (unsigned long long)T.cap_log ? T.ctr->log_count
+                                                                                 : (unsigned long long)T.cap_log;
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n;
+       i0 += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = i0 + lane;
+    const bool hit = i < n && T.log_node[i] == (unsigned int)node;
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if (!b) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned long long pos = base + __popc(b & ((1u << lane) - 1u));
+    if (hit && pos < (unsigned long long)max_out)
+      for (int k = 0; k < state_words; ++k) out[pos * state_words + k] = T.log_state[i * state_words + k];
+  }
+}
+
+struct KindInfo { int n_actions, obs_words, state_words; };
+
+static bool kind_info(const posg_model* m, KindInfo* k) {
+  if (!m) return false;
+  switch (m->kind) {
+    case KIND_DRIVING: *k = {DrivingSim::A, DrivingSim::OW, DrivingSim::SW}; return true;
+    default: return false;
+  }
+}
+
+static int make_tree(const posg_model* m, void* arena, long long cap_nodes, long long cap_log, search::Tree* T,
+                     KindInfo* k) {
+  if (!kind_info(m, k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  if (!arena || cap_nodes < 2 || cap_log < 1 || cap_nodes > 0x7fffffffLL / (k->n_actions + 1)) {
+    set_error("bad tree arena arguments");
+    return POSG_E_INVALID;
+  }
+  search::layout(T, (unsigned char*)arena, cap_nodes, cap_log, k->n_actions, k->obs_words, k->state_words);
+  return POSG_OK;
+}
+
+}  // namespace posg
+
+using namespace posg;
+
+extern "C" {
+
+int posg_model_info(posg_model_t m, int* n_actions, int* obs_words, int* state_words) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  if (n_actions) *n_actions = k.n_actions;
+  if (obs_words) *obs_words = k.obs_words;
+  if (state_words) *state_words = k.state_words;
+  return POSG_OK;
+}
+
+int64_t posg_tree_arena_bytes(posg_model_t m, int64_t cap_nodes, int64_t cap_log) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  return (int64_t)search::layout(nullptr, nullptr, cap_nodes, cap_log, k.n_actions, k.obs_words, k.state_words);
+}
+
+int posg_tree_reset(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root_t, double known_min,
+                    double known_max, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  // zero the node / action-node arrays (the particle log needs no clearing)
+  const size_t upto = (size_t)((unsigned char*)T.log_node - (unsigned char*)arena);
+  POSG_CUDA(cudaMemsetAsync(arena, 0, upto, s));
+  tree_init_kernel<<<sm_count() * 4, 256, 0, s>>>(T, k.n_actions, root_t, known_min, known_max);
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
+                const uint32_t* particles, int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
+                const posg_search_params* p, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(p && particles && n_particles > 0 && n_sims >= 0 && root >= 0 && root < cap_nodes, "bad search arguments");
+  POSG_REQUIRE(p->ego_agent >= 0 && p->ego_agent < m->num_agents, "ego_agent out of range");
+  POSG_REQUIRE(p->selection >= 0 && p->selection <= 2, "selection must be 0 (ucb), 1 (pucb) or 2 (uniform)");
+  if (n_sims == 0) return POSG_OK;
+  search::Params P;
+  P.discount = p->discount; P.c = p->c; P.known_min = p->known_min; P.known_max = p->known_max;
+  P.pucb_exploration_fraction = p->pucb_exploration_fraction;
+  P.depth_limit = p->depth_limit; P.step_limit = p->step_limit; P.selection = p->selection; P.ego = p->ego_agent;
+  P.seed = p->seed;
+  for (int i = 0; i < search::MAX_DEPTH; ++i) P.disc_pow[i] = pow(p->discount, (double)i);
+  const int grid = (int)((n_sims + SEARCH_THREADS - 1) / SEARCH_THREADS);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (m->kind) {
+    case KIND_DRIVING:
+      search_kernel<DrivingSim><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
+          (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, root, root_t, particles,
+          (long long)n_particles, (long long)n_sims, (unsigned long long)sim_id0);
+      break;
+    default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
+  }
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_tree_node_stats(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
+                         double* out_host, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(out_host && node >= 0 && node < cap_nodes, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int A = k.n_actions;
+  int vis[16], done[16], nv = 0; double tot[16]; search::Counters c; unsigned char fl = 0;
+  POSG_CUDA(cudaMemcpyAsync(vis, T.an_visits + (size_t)node * A, A * 4, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(done, T.an_done + (size_t)node * A, A * 4, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(tot, T.an_total + (size_t)node * A, A * 8, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(&nv, T.node_visits + node, 4, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(&fl, T.node_flags + node, 1, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(&c, T.ctr, sizeof(c), cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  for (int a = 0; a < A; ++a) { out_host[a] = vis[a]; out_host[A + a] = done[a]; out_host[2 * A + a] = tot[a]; }
+  double* e = out_host + 3 * A;
+  auto unkey = [](unsigned long long kk) {
+    unsigned long long b = (kk >> 63) ? (kk & 0x7fffffffffffffffULL) : ~kk;
+    double d; memcpy(&d, &b, 8); return d;
+  };
+  e[0] = nv; e[1] = (double)c.node_count; e[2] = (double)c.log_count; e[3] = c.max_depth;
+  e[4] = unkey(c.min_key); e[5] = unkey(c.max_key); e[6] = c.overflow; e[7] = (double)c.sims_done; e[8] = fl;
+  return POSG_OK;
+}
+
+int posg_tree_advance(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int action,
+                      const uint64_t* obs_host, int create_if_missing, int* out_host, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(obs_host && out_host && root >= 0 && root < cap_nodes && action >= 0 && action < k.n_actions, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* d_obs = nullptr; int* d_out = nullptr;
+  POSG_CUDA(cudaMallocAsync((void**)&d_obs, 8 * k.obs_words + 16, s));
+  d_out = (int*)(d_obs + k.obs_words);
+  POSG_CUDA(cudaMemcpyAsync(d_obs, obs_host, 8 * k.obs_words, cudaMemcpyHostToDevice, s));
+  if (k.obs_words == 1) tree_advance_kernel<1><<<1, 1, 0, s>>>(T, k.n_actions, root, action, d_obs, create_if_missing, d_out);
+  else tree_advance_kernel<2><<<1, 1, 0, s>>>(T, k.n_actions, root, action, d_obs, create_if_missing, d_out);
+  POSG_CUDA(cudaGetLastError());
+  POSG_CUDA(cudaMemcpyAsync(out_host, d_out, 16, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  cudaFreeAsync(d_obs, s);
+  return POSG_OK;
+}
+
+int posg_tree_gather_belief(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
+                            uint32_t* states_out, int64_t max_out, int64_t* count_host, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(states_out && count_host && max_out >= 0, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* d_cnt = nullptr;
+  POSG_CUDA(cudaMallocAsync((void**)&d_cnt, 8, s));
+  POSG_CUDA(cudaMemsetAsync(d_cnt, 0, 8, s));
+  gather_belief_kernel<<<sm_count() * 8, 256, 0, s>>>(T, k.state_words, node, states_out, (long long)max_out, d_cnt);
+  POSG_CUDA(cudaGetLastError());
+  unsigned long long cnt = 0;
+  POSG_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  cudaFreeAsync(d_cnt, s);
+  *count_host = (int64_t)cnt;
+  return POSG_OK;
+}
+
+static int belief_common(posg_model_t m, int obs_words, const uint64_t* obs_host, cudaStream_t s,
+                         unsigned long long** d_obs, long long** d_res) {
+  POSG_CUDA(cudaMallocAsync((void**)d_obs, 8 * obs_words + 32, s));
+  *d_res = (long long*)(*d_obs + obs_words);
+  POSG_CUDA(cudaMemcpyAsync(*d_obs, obs_host, 8 * obs_words, cudaMemcpyHostToDevice, s));
+  (void)m;
+  return POSG_OK;
+}
+
+int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, int64_t n_parent, int ego_agent,
+                             int action, const uint64_t* target_obs_host, int64_t n_needed, int64_t max_attempts,
+                             uint64_t seed, uint64_t draw_id, uint32_t* out_states, uint32_t* reject_scratch,
+                             int64_t* result_host, void* stream) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no belief support"); return POSG_E_UNSUPPORTED; }
+  POSG_REQUIRE(parent_particles && n_parent > 0 && target_obs_host && out_states && reject_scratch && result_host,
+               "bad arguments");
+  POSG_REQUIRE(ego_agent >= 0 && ego_agent < m->num_agents && action >= 0 && action < k.n_actions, "bad agent/action");
+  result_host[0] = result_host[1] = result_host[2] = 0;
+  if (n_needed <= 0) return POSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* d_obs; long long* d_res;
+  int rc = belief_common(m, k.obs_words, target_obs_host, s, &d_obs, &d_res); if (rc) return rc;
+  switch (m->kind) {
+    case KIND_DRIVING:
+      reinvigorate_kernel<DrivingSim><<<1, belief::CTA, m->blob_bytes, s>>>(
+          (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, parent_particles, (long long)n_parent,
+          ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,
+          reject_scratch, d_res);
+      break;
+    default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
+  }
+  POSG_CUDA(cudaGetLastError());
+  POSG_CUDA(cudaMemcpyAsync(result_host, d_res, 24, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  cudaFreeAsync(d_obs, s);
+  return POSG_OK;
+}
+
+int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_obs_host, int64_t n_needed,
+                        int64_t max_attempts, uint64_t seed, uint64_t draw_id, uint32_t* out_states,
+                        int64_t* result_host, void* stream) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no belief support"); return POSG_E_UNSUPPORTED; }
+  POSG_REQUIRE(target_obs_host && out_states && result_host && ego_agent >= 0 && ego_agent < m->num_agents,
+               "bad arguments");
+  result_host[0] = result_host[1] = result_host[2] = 0;
+  if (n_needed <= 0) return POSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* d_obs; long long* d_res;
+  int rc = belief_common(m, k.obs_words, target_obs_host, s, &d_obs, &d_res); if (rc) return rc;
+  switch (m->kind) {
+    case KIND_DRIVING:
+      initial_belief_kernel<DrivingSim><<<1, belief::CTA, m->blob_bytes, s>>>(
+          (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, ego_agent, d_obs, (long long)n_needed,
+          (long long)max_attempts, seed, draw_id, out_states, d_res);
+      break;
+    default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
+  }
+  POSG_CUDA(cudaGetLastError());
+  POSG_CUDA(cudaMemcpyAsync(result_host, d_res, 24, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  cudaFreeAsync(d_obs, s);
+  return POSG_OK;
+}
+
+}  // extern "C"

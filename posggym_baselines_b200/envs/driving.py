@@ -229,6 +229,18 @@ class BatchedDriving:
         return out
 
     @staticmethod
+    def pack_obs(obs) -> np.ndarray:
+        """One posggym observation tuple -> packed key words (uint64[1])."""
+        cells, speed, coord, dest, reached, crashed = obs
+        o = 0
+        for c, v in enumerate(cells):
+            o |= int(v) << (2 * c)
+        o |= int(speed) << 30
+        o |= (int(coord[0]) | (int(coord[1]) << 4) | (int(dest[0]) << 8) | (int(dest[1]) << 12)
+              | (int(reached) << 16) | (int(crashed) << 17)) << 32
+        return np.array([o], dtype=np.uint64)
+
+    @staticmethod
     def unpack_obs(packed) -> List[tuple]:
         """[n, A] packed words -> per env a tuple of per-agent posggym observations
         ``(cells[15], speed, (x, y), (dest x, dest y), dest_reached, crashed)``."""

@@ -1,0 +1,401 @@
+"""``MCTS`` / ``POMCP`` planner facade over the device search tree.
+
+Same surface as the reference engine (/root/reference/posggym_baselines/planning/
+mcts.py:22-739, pomcp.py:9-35): ``reset()``, ``step(obs) -> action``, ``update(action,
+obs)``, ``get_action()``, ``close()``, ``step_statistics`` (keys of mcts.py:140-153),
+``stat_tracker``, ``root.belief.size()``.  The tree, the particle beliefs, the descents,
+leaf rollouts, backups, the initial-belief rejection loop and reinvigoration all run in
+libposg_b200.so; this file only sequences launches and applies the wall-clock budget.
+
+Supported configuration = the POMCP one: ``RandomSearchPolicy`` for the ego agent,
+``RandomOtherAgentPolicy`` for the others, ``state_belief_only=True``; ``truncated`` is
+irrelevant because ``RandomSearchPolicy.get_value`` raises (rollout fallback,
+mcts.py:392-399).  Other plugins raise ``NotImplementedError``.
+
+Extra, B200-only knobs are keyword arguments of the constructor, never config fields:
+``max_sims`` (stop after that many simulations instead of / as well as the time limit),
+``wave_size`` (simulations per launch; 1 = the reference's strictly sequential search),
+``root_parallel`` (merge root statistics over torch.distributed ranks: one allreduce per
+decision).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import random
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from posggym_baselines_b200 import _lib
+from posggym_baselines_b200.planning.config import MCTSConfig
+from posggym_baselines_b200.planning.other_policy import OtherAgentPolicy, RandomOtherAgentPolicy
+from posggym_baselines_b200.planning.search_policy import RandomSearchPolicy, SearchPolicy
+from posggym_baselines_b200.planning.utils import PlanningStatTracker
+
+_SELECTION = {"ucb": 0, "pucb": 1, "uniform": 2}
+
+
+class _BeliefView:
+    """``planner.root.belief`` stand-in: ``size()`` and ``particles`` (packed states)."""
+
+    def __init__(self, planner):
+        self._p = planner
+
+    def size(self) -> int:
+        t = self._p._root_particles
+        return 0 if t is None else int(t.shape[0])
+
+    @property
+    def particles(self):
+        t = self._p._root_particles
+        return [] if t is None else self._p.model.batched.unpack_state(t)
+
+
+class _RootView:
+    def __init__(self, planner):
+        self._p = planner
+        self.belief = _BeliefView(planner)
+
+    @property
+    def t(self) -> int:
+        return self._p._root_t
+
+    @property
+    def is_absorbing(self) -> bool:
+        return self._p._root_absorbing
+
+    @property
+    def visits(self) -> int:
+        return int(self._p._stats()["node_visits"]) if self._p._arena is not None else 0
+
+
+class MCTS:
+    """Partially observable multi-agent Monte-Carlo planning on the GPU."""
+
+    def __init__(
+        self,
+        model,
+        agent_id: str,
+        config: MCTSConfig,
+        other_agent_policies: Dict[str, OtherAgentPolicy],
+        search_policy: SearchPolicy,
+        *,
+        max_sims: Optional[int] = None,
+        wave_size: Optional[int] = None,
+        max_wave: int = 16384,
+        node_capacity: int = 1 << 22,
+        log_capacity: int = 1 << 25,
+        root_parallel: bool = False,
+    ):
+        self.model = model
+        self.agent_id = agent_id
+        self.config = config
+        self.num_agents = len(model.possible_agents)
+        assert len(other_agent_policies) == self.num_agents - 1
+        assert agent_id not in other_agent_policies
+        self.other_agent_policies = other_agent_policies
+        self.search_policy = search_policy
+        if not isinstance(search_policy, RandomSearchPolicy) or not all(
+            isinstance(p, RandomOtherAgentPolicy) for p in other_agent_policies.values()
+        ):
+            raise NotImplementedError(
+                "the B200 planner executes RandomSearchPolicy / RandomOtherAgentPolicy in-kernel; "
+                "other plugins are not supported yet"
+            )
+        if not config.state_belief_only:
+            raise NotImplementedError("only state_belief_only=True (the POMCP configuration) is supported")
+        if not hasattr(model, "batched"):
+            raise TypeError("model must be a posggym_baselines_b200 model facade (needs `.batched`)")
+        self._b = model.batched
+        self._ego = list(model.possible_agents).index(agent_id)
+        self.action_space = list(range(model.action_spaces[agent_id].n))
+
+        if config.step_limit is not None:
+            self.step_limit = config.step_limit
+        elif model.spec is not None:
+            self.step_limit = model.spec.max_episode_steps
+        else:
+            self.step_limit = float("inf")
+
+        self._rng = random.Random(config.seed)
+        self._seed = config.seed if config.seed is not None else random.getrandbits(48)
+        self.max_sims = max_sims
+        self.wave_size = wave_size
+        self.max_wave = max_wave
+        self.root_parallel = root_parallel
+        self._cap_nodes, self._cap_log = int(node_capacity), int(log_capacity)
+
+        lib = _lib.lib()
+        na, ow, sw = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.posg_model_info(self._b._handle, C.byref(na), C.byref(ow), C.byref(sw)))
+        self._A, self._OW, self._SW = na.value, ow.value, sw.value
+        assert self._A == len(self.action_space)
+        self._arena: Optional[torch.Tensor] = None
+        self._params = _lib.SearchParams()
+        kb = config.known_bounds
+        self._params.discount = config.discount
+        self._params.c = config.c
+        self._params.known_min = kb.min if kb else 1.0
+        self._params.known_max = kb.max if kb else 0.0
+        self._params.pucb_exploration_fraction = config.pucb_exploration_fraction
+        self._params.depth_limit = config.depth_limit
+        self._params.step_limit = int(min(self.step_limit, 250))
+        self._params.selection = _SELECTION[config.action_selection]
+        self._params.ego_agent = self._ego
+        self._params.seed = self._seed & 0xFFFFFFFFFFFFFFFF
+
+        self.root = _RootView(self)
+        self._logger = logging.getLogger()
+        self.step_statistics: Dict[str, float] = {}
+        self.stat_tracker = PlanningStatTracker(self)
+        self.reset()
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return _lib.stream_ptr()
+
+    def _ensure_arena(self):
+        if self._arena is None:
+            lib = _lib.lib()
+            nbytes = lib.posg_tree_arena_bytes(self._b._handle, self._cap_nodes, self._cap_log)
+            _lib.check(int(nbytes))
+            self._arena = torch.empty(int(nbytes), dtype=torch.uint8, device=self._b.device)
+
+    def _stats(self, node: Optional[int] = None) -> Dict[str, object]:
+        out = np.zeros(3 * self._A + 9, np.float64)
+        with torch.cuda.device(self._b.device):
+            _lib.check(_lib.lib().posg_tree_node_stats(
+                self._b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log,
+                self._root if node is None else node, _lib.ptr(out), self._stream()))
+        A = self._A
+        e = out[3 * A:]
+        return {
+            "visits": out[:A].copy(), "done": out[A:2 * A].copy(), "total": out[2 * A:3 * A].copy(),
+            "node_visits": e[0], "node_count": e[1], "log_count": e[2], "max_depth": e[3],
+            "min_value": e[4], "max_value": e[5], "overflow": e[6], "sims_done": e[7], "flags": int(e[8]),
+        }
+
+    # ------------------------------------------------------------------ step / reset
+    def step(self, obs):
+        assert self._root_t <= self.step_limit
+        if self._root_absorbing:
+            for k in self.step_statistics:
+                self.step_statistics[k] = np.nan
+            return self._last_action
+        self._reset_step_statistics()
+        self.update(self._last_action, obs)
+        self._last_action = self.get_action()
+        self._step_num += 1
+        self.step_statistics["mem_usage"] = self._mem_usage()
+        self.stat_tracker.step()
+        return self._last_action
+
+    @staticmethod
+    def _mem_usage() -> float:
+        try:
+            import psutil
+
+            return psutil.Process().memory_info().rss / 1024**2
+        except Exception:
+            return 0.0
+
+    def reset(self):
+        self.stat_tracker.reset_episode()
+        self._step_num = 0
+        self._root = 0
+        self._root_t = 0
+        self._root_absorbing = False
+        self._root_particles: Optional[torch.Tensor] = None
+        self._last_action = None
+        self._sim_counter = 0
+        self._draw_counter = 0
+        self._min_value, self._max_value = float("inf"), -float("inf")
+        self._reset_step_statistics()
+
+    def _reset_step_statistics(self):
+        self.step_statistics = {
+            "search_time": 0.0, "update_time": 0.0, "reinvigoration_time": 0.0, "evaluation_time": 0.0,
+            "policy_calls": 0, "inference_time": 0.0, "search_depth": 0, "num_sims": 0, "mem_usage": 0,
+            "min_value": self._min_value, "max_value": self._max_value,
+        }
+
+    # ------------------------------------------------------------------ update
+    def update(self, action, obs):
+        if self._root_absorbing:
+            return
+        start = time.time()
+        if self._root_t == 0:
+            self._last_action = None
+            self._initial_update(obs)
+        else:
+            self._update(action, obs)
+        torch.cuda.synchronize(self._b.device)
+        self.step_statistics["update_time"] = time.time() - start
+
+    def _next_draw(self, n: int) -> int:
+        d = self._draw_counter
+        self._draw_counter += int(n)
+        return d
+
+    def _initial_update(self, init_obs):
+        cfg, b = self.config, self._b
+        self._ensure_arena()
+        need = cfg.num_particles + cfg.extra_particles
+        kb = cfg.known_bounds
+        out = torch.empty((need, self._SW), dtype=torch.int32, device=b.device)
+        res = np.zeros(3, np.int64)
+        key = np.ascontiguousarray(b.pack_obs(init_obs), dtype=np.uint64)
+        max_attempts = 1 << 26
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().posg_tree_reset(
+                b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, 1,
+                kb.min if kb else 1.0, kb.max if kb else 0.0, self._stream()))
+            _lib.check(_lib.lib().posg_belief_initial(
+                b._handle, self._ego, _lib.ptr(key), need, max_attempts, self._params.seed,
+                self._next_draw(max_attempts), _lib.ptr(out), _lib.ptr(res), self._stream()))
+        if res[0] < need:
+            raise RuntimeError(f"initial belief: only {res[0]} of {need} particles matched the first observation")
+        self._root, self._root_t, self._root_absorbing = 0, 1, False
+        self._root_particles = out
+
+    def _update(self, action, obs):
+        cfg, b = self.config, self._b
+        key = np.ascontiguousarray(b.pack_obs(obs), dtype=np.uint64)
+        out4 = np.zeros(4, np.int32)
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().posg_tree_advance(
+                b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, int(action),
+                _lib.ptr(key), 1, _lib.ptr(out4), self._stream()))
+        child, flags = int(out4[0]), int(out4[2])
+        if child < 0:
+            raise RuntimeError("search tree arena is full; raise node_capacity")
+        absorbing = bool(flags & 2)
+        if not absorbing:
+            t0 = time.time()
+            target = cfg.num_particles + cfg.extra_particles
+            # particles the searches left at the child (belief.add_particle, mcts.py:371)
+            log_count = int(self._stats()["log_count"])
+            buf = torch.empty((min(log_count, self._cap_log) + target, self._SW), dtype=torch.int32, device=b.device)
+            cnt = np.zeros(1, np.int64)
+            with torch.cuda.device(b.device):
+                _lib.check(_lib.lib().posg_tree_gather_belief(
+                    b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, child, _lib.ptr(buf),
+                    buf.shape[0] - target, _lib.ptr(cnt), self._stream()))
+            have = int(cnt[0])
+            need = target - have
+            if need > 0:
+                limit = int(cfg.reinvigoration_sample_limit_factor * need)
+                rej = torch.empty((need, self._SW), dtype=torch.int32, device=b.device)
+                res = np.zeros(3, np.int64)
+                with torch.cuda.device(b.device):
+                    _lib.check(_lib.lib().posg_belief_reinvigorate(
+                        b._handle, _lib.ptr(self._root_particles), self._root_particles.shape[0], self._ego,
+                        int(action), _lib.ptr(key), need, limit, self._params.seed ^ 0x5DEECE66D,
+                        self._next_draw(limit), _lib.ptr(buf[have:]), _lib.ptr(rej), _lib.ptr(res), self._stream()))
+                have += int(res[2])
+            self._root_particles = buf[:have]
+            self.step_statistics["reinvigoration_time"] += time.time() - t0
+        self._root = child
+        self._root_t += 1
+        self._root_absorbing = absorbing
+
+    # ------------------------------------------------------------------ search
+    def get_action(self):
+        if self._root_absorbing:
+            return self.action_space[0]
+        cfg, b = self.config, self._b
+        start = time.time()
+        n_sims = 0
+        wave = self.wave_size if self.wave_size else 32
+        lib = _lib.lib()
+        with torch.cuda.device(b.device):
+            stream = self._stream()
+            while True:
+                if self.max_sims is not None:
+                    if n_sims >= self.max_sims:
+                        break
+                    wave_now = min(wave, self.max_sims - n_sims)
+                else:
+                    wave_now = wave
+                _lib.check(lib.posg_search(
+                    b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, self._root_t,
+                    _lib.ptr(self._root_particles), self._root_particles.shape[0], wave_now, self._sim_counter,
+                    C.byref(self._params), stream))
+                self._sim_counter += wave_now
+                n_sims += wave_now
+                torch.cuda.current_stream().synchronize()
+                if self.max_sims is None and time.time() - start >= cfg.search_time_limit:
+                    break
+                if self.max_sims is not None and cfg.search_time_limit < float("inf") and self._respect_time \
+                        and time.time() - start >= cfg.search_time_limit:
+                    break
+                if not self.wave_size:
+                    wave = min(wave * 2, self.max_wave)
+        st = self._stats()
+        self._min_value, self._max_value = st["min_value"], st["max_value"]
+        self.step_statistics["search_time"] = time.time() - start
+        self.step_statistics["search_depth"] = int(st["max_depth"])
+        self.step_statistics["num_sims"] = n_sims
+        self.step_statistics["min_value"] = self._min_value
+        self.step_statistics["max_value"] = self._max_value
+        self._last_root_stats = st
+        return self._final_action(st)
+
+    _respect_time = False  # with max_sims set, the time limit only applies when asked for
+
+    def _final_action(self, st):
+        done, total = st["done"].copy(), st["total"].copy()
+        if self.root_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            # root-parallel merge: one allreduce of |A| x {visits, total_value} per decision
+            buf = torch.tensor(np.concatenate([done, total]), dtype=torch.float64, device=self._b.device)
+            torch.distributed.all_reduce(buf)
+            merged = buf.cpu().numpy()
+            done, total = merged[:self._A], merged[self._A:]
+            rng = random.Random((self._seed << 8) ^ self._step_num)  # identical tie-break on every rank
+        else:
+            rng = random
+        self._merged_root = (done, total)
+        if self.config.action_selection == "pucb":
+            # max_visit_action_selection (mcts.py:566-581)
+            if done.sum() == 0:
+                return rng.choice(self.action_space)
+            best = done.max()
+            return rng.choice([a for a in self.action_space if done[a] == best])
+        # max_value_action_selection (mcts.py:583-600); unvisited action nodes hold value 0.0
+        values = np.where(done > 0, total / np.maximum(done, 1), 0.0)
+        best = values.max()
+        return rng.choice([a for a in self.action_space if values[a] == best])
+
+    def root_action_values(self) -> np.ndarray:
+        done, total = self._merged_root
+        return np.where(done > 0, total / np.maximum(done, 1), 0.0)
+
+    # ------------------------------------------------------------------ misc
+    def close(self):
+        self.search_policy.close()
+        for policy in self.other_agent_policies.values():
+            policy.close()
+        self._arena = None
+        self._root_particles = None
+
+    def __str__(self):
+        return f"{self.__class__.__name__}"
+
+
+class POMCP(MCTS):
+    """POMCP = MCTS with random other agents and a belief over environment state only
+    (reference: planning/pomcp.py:9-35)."""
+
+    def __init__(self, model, agent_id: str, config: MCTSConfig, search_policy: SearchPolicy, **b200_options):
+        other_agent_policies = {
+            i: RandomOtherAgentPolicy(model, i) for i in model.possible_agents if i != agent_id
+        }
+        if not config.state_belief_only:
+            # creates copy of config with state_belief_only=True
+            config = config.replace(state_belief_only=True)
+        super().__init__(model, agent_id, config, other_agent_policies, search_policy, **b200_options)

@@ -1,0 +1,170 @@
+"""The CUDA POMCP planner: API smoke, sequential-vs-wave consistency and STATISTICAL
+parity with the unmodified reference planner (golden statistics generated on the CPU
+oracle by tests/golden/make_planner_golden.py).  Tolerances are stated per test."""
+import json
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(GOLDEN, "planner_driving.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def model():
+    from posggym_baselines_b200.envs.driving import DrivingModel
+
+    return DrivingModel()
+
+
+def make_planner(model, seed=0, **kw):
+    from posggym_baselines_b200.planning import POMCP, MCTSConfig, RandomSearchPolicy
+
+    opts = {k: kw.pop(k) for k in list(kw) if k in ("max_sims", "wave_size", "max_wave", "node_capacity", "log_capacity")}
+    cfg = dict(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb", seed=seed)
+    cfg.update(kw)
+    return POMCP(model, "0", MCTSConfig(**cfg), RandomSearchPolicy(model, "0"), **opts)
+
+
+def fields_to_obs(f):
+    return (tuple(f[:15]), f[15], (f[16], f[17]), (f[18], f[19]), f[20], f[21])
+
+
+def test_readme_loop(model):
+    """README.md:52-88 -- reset/step loop, statistics keys, wall-clock budget."""
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.planning import PlanningStatTracker
+
+    env = Env(model)
+    planner = make_planner(model, seed=1)   # README config: state_belief_only defaults False -> POMCP copies it
+    assert planner.config.state_belief_only and planner.config.num_particles == 10 and planner.config.depth_limit == 90
+    obs, _ = env.reset(seed=1)
+    planner.reset()
+    rng = random.Random(1)
+    done, steps = False, 0
+    while not done:
+        a = planner.step(obs["0"])
+        assert a in range(5)
+        st = planner.step_statistics
+        assert set(st) == set(PlanningStatTracker.STAT_KEYS)
+        if not math.isnan(st["num_sims"]):
+            assert st["num_sims"] >= 1000 and 0.1 <= st["search_time"] < 0.5
+        obs, rew, term, trunc, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+        steps += 1
+    assert steps <= 50
+    ep = planner.stat_tracker.get_episode()
+    assert "num_sims" in ep
+    planner.close()
+
+
+def run_root(model, scen, n_sims, reps, **opts):
+    vals, vis = [], []
+    for rep in range(reps):
+        p = make_planner(model, seed=rep, max_sims=n_sims, **opts)
+        p.reset()
+        p.update(None, fields_to_obs(scen["ego_obs"]))
+        p.get_action()
+        st = p._last_root_stats
+        vals.append(np.where(st["done"] > 0, st["total"] / np.maximum(st["done"], 1), 0.0))
+        vis.append(st["done"] / st["done"].sum())
+    return np.array(vals), np.array(vis)
+
+
+@pytest.mark.parametrize("wave", [1, 32])
+def test_root_statistics_match_reference(model, gold, wave):
+    """Root action values and visit shares after N simulations from the same first
+    observation: mean over independent planners within 4 standard errors (+0.02 abs) of the
+    reference planner's means; the best action agrees."""
+    for scen in gold["root_stats"]:
+        reps = 60
+        vals, vis = run_root(model, scen, scen["n_sims"], reps, wave_size=wave)
+        ref_mean, ref_std = np.array(scen["value_mean"]), np.array(scen["value_std"])
+        se = np.sqrt(ref_std**2 / scen["reps"] + vals.std(0) ** 2 / reps)
+        assert (np.abs(vals.mean(0) - ref_mean) < 4 * se + 0.02).all(), (vals.mean(0), ref_mean, se)
+        assert (np.abs(vis.mean(0) - np.array(scen["visit_frac_mean"])) < 0.05).all(), (vis.mean(0), scen["visit_frac_mean"])
+        order = np.argsort(ref_mean)
+        if ref_mean[order[-1]] - ref_mean[order[-2]] > 4 * se.max() + 0.02:   # only when the reference's best is clear
+            assert int(np.argmax(vals.mean(0))) == int(order[-1])
+
+
+def ks_2samp(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate([a, b])
+    cdf_a = np.searchsorted(a, allv, side="right") / len(a)
+    cdf_b = np.searchsorted(b, allv, side="right") / len(b)
+    d = np.abs(cdf_a - cdf_b).max()
+    en = math.sqrt(len(a) * len(b) / (len(a) + len(b)))
+    lam = (en + 0.12 + 0.11 / en) * d
+    p = 2 * sum((-1) ** (k - 1) * math.exp(-2 * k * k * lam * lam) for k in range(1, 101))
+    return d, max(0.0, min(1.0, p))
+
+
+def test_rollout_return_distribution_ks(model, gold):
+    """Kolmogorov-Smirnov two-sample test of the fused rollout kernel's returns against
+    MCTS._rollout of the reference (its own RNG streams): not rejected at p > 0.001."""
+    from posggym_baselines_b200.envs.driving import VehicleState
+
+    b = model.batched
+    for scen in gold["rollouts"]:
+        st = tuple(VehicleState((f[0], f[1]), f[2], f[3], (f[4], f[5]), f[6], f[7], f[8], f[9]) for f in scen["state"])
+        packed = torch.from_numpy(np.repeat(b.pack_state([st]), 50_000, axis=0)).to(b.device)
+        max_steps = min(scen["depth_limit"] + 1, scen["step_limit"] - 1 + 1)
+        ret, _, _ = b.rollout(packed, 0, max_steps, scen["discount"], seed=123)
+        d, p = ks_2samp(ret.cpu().numpy(), np.array(scen["returns_sorted"]))
+        assert p > 0.001, (d, p)
+
+
+def test_episode_returns_match_reference(model, gold):
+    """POMCP vs a uniform-random other agent at (about) the reference's simulation count
+    per decision: success rate within 3 binomial standard errors (+0.05)."""
+    from posggym_baselines_b200.envs.env import Env
+
+    ref = gold["episodes"]
+    n_sims = int(round(ref["mean_sims_per_decision"]))
+    env = Env(model)
+    wins, rets, n = 0, [], 60
+    for ep in range(n):
+        planner = make_planner(model, seed=ep, max_sims=n_sims, wave_size=1)
+        rng = random.Random(10_000 + ep)
+        obs, _ = env.reset(seed=ep)
+        planner.reset()
+        done, R = False, 0.0
+        while not done:
+            a = planner.step(obs["0"])
+            obs, rew, term, trunc, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+            R += rew["0"]
+        wins += env.state[0].dest_reached
+        rets.append(R)
+        planner.close()
+    p_ref = ref["outcomes"].count("WIN") / ref["n_episodes"]
+    p = wins / n
+    se = math.sqrt(p_ref * (1 - p_ref) / ref["n_episodes"] + p * (1 - p) / n)
+    assert abs(p - p_ref) < 3 * se + 0.05, (p, p_ref)
+    assert abs(np.mean(rets) - np.mean(ref["returns"])) < 3 * math.sqrt(
+        np.var(rets) / n + np.var(ref["returns"]) / ref["n_episodes"]) + 0.05
+
+
+def test_throughput_mode_beats_reference_by_1000x(model, gold):
+    """>= 1000x the reference's simulations per 0.1 s decision (north_star)."""
+    planner = make_planner(model, seed=5)
+    from posggym_baselines_b200.envs.env import Env
+
+    env = Env(model)
+    obs, _ = env.reset(seed=5)
+    planner.reset()
+    planner.step(obs["0"])
+    planner.step_statistics  # first decision includes allocation; measure the second
+    obs, *_ = env.step({"0": planner._last_action, "1": 0})
+    planner.step(obs["0"])
+    assert planner.step_statistics["num_sims"] >= 1000 * gold["episodes"]["mean_sims_per_decision"]
