@@ -20,6 +20,7 @@ namespace search {
 
 constexpr int MAX_DEPTH = 64;      // path stack (the in-scope envs stop at 50 steps)
 constexpr int SEL_UCB = 0, SEL_PUCB = 1, SEL_UNIFORM = 2;
+constexpr unsigned long long RESERVE = 1024;  // node slots search never takes
 
 struct Counters {               // first 64 bytes of the arena
   unsigned long long node_count;
@@ -119,8 +120,13 @@ __device__ int find_or_insert(const Tree& T, int anode, const unsigned long long
     for (int c = head; c >= 0 && c != stop; c = *((volatile int*)&T.node_next[c]))
       if (obs_eq<OW>(T.node_obs + (size_t)c * OW, obs)) return c;  // (a spare `mine` stays unused)
     if (mine < 0) {
+      // the last RESERVE slots are kept for the re-root (posg_tree_advance)
+      if (*((volatile unsigned long long*)&T.ctr->node_count) + RESERVE >= (unsigned long long)T.cap_nodes) {
+        atomicAdd(&T.ctr->overflow, 1u);
+        return -1;
+      }
       const unsigned long long id = atomicAdd(&T.ctr->node_count, 1ULL);
-      if (id >= (unsigned long long)T.cap_nodes) { atomicAdd(&T.ctr->overflow, 1u); return -1; }
+      if (id + RESERVE / 2 >= (unsigned long long)T.cap_nodes) { atomicAdd(&T.ctr->overflow, 1u); return -1; }
       mine = (int)id;
 #pragma unroll
       for (int w = 0; w < OW; ++w) T.node_obs[(size_t)mine * OW + w] = obs[w];
@@ -221,6 +227,7 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
   int depth = 0, node = root, t = root_t, npath = 0;
   double leaf = 0.0;
   bool descending = active;
+  bool virtual_leaf = false;  // arena full: the state just reached is evaluated but not stored
   if (active) {
     const uint4 w = philox_block(P.seed, sim_id, 0xFFFFu, STREAM_BELIEF);
     const long long pi = (long long)(((unsigned long long)w.x * (unsigned long long)n_particles) >> 32);
@@ -234,6 +241,9 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
     if (descending) {
       if (depth > P.depth_limit || t > P.step_limit || depth >= MAX_DEPTH - 1) {
         descending = false;  // returns 0 (mcts.py:315-316)
+      } else if (virtual_leaf) {
+        expand = true;
+        descending = false;
       } else {
         const unsigned char old = T.node_flags[node];
         if (!(old & 1u)) {
@@ -324,7 +334,10 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
       path_r[npath] = r;
       ++npath;
       if (child < 0) {
-        descending = false;  // arena full: evaluate nothing further (future return 0)
+        // arena full: no node for this history -- evaluate it by a rollout, store nothing
+        ++depth; ++t;
+        virtual_leaf = true;
+        if (done) descending = false;
       } else {
         const unsigned long long li = log_base + (unsigned long long)__popc(app & ((1u << lane) - 1u));
         if (li < (unsigned long long)T.cap_log) {

@@ -83,18 +83,27 @@ __global__ void tree_advance_kernel(search::Tree T, int n_actions, int root, int
     if (search::obs_eq<OW>(T.node_obs + (size_t)c * OW, obs)) { found = c; break; }
   int created = 0;
   if (found < 0 && create) {
-    const unsigned long long id = atomicAdd(&T.ctr->node_count, 1ULL);
-    if (id < (unsigned long long)T.cap_nodes) {
-      found = (int)id;
+    unsigned long long id = atomicAdd(&T.ctr->node_count, 1ULL);
+    // search never takes the last RESERVE/2 slots; when it has filled the arena the last
+    // slot serves as the (transient) new root -- the caller rebuilds the tree right after
+    if (id + search::RESERVE / 2 >= (unsigned long long)T.cap_nodes) id = (unsigned long long)T.cap_nodes - 1;
+    found = (int)id;
 #pragma unroll
-      for (int k = 0; k < OW; ++k) T.node_obs[(size_t)found * OW + k] = obs[k];
-      T.node_t[found] = (unsigned char)(T.node_t[root] + 1);
-      T.node_next[found] = T.an_first[anode];
-      T.an_first[anode] = found;
-      // obs_node.is_absorbing = self.root.is_absorbing (mcts.py:250)
-      if (T.node_flags[root] & 2u) T.node_flags[found] |= 2u;
-      created = 1;
+    for (int k = 0; k < OW; ++k) T.node_obs[(size_t)found * OW + k] = obs[k];
+    T.node_t[found] = (unsigned char)(T.node_t[root] + 1);
+    T.node_visits[found] = 0;
+    T.node_flags[found] = 0;
+    for (int a = 0; a < n_actions; ++a) {
+      T.an_first[found * n_actions + a] = -1;
+      T.an_visits[found * n_actions + a] = 0;
+      T.an_done[found * n_actions + a] = 0;
+      T.an_total[found * n_actions + a] = 0.0;
     }
+    T.node_next[found] = T.an_first[anode];
+    T.an_first[anode] = found;
+    // obs_node.is_absorbing = self.root.is_absorbing (mcts.py:250)
+    if (T.node_flags[root] & 2u) T.node_flags[found] |= 2u;
+    created = 1;
   }
   out[0] = found;
   out[1] = created;

@@ -16,7 +16,11 @@ Extra, B200-only knobs are keyword arguments of the constructor, never config fi
 ``max_sims`` (stop after that many simulations instead of / as well as the time limit),
 ``wave_size`` (simulations per launch; 1 = the reference's strictly sequential search),
 ``root_parallel`` (merge root statistics over torch.distributed ranks: one allreduce per
-decision).
+decision), ``node_capacity`` / ``log_capacity`` (size of the device arena).  The reference
+keeps the whole subtree under the new root for the rest of the episode (mcts.py:261-263);
+so does this planner while the arena has room -- when more than half of it is used at a
+re-root, the tree is rebuilt from the new root's belief alone (statistics below it are
+re-estimated by the next search, which runs >1000x the reference's simulations).
 """
 from __future__ import annotations
 
@@ -87,8 +91,8 @@ class MCTS:
         max_sims: Optional[int] = None,
         wave_size: Optional[int] = None,
         max_wave: int = 16384,
-        node_capacity: int = 1 << 22,
-        log_capacity: int = 1 << 25,
+        node_capacity: int = 1 << 24,
+        log_capacity: int = 1 << 26,
         root_parallel: bool = False,
     ):
         self.model = model
@@ -213,7 +217,10 @@ class MCTS:
         self._last_action = None
         self._sim_counter = 0
         self._draw_counter = 0
+        self._nodes_bound = 1
+        self._log_bound = 0
         self._min_value, self._max_value = float("inf"), -float("inf")
+        self.tree_rebuilds = 0
         self._reset_step_statistics()
 
     def _reset_step_statistics(self):
@@ -261,6 +268,7 @@ class MCTS:
             raise RuntimeError(f"initial belief: only {res[0]} of {need} particles matched the first observation")
         self._root, self._root_t, self._root_absorbing = 0, 1, False
         self._root_particles = out
+        self._nodes_bound, self._log_bound = 1, 0
 
     def _update(self, action, obs):
         cfg, b = self.config, self._b
@@ -302,6 +310,18 @@ class MCTS:
         self._root = child
         self._root_t += 1
         self._root_absorbing = absorbing
+        if not absorbing and (self._nodes_bound > self._cap_nodes // 2 or self._log_bound > self._cap_log // 2):
+            # arena pressure: keep the new root's belief, drop the statistics below it
+            kb = cfg.known_bounds
+            with torch.cuda.device(b.device):
+                _lib.check(_lib.lib().posg_tree_reset(
+                    b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root_t,
+                    self._min_value if self._min_value <= self._max_value else (kb.min if kb else 1.0),
+                    self._max_value if self._min_value <= self._max_value else (kb.max if kb else 0.0),
+                    self._stream()))
+            self._root = 0
+            self._nodes_bound, self._log_bound = 1, 0
+            self.tree_rebuilds += 1
 
     # ------------------------------------------------------------------ search
     def get_action(self):
@@ -321,6 +341,9 @@ class MCTS:
                     wave_now = min(wave, self.max_sims - n_sims)
                 else:
                     wave_now = wave
+                # every simulation adds at most one node (none once the arena is full: the
+                # kernel then evaluates unexpanded histories by rollouts without storing them)
+                self._nodes_bound = min(self._cap_nodes, self._nodes_bound + wave_now)
                 _lib.check(lib.posg_search(
                     b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, self._root_t,
                     _lib.ptr(self._root_particles), self._root_particles.shape[0], wave_now, self._sim_counter,
@@ -336,6 +359,7 @@ class MCTS:
                 if not self.wave_size:
                     wave = min(wave * 2, self.max_wave)
         st = self._stats()
+        self._nodes_bound, self._log_bound = int(st["node_count"]), int(st["log_count"])
         self._min_value, self._max_value = st["min_value"], st["max_value"]
         self.step_statistics["search_time"] = time.time() - start
         self.step_statistics["search_depth"] = int(st["max_depth"])

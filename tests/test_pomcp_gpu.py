@@ -32,6 +32,9 @@ def make_planner(model, seed=0, **kw):
     from posggym_baselines_b200.planning import POMCP, MCTSConfig, RandomSearchPolicy
 
     opts = {k: kw.pop(k) for k in list(kw) if k in ("max_sims", "wave_size", "max_wave", "node_capacity", "log_capacity")}
+    if opts.get("max_sims") is not None:   # fixed small budgets: a small arena is plenty
+        opts.setdefault("node_capacity", 1 << 18)
+        opts.setdefault("log_capacity", 1 << 21)
     cfg = dict(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb", seed=seed)
     cfg.update(kw)
     return POMCP(model, "0", MCTSConfig(**cfg), RandomSearchPolicy(model, "0"), **opts)
