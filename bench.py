@@ -119,6 +119,77 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
+    """README configuration (README.md:52-88): POMCP on Driving-v1 vs a uniform-random other
+    agent, discount 0.95, c 1.414, search_time_limit 0.1 s, UCB.  Simulations per decision on
+    the GPU (one search tree per rank) next to the restated reference planner on one host core
+    (the reference planner is single-threaded)."""
+    import random
+
+    import torch
+    import torch.distributed as dist
+
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.planning import POMCP, MCTSConfig, RandomSearchPolicy
+
+    model = DrivingModel(device=dev)
+    env = Env(model)
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb", seed=rank)
+    planner = POMCP(model, "0", cfg, RandomSearchPolicy(model, "0"))
+    rng = random.Random(rank)
+    obs, _ = env.reset(seed=100 + rank)
+    planner.reset()
+    sims, times = [], []
+    for d in range(decisions + 1):
+        a = planner.step(obs["0"])
+        if d > 0 and planner.step_statistics["num_sims"] == planner.step_statistics["num_sims"]:  # skip warm-up / NaN
+            sims.append(planner.step_statistics["num_sims"])
+            times.append(planner.step_statistics["search_time"])
+        obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+        if done:
+            obs, _ = env.reset()
+            planner.reset()
+    planner.close()
+    tot = torch.tensor([sum(sims), len(sims)], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([sum(times) / max(1, len(times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    out = {"config": "Driving-v1, discount 0.95, c 1.414, search_time_limit 0.1 s, ucb, RandomSearchPolicy",
+           "sims_per_decision_per_gpu": tot[0].item() / max(1.0, tot[1].item()),
+           "sims_per_decision_all_gpus": world * tot[0].item() / max(1.0, tot[1].item()),
+           "sims_per_s_all_gpus": world * tot[0].item() / max(1.0, tot[1].item()) / max(1e-9, tmax.item()),
+           "search_time_s": tmax.item(), "trees": world}
+    if cpu:
+        from oracle import shims
+
+        shims.install()
+        from oracle.driving import DrivingModel as CpuModel
+        from oracle.pomcp import OraclePOMCP
+
+        m = CpuModel()
+        m.seed(0)
+        m.spec = type("S", (), {"max_episode_steps": 50})()
+        p = OraclePOMCP(m, "0", 0.95, 0.1, 1.414, seed=0)
+        s = m.sample_initial_state()
+        o = m.sample_initial_obs(s)
+        p.reset()
+        c_sims = []
+        for d in range(12):
+            a = p.step(o["0"])
+            if p.step_statistics["num_sims"] == p.step_statistics["num_sims"]:
+                c_sims.append(p.step_statistics["num_sims"])
+            ts = m.step(s, {"0": a, "1": rng.randrange(5)})
+            s, o = ts.state, ts.observations
+            if ts.all_done:
+                break
+        out["cpu_reference_sims_per_decision"] = sum(c_sims) / max(1, len(c_sims))
+        out["cpu_reference"] = "oracle/pomcp.py (restated reference planner, pure Python, 1 core), same config"
+        out["ratio"] = out["sims_per_decision_per_gpu"] / max(1e-9, out["cpu_reference_sims_per_decision"])
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,6 +348,13 @@ def main():
                "sample": f"{r['env_steps']} env-steps of the same random-action depth-{DEPTH} Driving-v1 sweep in "
                          f"{r['seconds']:.1f} s, one Python process per core (the reference's model is pure Python)"}
 
+    # ---- POMCP simulations per 0.1 s decision (second half of BASELINE.json's metric) ----
+    pomcp = None
+    try:
+        pomcp = bench_pomcp(dev, rank, world, cpu=(rank == 0 and world == 1 and not args.no_cpu))
+    except Exception as ex:  # the headline number must not be lost to a planner problem
+        pomcp = {"error": repr(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -291,7 +369,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "posg::driving::step_kernel<2>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "launch_ms": launch_ms, "peak_source": peak_src},
-            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl,
+            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "pomcp": pomcp,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

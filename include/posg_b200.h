@@ -130,6 +130,42 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
                             unsigned long long* live_count_host);
 
 
+/* ------------------------------------------------------------------ PredatorPrey-v0 and
+ * the model-generic batch entry points (every model kind except Driving-v1, which has
+ * the hand-tuned posg_driving_* kernels above).
+ *
+ *   PredatorPrey state : 2 x uint32 -- word 0: predator 0 (x | y<<4) | predator 1 << 8 |
+ *                        caught bits << 16; word 1: prey 0 | prey 1 << 8 | prey 2 << 16
+ *   PredatorPrey obs   : uint64 per agent: 25 cells x 2 bits (EMPTY=0 WALL=1 PREDATOR=2
+ *                        PREY=3), cell index col*5 + row of the window centred on the agent
+ *   explicit noise     : PredatorPrey: 3 x uint32 per env (one word per prey: the single
+ *                        uniform choice that prey makes in the step) */
+
+/* posggym PredatorPreyModel.__init__ (posggym.make("PredatorPrey-v0", ...),
+ * baseline_exps/env_data/PredatorPrey-v0/env_kwargs.yaml).  block_rows: optional
+ * newline-separated '#'/'.' rows (NULL = no blocks, the "NxN" grids). */
+int posg_pp_create(int grid_size, const char* block_rows, int num_predators, int num_prey,
+                   int cooperative, int prey_strength, int obs_dim, posg_model_t* out);
+
+/* model.sample_initial_state (mcts.py:191).  picks: explicit noise (uint8 per pick). */
+int posg_model_sample_initial_state(posg_model_t m, int64_t n, const uint8_t* picks, uint64_t seed,
+                                    uint64_t particle_offset, uint32_t* state_out, void* stream);
+/* model.sample_initial_obs / observation of a state (mcts.py:192). */
+int posg_model_observe(posg_model_t m, int64_t n, const uint32_t* state, uint64_t* obs_out,
+                       void* stream);
+/* model.step (mcts.py:333,418; belief.py:165); NULL actions_in / noise_in -> Philox block
+ * (particle_offset + i, step_idx, stream 0xA0). */
+int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const uint8_t* actions_in,
+                    const uint32_t* noise_in, uint64_t seed, uint32_t step_idx,
+                    uint64_t particle_offset, uint32_t* state_out, uint64_t* obs_out,
+                    double* rewards_out, uint8_t* flags_out, uint8_t* actions_out,
+                    unsigned long long* live_count, void* stream);
+/* MCTS._rollout with uniform-random policies (mcts.py:405-452), see posg_driving_rollout. */
+int posg_model_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, int ego_agent,
+                       int max_steps, double discount, uint64_t seed, uint32_t step0,
+                       uint64_t particle_offset, double* returns_out, uint8_t* steps_out,
+                       uint32_t* state_out, unsigned long long* live_count, void* stream);
+
 /* ------------------------------------------------------------------ POMCP search tree
  * The tree (obs nodes, per-action statistics, child lists, particle log) lives in one
  * caller-owned device arena; see posggym_baselines_b200/csrc/search.cuh for the layout.

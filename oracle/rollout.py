@@ -70,3 +70,40 @@ def rollout(model, state, ego: str, max_steps: int, discount: float, seed: int, 
         if ts.terminations[ego] or ts.truncations[ego] or ts.all_done:
             break
     return float(agent_return), k, state
+
+
+# ---- PredatorPrey-v0 conventions (PPSim in posggym_baselines_b200/csrc/pp.cuh) ----------
+def pp_step_noise(seed: int, particles, step: int):
+    """(actions [n, 2], prey words [n, 3]): one Philox block per (particle, step): words
+    x, y, z -> prey 0..2; w -> joint action, idx = floor(w * 25 / 2**32), a0 = idx % 5,
+    a1 = idx // 5."""
+    particles = np.asarray(particles, dtype=np.uint64)
+    w = P.philox_block(seed, particles, step, P.STREAM_STEP)
+    idx = P.uniform_below(w[3], 25)
+    a1 = idx // 5
+    a0 = idx - 5 * a1
+    return np.stack([a0, a1], axis=-1), np.stack([w[0], w[1], w[2]], axis=-1).astype(np.uint32)
+
+
+def pp_initial_picks(model, seed: int, particles):
+    """Picks as the kernel derives them: block (particle, 0, 0xB0) words x, y -> predators;
+    block (particle, 0, 0xB1) words x, y, z -> prey."""
+    particles = np.asarray(particles, dtype=np.uint64)
+    a = P.philox_block(seed, particles, 0, P.STREAM_INIT)
+    b = P.philox_block(seed, particles, 0, P.STREAM_INIT2)
+    bounds = model.initial_noise_bounds()
+    words = [a[0], a[1], b[0], b[1], b[2]]
+    return np.stack([P.uniform_below(w, bd) for w, bd in zip(words, bounds)], axis=-1)
+
+
+def pp_rollout(model, state, ego: str, max_steps: int, discount: float, seed: int, particle: int, step0: int = 0):
+    agent_return, k = 0, 0
+    while k < max_steps:
+        acts, words = pp_step_noise(seed, np.asarray([particle], dtype=np.uint64), step0 + k)
+        ts = model.step_with_noise(state, {"0": int(acts[0, 0]), "1": int(acts[0, 1])}, [int(x) for x in words[0]])
+        agent_return += discount**k * ts.rewards[ego]
+        state = ts.state
+        k += 1
+        if ts.terminations[ego] or ts.truncations[ego] or ts.all_done:
+            break
+    return float(agent_return), k, state

@@ -45,6 +45,13 @@ SIGNATURES = {
         [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp],
     ),
     "posg_driving_sweep_host": (_int, [_vp, _i64, _vp, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "posg_pp_create": (_int, [_int, C.c_char_p, _int, _int, _int, _int, _int, C.POINTER(_vp)]),
+    "posg_model_sample_initial_state": (_int, [_vp, _i64, _vp, _u64, _u64, _vp, _vp]),
+    "posg_model_observe": (_int, [_vp, _i64, _vp, _vp, _vp]),
+    "posg_model_step": (
+        _int, [_vp, _i64, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "posg_model_rollout": (
+        _int, [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "posg_model_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "posg_tree_arena_bytes": (_i64, [_vp, _i64, _i64]),
     "posg_tree_reset": (_int, [_vp, _vp, _i64, _i64, _int, _dbl, _dbl, _vp]),

@@ -1,0 +1,196 @@
+// Model-generic batch kernels (one thread per env): model.step, observation, initial
+// state and the fused random rollout, for adapters that implement the batch concept
+// (see PPSim in pp.cuh).  Driving-v1 has its own hand-tuned kernels (driving_kernels.cu).
+#pragma once
+#include <stdint.h>
+
+#include "stage.cuh"
+
+namespace posg {
+namespace generic {
+
+constexpr int THREADS = 256;
+
+template <class M>
+__global__ void __launch_bounds__(THREADS)
+step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+            const uint32_t* __restrict__ state_in, const uint8_t* __restrict__ actions_in,
+            const uint32_t* __restrict__ noise_in, uint64_t seed, uint32_t step_idx, uint64_t particle_offset,
+            uint32_t* __restrict__ state_out, uint64_t* __restrict__ obs_out, double* __restrict__ rewards_out,
+            uint8_t* __restrict__ flags_out, uint8_t* __restrict__ actions_out,
+            unsigned long long* __restrict__ live_count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
+  unsigned live = 0;
+  const int64_t stride = (int64_t)gridDim.x * THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+    typename M::State s;
+#pragma unroll
+    for (int k = 0; k < SW; ++k) s.w[k] = __ldg(state_in + i * SW + k);
+    int act[NAG];
+    uint32_t noise[NW];
+    if (actions_in == nullptr || noise_in == nullptr)
+      M::noise_from_philox(seed, particle_offset + (uint64_t)i, step_idx, act, noise);
+    if (actions_in != nullptr) {
+#pragma unroll
+      for (int a = 0; a < NAG; ++a) act[a] = __ldg(actions_in + i * NAG + a);
+    }
+    if (noise_in != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NW; ++k) noise[k] = __ldg(noise_in + i * NW + k);
+    }
+    unsigned long long obs[NAG][OW];
+    double rew[NAG];
+    uint32_t flags;
+    bool was_live;
+    M::step_all(B, s, act, noise, obs, rew, flags, was_live);
+    live += was_live ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < SW; ++k) state_out[i * SW + k] = s.w[k];
+#pragma unroll
+    for (int a = 0; a < NAG; ++a) {
+#pragma unroll
+      for (int k = 0; k < OW; ++k) obs_out[(i * NAG + a) * OW + k] = obs[a][k];
+      rewards_out[i * NAG + a] = rew[a];
+      if (actions_out) actions_out[i * NAG + a] = (uint8_t)act[a];
+    }
+    flags_out[i] = (uint8_t)flags;
+  }
+  if (live_count != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
+    if ((threadIdx.x & 31) == 0 && live) atomicAdd(live_count, (unsigned long long)live);
+  }
+}
+
+template <class M>
+__global__ void __launch_bounds__(THREADS)
+observe_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+               const uint32_t* __restrict__ state, uint64_t* __restrict__ obs_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG;
+  const int64_t stride = (int64_t)gridDim.x * THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+    typename M::State s;
+#pragma unroll
+    for (int k = 0; k < SW; ++k) s.w[k] = __ldg(state + i * SW + k);
+    unsigned long long obs[NAG][OW];
+    M::observe_all(B, s, obs);
+#pragma unroll
+    for (int a = 0; a < NAG; ++a)
+#pragma unroll
+      for (int k = 0; k < OW; ++k) obs_out[(i * NAG + a) * OW + k] = obs[a][k];
+  }
+}
+
+template <class M>
+__global__ void __launch_bounds__(THREADS)
+initial_state_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+                     const uint8_t* __restrict__ picks, uint64_t seed, uint64_t particle_offset,
+                     uint32_t* __restrict__ state_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  constexpr int SW = M::SW, NPICK = M::NPICK;
+  const int64_t stride = (int64_t)gridDim.x * THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
+    typename M::State s;
+    if (picks != nullptr) {
+      int p[NPICK];
+#pragma unroll
+      for (int k = 0; k < NPICK; ++k) p[k] = __ldg(picks + i * NPICK + k);
+      M::initial_from_picks(B, p, s);
+    } else {
+      M::initial_state(B, seed, particle_offset + (uint64_t)i, s);
+    }
+#pragma unroll
+    for (int k = 0; k < SW; ++k) state_out[i * SW + k] = s.w[k];
+  }
+}
+
+struct DiscountTable { double v[256]; };
+
+// MCTS._rollout with uniform-random policies; lanes refill from a work counter when
+// their rollout ends (warp ballot compaction), as in the Driving rollout kernel.
+template <class M>
+__global__ void __launch_bounds__(THREADS)
+rollout_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+               const uint32_t* __restrict__ state_in, int ego, int max_steps,
+               const __grid_constant__ DiscountTable dtab, uint64_t seed, uint32_t step0,
+               uint64_t particle_offset, double* __restrict__ returns_out, uint8_t* __restrict__ steps_out,
+               uint32_t* __restrict__ state_out, unsigned long long* __restrict__ work_counter,
+               unsigned long long* __restrict__ live_count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  __shared__ double sdisc[256];
+  for (int t = threadIdx.x; t < 256; t += THREADS) sdisc[t] = dtab.v[t];
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  constexpr int SW = M::SW, NAG = M::NAG, NW = M::NW;
+  const unsigned lane = threadIdx.x & 31u;
+  typename M::State s;
+  int64_t item = -1;
+  int k = 0;
+  double ret = 0.0;
+  unsigned long long executed = 0;
+  bool exhausted = false;
+  while (true) {
+    const unsigned idle = __ballot_sync(0xffffffffu, item < 0);
+    if (idle && !exhausted) {
+      unsigned long long base = 0;
+      const int cnt = __popc(idle), leader = __ffs(idle) - 1;
+      if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)cnt);
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (item < 0) {
+        const int64_t mine = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+        if (mine < n) {
+          item = mine;
+#pragma unroll
+          for (int w = 0; w < SW; ++w) s.w[w] = __ldg(state_in + item * SW + w);
+          k = 0; ret = 0.0;
+        }
+      }
+      if ((int64_t)base + cnt >= n) exhausted = true;
+    }
+    if (__ballot_sync(0xffffffffu, item >= 0) == 0u) break;
+    if (item >= 0) {
+      bool finished = (k >= max_steps);
+      if (!finished) {
+        int act[NAG];
+        uint32_t noise[NW];
+        M::noise_from_philox(seed, particle_offset + (uint64_t)item, step0 + (uint32_t)k, act, noise);
+        double rew[NAG];
+        uint32_t term; bool all_done;
+        M::step_noobs(B, s, act, noise, rew, term, all_done);
+        double r = rew[0];
+#pragma unroll
+        for (int a = 1; a < NAG; ++a) r = (a == ego) ? rew[a] : r;
+        ret = __dadd_rn(ret, __dmul_rn(sdisc[k], r));
+        ++k; ++executed;
+        finished = ((term >> ego) & 1u) || all_done || (k >= max_steps);
+      }
+      if (finished) {
+        returns_out[item] = ret;
+        if (steps_out) steps_out[item] = (uint8_t)k;
+        if (state_out) {
+#pragma unroll
+          for (int w = 0; w < SW; ++w) state_out[item * SW + w] = s.w[w];
+        }
+        item = -1;
+      }
+    }
+  }
+  if (live_count != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) executed += __shfl_down_sync(0xffffffffu, executed, o);
+    if (lane == 0 && executed) atomicAdd(live_count, executed);
+  }
+}
+
+}  // namespace generic
+}  // namespace posg

@@ -1,0 +1,184 @@
+// Model-generic batch entry points of the C-ABI (posg_model_*), dispatched on the model
+// kind, and the PredatorPrey-v0 model builder.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "generic_kernels.cuh"
+#include "pp.cuh"
+
+namespace posg {
+
+template <typename K>
+static int persistent_grid(K kernel, size_t smem, int64_t work_items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, generic::THREADS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int64_t need = (work_items + generic::THREADS - 1) / generic::THREADS;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+static pp::Blob* build_pp_blob(int size, const char* blocks, int num_predators, int num_prey, int cooperative,
+                               int prey_strength, int obs_dim) {
+  if (size < 3 || size > 16) { set_error("grid size %d outside [3,16]", size); return nullptr; }
+  if (num_predators != pp::NP || num_prey != pp::NQ) {
+    set_error("the sm_100a kernels are specialised for 2 predators and 3 prey"); return nullptr;
+  }
+  if (obs_dim != 2) { set_error("obs_dim %d unsupported: kernels are specialised for obs_dim 2", obs_dim); return nullptr; }
+  if (prey_strength < 1 || prey_strength > num_predators) { set_error("bad prey_strength"); return nullptr; }
+  pp::Blob* b = (pp::Blob*)calloc(1, sizeof(pp::Blob));
+  bool blk[16][16];
+  memset(blk, 0, sizeof(blk));
+  if (blocks) {
+    // optional '#'/'.' rows
+    int x = 0, y = 0;
+    for (const char* p = blocks; *p; ++p) {
+      if (*p == '\n') { ++y; x = 0; continue; }
+      if (x < 16 && y < 16 && *p == '#') blk[y][x] = true;
+      ++x;
+    }
+  }
+  for (int l = 0; l < pp::LINES; ++l) b->rows[l] = 0xffffffffu;
+  for (int y = 0; y < size; ++y)
+    for (int x = 0; x < size; ++x)
+      if (!blk[y][x]) b->rows[y + pp::PAD] &= ~(1u << (x + pp::PAD));
+  // predator starts: corners and half-way along each side (itertools.product order: x outer)
+  const int v[3] = {0, size / 2, size - 1};
+  int n = 0;
+  for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) {
+      const int x = v[a], y = v[c];
+      if (x == 0 || x == size - 1 || y == 0 || y == size - 1) b->pred_start[n++] = (uint8_t)(x | (y << 4));
+    }
+  b->n_pred_start = (uint8_t)n;
+  // prey starts: whole rings around the centre until at least num_prey unblocked cells
+  const int cx = size / 2, cy = size / 2;
+  n = 0;
+  for (int ring = 0; n < num_prey && ring < size; ++ring)
+    for (int x = cx - ring; x <= cx + ring; ++x)
+      for (int y = cy - ring; y <= cy + ring; ++y) {
+        const int d = std::max(abs(x - cx), abs(y - cy));
+        if (d != ring || x < 0 || y < 0 || x >= size || y >= size || blk[y][x] || n >= 32) continue;
+        b->prey_start[n++] = (uint8_t)(x | (y << 4));
+      }
+  b->n_prey_start = (uint8_t)n;
+  b->size = (uint8_t)size; b->obs_dim = (uint8_t)obs_dim; b->prey_strength = (uint8_t)prey_strength;
+  b->cooperative = cooperative ? 1 : 0;
+  b->per_prey_reward = 1.0 / (double)num_prey;
+  for (int k = 0; k < 4; ++k) b->reward_k[k] = (double)k * b->per_prey_reward;
+  const int w = 2 * obs_dim + 1;
+  for (int y = 0; y < 16; ++y)
+    for (int x = 0; x < 16; ++x) {
+      unsigned long long cells = 0;
+      for (int col = 0; col < w; ++col)
+        for (int row = 0; row < w; ++row) {
+          const int gx = x + col - obs_dim, gy = y + row - obs_dim;
+          const bool wall = gx < 0 || gy < 0 || gx >= size || gy >= size || blk[gy][gx];
+          if (wall) cells |= (unsigned long long)pp::WALL << (2 * (col * w + row));
+        }
+      b->obs_base[x | (y << 4)] = cells;
+    }
+  return b;
+}
+
+}  // namespace posg
+
+using namespace posg;
+
+#define MODEL_DISPATCH(m, CALL)                                                   \
+  switch ((m)->kind) {                                                            \
+    case KIND_PREDATOR_PREY: { using M = PPSim; CALL; } break;                    \
+    default: set_error("posg_model_*: unsupported model kind %d", (m)->kind);     \
+             return POSG_E_UNSUPPORTED;                                           \
+  }
+
+extern "C" {
+
+int posg_pp_create(int grid_size, const char* block_rows, int num_predators, int num_prey, int cooperative,
+                   int prey_strength, int obs_dim, posg_model_t* out) {
+  POSG_REQUIRE(out, "null argument");
+  int ndev = posg_device_count();
+  if (ndev < 0) return ndev;
+  pp::Blob* h = build_pp_blob(grid_size, block_rows, num_predators, num_prey, cooperative, prey_strength, obs_dim);
+  if (!h) return POSG_E_UNSUPPORTED;
+  posg_model* m = new posg_model();
+  m->kind = KIND_PREDATOR_PREY; m->num_agents = num_predators; m->blob_bytes = (int)sizeof(pp::Blob);
+  m->h_blob = h; m->d_blob = nullptr;
+  cudaError_t e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, sizeof(pp::Blob));
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_blob, h, sizeof(pp::Blob), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { int rc = cuda_fail(e, "model upload"); posg_model_destroy(m); return rc; }
+  *out = m;
+  return POSG_OK;
+}
+
+int posg_model_sample_initial_state(posg_model_t m, int64_t n, const uint8_t* picks, uint64_t seed,
+                                    uint64_t particle_offset, uint32_t* state_out, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && state_out, "bad arguments");
+  MODEL_DISPATCH(m, (generic::initial_state_kernel<M><<<persistent_grid(generic::initial_state_kernel<M>, m->blob_bytes, n),
+                     generic::THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
+                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, picks, seed, particle_offset, state_out)));
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_model_observe(posg_model_t m, int64_t n, const uint32_t* state, uint64_t* obs_out, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && state && obs_out, "bad arguments");
+  MODEL_DISPATCH(m, (generic::observe_kernel<M><<<persistent_grid(generic::observe_kernel<M>, m->blob_bytes, n),
+                     generic::THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
+                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, obs_out)));
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const uint8_t* actions_in,
+                    const uint32_t* noise_in, uint64_t seed, uint32_t step_idx, uint64_t particle_offset,
+                    uint32_t* state_out, uint64_t* obs_out, double* rewards_out, uint8_t* flags_out,
+                    uint8_t* actions_out, unsigned long long* live_count, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && state_in && state_out && obs_out && rewards_out && flags_out, "bad arguments");
+  MODEL_DISPATCH(m, (generic::step_kernel<M><<<persistent_grid(generic::step_kernel<M>, m->blob_bytes, n),
+                     generic::THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
+                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, actions_in, noise_in, seed,
+                     step_idx, particle_offset, state_out, obs_out, rewards_out, flags_out, actions_out, live_count)));
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_model_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, int ego_agent, int max_steps,
+                       double discount, uint64_t seed, uint32_t step0, uint64_t particle_offset,
+                       double* returns_out, uint8_t* steps_out, uint32_t* state_out,
+                       unsigned long long* live_count, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  POSG_REQUIRE(ego_agent >= 0 && ego_agent < m->num_agents, "ego_agent out of range");
+  POSG_REQUIRE(max_steps >= 0 && max_steps <= 255, "max_steps outside [0,255]");
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && state_in && returns_out, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* counter = nullptr;
+  POSG_CUDA(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), s));
+  POSG_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+  generic::DiscountTable dtab;
+  for (int k = 0; k < 256; ++k) dtab.v[k] = pow(discount, (double)k);
+  MODEL_DISPATCH(m, (generic::rollout_kernel<M><<<persistent_grid(generic::rollout_kernel<M>, m->blob_bytes, n),
+                     generic::THREADS, m->blob_bytes, s>>>(
+                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, ego_agent, max_steps, dtab, seed,
+                     step0, particle_offset, returns_out, steps_out, state_out, counter, live_count)));
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(counter, s);
+  POSG_CUDA(e);
+  return POSG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,334 @@
+// PredatorPrey-v0 (2 predators, 3 prey) on packed integer state.  Semantics follow
+// posggym's PredatorPreyModel.step as consumed at planning/mcts.py:333,418 and
+// planning/belief.py:165 of the reference.
+//   state word 0: predator 0 (x | y<<4) | predator 1 << 8 | caught bits << 16
+//   state word 1: prey 0 (x | y<<4) | prey 1 << 8 | prey 2 << 16
+//   observation : 25 cells x 2 bits (EMPTY=0 WALL=1 PREDATOR=2 PREY=3), cell index
+//                 col*5 + row of the 5x5 window centred on the predator
+#pragma once
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace posg {
+namespace pp {
+
+constexpr int PAD = 4, LINES = 24;
+constexpr int NP = 2, NQ = 3;
+enum : int { EMPTY = 0, WALL = 1, PREDATOR = 2, PREY = 3 };
+
+struct alignas(16) Blob {
+  uint32_t rows[LINES];            // rows[y+PAD] bit (x+PAD): blocked or outside
+  uint8_t pred_start[16], prey_start[32];
+  uint8_t n_pred_start, n_prey_start, size, obs_dim, prey_strength, cooperative, pad_[10];
+  double reward_k[4];              // k * (1 / num_prey), k newly caught prey (cooperative)
+  double per_prey_reward;
+  double pad2_;
+  unsigned long long obs_base[256];  // wall cells of the window centred at (x, y)
+};
+static_assert(sizeof(Blob) % 16 == 0, "blob must be a multiple of 16 B");
+
+__device__ __forceinline__ bool blocked(const Blob& B, int x, int y) {
+  return (B.rows[y + PAD] >> (x + PAD)) & 1u;
+}
+__device__ __forceinline__ int mdist(int a, int b) {
+  return abs((a & 15) - (b & 15)) + abs((a >> 4) - (b >> 4));
+}
+__device__ __forceinline__ uint32_t pick_index(uint32_t word, uint32_t n) { return __umulhi(word, n); }
+
+struct Ents {           // unpacked entities
+  int pred[NP];
+  int prey[NQ];
+  uint32_t caught;      // bit i
+};
+
+__device__ __forceinline__ void unpack(uint32_t w0, uint32_t w1, Ents& e) {
+  e.pred[0] = w0 & 255; e.pred[1] = (w0 >> 8) & 255; e.caught = (w0 >> 16) & 7u;
+  e.prey[0] = w1 & 255; e.prey[1] = (w1 >> 8) & 255; e.prey[2] = (w1 >> 16) & 255;
+}
+__device__ __forceinline__ void pack(const Ents& e, uint32_t& w0, uint32_t& w1) {
+  w0 = (uint32_t)e.pred[0] | ((uint32_t)e.pred[1] << 8) | (e.caught << 16);
+  w1 = (uint32_t)e.prey[0] | ((uint32_t)e.prey[1] << 8) | ((uint32_t)e.prey[2] << 16);
+}
+
+// free = inside, not a block, not occupied by a predator or an uncaught prey (cur[] =
+// positions with the moves made so far applied)
+__device__ __forceinline__ bool cell_free(const Blob& B, const Ents& e, const int (&cur)[NQ], int x, int y) {
+  if (blocked(B, x, y)) return false;
+  const int c = x | (y << 4);
+  bool occ = (c == e.pred[0]) || (c == e.pred[1]);
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) occ |= (!((e.caught >> j) & 1u)) && (cur[j] == c);
+  return !occ;
+}
+
+// flee from the closest of `threats` (index order) if within obs_dim; returns -1 if none in sight
+__device__ __forceinline__ int move_away(const Blob& B, const Ents& e, const int (&cur)[NQ], int coord,
+                                         const int* threats, int nthreats, uint32_t word) {
+  int dmin = 1 << 20, nclose = 0;
+  for (int k = 0; k < nthreats; ++k) { const int d = mdist(coord, threats[k]); dmin = d < dmin ? d : dmin; }
+  if (nthreats == 0 || dmin > (int)B.obs_dim) return -1;
+  for (int k = 0; k < nthreats; ++k) nclose += (mdist(coord, threats[k]) == dmin);
+  const int want = (int)pick_index(word, (uint32_t)nclose);
+  int threat = threats[0], seen = 0;
+  for (int k = 0; k < nthreats; ++k)
+    if (mdist(coord, threats[k]) == dmin) { if (seen == want) threat = threats[k]; ++seen; }
+  // current cell, then neighbours N, E, S, W; keep the max of (dist, x, y)
+  int best = coord, bd = mdist(coord, threat);
+  const int x = coord & 15, y = coord >> 4;
+  const int nx[4] = {x, x + 1, x, x - 1}, ny[4] = {y - 1, y, y + 1, y};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!cell_free(B, e, cur, nx[k], ny[k])) continue;
+    const int c = nx[k] | (ny[k] << 4);
+    const int d = mdist(c, threat);
+    const bool better = d > bd || (d == bd && (nx[k] > (best & 15) || (nx[k] == (best & 15) && ny[k] > (best >> 4))));
+    if (better) { best = c; bd = d; }
+  }
+  return best;
+}
+
+// joint transition; rew[] per predator; returns all_done
+__device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&act)[NP], const uint32_t (&words)[NQ],
+                                           double (&rew)[NP]) {
+  int cur[NQ];
+  bool moved[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) { cur[i] = e.prey[i]; moved[i] = (e.caught >> i) & 1u; }
+  // 1. flee from predators
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if (moved[i]) continue;
+    const int nxt = move_away(B, e, cur, e.prey[i], e.pred, NP, words[i]);
+    if (nxt >= 0) { cur[i] = nxt; moved[i] = true; }
+  }
+  // 2. keep away from other prey (their positions before this step)
+  if (NQ - __popc(e.caught) > 1) {
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      if (moved[i]) continue;
+      int others[NQ], no = 0;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j)
+        if (j != i && !((e.caught >> j) & 1u)) others[no++] = e.prey[j];
+      const int nxt = move_away(B, e, cur, e.prey[i], others, no, words[i]);
+      if (nxt >= 0) { cur[i] = nxt; moved[i] = true; }
+    }
+  }
+  // 3. random move among free neighbours (N, E, S, W) and staying
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if (moved[i]) continue;
+    const int x = e.prey[i] & 15, y = e.prey[i] >> 4;
+    const int nx[4] = {x, x + 1, x, x - 1}, ny[4] = {y - 1, y, y + 1, y};
+    int cands[5], nc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (cell_free(B, e, cur, nx[k], ny[k])) cands[nc++] = nx[k] | (ny[k] << 4);
+    cands[nc++] = e.prey[i];
+    cur[i] = cands[pick_index(words[i], (uint32_t)nc)];
+    moved[i] = true;
+  }
+  // predators: simultaneous moves; prey cells and shared targets block
+  int pot[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int a = act[i], x = e.pred[i] & 15, y = e.pred[i] >> 4;
+    const int dx = (a == 4) - (a == 3), dy = (a == 2) - (a == 1);
+    int c = e.pred[i];
+    if (a != 0 && !blocked(B, x + dx, y + dy)) c = (x + dx) | ((y + dy) << 4);
+    bool on_prey = false;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) on_prey |= (!((e.caught >> j) & 1u)) && (cur[j] == c);
+    pot[i] = on_prey ? e.pred[i] : c;
+  }
+  const bool clash = pot[0] == pot[1];
+  const int p0 = clash ? e.pred[0] : pot[0], p1 = clash ? e.pred[1] : pot[1];
+  // captures
+  uint32_t newly = 0;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    if ((e.caught >> j) & 1u) continue;
+    const int adj = (mdist(cur[j], p0) <= 1) + (mdist(cur[j], p1) <= 1);
+    if (adj >= (int)B.prey_strength) newly |= 1u << j;
+  }
+  rew[0] = 0.0; rew[1] = 0.0;
+  if (newly) {
+    if (B.cooperative) {
+      rew[0] = rew[1] = B.reward_k[__popc(newly)];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        if (!((newly >> j) & 1u)) continue;
+        const bool i0 = mdist(cur[j], p0) <= 1, i1 = mdist(cur[j], p1) <= 1;
+        const double share = __ddiv_rn(B.per_prey_reward, (double)((int)i0 + (int)i1));
+        if (i0) rew[0] = __dadd_rn(rew[0], share);
+        if (i1) rew[1] = __dadd_rn(rew[1], share);
+      }
+    }
+  }
+  e.pred[0] = p0; e.pred[1] = p1;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) e.prey[j] = cur[j];
+  e.caught |= newly;
+  return e.caught == 7u;
+}
+
+// window cell index (col*5 + row) of grid cell c seen from predator at p, or -1
+__device__ __forceinline__ int window_cell(int p, int c, int obs_dim) {
+  const int col = (c & 15) - (p & 15) + obs_dim, row = (c >> 4) - (p >> 4) + obs_dim;
+  const int w = 2 * obs_dim + 1;
+  return ((unsigned)col < (unsigned)w && (unsigned)row < (unsigned)w) ? col * w + row : -1;
+}
+
+__device__ __forceinline__ unsigned long long observe(const Blob& B, const Ents& e, int i) {
+  const int p = e.pred[i];
+  unsigned long long cells = B.obs_base[p];
+  const int od = B.obs_dim;
+  // prey first, predators after (a predator takes priority; cells never coincide anyway)
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const int k = ((e.caught >> j) & 1u) ? -1 : window_cell(p, e.prey[j], od);
+    if (k >= 0) cells = (cells & ~(3ULL << (2 * k))) | ((unsigned long long)PREY << (2 * k));
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int k = window_cell(p, e.pred[j], od);
+    if (k >= 0) cells = (cells & ~(3ULL << (2 * k))) | ((unsigned long long)PREDATOR << (2 * k));
+  }
+  return cells;
+}
+
+__device__ __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NP + NQ], Ents& e) {
+  uint32_t used = 0;
+  for (int i = 0; i < NP; ++i) {
+    int k = 0, sel = 0;
+    for (int c = 0; c < B.n_pred_start; ++c) {
+      if ((used >> c) & 1u) continue;
+      if (k == picks[i]) sel = c;
+      ++k;
+    }
+    used |= 1u << sel;
+    e.pred[i] = B.pred_start[sel];
+  }
+  used = 0;
+  for (int i = 0; i < NQ; ++i) {
+    int k = 0, sel = 0;
+    for (int c = 0; c < B.n_prey_start; ++c) {
+      if ((used >> c) & 1u) continue;
+      if (k == picks[NP + i]) sel = c;
+      ++k;
+    }
+    used |= 1u << sel;
+    e.prey[i] = B.prey_start[sel];
+  }
+  e.caught = 0;
+}
+
+}  // namespace pp
+
+// Adapter for the generic batch / search / belief kernels.
+struct PPSim {
+  using Blob = pp::Blob;
+  static constexpr int A = 5, OW = 1, SW = 2, NAG = 2, NW = 3, NPICK = 5;
+  struct State { uint32_t w[SW]; };
+
+  // explicit-noise joint step (model.step): obs / rewards for every agent
+  __device__ static __forceinline__ void step_all(const Blob& B, State& s, const int (&act)[NAG],
+                                                  const uint32_t (&noise)[NW],
+                                                  unsigned long long (&obs)[NAG][OW], double (&rew)[NAG],
+                                                  uint32_t& flags, bool& was_live) {
+    pp::Ents e;
+    pp::unpack(s.w[0], s.w[1], e);
+    was_live = e.caught != 7u;
+    const bool all_done = pp::transition(B, e, act, noise, rew);
+    pp::pack(e, s.w[0], s.w[1]);
+    obs[0][0] = pp::observe(B, e, 0);
+    obs[1][0] = pp::observe(B, e, 1);
+    flags = all_done ? (0x80u | 3u) : 0u;
+  }
+  // the same without observations (rollouts); term = per-agent terminated bits
+  __device__ static __forceinline__ void step_noobs(const Blob& B, State& s, const int (&act)[NAG],
+                                                    const uint32_t (&noise)[NW], double (&rew)[NAG],
+                                                    uint32_t& term, bool& all_done) {
+    pp::Ents e;
+    pp::unpack(s.w[0], s.w[1], e);
+    all_done = pp::transition(B, e, act, noise, rew);
+    pp::pack(e, s.w[0], s.w[1]);
+    term = all_done ? 3u : 0u;
+  }
+  // uniform joint action + prey words from one Philox block (particle, step, STREAM_STEP)
+  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
+                                                           int (&act)[NAG], uint32_t (&noise)[NW]) {
+    const uint4 w = philox_block(seed, particle, step, STREAM_STEP);
+    noise[0] = w.x; noise[1] = w.y; noise[2] = w.z;
+    const uint32_t idx = uniform_below(w.w, 25u);
+    act[1] = (int)(idx / 5u);
+    act[0] = (int)(idx - 5u * (uint32_t)act[1]);
+  }
+  __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
+    pp::Ents e;
+    pp::unpack(s.w[0], s.w[1], e);
+    obs[0][0] = pp::observe(B, e, 0);
+    obs[1][0] = pp::observe(B, e, 1);
+  }
+  __device__ static __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NPICK], State& s) {
+    pp::Ents e;
+    pp::initial_from_picks(B, picks, e);
+    pp::pack(e, s.w[0], s.w[1]);
+  }
+  // picks from Philox: block (particle, 0, STREAM_INIT) words x,y -> predators; block
+  // (particle, 0, STREAM_INIT2) words x,y,z -> prey
+  __device__ static __forceinline__ void initial_state(const Blob& B, uint64_t seed, uint64_t particle, State& s) {
+    const uint4 a = philox_block(seed, particle, 0u, STREAM_INIT);
+    const uint4 b = philox_block(seed, particle, 0u, STREAM_INIT2);
+    int picks[NPICK];
+    picks[0] = (int)uniform_below(a.x, (uint32_t)B.n_pred_start);
+    picks[1] = (int)uniform_below(a.y, (uint32_t)B.n_pred_start - 1u);
+    picks[2] = (int)uniform_below(b.x, (uint32_t)B.n_prey_start);
+    picks[3] = (int)uniform_below(b.y, (uint32_t)B.n_prey_start - 1u);
+    picks[4] = (int)uniform_below(b.z, (uint32_t)B.n_prey_start - 2u);
+    initial_from_picks(B, picks, s);
+  }
+
+  // ---- search / belief adapter ---------------------------------------------------
+  __device__ static __forceinline__ void step(const Blob& B, State& s, int ego, int ego_action, uint32_t word,
+                                              unsigned long long (&obs)[OW], double& r, bool& done) {
+    // `word` seeds the other predator's action and the three prey words
+    const uint4 w = philox4x32_10(word, 0x9E3779B9u, 0x7F4A7C15u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu);
+    int act[NAG];
+    const int other = (int)uniform_below(w.w, 5u);
+    act[0] = ego == 0 ? ego_action : other;
+    act[1] = ego == 1 ? ego_action : other;
+    const uint32_t noise[NW] = {w.x, w.y, w.z};
+    pp::Ents e;
+    pp::unpack(s.w[0], s.w[1], e);
+    double rew[NAG];
+    done = pp::transition(B, e, act, noise, rew);
+    pp::pack(e, s.w[0], s.w[1]);
+    r = rew[ego];
+    obs[0] = pp::observe(B, e, ego);
+  }
+  __device__ static __forceinline__ void rollout_step(const Blob& B, State& s, int ego, uint32_t word, double& r,
+                                                      bool& done) {
+    const uint4 w = philox4x32_10(word, 0x9E3779B9u, 0x7F4A7C15u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu);
+    int act[NAG];
+    const uint32_t idx = uniform_below(w.w, 25u);
+    act[1] = (int)(idx / 5u);
+    act[0] = (int)(idx - 5u * (uint32_t)act[1]);
+    const uint32_t noise[NW] = {w.x, w.y, w.z};
+    pp::Ents e;
+    pp::unpack(s.w[0], s.w[1], e);
+    double rew[NAG];
+    done = pp::transition(B, e, act, noise, rew);
+    pp::pack(e, s.w[0], s.w[1]);
+    r = rew[ego];
+  }
+  __device__ static __forceinline__ void observe(const Blob& B, const State& s, int ego, unsigned long long (&obs)[OW]) {
+    pp::Ents e;
+    pp::unpack(s.w[0], s.w[1], e);
+    obs[0] = pp::observe(B, e, ego);
+  }
+};
+
+}  // namespace posg

@@ -6,6 +6,7 @@
 #include "belief.cuh"
 #include "common.h"
 #include "driving_sim.cuh"
+#include "pp.cuh"
 #include "search.cuh"
 #include "stage.cuh"
 
@@ -138,6 +139,7 @@ static bool kind_info(const posg_model* m, KindInfo* k) {
   if (!m) return false;
   switch (m->kind) {
     case KIND_DRIVING: *k = {DrivingSim::A, DrivingSim::OW, DrivingSim::SW}; return true;
+    case KIND_PREDATOR_PREY: *k = {PPSim::A, PPSim::OW, PPSim::SW}; return true;
     default: return false;
   }
 }
@@ -208,6 +210,11 @@ int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log,
     case KIND_DRIVING:
       search_kernel<DrivingSim><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
           (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, root, root_t, particles,
+          (long long)n_particles, (long long)n_sims, (unsigned long long)sim_id0);
+      break;
+    case KIND_PREDATOR_PREY:
+      search_kernel<PPSim><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
+          (const PPSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, root, root_t, particles,
           (long long)n_particles, (long long)n_sims, (unsigned long long)sim_id0);
       break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
@@ -310,6 +317,12 @@ int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, i
           ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,
           reject_scratch, d_res);
       break;
+    case KIND_PREDATOR_PREY:
+      reinvigorate_kernel<PPSim><<<1, belief::CTA, m->blob_bytes, s>>>(
+          (const PPSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, parent_particles, (long long)n_parent,
+          ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,
+          reject_scratch, d_res);
+      break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
   }
   POSG_CUDA(cudaGetLastError());
@@ -335,6 +348,11 @@ int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_ob
     case KIND_DRIVING:
       initial_belief_kernel<DrivingSim><<<1, belief::CTA, m->blob_bytes, s>>>(
           (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, ego_agent, d_obs, (long long)n_needed,
+          (long long)max_attempts, seed, draw_id, out_states, d_res);
+      break;
+    case KIND_PREDATOR_PREY:
+      initial_belief_kernel<PPSim><<<1, belief::CTA, m->blob_bytes, s>>>(
+          (const PPSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, ego_agent, d_obs, (long long)n_needed,
           (long long)max_attempts, seed, draw_id, out_states, d_res);
       break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;

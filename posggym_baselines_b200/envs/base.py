@@ -1,0 +1,167 @@
+"""Model-generic batched wrapper over the ``posg_model_*`` C-ABI entry points and the
+scalar ``POSGModel`` facade built on it."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import Dict, List, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from posggym_baselines_b200 import _lib
+
+FLAG_ALL_DONE = 0x80
+
+
+class StepOut(NamedTuple):
+    state: torch.Tensor     # int32 [n, SW]
+    obs: torch.Tensor       # int64 [n, A, OW]
+    rewards: torch.Tensor   # float64 [n, A]
+    flags: torch.Tensor     # uint8 [n]
+    actions: Optional[torch.Tensor]  # uint8 [n, A]
+
+
+class Spec:
+    def __init__(self, id: str, max_episode_steps: Optional[int]):
+        self.id = id
+        self.max_episode_steps = max_episode_steps
+
+
+class JointTimestep(NamedTuple):
+    state: tuple
+    observations: Dict[str, tuple]
+    rewards: Dict[str, float]
+    terminations: Dict[str, bool]
+    truncations: Dict[str, bool]
+    all_done: bool
+    infos: Dict[str, dict]
+
+
+def to_numpy(t) -> np.ndarray:
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+class BatchedModel:
+    """Subclasses set ``num_agents``, ``state_words``, ``obs_words``, ``noise_words``,
+    ``num_picks`` and create ``self._handle``."""
+
+    num_agents: int
+    state_words: int
+    obs_words: int
+    noise_words: int
+    num_picks: int
+
+    def _init_device(self, device):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None:
+            raise _lib.PosgB200Error("no CUDA device: posggym_baselines_b200 has no CPU fallback")
+        self.device = torch.device(device)
+        self._handle = C.c_void_p()
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().posg_model_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def sample_initial_state(self, n: int, seed: int = 0, particle_offset: int = 0, picks=None, out=None):
+        state = out if out is not None else self._empty((n, self.state_words), torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().posg_model_sample_initial_state(
+                self._handle, n, _lib.ptr(picks), seed, particle_offset, _lib.ptr(state), _lib.stream_ptr()))
+        return state
+
+    def observe(self, state, out=None):
+        n = state.shape[0]
+        obs = out if out is not None else self._empty((n, self.num_agents, self.obs_words), torch.int64)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().posg_model_observe(self._handle, n, _lib.ptr(state), _lib.ptr(obs), _lib.stream_ptr()))
+        return obs
+
+    def step(self, state, actions=None, noise=None, seed: int = 0, step_idx: int = 0, particle_offset: int = 0,
+             out: Optional[StepOut] = None, live_count=None, want_actions: bool = True) -> StepOut:
+        n, a = state.shape[0], self.num_agents
+        if out is None:
+            out = StepOut(
+                self._empty((n, self.state_words), torch.int32), self._empty((n, a, self.obs_words), torch.int64),
+                self._empty((n, a), torch.float64), self._empty((n,), torch.uint8),
+                self._empty((n, a), torch.uint8) if (actions is None and want_actions) else None)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().posg_model_step(
+                self._handle, n, _lib.ptr(state), _lib.ptr(actions), _lib.ptr(noise), seed, step_idx,
+                particle_offset, _lib.ptr(out.state), _lib.ptr(out.obs), _lib.ptr(out.rewards),
+                _lib.ptr(out.flags), _lib.ptr(out.actions), _lib.ptr(live_count), _lib.stream_ptr()))
+        return out
+
+    def rollout(self, state, ego_agent: int, max_steps: int, discount: float, seed: int = 0, step0: int = 0,
+                particle_offset: int = 0, want_state: bool = False, live_count=None):
+        n = state.shape[0]
+        returns = self._empty((n,), torch.float64)
+        steps = self._empty((n,), torch.uint8)
+        final = self._empty((n, self.state_words), torch.int32) if want_state else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().posg_model_rollout(
+                self._handle, n, _lib.ptr(state), ego_agent, max_steps, discount, seed, step0, particle_offset,
+                _lib.ptr(returns), _lib.ptr(steps), _lib.ptr(final), _lib.ptr(live_count), _lib.stream_ptr()))
+        return returns, steps, final
+
+
+class ModelFacade:
+    """Scalar ``posggym.model.POSGModel`` surface over a BatchedModel (batch of one)."""
+
+    is_symmetric = True
+
+    def _init_facade(self, batched: BatchedModel, env_id: str, max_episode_steps: int):
+        self.batched = batched
+        self.possible_agents = tuple(str(i) for i in range(batched.num_agents))
+        self.spec = Spec(env_id, max_episode_steps)
+        self._rng = random.Random()
+
+    @property
+    def rng(self) -> random.Random:
+        return self._rng
+
+    def seed(self, seed: Optional[int] = None):
+        self._rng = random.Random(seed)
+        for k, sp in enumerate(self.action_spaces.values()):
+            sp.seed(None if seed is None else seed + 1 + k)
+
+    def get_agents(self, state) -> List[str]:
+        return list(self.possible_agents)
+
+    def sample_initial_state(self):
+        b = self.batched
+        return b.unpack_state(b.sample_initial_state(1, seed=self._rng.getrandbits(63)))[0]
+
+    def sample_initial_obs(self, state):
+        b = self.batched
+        packed = torch.from_numpy(b.pack_state([state])).to(b.device)
+        obs = b.unpack_obs(b.observe(packed))[0]
+        return {i: obs[k] for k, i in enumerate(self.possible_agents)}
+
+    def sample_agent_initial_state(self, agent_id: str, obs):
+        raise NotImplementedError
+
+    def step(self, state, actions: Dict[str, int]) -> JointTimestep:
+        b = self.batched
+        packed = torch.from_numpy(b.pack_state([state])).to(b.device)
+        act = torch.tensor([[int(actions[i]) for i in self.possible_agents]], dtype=torch.uint8, device=b.device)
+        noise = np.array([[self._rng.getrandbits(32) for _ in range(b.noise_words)]], dtype=np.uint32)
+        out = b.step(packed, act, torch.from_numpy(noise.view(np.int32)).to(b.device))
+        nstate = b.unpack_state(out.state)[0]
+        obs = b.unpack_obs(out.obs)[0]
+        rew = out.rewards.cpu().numpy()[0]
+        flags = int(out.flags.cpu()[0])
+        ids = self.possible_agents
+        return JointTimestep(
+            nstate, {i: obs[k] for k, i in enumerate(ids)}, {i: float(rew[k]) for k, i in enumerate(ids)},
+            {i: bool((flags >> k) & 1) for k, i in enumerate(ids)}, {i: False for i in ids},
+            bool(flags & FLAG_ALL_DONE), {i: {} for i in ids})

@@ -117,7 +117,83 @@ def driving_rollout_cases(n=512, seed=7, discount=0.95, max_steps=50):
                 steps=np.array(steps, np.uint8), final_state=np.array(finals, np.int16))
 
 
+# ---------------------------------------------------------------- PredatorPrey-v0
+def pp_fields(s):
+    return [*[v for c in s.predator_coords for v in c], *[v for c in s.prey_coords for v in c], *s.prey_caught]
+
+
+def pp_step_cases(n_play=2500, n_syn=2500, seed=20261019):
+    from oracle.predator_prey import PPState, PredatorPreyModel
+
+    m = PredatorPreyModel()
+    m.seed(seed)
+    rng = random.Random(seed)
+    states = []
+    while len(states) < n_play:
+        s = m.sample_initial_state()
+        for _ in range(51):
+            states.append(s)
+            # chase the prey a bit so that captures and crowded cells occur
+            acts = {i: rng.randrange(5) for i in m.possible_agents}
+            ts = m.step(s, acts)
+            s = ts.state
+            if ts.all_done and rng.random() < 0.7:
+                break
+    cells = [(x, y) for x in range(10) for y in range(10)]
+    for _ in range(n_syn):
+        c0 = rng.choice(cells)
+        near = [c for c in cells if c != c0 and abs(c[0] - c0[0]) + abs(c[1] - c0[1]) <= 3]
+        picks = [c0] + rng.sample(near, 4) if rng.random() < 0.8 else rng.sample(cells, 5)
+        rng.shuffle(picks)
+        caught = tuple(int(rng.random() < 0.2) for _ in range(3))
+        states.append(PPState(tuple(picks[:2]), tuple(picks[2:]), caught))
+    S, A, W, S2, O, RW, AD = [], [], [], [], [], [], []
+    for s in states:
+        a = [rng.randrange(5), rng.randrange(5)]
+        w = [rng.getrandbits(32) for _ in range(3)]
+        ts = m.step_with_noise(s, {"0": a[0], "1": a[1]}, w)
+        S.append(pp_fields(s)); A.append(a); W.append(w); S2.append(pp_fields(ts.state))
+        O.append([list(ts.observations[i]) for i in m.possible_agents])
+        RW.append([ts.rewards[i] for i in m.possible_agents]); AD.append(ts.all_done)
+    return dict(state=np.array(S, np.int8), action=np.array(A, np.uint8), noise=np.array(W, np.uint32),
+                next_state=np.array(S2, np.int8), obs=np.array(O, np.int8), reward=np.array(RW, np.float64),
+                all_done=np.array(AD, np.bool_))
+
+
+def pp_init_cases(n=400, seed=5):
+    from oracle.predator_prey import PredatorPreyModel
+
+    m = PredatorPreyModel()
+    rng = random.Random(seed)
+    picks, S, O = [], [], []
+    for _ in range(n):
+        p = [rng.randrange(b) for b in m.initial_noise_bounds()]
+        s = m.initial_state_from_noise(p)
+        o = m.sample_initial_obs(s)
+        picks.append(p); S.append(pp_fields(s)); O.append([list(o[i]) for i in m.possible_agents])
+    return dict(picks=np.array(picks, np.uint8), state=np.array(S, np.int8), obs=np.array(O, np.int8))
+
+
+def pp_rollout_cases(n=384, seed=9, discount=0.95, max_steps=50):
+    from oracle.predator_prey import PredatorPreyModel
+
+    m = PredatorPreyModel()
+    particles = np.arange(n, dtype=np.uint64) + np.uint64(777)
+    picks = R.pp_initial_picks(m, seed, particles)
+    rets, steps, finals, inits = [], [], [], []
+    for p, pk in zip(particles, picks):
+        s0 = m.initial_state_from_noise([int(v) for v in pk])
+        ret, k, s = R.pp_rollout(m, s0, "1", max_steps, discount, seed, int(p))
+        rets.append(ret); steps.append(k); inits.append(pp_fields(s0)); finals.append(pp_fields(s))
+    return dict(seed=np.array(seed), particle=particles, discount=np.array(discount), max_steps=np.array(max_steps),
+                ego=np.array(1), init_state=np.array(inits, np.int8), ret=np.array(rets, np.float64),
+                steps=np.array(steps, np.uint8), final_state=np.array(finals, np.int8))
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "pp_step.npz"), **pp_step_cases())
+    np.savez_compressed(os.path.join(HERE, "pp_init.npz"), **pp_init_cases())
+    np.savez_compressed(os.path.join(HERE, "pp_rollout.npz"), **pp_rollout_cases())
     np.savez_compressed(os.path.join(HERE, "driving_step.npz"), **driving_step_cases())
     np.savez_compressed(os.path.join(HERE, "driving_init.npz"), **driving_init_cases())
     np.savez_compressed(os.path.join(HERE, "driving_rollout.npz"), **driving_rollout_cases())
