@@ -161,6 +161,47 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
            "sims_per_decision_all_gpus": world * tot[0].item() / max(1.0, tot[1].item()),
            "sims_per_s_all_gpus": world * tot[0].item() / max(1.0, tot[1].item()) / max(1e-9, tmax.item()),
            "search_time_s": tmax.item(), "trees": world}
+    # BASELINE.json configs[2]: root-parallel POMCP on PredatorPrey-v0 -- every rank grows its own
+    # tree from the same root belief; root visit counts and value sums merged by ONE allreduce
+    # per decision (NCCL); every rank then takes the same action.
+    try:
+        from posggym_baselines_b200.envs.predator_prey import PredatorPreyModel
+
+        pp_model = PredatorPreyModel(device=dev)
+        pp_env = Env(pp_model)
+        pp_cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb", seed=7)
+        pp_planner = POMCP(pp_model, "0", pp_cfg, RandomSearchPolicy(pp_model, "0"), root_parallel=True)
+        pp_rng = random.Random(7)
+        pp_obs, _ = pp_env.reset(seed=7)   # identical env trajectory on every rank
+        pp_planner.reset()
+        pp_sims, pp_ar, pp_actions = [], [], []
+        for d in range(decisions + 1):
+            a = pp_planner.step(pp_obs["0"])
+            if d > 0 and pp_planner.step_statistics["num_sims"] == pp_planner.step_statistics["num_sims"]:
+                pp_sims.append(pp_planner.step_statistics["num_sims"])
+                pp_ar.append(pp_planner.allreduce_time)
+            pp_actions.append(a)
+            pp_obs, _, _, _, done, _ = pp_env.step({"0": a, "1": pp_rng.randrange(5)})
+            if done:
+                break
+        pp_planner.close()
+        tot_pp = torch.tensor([sum(pp_sims), len(pp_sims)], dtype=torch.float64, device=dev)
+        act_t = torch.tensor(pp_actions + [0] * (decisions + 1 - len(pp_actions)), dtype=torch.int64, device=dev)
+        agree = True
+        if world > 1:
+            dist.all_reduce(tot_pp)
+            ref = act_t.clone()
+            dist.broadcast(ref, 0)
+            agree_t = torch.tensor([int(torch.equal(ref, act_t))], device=dev)
+            dist.all_reduce(agree_t, op=dist.ReduceOp.MIN)
+            agree = bool(agree_t.item())
+        out["predator_prey_root_parallel"] = {
+            "config": "PredatorPrey-v0 10x10, 2 predators, 3 prey, same MCTSConfig, one tree per GPU",
+            "total_sims_per_decision": tot_pp[0].item() / max(1.0, tot_pp[1].item() / world),
+            "allreduce_us_mean": 1e6 * sum(pp_ar) / max(1, len(pp_ar)), "allreduce_bytes": 80,
+            "ranks_agree_on_actions": agree}
+    except Exception as ex:
+        out["predator_prey_root_parallel"] = {"error": repr(ex)}
     if cpu:
         from oracle import shims
 

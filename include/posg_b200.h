@@ -222,6 +222,26 @@ int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_ob
                         int64_t n_needed, int64_t max_attempts, uint64_t seed, uint64_t draw_id,
                         uint32_t* out_states, int64_t* result_host, void* stream);
 
+/* ------------------------------------------------------------------ vector env (PPO collector)
+ * One call = envs.step(actions) of StackEnv(RecordEpisodeStatistics(SyncVectorEnv(
+ * [FlattenObservations(env)] * n))) as built by PPOConfig.load_vec_env
+ * (ppo/config.py:223-232) and consumed by run_rollout_worker (ppo/worker.py:82-86,
+ * 176-216): model.step, TimeLimit truncation, episode statistics, auto-reset (the reset
+ * observation is returned), one-hot flattened float32 observations, rows env-major
+ * (row = env * num_agents + agent).  All buffers are device memory owned by the caller:
+ *   state [n, SW] u32, ep_t [n] u16, ep_ret [n, A] f64, ep_count [n] u32  (carried state)
+ *   actions [n * A] i64 (worker.py:177)
+ *   obs_out [n * A, flat_dim] f32, rew_out [n * A] f32, term_out / trunc_out [n * A] u8,
+ *   done_out [n] u8, stat_r [n, A] f32 and stat_l [n] i32 (episode return / length, valid
+ *   where done_out is set: infos[agent]["episode"]["r"/"l"], worker.py:208-216).
+ * Step noise: Philox counter (env_offset + i, global_step); reset_only != 0 = envs.reset(). */
+int posg_vec_flat_dim(posg_model_t m);
+int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_t, double* ep_ret,
+                  uint32_t* ep_count, const int64_t* actions, uint64_t seed, uint32_t global_step,
+                  uint64_t env_offset, int max_episode_steps, int reset_only, float* obs_out,
+                  float* rew_out, uint8_t* term_out, uint8_t* trunc_out, uint8_t* done_out,
+                  float* stat_r, int32_t* stat_l, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,4 +41,6 @@ struct posg_model {
   int blob_bytes;
   void* d_blob;   // device copy of the immutable model blob
   void* h_blob;   // host copy (for the *_host entry points / introspection)
+  void* d_flat_desc = nullptr;  // one-hot descriptors of the flattened observation (vec env)
+  int flat_dim = 0;
 };

@@ -9,7 +9,35 @@ struct DrivingSim {
   static constexpr int A = 5;    // ego actions
   static constexpr int OW = 1;   // 64-bit words per observation key
   static constexpr int SW = 2;   // 32-bit words per state
+  static constexpr int NAG = 2;  // agents
+  static constexpr int NW = 1;   // explicit noise words per step (processing order)
   struct State { uint32_t w[SW]; };
+
+  // ---- batch concept (generic_kernels.cuh / vec_env.cuh) ---------------------------
+  __device__ static __forceinline__ void step_all(const Blob& B, State& s, const int (&act)[NAG],
+                                                  const uint32_t (&noise)[NW], unsigned long long (&obs)[NAG][OW],
+                                                  double (&rew)[NAG], uint32_t& flags, bool& was_live) {
+    const uint32_t b0 = s.w[0], b1 = s.w[1];
+    was_live = !(driving::vdone(b0) && driving::vdone(b1));
+    int c0, c1;
+    driving::transition(B, s.w[0], s.w[1], act[0], act[1], (int)(noise[0] & 1u), c0, c1);
+    obs[0][0] = driving::observe(B, s.w[0], s.w[1]);
+    obs[1][0] = driving::observe(B, s.w[1], s.w[0]);
+    rew[0] = driving::reward(B, b0, s.w[0], c0);
+    rew[1] = driving::reward(B, b1, s.w[1], c1);
+    const uint32_t t0 = driving::vdone(s.w[0]) ? 1u : 0u, t1 = driving::vdone(s.w[1]) ? 1u : 0u;
+    flags = t0 | (t1 << 1) | ((t0 & t1) ? 0x80u : 0u);
+  }
+  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
+                                                           int (&act)[NAG], uint32_t (&noise)[NW]) {
+    int order;
+    driving::sample_step_noise(seed, particle, step, act[0], act[1], order);
+    noise[0] = (uint32_t)order;
+  }
+  __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
+    obs[0][0] = driving::observe(B, s.w[0], s.w[1]);
+    obs[1][0] = driving::observe(B, s.w[1], s.w[0]);
+  }
 
   // model.step with the ego action fixed and the other vehicle uniform random
   // (RandomOtherAgentPolicy, other_policy.py:150-151); `word` = one Philox word

@@ -131,6 +131,8 @@ class MCTS:
         self.wave_size = wave_size
         self.max_wave = max_wave
         self.root_parallel = root_parallel
+        self.allreduce_time = 0.0
+        self._seed_shared = config.seed if config.seed is not None else 0
         self._cap_nodes, self._cap_log = int(node_capacity), int(log_capacity)
 
         lib = _lib.lib()
@@ -151,6 +153,14 @@ class MCTS:
         self._params.selection = _SELECTION[config.action_selection]
         self._params.ego_agent = self._ego
         self._params.seed = self._seed & 0xFFFFFFFFFFFFFFFF
+        if root_parallel:
+            from posggym_baselines_b200 import parallel
+
+            # same root belief on every rank (belief draws use the shared seed); the simulations
+            # of rank r use the Philox sub-sequence starting at r * 2**40
+            self._sim_base = parallel.world()[0] << 40
+        else:
+            self._sim_base = 0
 
         self.root = _RootView(self)
         self._logger = logging.getLogger()
@@ -346,7 +356,8 @@ class MCTS:
                 self._nodes_bound = min(self._cap_nodes, self._nodes_bound + wave_now)
                 _lib.check(lib.posg_search(
                     b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, self._root_t,
-                    _lib.ptr(self._root_particles), self._root_particles.shape[0], wave_now, self._sim_counter,
+                    _lib.ptr(self._root_particles), self._root_particles.shape[0], wave_now,
+                    self._sim_base + self._sim_counter,
                     C.byref(self._params), stream))
                 self._sim_counter += wave_now
                 n_sims += wave_now
@@ -372,28 +383,31 @@ class MCTS:
     _respect_time = False  # with max_sims set, the time limit only applies when asked for
 
     def _final_action(self, st):
+        from posggym_baselines_b200 import parallel
+
         done, total = st["done"].copy(), st["total"].copy()
-        if self.root_parallel and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
+        merged = False
+        if self.root_parallel and parallel.world()[1] > 1:
             # root-parallel merge: one allreduce of |A| x {visits, total_value} per decision
-            buf = torch.tensor(np.concatenate([done, total]), dtype=torch.float64, device=self._b.device)
-            torch.distributed.all_reduce(buf)
-            merged = buf.cpu().numpy()
-            done, total = merged[:self._A], merged[self._A:]
-            rng = random.Random((self._seed << 8) ^ self._step_num)  # identical tie-break on every rank
-        else:
-            rng = random
+            t0 = time.time()
+            done, total = parallel.merge_root_statistics(done, total, device=self._b.device)
+            self.allreduce_time = time.time() - t0
+            merged = True
         self._merged_root = (done, total)
+        if merged:
+            return parallel.select_root_action(done, total, self.action_space, self.config.action_selection,
+                                               (self._seed_shared << 8) ^ self._step_num)
+        # single tree: the reference's selection with its global-`random` tie-break
         if self.config.action_selection == "pucb":
             # max_visit_action_selection (mcts.py:566-581)
             if done.sum() == 0:
-                return rng.choice(self.action_space)
+                return random.choice(self.action_space)
             best = done.max()
-            return rng.choice([a for a in self.action_space if done[a] == best])
+            return random.choice([a for a in self.action_space if done[a] == best])
         # max_value_action_selection (mcts.py:583-600); unvisited action nodes hold value 0.0
         values = np.where(done > 0, total / np.maximum(done, 1), 0.0)
         best = values.max()
-        return rng.choice([a for a in self.action_space if values[a] == best])
+        return random.choice([a for a in self.action_space if values[a] == best])
 
     def root_action_values(self) -> np.ndarray:
         done, total = self._merged_root

@@ -1,0 +1,121 @@
+"""GPU vector env with the contract of the reference's
+``StackEnv(RecordEpisodeStatistics(SyncVectorEnv([FlattenObservations(env)] * n)))``
+(/root/reference/posggym_baselines/ppo/config.py:223-232) as the rollout worker uses it
+(ppo/worker.py:82-86,176-216):
+
+    obs, infos = envs.reset()
+    obs, reward, terminated, truncated, dones, infos = envs.step(flat_int_actions)
+
+``obs`` has ``num_envs * num_agents`` rows (env-major) of one-hot flattened float32
+observations, ``reward`` / ``terminated`` / ``truncated`` the same number of rows, ``dones``
+one entry per env, ``infos[agent_id]["episode"]`` holds ``r``, ``l``, ``t`` arrays indexed by
+env on the steps where some episode ended.  Finished envs are auto-reset in the same call
+(the worker never calls ``reset`` again).  Everything is computed by one kernel launch
+(posg_vec_step); tensors stay on the GPU unless ``as_numpy=True``.
+
+Sharding: ``env_offset`` gives this shard's first global env index (Philox counters are
+global env indices, so a 65 536-env job split over 8 GPUs is the same job).
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from posggym_baselines_b200 import _lib
+
+
+class BatchedVecEnv:
+    def __init__(self, model, num_envs: int, max_episode_steps: Optional[int] = None, seed: int = 0,
+                 env_offset: int = 0, as_numpy: bool = False):
+        self.model = model
+        self._b = model.batched
+        self.num_envs = int(num_envs)
+        self.possible_agents = tuple(model.possible_agents)
+        self.num_agents = len(self.possible_agents)
+        self.max_episode_steps = int(max_episode_steps if max_episode_steps is not None
+                                     else model.spec.max_episode_steps)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.env_offset = int(env_offset)
+        self.as_numpy = as_numpy
+        self.action_spaces = model.action_spaces
+        dev = self._b.device
+        n, a = self.num_envs, self.num_agents
+        lib = _lib.lib()
+        self.flat_dim = _lib.check(lib.posg_vec_flat_dim(self._b._handle))
+        sw = getattr(self._b, "state_words", 2)
+        self._state = torch.zeros((n, sw), dtype=torch.int32, device=dev)
+        self._ep_t = torch.zeros(n, dtype=torch.int16, device=dev)
+        self._ep_ret = torch.zeros((n, a), dtype=torch.float64, device=dev)
+        self._ep_count = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._obs = torch.empty((n * a, self.flat_dim), dtype=torch.float32, device=dev)
+        self._rew = torch.zeros(n * a, dtype=torch.float32, device=dev)
+        self._term = torch.zeros(n * a, dtype=torch.uint8, device=dev)
+        self._trunc = torch.zeros(n * a, dtype=torch.uint8, device=dev)
+        self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._stat_r = torch.zeros((n, a), dtype=torch.float32, device=dev)
+        self._stat_l = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._t0 = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._global_step = 0
+
+    @property
+    def single_observation_shape(self):
+        return (self.flat_dim,)
+
+    def _launch(self, actions, reset_only: int):
+        with torch.cuda.device(self._b.device):
+            _lib.check(_lib.lib().posg_vec_step(
+                self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._ep_t), _lib.ptr(self._ep_ret),
+                _lib.ptr(self._ep_count), _lib.ptr(actions), self.seed, self._global_step, self.env_offset,
+                self.max_episode_steps, reset_only, _lib.ptr(self._obs), _lib.ptr(self._rew), _lib.ptr(self._term),
+                _lib.ptr(self._trunc), _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l),
+                _lib.stream_ptr()))
+
+    def _out(self, t):
+        return t.cpu().numpy() if self.as_numpy else t
+
+    def reset(self, seed: Optional[int] = None, options=None):
+        if seed is not None:
+            self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._global_step = 0
+        self._launch(None, 1)
+        self._t0.fill_(time.perf_counter())
+        return self._out(self._obs), {i: {} for i in self.possible_agents}
+
+    def step(self, actions):
+        """``actions``: flat integer array / tensor of ``num_envs * num_agents`` entries, env-major."""
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions))
+        actions = actions.to(device=self._b.device, dtype=torch.int64).reshape(-1).contiguous()
+        assert actions.numel() == self.num_envs * self.num_agents
+        self._global_step += 1
+        self._launch(actions, 0)
+        infos: Dict[str, dict] = {i: {} for i in self.possible_agents}
+        dones = self._done.bool()
+        if bool(dones.any()):  # one sync per step, as cheap as the worker's own `for env_done in dones`
+            now = time.perf_counter()
+            el = torch.where(dones, now - self._t0, torch.zeros_like(self._t0))
+            self._t0 = torch.where(dones, torch.full_like(self._t0, now), self._t0)
+            for k, i in enumerate(self.possible_agents):
+                infos[i]["episode"] = {"r": self._out(self._stat_r[:, k]), "l": self._out(self._stat_l),
+                                       "t": self._out(el)}
+        return (self._out(self._obs), self._out(self._rew), self._out(self._term.bool()),
+                self._out(self._trunc.bool()), self._out(dones), infos)
+
+    def close(self):
+        pass
+
+
+def load_vec_env(env_id: str, env_kwargs: Optional[dict] = None, num_envs: int = 32, seed: int = 0,
+                 env_offset: int = 0, device=None, as_numpy: bool = False) -> BatchedVecEnv:
+    """``PPOConfig.load_vec_env`` (ppo/config.py:223-232) for the in-scope envs."""
+    from posggym_baselines_b200.envs.env import make
+
+    kw = dict(env_kwargs or {})
+    if device is not None:
+        kw["device"] = device
+    env = make(env_id, **kw)
+    return BatchedVecEnv(env.model, num_envs, env.max_episode_steps, seed=seed, env_offset=env_offset,
+                         as_numpy=as_numpy)

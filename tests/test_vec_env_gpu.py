@@ -1,0 +1,129 @@
+"""The GPU vector env against the reference's vec-env stack restated on the CPU oracle
+(oracle/vec_env.py): same shapes / dtypes / auto-reset / episode statistics, and -- with
+the model noise replayed -- the same numbers."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_contract_shapes_and_autoreset():
+    from posggym_baselines_b200.vector import load_vec_env
+
+    n = 4096
+    envs = load_vec_env("Driving-v1", {"grid": "14x14RoundAbout", "num_agents": 2, "obs_dim": (3, 1, 1)}, num_envs=n, seed=1)
+    obs, infos = envs.reset()
+    assert obs.shape == (n * 2, 124) and obs.dtype == torch.float32
+    assert set(infos) == set(envs.possible_agents) == {"0", "1"}
+    # every one-hot block sums to one: 15 cells + speed + 4 coords + 2 flags = 22 ones per row
+    assert torch.equal(obs.sum(1), torch.full((n * 2,), 22.0, device=obs.device))
+    g = torch.Generator(device="cpu").manual_seed(0)
+    ep_lens, ep_rets, steps = [], [], 0
+    for _ in range(120):
+        act = torch.randint(0, 5, (n * 2,), generator=g)
+        obs, rew, term, trunc, dones, infos = envs.step(act.numpy())
+        steps += 1
+        assert obs.shape == (n * 2, 124) and rew.shape == (n * 2,) and rew.dtype == torch.float32
+        assert term.shape == trunc.shape == (n * 2,) and dones.shape == (n,)
+        assert torch.equal(obs.sum(1), torch.full((n * 2,), 22.0, device=obs.device))
+        if dones.any():
+            ep = infos["0"]["episode"]
+            assert ep["r"].shape == (n,) and ep["l"].shape == (n,)
+            ep_lens.append(ep["l"][dones].cpu())
+            ep_rets.append(ep["r"][dones].cpu())
+            # truncation fires exactly at the 50-step limit, for both agents of the env
+            tr = trunc.reshape(n, 2)
+            assert ((ep["l"] == 50) == tr[:, 0])[dones].all()
+            # auto-reset: the returned observation is a first observation (speed STOPPED, not done)
+            first = obs.reshape(n, 2, 124)[dones]
+            assert (first[:, :, 61] == 1).all() and (first[:, :, 120] == 1).all() and (first[:, :, 122] == 1).all()
+    lens = torch.cat(ep_lens)
+    assert lens.max() == 50 and lens.min() >= 1 and (lens == 50).float().mean() > 0.6
+    rets = torch.cat(ep_rets)
+    # uniform-random joint play (div_results.csv): mean return about -0.1, crashes in ~20 % of episodes
+    assert -0.25 < rets.mean().item() < 0.05
+
+
+def test_matches_cpu_vec_env_stack(oracle_env):
+    """Replay: the GPU env and the oracle stack are driven with the same actions and the
+    same model noise / initial states; observations, rewards, flags and episode statistics
+    must be identical at every step (float32 rewards as StackEnv returns them)."""
+    import posggym
+    from gymnasium import spaces
+
+    from oracle import rollout as R
+    from oracle.driving import DrivingModel
+    from oracle.vec_env import FlattenObservations
+    from posggym_baselines_b200.vector import load_vec_env
+
+    n, seed = 96, 5
+    envs = load_vec_env("Driving-v1", num_envs=n, seed=seed)
+    obs, _ = envs.reset()
+    m = DrivingModel()
+    sp = m.observation_spaces["0"]
+
+    def first_state(env, ep):
+        s = seed ^ ((0x9E3779B97F4A7C15 * ep) & 0xFFFFFFFFFFFFFFFF) if ep else seed
+        return m.initial_state_from_noise(R.driving_initial_picks(m, s, np.array([env], dtype=np.uint64))[0])
+
+    states = [first_state(e, 0) for e in range(n)]
+    eps = [0] * n
+    t = [0] * n
+    ret = np.zeros((n, 2))
+    flat = lambda o: np.concatenate([spaces.flatten(sp, o["0"]), spaces.flatten(sp, o["1"])]).reshape(2, -1)  # noqa: E731
+    cpu_obs = np.stack([flat(m.sample_initial_obs(s)) for s in states]).reshape(n * 2, -1)
+    assert (obs.cpu().numpy() == cpu_obs).all()
+    rng = np.random.default_rng(0)
+    for step in range(1, 131):
+        act = rng.integers(0, 5, size=(n, 2))
+        obs, rew, term, trunc, dones, infos = envs.step(act.reshape(-1))
+        _, order = R.driving_step_noise(seed, np.arange(n, dtype=np.uint64), step)
+        c_obs, c_rew, c_term, c_trunc, c_done = [], [], [], [], []
+        c_r, c_l = np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+        for e in range(n):
+            ts = m.step_with_noise(states[e], {"0": int(act[e, 0]), "1": int(act[e, 1])}, int(order[e]))
+            t[e] += 1
+            tr = t[e] >= 50
+            d = ts.all_done or tr
+            ret[e] += [ts.rewards["0"], ts.rewards["1"]]
+            c_rew.append([np.float32(ts.rewards["0"]), np.float32(ts.rewards["1"])])
+            c_term.append([ts.terminations["0"], ts.terminations["1"]])
+            c_trunc.append([tr, tr]); c_done.append(d)
+            if d:
+                c_r[e], c_l[e] = ret[e].astype(np.float32), t[e]
+                eps[e] += 1
+                states[e] = first_state(e, eps[e]); t[e] = 0; ret[e] = 0
+                c_obs.append(flat(m.sample_initial_obs(states[e])))
+            else:
+                states[e] = ts.state
+                c_obs.append(flat(ts.observations))
+        assert (obs.cpu().numpy() == np.stack(c_obs).reshape(n * 2, -1)).all(), step
+        assert (rew.cpu().numpy() == np.array(c_rew, np.float32).reshape(-1)).all(), step
+        assert (term.cpu().numpy() == np.array(c_term).reshape(-1)).all()
+        assert (trunc.cpu().numpy() == np.array(c_trunc).reshape(-1)).all()
+        assert (dones.cpu().numpy() == np.array(c_done)).all()
+        if any(c_done):
+            assert (infos["0"]["episode"]["l"].cpu().numpy() == c_l).all()
+            assert (infos["0"]["episode"]["r"].cpu().numpy() == c_r[:, 0]).all()
+            assert (infos["1"]["episode"]["r"].cpu().numpy() == c_r[:, 1]).all()
+
+
+def test_predator_prey_vec_env_and_sharding():
+    from posggym_baselines_b200.vector import load_vec_env
+
+    n = 2048
+    full = load_vec_env("PredatorPrey-v0", num_envs=n, seed=3)
+    lo = load_vec_env("PredatorPrey-v0", num_envs=n // 2, seed=3, env_offset=0)
+    hi = load_vec_env("PredatorPrey-v0", num_envs=n // 2, seed=3, env_offset=n // 2)
+    o, ol, oh = full.reset()[0], lo.reset()[0], hi.reset()[0]
+    assert o.shape == (n * 2, 100)
+    assert torch.equal(o, torch.cat([ol, oh]))
+    g = torch.Generator().manual_seed(1)
+    for _ in range(60):
+        act = torch.randint(0, 5, (n * 2,), generator=g)
+        a = full.step(act)
+        b = lo.step(act[: n])
+        c = hi.step(act[n:])
+        for k in range(5):
+            assert torch.equal(a[k], torch.cat([b[k], c[k]])), k
