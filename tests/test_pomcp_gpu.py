@@ -61,7 +61,8 @@ def test_readme_loop(model):
         assert a in range(5)
         st = planner.step_statistics
         assert set(st) == set(PlanningStatTracker.STAT_KEYS)
-        if not math.isnan(st["num_sims"]):
+        # once the ego vehicle is done the root is absorbing: no search (mcts.py:270-272)
+        if not math.isnan(st["num_sims"]) and not planner.root.is_absorbing:
             assert st["num_sims"] >= 1000 and 0.1 <= st["search_time"] < 0.5
         obs, rew, term, trunc, done, _ = env.step({"0": a, "1": rng.randrange(5)})
         steps += 1
