@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-sweep", action="store_true", help="skip the rollout / vec-env / POMCP side sections")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -327,13 +328,13 @@ def main():
     # ---- fused rollout kernel (not HBM-bound; reported beside the step sweep) ----
     rl = None
     r_live = torch.zeros(1, dtype=torch.int64, device=dev)
-    for _ in range(3):
+    for _ in range(0 if args.only_sweep else 3):
         env.rollout(st0, 0, DEPTH, 0.95, seed=seed, particle_offset=offset)
     barrier()
     r_live.zero_()
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     r0.record()
-    for _ in range(args.steps):
+    for _ in range(1 if args.only_sweep else args.steps):
         env.rollout(st0, 0, DEPTH, 0.95, seed=seed, particle_offset=offset, live_count=r_live)
     r1.record()
     barrier()
@@ -389,9 +390,47 @@ def main():
                "sample": f"{r['env_steps']} env-steps of the same random-action depth-{DEPTH} Driving-v1 sweep in "
                          f"{r['seconds']:.1f} s, one Python process per core (the reference's model is pure Python)"}
 
+    # ---- PPO vector-env collection (configs[4] shape: 65 536 envs over 8 GPUs = 8 192 per GPU;
+    # also a large batch to show the HBM-bound regime).  LBF-v3 is not built yet: Driving-v1 here.
+    vec = None
+    try:
+        if args.only_sweep:
+            raise RuntimeError("skipped (--only-sweep)")
+        from posggym_baselines_b200.vector import BatchedVecEnv
+        from posggym_baselines_b200.envs.driving import DrivingModel as _DM
+
+        vm = _DM(device=dev)
+        vec = {"env": "Driving-v1 (LevelBasedForaging-v3 not built yet)", "obs_dim": 124, "rollout_steps": 64}
+        for label, nv in (("envs_8192_per_gpu", 8192), ("envs_1048576_per_gpu", 1 << 20)):
+            ve = BatchedVecEnv(vm, nv, seed=seed, env_offset=rank * nv)
+            ve.reset()
+            acts = torch.randint(0, 5, (64, nv * 2), device=dev, dtype=torch.int64)
+            for k in range(8):
+                ve._global_step += 1
+                ve._launch(acts[k], 0)
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for k in range(64):      # num_rollout_steps = 64 (exp_utils.py:81)
+                ve._global_step += 1
+                ve._launch(acts[k], 0)
+            v1.record()
+            barrier()
+            vms = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(vms, op=dist.ReduceOp.MAX)
+            bytes_per = 8 + 16 + 8 + 2 * 124 * 4 + 8 + 2 + 2 + 1 + 8 + 4
+            vec[label] = {"env_steps_per_s": world * nv * 64 / (vms.item() / 1e3), "us_per_step": 1e3 * vms.item() / 64,
+                          "hbm_gbs": bytes_per * nv * 64 / (vms.item() / 1e3) / 1e9, "bytes_per_env_step": bytes_per}
+            del ve
+    except Exception as ex:
+        vec = {"error": repr(ex)}
+
     # ---- POMCP simulations per 0.1 s decision (second half of BASELINE.json's metric) ----
     pomcp = None
     try:
+        if args.only_sweep:
+            raise RuntimeError("skipped (--only-sweep)")
         pomcp = bench_pomcp(dev, rank, world, cpu=(rank == 0 and world == 1 and not args.no_cpu))
     except Exception as ex:  # the headline number must not be lost to a planner problem
         pomcp = {"error": repr(ex)}
@@ -410,7 +449,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "posg::driving::step_kernel<2>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "launch_ms": launch_ms, "peak_source": peak_src},
-            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "pomcp": pomcp,
+            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "pomcp": pomcp, "vec_env": vec,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -37,7 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *sources(), "-lcudart"]
+    extra = os.environ.get("POSG_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB, *sources(), "-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

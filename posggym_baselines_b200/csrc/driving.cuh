@@ -34,8 +34,15 @@ struct alignas(16) Blob {
   uint8_t n_agents, obs_front, obs_back, obs_side;
   uint8_t obstacle_collisions, pad_[7];
   uint8_t win_lut[4][64];            // [facing][(dy+3)*8 + (dx+3)] -> window cell 0..14, 15 = outside
-  double progress[MAX_D0 * 3];       // 0.5 * (p / D0), p in 0..2
+  // control table [action*16 + speed*4 + facing] -> next speed | facing<<2 | move dir<<4 | cells<<6
+  uint8_t ctrl[80];
+  // reward table [(D0*3 + progress)*4 + kind], kind 0 plain, 1 destination reached, 2 crash,
+  // 3 already done (0.0): base + 0.5 * (progress / D0)
+  double reward_tab[MAX_D0 * 3 * 4];
   uint8_t dist[MAX_CELLS][256];      // dist[dest][y*16+x]; 255 = unreachable
+  // move table [dir*256 + y*16 + x] -> cell after 1 step | cell after 2 steps << 8 |
+  // blocked at step 1 << 16 | blocked at step 2 << 17
+  uint32_t move_tab[4 * 256];
   // 30-bit local-cell codes of a lone vehicle (walls, own destination, ego cell):
   // obs_base[(dest*4 + facing) * 256 + y*16 + x]
   uint32_t obs_base[1];
@@ -65,85 +72,63 @@ __host__ __device__ __forceinline__ uint32_t vpack(int x, int y, int dir, int sp
 }
 
 // ---- transition -------------------------------------------------------------------
-// next speed, 2 bits per (action*4 + speed):
-//   DO_NOTHING 0,1,2,3 | ACCELERATE 1,2,3,3 | DECELERATE 0,0,1,2 | TURN_* 0,1,2,2
-constexpr unsigned long long SPEED_LUT =
-    (0xE4ULL) | (0xF9ULL << 8) | (0x90ULL << 16) | (0xA4ULL << 24) | (0xA4ULL << 32);
-// facing increment, 2 bits per action: TURN_RIGHT +1, TURN_LEFT +3
-constexpr unsigned TURN_LUT = (1u << 6) | (3u << 8);
-
 // One vehicle's move.  `other` is the only other vehicle (its current cell blocks).
-__device__ __forceinline__ void move_vehicle(const Blob& B, uint32_t& me, uint32_t& other, int a,
-                                             int& coll_me, int& coll_other) {
+// Speed / heading arithmetic and the wall tests are table lookups (shared memory); what
+// remains is the interaction with the other vehicle.
+__device__ __forceinline__ void move_vehicle(const Blob& B, uint32_t& me, uint32_t& other, int a) {
   const bool active = !vdone(me);  // reached / crashed earlier, or hit earlier this step
-  const int sp = vspeed(me), dir = vdir(me);
-  int nsp = (int)((SPEED_LUT >> (2 * (a * 4 + sp))) & 3ULL);
-  const int tdir = (dir + (int)((TURN_LUT >> (2 * a)) & 3u)) & 3;
-  const bool rev = (nsp == REVERSE);
-  const int mdir = rev ? (dir ^ 2) : tdir;
-  const int ndir = rev ? dir : tdir;  // a reversing vehicle keeps its facing
-  const int dx = (mdir == 1) - (mdir == 3);
-  const int dy = (mdir == 2) - (mdir == 0);
-  const int nmoves = rev ? 1 : nsp - 1;
-  const int oxy = vxy(other);
-  int x = vx(me), y = vy(me);
-  // first cell
-  int nx = x + dx, ny = y + dy;
-  const bool b1 = (B.rows[ny + PAD] >> (nx + PAD)) & 1u;
-  const bool h1 = !b1 && ((nx | (ny << 4)) == oxy);
-  const bool try1 = active && nmoves >= 1;
+  const uint32_t c = B.ctrl[a * 16 + ((me >> 8) & 15u)];
+  uint32_t nsp = c & 3u;
+  const uint32_t ndir = (c >> 2) & 3u, mdir = (c >> 4) & 3u, nmoves = c >> 6;
+  const uint32_t xy0 = me & 255u, oxy = other & 255u;
+  const uint32_t e = B.move_tab[(mdir << 8) | xy0];
+  const uint32_t c1 = e & 255u, c2 = (e >> 8) & 255u;
+  const bool b1 = (e >> 16) & 1u, b2 = (e >> 17) & 1u;
+  const bool h1 = !b1 && (c1 == oxy);
+  const bool try1 = active && nmoves >= 1u;
   const bool ok1 = try1 && !b1 && !h1;
-  x = ok1 ? nx : x; y = ok1 ? ny : y;
-  // second cell (FORWARD_FAST only)
-  nx = x + dx; ny = y + dy;
-  const bool b2 = (B.rows[ny + PAD] >> (nx + PAD)) & 1u;
-  const bool h2 = !b2 && ((nx | (ny << 4)) == oxy);
-  const bool try2 = ok1 && nmoves == 2;
+  const bool h2 = !b2 && (c2 == oxy);
+  const bool try2 = ok1 && nmoves == 2u;
   const bool ok2 = try2 && !b2 && !h2;
-  x = ok2 ? nx : x; y = ok2 ? ny : y;
+  const uint32_t xy = ok2 ? c2 : (ok1 ? c1 : xy0);
   const bool obst = (try1 && b1) || (try2 && b2);
   const bool hit = (try1 && h1) || (try2 && h2);
   const bool crashed = hit || (obst && B.obstacle_collisions);
-  nsp = crashed ? (int)STOPPED : nsp;
-  const int xy = x | (y << 4);
-  const int dest = vdest(me);
-  const int mind = min(vmindist(me), (int)B.dist[dest][xy]);
-  const uint32_t reached = (xy == (int)B.dest_xy[dest]) ? 1u : 0u;
-  const uint32_t moved = (uint32_t)xy | ((uint32_t)ndir << 8) | ((uint32_t)nsp << 10) | (me & (7u << 12)) |
-                         (reached << 15) | ((crashed ? 1u : 0u) << 16) | ((uint32_t)mind << 17) |
-                         (me & (127u << 24));
+  nsp = crashed ? (uint32_t)STOPPED : nsp;
+  const uint32_t dest = (me >> 12) & 7u;
+  const uint32_t d = B.dist[dest][xy];
+  const uint32_t mind = min((me >> 17) & 127u, d);
+  const uint32_t reached = (d == 0u) ? 1u : 0u;   // distance 0 <=> on the own destination
+  const uint32_t moved = xy | (ndir << 8) | (nsp << 10) | (me & (7u << 12)) | (reached << 15) |
+                         ((crashed ? 1u : 0u) << 16) | (mind << 17) | (me & (127u << 24));
   me = active ? moved : me;
-  coll_me = active ? (hit ? (int)VEHICLE_COLLISION : (obst ? (int)OBSTACLE_COLLISION : (int)NO_COLLISION)) : coll_me;
   // the vehicle that was run into: stopped + crashed
   other = hit ? ((other & ~(3u << 10)) | ((uint32_t)STOPPED << 10) | (1u << 16)) : other;
-  coll_other = hit ? (int)VEHICLE_COLLISION : coll_other;
 }
 
 // joint transition of both vehicles; order_idx 0 -> vehicle 0 first, 1 -> vehicle 1 first
 __device__ __forceinline__ void transition(const Blob& B, uint32_t& v0, uint32_t& v1, int a0, int a1,
-                                           int order_idx, int& c0, int& c1) {
+                                           int order_idx) {
   const bool sw = order_idx != 0;
   uint32_t first = sw ? v1 : v0, second = sw ? v0 : v1;
   const int af = sw ? a1 : a0, as = sw ? a0 : a1;
-  int cf = NO_COLLISION, cs = NO_COLLISION;
-  move_vehicle(B, first, second, af, cf, cs);
-  move_vehicle(B, second, first, as, cs, cf);
+  move_vehicle(B, first, second, af);
+  move_vehicle(B, second, first, as);
   v0 = sw ? second : first; v1 = sw ? first : second;
-  c0 = sw ? cs : cf; c1 = sw ? cf : cs;
 }
 
-// reward of a vehicle given its state before / after the transition
-__device__ __forceinline__ double reward(const Blob& B, uint32_t before, uint32_t after, int coll) {
-  double r = 0.0;
-  const bool crash = (coll == VEHICLE_COLLISION) || (B.obstacle_collisions && coll == OBSTACLE_COLLISION);
-  r = vreached(after) ? 0.5 : r;
-  r = crash ? -1.0 : r;
+// Reward of a vehicle given its state before / after the transition.  For a vehicle that
+// was not done before, the crashed bit after the step is set exactly when it crashed in
+// this step -- as the mover (vehicle collision, or obstacle collision if those count) or as
+// the vehicle that was run into -- which is the reference's crash-reward condition.
+__device__ __forceinline__ double reward(const Blob& B, uint32_t before, uint32_t after) {
+  const uint32_t fl = (after >> 15) & 3u;                 // bit 0 reached, bit 1 crashed
+  const uint32_t kind = vdone(before) ? 3u : (fl > 2u ? 2u : fl);
   int p = vmindist(before) - vmindist(after);
   p = p < 0 ? 0 : (p > 2 ? 2 : p);
   int d0 = vinitdist(before);
   d0 = d0 < 1 ? 1 : (d0 >= MAX_D0 ? MAX_D0 - 1 : d0);
-  r = __dadd_rn(r, B.progress[d0 * 3 + p]);
-  return vdone(before) ? 0.0 : r;
+  return B.reward_tab[(d0 * 3 + p) * 4 + kind];
 }
 
 // ---- observation --------------------------------------------------------------------

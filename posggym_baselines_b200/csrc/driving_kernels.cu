@@ -32,14 +32,13 @@ struct EnvOut { uint32_t v0, v1; uint64_t o0, o1; double r0, r1; uint32_t flags;
 
 __device__ __forceinline__ EnvOut step_env(const Blob& B, uint32_t v0, uint32_t v1, int a0, int a1, int order_idx) {
   const uint32_t b0 = v0, b1 = v1;
-  int c0, c1;
-  transition(B, v0, v1, a0, a1, order_idx, c0, c1);
+  transition(B, v0, v1, a0, a1, order_idx);
   EnvOut e;
   e.v0 = v0; e.v1 = v1;
   e.o0 = observe(B, v0, v1);
   e.o1 = observe(B, v1, v0);
-  e.r0 = reward(B, b0, v0, c0);
-  e.r1 = reward(B, b1, v1, c1);
+  e.r0 = reward(B, b0, v0);
+  e.r1 = reward(B, b1, v1);
   const uint32_t t0 = vdone(v0) ? 1u : 0u, t1 = vdone(v1) ? 1u : 0u;
   e.flags = t0 | (t1 << 1) | ((t0 & t1) ? POSG_FLAG_ALL_DONE : 0u);
   return e;
@@ -251,12 +250,12 @@ rollout_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
     if (item >= 0) {
       bool finished = (k >= max_steps);
       if (!finished) {
-        int a0, a1, order_idx, c0, c1;
+        int a0, a1, order_idx;
         sample_step_noise(seed, particle_offset + (uint64_t)item, step0 + (uint32_t)k, a0, a1, order_idx);
         const uint32_t before = ego ? v1 : v0;
-        transition(B, v0, v1, a0, a1, order_idx, c0, c1);
+        transition(B, v0, v1, a0, a1, order_idx);
         const uint32_t after = ego ? v1 : v0;
-        const double r = reward(B, before, after, ego ? c1 : c0);
+        const double r = reward(B, before, after);
         ret = __dadd_rn(ret, __dmul_rn(sdisc[k], r));
         ++k; ++executed;
         finished = vdone(after) || (vdone(v0) && vdone(v1)) || (k >= max_steps);
@@ -367,8 +366,44 @@ static Blob* build_blob(const char* grid_rows, int num_agents, int obs_front, in
     }
   }
   for (int d0 = 0; d0 < MAX_D0; ++d0)
-    for (int p = 0; p < 3; ++p)
-      out->progress[d0 * 3 + p] = 0.5 * ((double)p / (double)(d0 < 1 ? 1 : d0));
+    for (int p = 0; p < 3; ++p) {
+      // r = base; r += R_PROGRESS * (progress / D0)   (base: step cost 0, destination 0.5, crash -1)
+      const double prog = 0.5 * ((double)p / (double)(d0 < 1 ? 1 : d0));
+      double* r = out->reward_tab + (d0 * 3 + p) * 4;
+      r[0] = 0.0 + prog; r[1] = 0.5 + prog; r[2] = -1.0 + prog; r[3] = 0.0;
+    }
+  // control table: (action, speed, facing) -> next speed, next facing, move direction, cells moved
+  for (int a = 0; a < 5; ++a)
+    for (int sp = 0; sp < 4; ++sp)
+      for (int dir = 0; dir < 4; ++dir) {
+        int nsp = sp;
+        if (a == ACCELERATE) nsp = sp + 1 > FORWARD_FAST ? (int)FORWARD_FAST : sp + 1;
+        else if (a == DECELERATE) nsp = sp - 1 < REVERSE ? (int)REVERSE : sp - 1;
+        else if ((a == TURN_RIGHT || a == TURN_LEFT) && sp == FORWARD_FAST) nsp = FORWARD_SLOW;
+        int tdir = dir;
+        if (a == TURN_RIGHT) tdir = (dir + 1) & 3;
+        else if (a == TURN_LEFT) tdir = (dir + 3) & 3;
+        const bool rev = nsp == REVERSE;
+        const int mdir = rev ? ((dir + 2) & 3) : tdir;
+        const int ndir = rev ? dir : tdir;   // a reversing vehicle keeps its facing
+        const int nmoves = rev ? 1 : nsp - STOPPED;
+        out->ctrl[a * 16 + sp * 4 + dir] = (uint8_t)(nsp | (ndir << 2) | (mdir << 4) | (nmoves << 6));
+      }
+  // move table: up to two cells in a direction, stopping in front of walls / the grid edge
+  for (int dir = 0; dir < 4; ++dir)
+    for (int y = 0; y < 16; ++y)
+      for (int x = 0; x < 16; ++x) {
+        const int dx = (dir == 1) - (dir == 3), dy = (dir == 2) - (dir == 0);
+        auto wall = [&](int cx, int cy) { return cx < 0 || cy < 0 || cx >= W || cy >= H || blk[cy][cx]; };
+        const int x1 = x + dx, y1 = y + dy;
+        const bool b1 = wall(x1, y1);
+        const int c1 = b1 ? (x | (y << 4)) : (x1 | (y1 << 4));
+        const int x2 = x1 + dx, y2 = y1 + dy;
+        const bool b2 = b1 || wall(x2, y2);
+        const int c2 = b2 ? c1 : (x2 | (y2 << 4));
+        out->move_tab[(dir << 8) | (y << 4) | x] =
+            (uint32_t)c1 | ((uint32_t)c2 << 8) | ((b1 ? 1u : 0u) << 16) | ((b2 ? 1u : 0u) << 17);
+      }
   // window lookup: where inside the 5x3 window does the grid offset (dx, dy) fall?
   memset(out->win_lut, 15, sizeof(out->win_lut));
   for (int dir = 0; dir < 4; ++dir)

@@ -16,7 +16,8 @@
 namespace posg {
 namespace vec {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 128;
+constexpr int MAX_FLAT = 320;   // widest flattened per-agent observation supported
 
 // one-hot descriptor of a flattened position: which packed word, shift, mask, hot value
 struct FlatDesc { uint8_t word, shift, mask, value; };
@@ -35,8 +36,23 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
   __shared__ unsigned long long s_obs[THREADS * NAG * OW];
-  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  __shared__ FlatDesc s_desc[MAX_FLAT];
+  for (int p = threadIdx.x; p < flat_dim; p += THREADS) s_desc[p] = desc[p];
+  stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  // per-lane descriptors of positions lane, lane + 32, ...: shift (mod 32) | mask << 8 |
+  // value << 16 | 32-bit half index (2 * word + (shift >= 32)) << 24
+  constexpr int MAXK = MAX_FLAT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = (flat_dim + 31) / 32;
+  uint32_t ldesc[MAXK];
+#pragma unroll
+  for (int k = 0; k < MAXK; ++k) {
+    const int p = lane + 32 * k;
+    const FlatDesc d = s_desc[p < flat_dim ? p : 0];
+    ldesc[k] = (uint32_t)(d.shift & 31) | ((uint32_t)d.mask << 8) | ((uint32_t)d.value << 16) |
+               ((uint32_t)(2 * d.word + (d.shift >> 5)) << 24);
+  }
 
   for (int64_t base = (int64_t)blockIdx.x * THREADS; base < n; base += (int64_t)gridDim.x * THREADS) {
     const int64_t i = base + threadIdx.x;
@@ -95,15 +111,29 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
         for (int k = 0; k < OW; ++k) s_obs[(threadIdx.x * NAG + a) * OW + k] = obs[a][k];
     }
     __syncthreads();
-    // cooperative one-hot expansion: rows of this CTA are contiguous in obs_out
-    const int64_t rows = ((n - base) < THREADS ? (n - base) : THREADS) * NAG;
-    const int64_t total = rows * flat_dim;
+    // cooperative one-hot expansion: one warp per (env, agent) row, lane L owns positions
+    // L, L+32, ... (their descriptors are decoded once, above) -> every store instruction
+    // writes 32 consecutive floats
+    const int rows = (int)(((n - base) < THREADS ? (n - base) : THREADS) * NAG);
     float* out = obs_out + base * NAG * flat_dim;
-    for (int64_t q = threadIdx.x; q < total; q += THREADS) {
-      const int row = (int)(q / flat_dim), p = (int)(q - (int64_t)row * flat_dim);
-      const FlatDesc d = desc[p];
-      const unsigned long long w = s_obs[row * OW + d.word];
-      out[q] = (((unsigned)(w >> d.shift) & d.mask) == d.value) ? 1.0f : 0.0f;
+    for (int row = warp; row < rows; row += THREADS / 32) {
+      uint32_t w32[2 * OW];
+#pragma unroll
+      for (int k = 0; k < OW; ++k) {
+        const unsigned long long w = s_obs[row * OW + k];
+        w32[2 * k] = (uint32_t)w; w32[2 * k + 1] = (uint32_t)(w >> 32);
+      }
+      float* orow = out + (int64_t)row * flat_dim + lane;
+#pragma unroll
+      for (int k = 0; k < MAXK; ++k) {
+        if (k < K && lane + 32 * k < flat_dim) {
+          const uint32_t d = ldesc[k];
+          uint32_t ww = w32[0];
+#pragma unroll
+          for (int h = 1; h < 2 * OW; ++h) ww = ((d >> 24) == (uint32_t)h) ? w32[h] : ww;
+          orow[32 * k] = (((ww >> (d & 31u)) & ((d >> 8) & 255u)) == ((d >> 16) & 255u)) ? 1.0f : 0.0f;
+        }
+      }
     }
     __syncthreads();
   }

@@ -31,7 +31,7 @@ static std::vector<vec::FlatDesc> build_desc(const posg_model* m) {
 static int ensure_desc(posg_model* m) {
   if (m->d_flat_desc) return POSG_OK;
   std::vector<vec::FlatDesc> d = build_desc(m);
-  if (d.empty()) { set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED; }
+  if (d.empty() || d.size() > (size_t)vec::MAX_FLAT) { set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED; }
   POSG_CUDA(cudaMalloc(&m->d_flat_desc, d.size() * sizeof(vec::FlatDesc)));
   POSG_CUDA(cudaMemcpy(m->d_flat_desc, d.data(), d.size() * sizeof(vec::FlatDesc), cudaMemcpyHostToDevice));
   m->flat_dim = (int)d.size();

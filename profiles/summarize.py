@@ -31,15 +31,22 @@ def main():
             if k in KEYS or ("issue_stalled" in k and k.endswith("per_issue_active.ratio")):
                 i = hdr.index(k)
                 try:
-                    d[k + " [" + units[i] + "]"] = float(r[i])
+                    v, u = float(r[i].replace(",", "")), units[i]
+                    scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u)
+                    if scale is not None:
+                        v, u = v * scale, "byte"
+                    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u) if k.startswith("gpu__time") else None
+                    if tscale is not None:
+                        v, u = v * tscale, "us"
+                    d[k + " [" + u + "]"] = v
                 except ValueError:
                     d[k] = r[i]
         launches.append(d)
     summary = {"report": rep, "launches": launches}
     if particles and launches:
         l0 = launches[0]
-        rd = l0["dram__bytes_read.sum [Mbyte]"] * 1e6
-        wr = l0["dram__bytes_write.sum [Mbyte]"] * 1e6
+        rd = l0["dram__bytes_read.sum [byte]"]
+        wr = l0["dram__bytes_write.sum [byte]"]
         summary["particles"] = particles
         summary["dram_bytes_per_launch"] = rd + wr
         summary["dram_bytes_per_env_step"] = (rd + wr) / particles
@@ -47,7 +54,7 @@ def main():
         summary["thread_instructions_per_env_step"] = (
             l0["smsp__inst_executed.sum [inst]"] * l0["smsp__thread_inst_executed_per_inst_executed.ratio []"] / particles)
     json.dump(summary, open(out + ".json", "w"), indent=1)
-    print(json.dumps(summary, indent=1)[:3000])
+    print(out + ".json written")
 
 
 if __name__ == "__main__":
