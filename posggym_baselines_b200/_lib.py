@@ -6,7 +6,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libposg_b200.so")
+_LIB_PATH = os.environ.get("POSG_B200_LIB") or os.path.join(_HERE, "libposg_b200.so")  # override: kernel A/B runs
 
 
 class PosgB200Error(RuntimeError):
