@@ -182,6 +182,7 @@ typedef struct posg_search_params {
   int step_limit;                   /* MCTS.step_limit (mcts.py:53-58) */
   int selection;                    /* 0 ucb, 1 pucb, 2 uniform (mcts.py:66-74) */
   int ego_agent;
+  int intmcp_depth_rule;            /* 1: INTMCP._simulate's stop rule node.t + depth > step_limit (intmcp.py:450-453) */
   uint64_t seed;
 } posg_search_params;
 
@@ -221,6 +222,45 @@ int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, i
 int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_obs_host,
                         int64_t n_needed, int64_t max_attempts, uint64_t seed, uint64_t draw_id,
                         uint32_t* out_states, int64_t* result_host, void* stream);
+
+/* ------------------------------------------------------------------ I-NTMCP (nesting level 1)
+ * The ego agent's tree is searched with the other agent acting by its own level-0 tree
+ * (planning/intmcp.py).  A nested handle has the base model's blob and one extra state word
+ * per particle: the node of the other agent's tree its history leads to. */
+int posg_nested_create(posg_model_t base, posg_model_t* out);
+/* INTMCP._nested_sim for search_level == nesting_level (intmcp.py:437-442 -> _simulate
+ * 444-517): other agent's actions from INTMCP.sample_action (763-791) on `other_arena`,
+ * histories extended by INTMCP.traverse (797-809). */
+int posg_search_nested(posg_model_t nested, void* arena, int64_t cap_nodes, int64_t cap_log,
+                       void* other_arena, int64_t other_cap_nodes, int64_t other_cap_log,
+                       int other_agent, int root, int root_t, const uint32_t* particles,
+                       int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
+                       const posg_search_params* p, void* stream);
+/* INTMCP._nested_sim for search_level < nesting_level (intmcp.py:433-436): simulation i draws
+ * entry e of [0, n_sel) -- a particle of the parent tree's root belief -- and searches this
+ * tree from node sel_root[e] with a particle of particles[sel_off[e] .. +sel_cnt[e]). */
+int posg_search_multi(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root_t,
+                      const uint32_t* particles, int64_t n_particles, const int32_t* sel_root,
+                      const int64_t* sel_off, const int32_t* sel_cnt, int64_t n_sel, int64_t n_sims,
+                      uint64_t sim_id0, const posg_search_params* p, void* stream);
+/* INTMCP.traverse, one step, for a batch (device arrays): child of (parent, action, obs). */
+int posg_tree_advance_batch(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log,
+                            int64_t n, const int32_t* parents, const int32_t* actions,
+                            const uint64_t* obs, int32_t* children_out, void* stream);
+/* (parent obs node, action, observation, t) of a batch of nodes = the last step of the
+ * histories they stand for (hist.get_last_step(), intmcp.py:293). Device arrays. */
+int posg_tree_node_info(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int64_t n,
+                        const int32_t* nodes, int32_t* parent_out, int32_t* action_out,
+                        uint64_t* obs_out, int32_t* t_out, void* stream);
+/* INTMCP._reinvigorate with _reinvigorate_action_fn (intmcp.py:843-915): the other agent acts
+ * by its tree; new particles carry the extended history node. */
+int posg_belief_reinvigorate_nested(posg_model_t nested, void* other_arena, int64_t other_cap_nodes,
+                                    int64_t other_cap_log, int other_agent,
+                                    const uint32_t* parent_particles, int64_t n_parent, int ego_agent,
+                                    int action, const uint64_t* target_obs_host, int64_t n_needed,
+                                    int64_t max_attempts, uint64_t seed, uint64_t draw_id,
+                                    uint32_t* out_states, uint32_t* reject_scratch,
+                                    int64_t* result_host, void* stream);
 
 /* ------------------------------------------------------------------ vector env (PPO collector)
  * One call = envs.step(actions) of StackEnv(RecordEpisodeStatistics(SyncVectorEnv(

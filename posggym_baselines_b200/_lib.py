@@ -52,6 +52,14 @@ SIGNATURES = {
         _int, [_vp, _i64, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "posg_model_rollout": (
         _int, [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "posg_nested_create": (_int, [_vp, C.POINTER(_vp)]),
+    "posg_search_nested": (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _int, _int, _int, _vp, _i64, _i64, _u64,
+                                   _vp, _vp]),
+    "posg_search_multi": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _u64, _vp, _vp]),
+    "posg_tree_advance_batch": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "posg_tree_node_info": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "posg_belief_reinvigorate_nested": (
+        _int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _int, _int, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
     "posg_vec_flat_dim": (_int, [_vp]),
     "posg_vec_step": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _int, _int, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp, _vp]),
@@ -74,7 +82,7 @@ class SearchParams(C.Structure):
     _fields_ = [
         ("discount", _dbl), ("c", _dbl), ("known_min", _dbl), ("known_max", _dbl),
         ("pucb_exploration_fraction", _dbl), ("depth_limit", _int), ("step_limit", _int),
-        ("selection", _int), ("ego_agent", _int), ("seed", _u64),
+        ("selection", _int), ("ego_agent", _int), ("intmcp_depth_rule", _int), ("seed", _u64),
     ]
 
 _lib: Optional[C.CDLL] = None

@@ -37,7 +37,8 @@ __device__ __forceinline__ int block_scan(bool flag, int* warp_sums, int& total)
 // out[0 .. n_needed) <- accepted next-states in attempt order, padded with rejected ones.
 // result[0] = accepted count (<= n_needed), result[1] = attempts made.
 template <class M>
-__device__ void reinvigorate(const typename M::Blob& B, const uint32_t* __restrict__ parent, long long n_parent,
+__device__ void reinvigorate(const typename M::Blob& B, const typename M::Ctx& ctx,
+                             const uint32_t* __restrict__ parent, long long n_parent,
                              int ego, int action, const unsigned long long* __restrict__ target_obs,
                              long long n_needed, long long max_attempts, uint64_t seed, uint64_t draw_id,
                              uint32_t* __restrict__ out, uint32_t* __restrict__ rej_scratch,
@@ -60,7 +61,7 @@ __device__ void reinvigorate(const typename M::Blob& B, const uint32_t* __restri
       for (int k = 0; k < SW; ++k) st.w[k] = parent[pi * SW + k];
       unsigned long long obs[OW];
       double r; bool done;
-      M::step(B, st, ego, action, w.y, obs, r, done);
+      M::step(B, ctx, st, ego, action, w.y, w.z, obs, r, done);
       ok = true;
 #pragma unroll
       for (int k = 0; k < OW; ++k) ok &= (obs[k] == tgt[k]);

@@ -56,9 +56,11 @@ int posg_device_count(void) {
 
 int posg_model_destroy(posg_model_t m) {
   if (!m) return POSG_OK;
-  if (m->d_blob) cudaFree(m->d_blob);
+  if (!m->borrowed) {
+    if (m->d_blob) cudaFree(m->d_blob);
+    free(m->h_blob);
+  }
   if (m->d_flat_desc) cudaFree(m->d_flat_desc);
-  free(m->h_blob);
   delete m;
   return POSG_OK;
 }

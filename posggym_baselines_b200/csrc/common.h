@@ -30,7 +30,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // SM count of the current device (cached per device).
 int sm_count();
 
-enum ModelKind : int { KIND_DRIVING = 1, KIND_PREDATOR_PREY = 2, KIND_LBF = 3 };
+enum ModelKind : int { KIND_DRIVING = 1, KIND_PREDATOR_PREY = 2, KIND_LBF = 3, KIND_NESTED = 0x100 };
 
 }  // namespace posg
 
@@ -43,4 +43,5 @@ struct posg_model {
   void* h_blob;   // host copy (for the *_host entry points / introspection)
   void* d_flat_desc = nullptr;  // one-hot descriptors of the flattened observation (vec env)
   int flat_dim = 0;
+  int borrowed = 0;             // blob pointers belong to another handle (posg_nested_create)
 };

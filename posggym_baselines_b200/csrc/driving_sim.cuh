@@ -6,6 +6,7 @@ namespace posg {
 
 struct DrivingSim {
   using Blob = driving::Blob;
+  using Ctx = NoCtx;
   static constexpr int A = 5;    // ego actions
   static constexpr int OW = 1;   // 64-bit words per observation key
   static constexpr int SW = 2;   // 32-bit words per state
@@ -33,6 +34,10 @@ struct DrivingSim {
     driving::sample_step_noise(seed, particle, step, act[0], act[1], order);
     noise[0] = (uint32_t)order;
   }
+  // step noise from one 32-bit word (nested search): the processing order
+  __device__ static __forceinline__ void noise_from_word(uint32_t word, uint32_t (&noise)[NW]) {
+    noise[0] = word >> 31;
+  }
   __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
     obs[0][0] = driving::observe(B, s.w[0], s.w[1]);
     obs[1][0] = driving::observe(B, s.w[1], s.w[0]);
@@ -40,8 +45,9 @@ struct DrivingSim {
 
   // model.step with the ego action fixed and the other vehicle uniform random
   // (RandomOtherAgentPolicy, other_policy.py:150-151); `word` = one Philox word
-  __device__ static __forceinline__ void step(const Blob& B, State& s, int ego, int ego_action, uint32_t word,
-                                              unsigned long long (&obs)[OW], double& r, bool& done) {
+  __device__ static __forceinline__ void step(const Blob& B, const Ctx&, State& s, int ego, int ego_action,
+                                              uint32_t word, uint32_t /*word2*/, unsigned long long (&obs)[OW],
+                                              double& r, bool& done) {
     int a0, a1, ord;
     driving::decode_step_noise(word, a0, a1, ord);
     if (ego == 0) a0 = ego_action; else a1 = ego_action;
@@ -55,8 +61,8 @@ struct DrivingSim {
   }
 
   // one step of MCTS._rollout: every agent uniform random (RandomSearchPolicy)
-  __device__ static __forceinline__ void rollout_step(const Blob& B, State& s, int ego, uint32_t word, double& r,
-                                                      bool& done) {
+  __device__ static __forceinline__ void rollout_step(const Blob& B, const Ctx&, State& s, int ego, uint32_t word,
+                                                      double& r, bool& done) {
     int a0, a1, ord;
     driving::decode_step_noise(word, a0, a1, ord);
     const uint32_t before = ego ? s.w[1] : s.w[0];

@@ -6,6 +6,8 @@
 
 namespace posg {
 
+struct NoCtx {};   // context of model adapters that need none (see search.cuh)
+
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
 constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;

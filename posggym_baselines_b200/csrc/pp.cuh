@@ -230,6 +230,7 @@ __device__ __forceinline__ void initial_from_picks(const Blob& B, const int (&pi
 // Adapter for the generic batch / search / belief kernels.
 struct PPSim {
   using Blob = pp::Blob;
+  using Ctx = NoCtx;
   static constexpr int A = 5, OW = 1, SW = 2, NAG = 2, NW = 3, NPICK = 5;
   struct State { uint32_t w[SW]; };
 
@@ -266,6 +267,10 @@ struct PPSim {
     act[1] = (int)(idx / 5u);
     act[0] = (int)(idx - 5u * (uint32_t)act[1]);
   }
+  __device__ static __forceinline__ void noise_from_word(uint32_t word, uint32_t (&noise)[NW]) {
+    const uint4 w = philox4x32_10(word, 0x9E3779B9u, 0x7F4A7C15u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu);
+    noise[0] = w.x; noise[1] = w.y; noise[2] = w.z;
+  }
   __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
     pp::Ents e;
     pp::unpack(s.w[0], s.w[1], e);
@@ -292,8 +297,9 @@ struct PPSim {
   }
 
   // ---- search / belief adapter ---------------------------------------------------
-  __device__ static __forceinline__ void step(const Blob& B, State& s, int ego, int ego_action, uint32_t word,
-                                              unsigned long long (&obs)[OW], double& r, bool& done) {
+  __device__ static __forceinline__ void step(const Blob& B, const Ctx&, State& s, int ego, int ego_action,
+                                              uint32_t word, uint32_t /*word2*/, unsigned long long (&obs)[OW],
+                                              double& r, bool& done) {
     // `word` seeds the other predator's action and the three prey words
     const uint4 w = philox4x32_10(word, 0x9E3779B9u, 0x7F4A7C15u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu);
     int act[NAG];
@@ -309,8 +315,8 @@ struct PPSim {
     r = rew[ego];
     obs[0] = pp::observe(B, e, ego);
   }
-  __device__ static __forceinline__ void rollout_step(const Blob& B, State& s, int ego, uint32_t word, double& r,
-                                                      bool& done) {
+  __device__ static __forceinline__ void rollout_step(const Blob& B, const Ctx&, State& s, int ego, uint32_t word,
+                                                      double& r, bool& done) {
     const uint4 w = philox4x32_10(word, 0x9E3779B9u, 0x7F4A7C15u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu);
     int act[NAG];
     const uint32_t idx = uniform_below(w.w, 25u);

@@ -43,6 +43,7 @@ struct Params {
   int step_limit;               // max_episode_steps (node.t may not exceed it)
   int selection;                // SEL_*
   int ego;
+  int intmcp_depth_rule;        // 1: stop when node.t + depth > step_limit (intmcp.py:450-453)
   uint64_t seed;
   double disc_pow[MAX_DEPTH];   // discount**k from libm pow (mcts.py:421)
 };
@@ -52,6 +53,7 @@ struct Tree {
   Counters* ctr;
   int* node_visits;
   int* node_next;
+  int* node_parent;             // parent action node (node * |A| + a), -1 for roots
   unsigned char* node_flags;    // bit 0 expanded, bit 1 absorbing
   unsigned char* node_t;
   unsigned long long* node_obs;
@@ -75,6 +77,7 @@ __host__ __device__ inline size_t layout(Tree* t, unsigned char* base, long long
   p = take(sizeof(Counters)); if (t) t->ctr = (Counters*)p;
   p = take((size_t)cap_nodes * 4); if (t) t->node_visits = (int*)p;
   p = take((size_t)cap_nodes * 4); if (t) t->node_next = (int*)p;
+  p = take((size_t)cap_nodes * 4); if (t) t->node_parent = (int*)p;
   p = take((size_t)cap_nodes); if (t) t->node_flags = p;
   p = take((size_t)cap_nodes); if (t) t->node_t = p;
   p = take((size_t)cap_nodes * 8 * obs_words); if (t) t->node_obs = (unsigned long long*)p;
@@ -131,6 +134,7 @@ __device__ int find_or_insert(const Tree& T, int anode, const unsigned long long
 #pragma unroll
       for (int w = 0; w < OW; ++w) T.node_obs[(size_t)mine * OW + w] = obs[w];
       T.node_t[mine] = (unsigned char)t;
+      T.node_parent[mine] = anode;
       // visits / flags / action-node arrays were zeroed (an_first: -1) by posg_tree_reset
     }
     T.node_next[mine] = head;
@@ -208,6 +212,17 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
   return mine;
 }
 
+// Optional per-simulation root selection (I-NTMCP level-0 phase, intmcp.py:410-442): the
+// simulation first draws entry i of [0, n_sel) uniformly -- a particle of the PARENT tree's
+// root belief -- and then searches this tree from node sel_root[i] with a particle drawn
+// from particles[sel_off[i] .. sel_off[i] + sel_cnt[i]) (that node's belief).
+struct RootSelect {
+  const int* sel_root;
+  const long long* sel_off;
+  const int* sel_cnt;
+  long long n_sel;   // 0: single root
+};
+
 // Model concept (see driving_sim.cuh):
 //   using Blob; static constexpr int A, OW, SW;
 //   struct State { uint32_t w[SW]; };
@@ -215,9 +230,9 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
 //                    unsigned long long (&obs)[OW], double& reward, bool& done);
 //   static void rollout_step(const Blob&, State&, int ego, uint32_t word, double& reward, bool& done);
 template <class M>
-__device__ void simulate(const typename M::Blob& B, const Tree& T, const Params& P, int root, int root_t,
-                         const uint32_t* __restrict__ root_particles, long long n_particles,
-                         unsigned long long sim_id, bool active) {
+__device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, const Tree& T, const Params& P,
+                         int root, int root_t, const uint32_t* __restrict__ root_particles, long long n_particles,
+                         const RootSelect& sel, unsigned long long sim_id, bool active) {
   constexpr int A = M::A, OW = M::OW, SW = M::SW;
   const unsigned full = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
@@ -230,16 +245,25 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
   bool virtual_leaf = false;  // arena full: the state just reached is evaluated but not stored
   if (active) {
     const uint4 w = philox_block(P.seed, sim_id, 0xFFFFu, STREAM_BELIEF);
-    const long long pi = (long long)(((unsigned long long)w.x * (unsigned long long)n_particles) >> 32);
+    long long pi;
+    if (sel.n_sel > 0) {
+      const long long e = (long long)(((unsigned long long)w.x * (unsigned long long)sel.n_sel) >> 32);
+      root = sel.sel_root[e];
+      pi = sel.sel_off[e] + (long long)(((unsigned long long)w.y * (unsigned long long)sel.sel_cnt[e]) >> 32);
+    } else {
+      pi = (long long)(((unsigned long long)w.x * (unsigned long long)n_particles) >> 32);
+    }
 #pragma unroll
     for (int k = 0; k < SW; ++k) st.w[k] = __ldg(root_particles + pi * SW + k);
+    node = root;
   }
 
   while (__any_sync(full, descending)) {
     // ---- stop conditions / leaf expansion ------------------------------------------
     bool expand = false;
     if (descending) {
-      if (depth > P.depth_limit || t > P.step_limit || depth >= MAX_DEPTH - 1) {
+      const int t_rule = P.intmcp_depth_rule ? t + depth : t;
+      if (depth > P.depth_limit || t_rule > P.step_limit || depth >= MAX_DEPTH - 1) {
         descending = false;  // returns 0 (mcts.py:315-316)
       } else if (virtual_leaf) {
         expand = true;
@@ -263,7 +287,7 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
         if ((k & 3) == 0) blk = philox_block(P.seed, sim_id, 0x10000u + (uint32_t)(k >> 2), STREAM_TREE);
         const uint32_t word = (k & 3) == 0 ? blk.x : (k & 3) == 1 ? blk.y : (k & 3) == 2 ? blk.z : blk.w;
         double r; bool done;
-        M::rollout_step(B, st, P.ego, word, r, done);
+        M::rollout_step(B, ctx, st, P.ego, word, r, done);
         ret = __dadd_rn(ret, __dmul_rn(P.disc_pow[k], r));
         if (done) break;
         ++d; ++tt; ++k;
@@ -301,7 +325,7 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
     bool done = false;
     int anode = -1;
     if (descending) {
-      M::step(B, st, P.ego, action, w.y, obs, r, done);
+      M::step(B, ctx, st, P.ego, action, w.y, w.w, obs, r, done);
       anode = node * A + action;
     }
     // lanes with the same (action node, observation) resolve the child once
@@ -367,8 +391,10 @@ __device__ void simulate(const typename M::Blob& B, const Tree& T, const Params&
   }
   const unsigned act = __ballot_sync(full, active);
   const unsigned int dmax = __reduce_max_sync(full, active ? (unsigned int)depth : 0u);
+  // self.root.visits += 1 per simulation (mcts.py:288); lanes may have different roots
+  const unsigned same_root = __match_any_sync(full, active ? root : -1 - (int)lane);
+  if (active && (int)lane == __ffs(same_root) - 1) atomicAdd(&T.node_visits[root], __popc(same_root));
   if (act && (int)lane == __ffs(act) - 1) {
-    atomicAdd(&T.node_visits[root], __popc(act));  // self.root.visits += 1 per simulation (mcts.py:288)
     atomicAdd(&T.ctr->sims_done, (unsigned long long)__popc(act));
     if (dmax > *((volatile unsigned int*)&T.ctr->max_depth)) atomicMax(&T.ctr->max_depth, dmax);
   }

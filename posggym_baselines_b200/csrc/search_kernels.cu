@@ -7,6 +7,7 @@
 #include "common.h"
 #include "driving_sim.cuh"
 #include "pp.cuh"
+#include "nested_sim.cuh"
 #include "search.cuh"
 #include "stage.cuh"
 
@@ -17,22 +18,22 @@ constexpr int SEARCH_THREADS = 128;
 template <class M>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, search::Tree T,
-              const __grid_constant__ search::Params P, int root, int root_t,
-              const uint32_t* __restrict__ particles, long long n_particles, long long n_sims,
-              unsigned long long sim_id0) {
+              const __grid_constant__ search::Params P, const __grid_constant__ typename M::Ctx ctx, int root,
+              int root_t, const uint32_t* __restrict__ particles, long long n_particles, search::RootSelect sel,
+              long long n_sims, unsigned long long sim_id0) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   stage_blob(smem_raw, gblob, blob_size, &mbar);
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
   const long long i = (long long)blockIdx.x * SEARCH_THREADS + threadIdx.x;
   // whole warps enter (warp collectives inside); lanes past n_sims are inactive
-  search::simulate<M>(B, T, P, root, root_t, particles, n_particles, sim_id0 + (unsigned long long)i, i < n_sims);
+  search::simulate<M>(B, ctx, T, P, root, root_t, particles, n_particles, sel, sim_id0 + (unsigned long long)i, i < n_sims);
 }
 
 template <class M>
 __global__ void __launch_bounds__(belief::CTA)
 reinvigorate_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
-                    const uint32_t* __restrict__ parent, long long n_parent, int ego, int action,
+                    const __grid_constant__ typename M::Ctx ctx, const uint32_t* __restrict__ parent, long long n_parent, int ego, int action,
                     const unsigned long long* __restrict__ target_obs, long long n_needed, long long max_attempts,
                     uint64_t seed, uint64_t draw_id, uint32_t* __restrict__ out, uint32_t* __restrict__ rej,
                     long long* __restrict__ result) {
@@ -40,7 +41,7 @@ reinvigorate_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_si
   __shared__ alignas(8) uint64_t mbar;
   stage_blob(smem_raw, gblob, blob_size, &mbar);
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
-  belief::reinvigorate<M>(B, parent, n_parent, ego, action, target_obs, n_needed, max_attempts, seed, draw_id, out,
+  belief::reinvigorate<M>(B, ctx, parent, n_parent, ego, action, target_obs, n_needed, max_attempts, seed, draw_id, out,
                           rej, result);
 }
 
@@ -69,6 +70,7 @@ __global__ void tree_init_kernel(search::Tree T, int n_actions, int root_t, doub
     T.ctr->max_key = known ? search::dkey(known_max) : search::KEY_NEG_INF;
     T.ctr->max_depth = 0; T.ctr->overflow = 0; T.ctr->sims_done = 0;
     T.node_t[0] = (unsigned char)root_t;
+    T.node_parent[0] = -1;
   }
 }
 
@@ -92,6 +94,7 @@ __global__ void tree_advance_kernel(search::Tree T, int n_actions, int root, int
 #pragma unroll
     for (int k = 0; k < OW; ++k) T.node_obs[(size_t)found * OW + k] = obs[k];
     T.node_t[found] = (unsigned char)(T.node_t[root] + 1);
+    T.node_parent[found] = anode;
     T.node_visits[found] = 0;
     T.node_flags[found] = 0;
     for (int a = 0; a < n_actions; ++a) {
@@ -110,6 +113,42 @@ __global__ void tree_advance_kernel(search::Tree T, int n_actions, int root, int
   out[1] = created;
   out[2] = found >= 0 ? (int)T.node_flags[found] : 0;
   out[3] = found >= 0 ? (int)T.node_t[found] : 0;
+}
+
+// traverse one (action, observation) step for a batch of (parent node, action, obs) triples,
+// creating missing nodes with zero visits (INTMCP.traverse, intmcp.py:797-809)
+template <int A, int OW>
+__global__ void tree_advance_batch_kernel(search::Tree T, long long n, const int* __restrict__ parents,
+                                          const int* __restrict__ actions, const unsigned long long* __restrict__ obs_in,
+                                          int* __restrict__ children) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long obs[OW];
+#pragma unroll
+  for (int k = 0; k < OW; ++k) obs[k] = obs_in[i * OW + k];
+  const int parent = parents[i];
+  int child = -1;
+  if (parent >= 0) {
+    bool created;
+    child = search::find_or_insert<A, OW>(T, parent * A + actions[i], obs, (int)T.node_t[parent] + 1, created);
+  }
+  children[i] = child;
+}
+
+// parent obs node, action and observation of a batch of nodes (for nested belief updates)
+template <int OW>
+__global__ void tree_node_info_kernel(search::Tree T, int n_actions, long long n, const int* __restrict__ nodes,
+                                      int* __restrict__ parent_out, int* __restrict__ action_out,
+                                      unsigned long long* __restrict__ obs_out, int* __restrict__ t_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int node = nodes[i];
+  const int an = T.node_parent[node];
+  parent_out[i] = an / n_actions;
+  action_out[i] = an % n_actions;
+#pragma unroll
+  for (int k = 0; k < OW; ++k) obs_out[i * OW + k] = T.node_obs[(size_t)node * OW + k];
+  t_out[i] = T.node_t[node];
 }
 
 // belief of `node`: every logged particle that passed through it (order irrelevant)
@@ -140,6 +179,8 @@ static bool kind_info(const posg_model* m, KindInfo* k) {
   switch (m->kind) {
     case KIND_DRIVING: *k = {DrivingSim::A, DrivingSim::OW, DrivingSim::SW}; return true;
     case KIND_PREDATOR_PREY: *k = {PPSim::A, PPSim::OW, PPSim::SW}; return true;
+    case KIND_NESTED | KIND_DRIVING: *k = {DrivingSim::A, DrivingSim::OW, DrivingSim::SW + 1}; return true;
+    case KIND_NESTED | KIND_PREDATOR_PREY: *k = {PPSim::A, PPSim::OW, PPSim::SW + 1}; return true;
     default: return false;
   }
 }
@@ -189,36 +230,161 @@ int posg_tree_reset(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_
   return POSG_OK;
 }
 
-int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
-                const uint32_t* particles, int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
-                const posg_search_params* p, void* stream) {
-  search::Tree T; KindInfo k;
-  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
-  POSG_REQUIRE(p && particles && n_particles > 0 && n_sims >= 0 && root >= 0 && root < cap_nodes, "bad search arguments");
+}  // extern "C" (helpers and templates below have C++ linkage)
+
+static int fill_params(const posg_model* m, const posg_search_params* p, search::Params* P) {
+  POSG_REQUIRE(p, "null search params");
   POSG_REQUIRE(p->ego_agent >= 0 && p->ego_agent < m->num_agents, "ego_agent out of range");
   POSG_REQUIRE(p->selection >= 0 && p->selection <= 2, "selection must be 0 (ucb), 1 (pucb) or 2 (uniform)");
-  if (n_sims == 0) return POSG_OK;
-  search::Params P;
-  P.discount = p->discount; P.c = p->c; P.known_min = p->known_min; P.known_max = p->known_max;
-  P.pucb_exploration_fraction = p->pucb_exploration_fraction;
-  P.depth_limit = p->depth_limit; P.step_limit = p->step_limit; P.selection = p->selection; P.ego = p->ego_agent;
-  P.seed = p->seed;
-  for (int i = 0; i < search::MAX_DEPTH; ++i) P.disc_pow[i] = pow(p->discount, (double)i);
+  P->discount = p->discount; P->c = p->c; P->known_min = p->known_min; P->known_max = p->known_max;
+  P->pucb_exploration_fraction = p->pucb_exploration_fraction;
+  P->depth_limit = p->depth_limit; P->step_limit = p->step_limit; P->selection = p->selection; P->ego = p->ego_agent;
+  P->intmcp_depth_rule = p->intmcp_depth_rule;
+  P->seed = p->seed;
+  for (int i = 0; i < search::MAX_DEPTH; ++i) P->disc_pow[i] = pow(p->discount, (double)i);
+  return POSG_OK;
+}
+
+template <class M>
+static void launch_search(const posg_model* m, const search::Tree& T, const search::Params& P,
+                          const typename M::Ctx& ctx, int root, int root_t, const uint32_t* particles,
+                          long long n_particles, const search::RootSelect& sel, long long n_sims,
+                          unsigned long long sim_id0, cudaStream_t s) {
   const int grid = (int)((n_sims + SEARCH_THREADS - 1) / SEARCH_THREADS);
+  search_kernel<M><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
+      (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, ctx, root, root_t, particles, n_particles,
+      sel, n_sims, sim_id0);
+}
+
+static int search_common(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
+                         const uint32_t* particles, int64_t n_particles, const search::RootSelect& sel, int64_t n_sims,
+                         uint64_t sim_id0, const posg_search_params* p, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(particles && n_particles > 0 && n_sims >= 0 && root >= 0 && root < cap_nodes, "bad search arguments");
+  search::Params P;
+  rc = fill_params(m, p, &P); if (rc) return rc;
+  if (n_sims == 0) return POSG_OK;
   cudaStream_t s = (cudaStream_t)stream;
   switch (m->kind) {
     case KIND_DRIVING:
-      search_kernel<DrivingSim><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
-          (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, root, root_t, particles,
-          (long long)n_particles, (long long)n_sims, (unsigned long long)sim_id0);
-      break;
+      launch_search<DrivingSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
     case KIND_PREDATOR_PREY:
-      search_kernel<PPSim><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
-          (const PPSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, root, root_t, particles,
-          (long long)n_particles, (long long)n_sims, (unsigned long long)sim_id0);
-      break;
+      launch_search<PPSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
   }
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+// context of a nested (level-1) model: the other agent's level-0 tree
+template <class Base>
+static int nested_ctx(posg_model_t nested, void* arena0, int64_t cap_nodes0, int64_t cap_log0, int other_agent,
+                      typename NestedSim<Base>::Ctx* ctx) {
+  posg_model base = *nested;
+  base.kind = nested->kind & ~KIND_NESTED;
+  KindInfo k0;
+  int rc = make_tree(&base, arena0, cap_nodes0, cap_log0, &ctx->other_tree, &k0); if (rc) return rc;
+  POSG_REQUIRE(other_agent >= 0 && other_agent < nested->num_agents, "other_agent out of range");
+  ctx->other = other_agent;
+  return POSG_OK;
+}
+
+extern "C" {
+
+int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
+                const uint32_t* particles, int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
+                const posg_search_params* p, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  search::RootSelect sel = {nullptr, nullptr, nullptr, 0};
+  return search_common(m, arena, cap_nodes, cap_log, root, root_t, particles, n_particles, sel, n_sims, sim_id0, p,
+                       stream);
+}
+
+int posg_search_multi(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root_t,
+                      const uint32_t* particles, int64_t n_particles, const int32_t* sel_root,
+                      const int64_t* sel_off, const int32_t* sel_cnt, int64_t n_sel, int64_t n_sims,
+                      uint64_t sim_id0, const posg_search_params* p, void* stream) {
+  POSG_REQUIRE(m && sel_root && sel_off && sel_cnt && n_sel > 0, "bad selection arguments");
+  search::RootSelect sel = {sel_root, (const long long*)sel_off, sel_cnt, (long long)n_sel};
+  return search_common(m, arena, cap_nodes, cap_log, 0, root_t, particles, n_particles, sel, n_sims, sim_id0, p,
+                       stream);
+}
+
+int posg_search_nested(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, void* other_arena,
+                       int64_t other_cap_nodes, int64_t other_cap_log, int other_agent, int root, int root_t,
+                       const uint32_t* particles, int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
+                       const posg_search_params* p, void* stream) {
+  POSG_REQUIRE(m && (m->kind & KIND_NESTED), "posg_search_nested needs a handle from posg_nested_create");
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(particles && n_particles > 0 && n_sims >= 0 && root >= 0 && root < cap_nodes, "bad search arguments");
+  search::Params P;
+  rc = fill_params(m, p, &P); if (rc) return rc;
+  POSG_REQUIRE(other_agent != p->ego_agent, "other_agent must differ from the ego agent");
+  if (n_sims == 0) return POSG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  search::RootSelect sel = {nullptr, nullptr, nullptr, 0};
+  switch (m->kind & ~KIND_NESTED) {
+    case KIND_DRIVING: {
+      NestedSim<DrivingSim>::Ctx ctx;
+      rc = nested_ctx<DrivingSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
+      launch_search<NestedSim<DrivingSim>>(m, T, P, ctx, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s);
+    } break;
+    case KIND_PREDATOR_PREY: {
+      NestedSim<PPSim>::Ctx ctx;
+      rc = nested_ctx<PPSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
+      launch_search<NestedSim<PPSim>>(m, T, P, ctx, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s);
+    } break;
+    default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
+  }
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_nested_create(posg_model_t base, posg_model_t* out) {
+  POSG_REQUIRE(base && out && !(base->kind & KIND_NESTED), "bad arguments");
+  KindInfo k;
+  if (!kind_info(base, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  posg_model* m = new posg_model(*base);
+  m->kind = base->kind | KIND_NESTED;   // same blob (borrowed), one extra state word per particle
+  m->borrowed = 1;
+  m->d_flat_desc = nullptr; m->flat_dim = 0;
+  *out = m;
+  return POSG_OK;
+}
+
+int posg_tree_advance_batch(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int64_t n,
+                            const int32_t* parents, const int32_t* actions, const uint64_t* obs,
+                            int32_t* children_out, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && parents && actions && obs && children_out, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (int)((n + 127) / 128);
+  if (k.n_actions == 5 && k.obs_words == 1)
+    tree_advance_batch_kernel<5, 1><<<grid, 128, 0, s>>>(T, n, parents, actions, (const unsigned long long*)obs, children_out);
+  else { set_error("unsupported (actions, obs words) combination"); return POSG_E_UNSUPPORTED; }
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_tree_node_info(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int64_t n,
+                        const int32_t* nodes, int32_t* parent_out, int32_t* action_out, uint64_t* obs_out,
+                        int32_t* t_out, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && nodes && parent_out && action_out && obs_out && t_out, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (int)((n + 127) / 128);
+  if (k.obs_words == 1)
+    tree_node_info_kernel<1><<<grid, 128, 0, s>>>(T, k.n_actions, n, nodes, parent_out, action_out,
+                                                  (unsigned long long*)obs_out, t_out);
+  else
+    tree_node_info_kernel<2><<<grid, 128, 0, s>>>(T, k.n_actions, n, nodes, parent_out, action_out,
+                                                  (unsigned long long*)obs_out, t_out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
@@ -296,10 +462,11 @@ static int belief_common(posg_model_t m, int obs_words, const uint64_t* obs_host
   return POSG_OK;
 }
 
-int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, int64_t n_parent, int ego_agent,
-                             int action, const uint64_t* target_obs_host, int64_t n_needed, int64_t max_attempts,
-                             uint64_t seed, uint64_t draw_id, uint32_t* out_states, uint32_t* reject_scratch,
-                             int64_t* result_host, void* stream) {
+static int reinvigorate_common(posg_model_t m, void* other_arena, int64_t other_cap_nodes, int64_t other_cap_log,
+                               int other_agent, const uint32_t* parent_particles, int64_t n_parent, int ego_agent,
+                               int action, const uint64_t* target_obs_host, int64_t n_needed, int64_t max_attempts,
+                               uint64_t seed, uint64_t draw_id, uint32_t* out_states, uint32_t* reject_scratch,
+                               int64_t* result_host, void* stream) {
   KindInfo k;
   if (!kind_info(m, &k)) { set_error("model kind has no belief support"); return POSG_E_UNSUPPORTED; }
   POSG_REQUIRE(parent_particles && n_parent > 0 && target_obs_host && out_states && reject_scratch && result_host,
@@ -310,26 +477,53 @@ int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, i
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long* d_obs; long long* d_res;
   int rc = belief_common(m, k.obs_words, target_obs_host, s, &d_obs, &d_res); if (rc) return rc;
+#define REINV(MODEL, CTX)                                                                                   \
+  reinvigorate_kernel<MODEL><<<1, belief::CTA, m->blob_bytes, s>>>(                                         \
+      (const MODEL::Blob*)m->d_blob, (uint32_t)m->blob_bytes, CTX, parent_particles, (long long)n_parent,   \
+      ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,    \
+      reject_scratch, d_res)
   switch (m->kind) {
-    case KIND_DRIVING:
-      reinvigorate_kernel<DrivingSim><<<1, belief::CTA, m->blob_bytes, s>>>(
-          (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, parent_particles, (long long)n_parent,
-          ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,
-          reject_scratch, d_res);
-      break;
-    case KIND_PREDATOR_PREY:
-      reinvigorate_kernel<PPSim><<<1, belief::CTA, m->blob_bytes, s>>>(
-          (const PPSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, parent_particles, (long long)n_parent,
-          ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,
-          reject_scratch, d_res);
-      break;
+    case KIND_DRIVING: REINV(DrivingSim, NoCtx{}); break;
+    case KIND_PREDATOR_PREY: REINV(PPSim, NoCtx{}); break;
+    case KIND_NESTED | KIND_DRIVING: {
+      NestedSim<DrivingSim>::Ctx ctx;
+      rc = nested_ctx<DrivingSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
+      REINV(NestedSim<DrivingSim>, ctx);
+    } break;
+    case KIND_NESTED | KIND_PREDATOR_PREY: {
+      NestedSim<PPSim>::Ctx ctx;
+      rc = nested_ctx<PPSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
+      REINV(NestedSim<PPSim>, ctx);
+    } break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
   }
+#undef REINV
   POSG_CUDA(cudaGetLastError());
   POSG_CUDA(cudaMemcpyAsync(result_host, d_res, 24, cudaMemcpyDeviceToHost, s));
   POSG_CUDA(cudaStreamSynchronize(s));
   cudaFreeAsync(d_obs, s);
   return POSG_OK;
+}
+
+int posg_belief_reinvigorate(posg_model_t m, const uint32_t* parent_particles, int64_t n_parent, int ego_agent,
+                             int action, const uint64_t* target_obs_host, int64_t n_needed, int64_t max_attempts,
+                             uint64_t seed, uint64_t draw_id, uint32_t* out_states, uint32_t* reject_scratch,
+                             int64_t* result_host, void* stream) {
+  POSG_REQUIRE(m && !(m->kind & KIND_NESTED), "use posg_belief_reinvigorate_nested for nested handles");
+  return reinvigorate_common(m, nullptr, 0, 0, 0, parent_particles, n_parent, ego_agent, action, target_obs_host,
+                             n_needed, max_attempts, seed, draw_id, out_states, reject_scratch, result_host, stream);
+}
+
+int posg_belief_reinvigorate_nested(posg_model_t m, void* other_arena, int64_t other_cap_nodes,
+                                    int64_t other_cap_log, int other_agent, const uint32_t* parent_particles,
+                                    int64_t n_parent, int ego_agent, int action, const uint64_t* target_obs_host,
+                                    int64_t n_needed, int64_t max_attempts, uint64_t seed, uint64_t draw_id,
+                                    uint32_t* out_states, uint32_t* reject_scratch, int64_t* result_host,
+                                    void* stream) {
+  POSG_REQUIRE(m && (m->kind & KIND_NESTED), "needs a handle from posg_nested_create");
+  return reinvigorate_common(m, other_arena, other_cap_nodes, other_cap_log, other_agent, parent_particles, n_parent,
+                             ego_agent, action, target_obs_host, n_needed, max_attempts, seed, draw_id, out_states,
+                             reject_scratch, result_host, stream);
 }
 
 int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_obs_host, int64_t n_needed,
