@@ -202,6 +202,43 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
             "ranks_agree_on_actions": agree}
     except Exception as ex:
         out["predator_prey_root_parallel"] = {"error": repr(ex)}
+    # BASELINE.json configs[3]: I-NTMCP nesting level 1 on Driving-v1 (tests/planning/test_intmcp.py:34-48:
+    # search_time_limit 0.2 s, UCB, state_belief_only=False); two device trees per rank.
+    try:
+        import json as _json
+        import math as _math
+
+        from posggym_baselines_b200.planning import INTMCP
+
+        icfg = MCTSConfig(discount=0.95, search_time_limit=0.2, c=_math.sqrt(2), truncated=False,
+                          action_selection="ucb", state_belief_only=False, seed=rank)
+        ipl = INTMCP.initialize(model, "0", icfg, nesting_level=1, search_policies=None)
+        irng = random.Random(50 + rank)
+        iobs, _ = env.reset(seed=200 + rank)
+        ipl.reset()
+        isims, itimes = [], []
+        for d in range(6):
+            a = ipl.step(iobs["0"])
+            if d > 0 and ipl.step_statistics["num_sims"] == ipl.step_statistics["num_sims"] and not ipl._absorbing:
+                isims.append(ipl.step_statistics["num_sims"])
+                itimes.append(ipl.step_statistics["search_time"])
+            iobs, _, _, _, done, _ = env.step({"0": a, "1": irng.randrange(5)})
+            if done:
+                break
+        ipl.close()
+        ref_sims = None
+        gp = os.path.join(ROOT, "tests", "golden", "intmcp_driving.json")
+        if os.path.exists(gp):
+            ref_sims = _json.load(open(gp))["episodes"]["mean_sims_per_decision"]
+        out["intmcp_level1"] = {
+            "config": "Driving-v1, nesting_level 1, discount 0.95, search_time_limit 0.2 s, ucb",
+            "sims_per_decision_per_gpu": sum(isims) / max(1, len(isims)),
+            "search_time_s": sum(itimes) / max(1, len(itimes)),
+            "note": "simulations per decision are capped by the tree arena budget (node_capacity / (step_limit + 2) per level)",
+            "reference_sims_per_decision_build_container": ref_sims,
+            "reference_source": "unmodified reference INTMCP on the CPU oracle, 1 core, tests/golden/make_intmcp_golden.py"}
+    except Exception as ex:
+        out["intmcp_level1"] = {"error": repr(ex)}
     if cpu:
         from oracle import shims
 

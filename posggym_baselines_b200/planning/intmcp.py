@@ -50,7 +50,8 @@ class INTMCP:
     def __init__(self, model, agent_id: str, config: MCTSConfig, nesting_level: int,
                  other_agent_policies: Optional[Dict[str, "INTMCP"]], search_policies: Dict[str, SearchPolicy], *,
                  max_sims_per_level: Optional[int] = None, wave_size: Optional[int] = None, max_wave: int = 8192,
-                 node_capacity: int = 1 << 23, log_capacity: int = 1 << 25):
+                 node_capacity: int = 1 << 23, log_capacity: int = 1 << 25, belief_cap: int = 4096,
+                 max_histories: int = 64, history_belief_cap: int = 256):
         if nesting_level != 1 or len(model.possible_agents) != 2:
             raise NotImplementedError("the B200 I-NTMCP supports nesting_level=1 with two agents")
         if not all(isinstance(p, RandomSearchPolicy) for p in search_policies.values()):
@@ -78,6 +79,11 @@ class INTMCP:
         self.wave_size, self.max_wave = wave_size, max_wave
         self._cap_nodes, self._cap_log = int(node_capacity), int(log_capacity)
         self.max_sims_per_level = max_sims_per_level
+        # the reference's beliefs hold tens of particles; a search that runs millions of
+        # simulations leaves millions at a child, so beliefs are capped (a subset of a particle
+        # set is a particle set of the same distribution) and only the `max_histories` most
+        # probable histories of the other agent keep a level-0 belief
+        self.belief_cap, self.max_histories, self.history_belief_cap = belief_cap, max_histories, history_belief_cap
 
         lib = _lib.lib()
         self._nested = C.c_void_p()
@@ -248,14 +254,13 @@ class INTMCP:
             return
         t0 = time.time()
         sw1 = self._SW + 1
-        log_count = int(self._stats(1, child)["log_count"])
-        buf = torch.empty((min(log_count, self._cap_log) + n_total, sw1), dtype=torch.int32, device=b.device)
+        buf = torch.empty((self.belief_cap + n_total, sw1), dtype=torch.int32, device=b.device)
         cnt = np.zeros(1, np.int64)
         with self._dev():
             _lib.check(lib.posg_tree_gather_belief(self._nested, _lib.ptr(self._arena1), self._cap_nodes, self._cap_log,
                                                    child, _lib.ptr(buf), buf.shape[0] - n_total, _lib.ptr(cnt),
                                                    self._stream()))
-        have = int(cnt[0])
+        have = min(int(cnt[0]), self.belief_cap)
         need = n_total - have
         if need > 0:
             limit = int(cfg.reinvigoration_sample_limit_factor * need)
@@ -273,6 +278,9 @@ class INTMCP:
         n0 = self._P1[:, self._SW].contiguous()
         n0_h = n0.cpu().numpy()
         uniq, counts = np.unique(n0_h[n0_h >= 0], return_counts=True)
+        if len(uniq) > self.max_histories:
+            keep = np.argsort(-counts, kind="stable")[: self.max_histories]
+            uniq, counts = uniq[keep], counts[keep]
         new_beliefs: Dict[int, torch.Tensor] = {}
         if len(uniq):
             nodes = torch.from_numpy(uniq.astype(np.int32)).to(b.device)
@@ -286,17 +294,17 @@ class INTMCP:
                                                    _lib.ptr(ob), _lib.ptr(tt), self._stream()))
             par_h, act_h = par.cpu().numpy(), act.cpu().numpy()
             ob_h = ob.cpu().numpy().view(np.uint64)
-            log0 = int(self._stats(0, 0)["log_count"])
             n_p1 = len(n0_h)
+            hcap = self.history_belief_cap
             for j, u in enumerate(uniq):
                 target = math.ceil(counts[j] / n_p1 * n_total)
-                bbuf = torch.empty((min(log0, self._cap_log) + target, self._SW), dtype=torch.int32, device=b.device)
+                bbuf = torch.empty((hcap + target, self._SW), dtype=torch.int32, device=b.device)
                 c0 = np.zeros(1, np.int64)
                 with self._dev():
                     _lib.check(lib.posg_tree_gather_belief(b._handle, _lib.ptr(self._arena0), self._cap_nodes,
                                                            self._cap_log, int(u), _lib.ptr(bbuf),
                                                            bbuf.shape[0] - target, _lib.ptr(c0), self._stream()))
-                h = int(c0[0])
+                h = min(int(c0[0]), hcap)
                 miss = target - h
                 parent_belief = self._t0_beliefs.get(int(par_h[j]))
                 if miss > 0 and parent_belief is not None and parent_belief.shape[0] > 0:
