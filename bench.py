@@ -423,7 +423,13 @@ def main():
 
         cores = os.cpu_count() or 1
         r = cpu_bench.driving_sweep(budget_s=args.cpu_seconds, depth=DEPTH, procs=cores, seed=0)
-        cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+        try:
+            rc = cpu_bench.driving_sweep_compiled(budget_s=min(5.0, args.cpu_seconds), depth=DEPTH, threads=cores, seed=0)
+            compiled = {"value": rc["env_steps_per_s"], "unit": UNIT, "cores": cores,
+                        "what": "C restatement of the model (oracle/c/driving_oracle.c, gcc -O2), one thread per core"}
+        except Exception as ex:
+            compiled = {"error": repr(ex)}
+        cpu = {"value": r["env_steps_per_s"], "unit": UNIT, "cores": cores, "kind": "port", "compiled_port": compiled,
                "sample": f"{r['env_steps']} env-steps of the same random-action depth-{DEPTH} Driving-v1 sweep in "
                          f"{r['seconds']:.1f} s, one Python process per core (the reference's model is pure Python)"}
 

@@ -48,3 +48,24 @@ def driving_sweep(budget_s: float = 10.0, depth: int = 50, procs: int | None = N
     live = sum(r[0] for r in res)
     wall = max(r[2] for r in res)
     return {"env_steps": live, "seconds": wall, "env_steps_per_s": live / wall, "cores": procs}
+
+
+def driving_sweep_compiled(budget_s: float = 5.0, depth: int = 50, threads: int | None = None, seed: int = 0):
+    """The same sweep through the C restatement (oracle/c/driving_oracle.c), one thread per
+    core (ctypes releases the GIL).  A compiled-code CPU baseline beside the pure-Python one."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import native
+
+    h = native.init_driving()
+    threads = threads or os.cpu_count() or 1
+    # calibrate: steps per second per thread
+    t0 = time.perf_counter()
+    h.drv_sweep(seed, depth, 200_000)
+    rate = 200_000 / (time.perf_counter() - t0)
+    budget = int(rate * budget_s)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        done = sum(ex.map(lambda k: h.drv_sweep(seed + 1 + k, depth, budget), range(threads)))
+    wall = time.perf_counter() - t0
+    return {"env_steps": int(done), "seconds": wall, "env_steps_per_s": done / wall, "cores": threads}
