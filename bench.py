@@ -112,7 +112,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "Driving-v1 14x14RoundAbout 2 agents random-action sweep depth 50 (bounded CPU sample)"},
+        "config": {"workload": f"Driving-v1 14x14RoundAbout, 2 agents, obs_dim (3,1,1): random-action model.step sweep, "
+                               f"{args.particles} particles per GPU x depth {DEPTH} (BASELINE.json configs[1])",
+                   "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -90,8 +90,8 @@ class MCTS:
         *,
         max_sims: Optional[int] = None,
         wave_size: Optional[int] = None,
-        max_wave: int = 16384,
-        node_capacity: int = 1 << 24,
+        max_wave: int = 65536,
+        node_capacity: int = 1 << 25,
         log_capacity: int = 1 << 26,
         root_parallel: bool = False,
     ):
