@@ -208,6 +208,13 @@ int posg_tree_node_stats(posg_model_t m, void* arena, int64_t cap_nodes, int64_t
 int posg_tree_advance(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root,
                       int action, const uint64_t* obs_host, int create_if_missing, int* out_host,
                       void* stream);
+/* MCTS._update (mcts.py:261-263): the subtree under `new_root` (statistics, child lists and
+ * every logged particle of its nodes) is copied, renumbered breadth-first so that the new
+ * root is node 0, into `dst_arena`; everything else is dropped.  `scratch`: 3 * cap_nodes
+ * int32 (device).  result_host = {nodes kept, particles kept}. */
+int posg_tree_reroot(posg_model_t m, void* src_arena, void* dst_arena, int64_t cap_nodes,
+                     int64_t cap_log, int new_root, int32_t* scratch, int64_t* result_host,
+                     void* stream);
 /* obs_node.belief.particles: every particle logged at `node` -> states_out (device). */
 int posg_tree_gather_belief(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
                             uint32_t* states_out, int64_t max_out, int64_t* count_host, void* stream);

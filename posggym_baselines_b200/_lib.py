@@ -69,6 +69,7 @@ SIGNATURES = {
     "posg_search": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _u64, _vp, _vp]),
     "posg_tree_node_stats": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "posg_tree_advance": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _int, _vp, _vp]),
+    "posg_tree_reroot": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "posg_tree_gather_belief": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp, _vp]),
     "posg_belief_reinvigorate": (
         _int, [_vp, _vp, _i64, _int, _int, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),

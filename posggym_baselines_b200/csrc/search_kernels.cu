@@ -74,6 +74,77 @@ __global__ void tree_init_kernel(search::Tree T, int n_actions, int root_t, doub
   }
 }
 
+
+// ---- re-rooting: keep the subtree under the new root (MCTS._update, mcts.py:229-263: "remove
+// reference to parent, effectively pruning dead branches") by copying it, renumbered, into a
+// second arena.  Breadth-first marking, one launch per tree level.
+__global__ void reroot_expand_kernel(search::Tree S, int n_actions, const int* __restrict__ frontier, int n_front,
+                                     int* __restrict__ mark, int* __restrict__ next_frontier,
+                                     unsigned int* __restrict__ counters /* [0] next frontier size, [1] new node count */) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_front * n_actions) return;
+  const int f = frontier[i / n_actions], a = (int)(i % n_actions);
+  for (int c = S.an_first[f * n_actions + a]; c >= 0; c = S.node_next[c]) {
+    mark[c] = (int)atomicAdd(&counters[1], 1u);
+    next_frontier[atomicAdd(&counters[0], 1u)] = c;
+  }
+}
+
+__global__ void reroot_copy_kernel(search::Tree S, search::Tree D, int n_actions, int obs_words,
+                                   const int* __restrict__ mark, long long n_old) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_old;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = mark[i];
+    if (j < 0) continue;
+    D.node_visits[j] = S.node_visits[i];
+    D.node_flags[j] = S.node_flags[i];
+    D.node_t[j] = S.node_t[i];
+    for (int k = 0; k < obs_words; ++k) D.node_obs[(size_t)j * obs_words + k] = S.node_obs[(size_t)i * obs_words + k];
+    const int nx = S.node_next[i], pa = S.node_parent[i];
+    D.node_next[j] = (j == 0 || nx < 0) ? -1 : mark[nx];
+    D.node_parent[j] = (j == 0 || pa < 0) ? -1 : mark[pa / n_actions] * n_actions + pa % n_actions;
+    for (int a = 0; a < n_actions; ++a) {
+      const long long so = i * n_actions + a, dn = (long long)j * n_actions + a;
+      const int first = S.an_first[so];
+      D.an_first[dn] = first >= 0 ? mark[first] : -1;
+      D.an_visits[dn] = S.an_visits[so];
+      D.an_done[dn] = S.an_done[so];
+      D.an_total[dn] = S.an_total[so];
+    }
+  }
+}
+
+__global__ void reroot_log_kernel(search::Tree S, search::Tree D, int state_words, const int* __restrict__ mark,
+                                  unsigned long long n_log, unsigned long long* __restrict__ out_count) {
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n_log;
+       i0 += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = i0 + lane;
+    const int j = i < n_log ? mark[S.log_node[i]] : -1;
+    const unsigned b = __ballot_sync(0xffffffffu, j >= 0);
+    if (!b) continue;
+    unsigned long long base = 0;
+    const int leader = __ffs(b) - 1;
+    if ((int)lane == leader) base = atomicAdd(out_count, (unsigned long long)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (j >= 0) {
+      const unsigned long long pos = base + __popc(b & ((1u << lane) - 1u));
+      D.log_node[pos] = (unsigned int)j;
+      for (int k = 0; k < state_words; ++k) D.log_state[pos * state_words + k] = S.log_state[i * state_words + k];
+    }
+  }
+}
+
+__global__ void reroot_finish_kernel(search::Tree S, search::Tree D, const unsigned int* __restrict__ counters,
+                                     const unsigned long long* __restrict__ log_count) {
+  D.ctr->node_count = counters[1];
+  D.ctr->log_count = *log_count;
+  D.ctr->min_key = S.ctr->min_key;
+  D.ctr->max_key = S.ctr->max_key;
+  D.ctr->max_depth = 0; D.ctr->overflow = 0;
+  D.ctr->sims_done = S.ctr->sims_done;
+}
+
 template <int OW>
 __global__ void tree_advance_kernel(search::Tree T, int n_actions, int root, int action,
                                     const unsigned long long* __restrict__ obs_in, int create, int* __restrict__ out) {
@@ -227,6 +298,62 @@ int posg_tree_reset(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_
   POSG_CUDA(cudaMemsetAsync(arena, 0, upto, s));
   tree_init_kernel<<<sm_count() * 4, 256, 0, s>>>(T, k.n_actions, root_t, known_min, known_max);
   POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_tree_reroot(posg_model_t m, void* src_arena, void* dst_arena, int64_t cap_nodes, int64_t cap_log,
+                     int new_root, int32_t* scratch, int64_t* result_host, void* stream) {
+  search::Tree S, D; KindInfo k;
+  int rc = make_tree(m, src_arena, cap_nodes, cap_log, &S, &k); if (rc) return rc;
+  rc = make_tree(m, dst_arena, cap_nodes, cap_log, &D, &k); if (rc) return rc;
+  POSG_REQUIRE(src_arena != dst_arena && scratch && result_host && new_root >= 0 && new_root < cap_nodes, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  search::Counters c;
+  POSG_CUDA(cudaMemcpyAsync(&c, S.ctr, sizeof(c), cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  const long long n_old = (long long)(c.node_count < (unsigned long long)cap_nodes ? c.node_count : (unsigned long long)cap_nodes);
+  const unsigned long long n_log = c.log_count < (unsigned long long)cap_log ? c.log_count : (unsigned long long)cap_log;
+  // clean destination (an_first = -1, everything else 0)
+  rc = posg_tree_reset(m, dst_arena, cap_nodes, cap_log, 0, 1.0, 0.0, stream); if (rc) return rc;
+  int* mark = scratch;
+  int* front[2] = {scratch + cap_nodes, scratch + 2 * cap_nodes};
+  unsigned int* counters = nullptr;   // [0] next frontier size, [1] new node count, then the 64-bit log counter
+  POSG_CUDA(cudaMallocAsync((void**)&counters, 32, s));
+  unsigned long long* d_log = (unsigned long long*)(counters + 4);
+  POSG_CUDA(cudaMemsetAsync(counters, 0, 32, s));
+  POSG_CUDA(cudaMemsetAsync(mark, 0xFF, (size_t)n_old * 4, s));
+  const int zero = 0; const unsigned int one = 1;
+  POSG_CUDA(cudaMemcpyAsync(mark + new_root, &zero, 4, cudaMemcpyHostToDevice, s));
+  POSG_CUDA(cudaMemcpyAsync(front[0], &new_root, 4, cudaMemcpyHostToDevice, s));
+  POSG_CUDA(cudaMemcpyAsync(counters + 1, &one, 4, cudaMemcpyHostToDevice, s));
+  int n_front = 1, cur = 0;
+  while (n_front > 0) {
+    POSG_CUDA(cudaMemsetAsync(counters, 0, 4, s));
+    const long long work = (long long)n_front * k.n_actions;
+    reroot_expand_kernel<<<(int)((work + 255) / 256), 256, 0, s>>>(S, k.n_actions, front[cur], n_front, mark,
+                                                                    front[cur ^ 1], counters);
+    POSG_CUDA(cudaGetLastError());
+    unsigned int nf = 0;
+    POSG_CUDA(cudaMemcpyAsync(&nf, counters, 4, cudaMemcpyDeviceToHost, s));
+    POSG_CUDA(cudaStreamSynchronize(s));
+    n_front = (int)nf;
+    cur ^= 1;
+  }
+  reroot_copy_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.n_actions, k.obs_words, mark, n_old);
+  POSG_CUDA(cudaGetLastError());
+  if (n_log > 0) {
+    reroot_log_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.state_words, mark, n_log, d_log);
+    POSG_CUDA(cudaGetLastError());
+  }
+  reroot_finish_kernel<<<1, 1, 0, s>>>(S, D, counters, d_log);
+  POSG_CUDA(cudaGetLastError());
+  unsigned int h_cnt[4]; unsigned long long h_log = 0;
+  POSG_CUDA(cudaMemcpyAsync(h_cnt, counters, 16, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(&h_log, d_log, 8, cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaStreamSynchronize(s));
+  cudaFreeAsync(counters, s);
+  result_host[0] = h_cnt[1];
+  result_host[1] = (int64_t)h_log;
   return POSG_OK;
 }
 

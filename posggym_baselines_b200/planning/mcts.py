@@ -16,11 +16,10 @@ Extra, B200-only knobs are keyword arguments of the constructor, never config fi
 ``max_sims`` (stop after that many simulations instead of / as well as the time limit),
 ``wave_size`` (simulations per launch; 1 = the reference's strictly sequential search),
 ``root_parallel`` (merge root statistics over torch.distributed ranks: one allreduce per
-decision), ``node_capacity`` / ``log_capacity`` (size of the device arena).  The reference
-keeps the whole subtree under the new root for the rest of the episode (mcts.py:261-263);
-so does this planner while the arena has room -- when more than half of it is used at a
-re-root, the tree is rebuilt from the new root's belief alone (statistics below it are
-re-estimated by the next search, which runs >1000x the reference's simulations).
+decision), ``node_capacity`` / ``log_capacity`` (size of the device arenas).  Like the
+reference (mcts.py:261-263) the planner keeps the whole subtree under the new root -- its
+statistics, child lists and the particles logged at its nodes -- and drops the rest: at
+every re-root the subtree is copied, renumbered, into a second arena (posg_tree_reroot).
 """
 from __future__ import annotations
 
@@ -178,6 +177,8 @@ class MCTS:
             nbytes = lib.posg_tree_arena_bytes(self._b._handle, self._cap_nodes, self._cap_log)
             _lib.check(int(nbytes))
             self._arena = torch.empty(int(nbytes), dtype=torch.uint8, device=self._b.device)
+            self._arena_spare = torch.empty(int(nbytes), dtype=torch.uint8, device=self._b.device)
+            self._reroot_scratch = torch.empty(3 * self._cap_nodes, dtype=torch.int32, device=self._b.device)
 
     def _stats(self, node: Optional[int] = None) -> Dict[str, object]:
         out = np.zeros(3 * self._A + 9, np.float64)
@@ -230,7 +231,7 @@ class MCTS:
         self._nodes_bound = 1
         self._log_bound = 0
         self._min_value, self._max_value = float("inf"), -float("inf")
-        self.tree_rebuilds = 0
+        self.tree_compactions = 0
         self._reset_step_statistics()
 
     def _reset_step_statistics(self):
@@ -320,18 +321,16 @@ class MCTS:
         self._root = child
         self._root_t += 1
         self._root_absorbing = absorbing
-        if not absorbing and (self._nodes_bound > self._cap_nodes // 2 or self._log_bound > self._cap_log // 2):
-            # arena pressure: keep the new root's belief, drop the statistics below it
-            kb = cfg.known_bounds
-            with torch.cuda.device(b.device):
-                _lib.check(_lib.lib().posg_tree_reset(
-                    b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root_t,
-                    self._min_value if self._min_value <= self._max_value else (kb.min if kb else 1.0),
-                    self._max_value if self._min_value <= self._max_value else (kb.max if kb else 0.0),
-                    self._stream()))
-            self._root = 0
-            self._nodes_bound, self._log_bound = 1, 0
-            self.tree_rebuilds += 1
+        # keep the subtree under the new root, drop everything else (mcts.py:261-263)
+        res = np.zeros(2, np.int64)
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().posg_tree_reroot(
+                b._handle, _lib.ptr(self._arena), _lib.ptr(self._arena_spare), self._cap_nodes, self._cap_log,
+                child, _lib.ptr(self._reroot_scratch), _lib.ptr(res), self._stream()))
+        self._arena, self._arena_spare = self._arena_spare, self._arena
+        self._root = 0
+        self._nodes_bound, self._log_bound = int(res[0]), int(res[1])
+        self.tree_compactions += 1
 
     # ------------------------------------------------------------------ search
     def get_action(self):
@@ -418,7 +417,7 @@ class MCTS:
         self.search_policy.close()
         for policy in self.other_agent_policies.values():
             policy.close()
-        self._arena = None
+        self._arena = self._arena_spare = self._reroot_scratch = None
         self._root_particles = None
 
     def __str__(self):

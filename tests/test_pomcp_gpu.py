@@ -172,3 +172,48 @@ def test_throughput_mode_beats_reference_by_1000x(model, gold):
     obs, *_ = env.step({"0": planner._last_action, "1": 0})
     planner.step(obs["0"])
     assert planner.step_statistics["num_sims"] >= 1000 * gold["episodes"]["mean_sims_per_decision"]
+
+
+def test_reroot_keeps_the_subtree(model):
+    """MCTS._update (mcts.py:229-263) re-roots at the (action, observation) child and keeps its
+    subtree: after posg_tree_reroot the new root (node 0) has the child's statistics, the
+    particles logged at it are the new root belief, and deeper nodes are still reachable."""
+    import numpy as np
+
+    from posggym_baselines_b200 import _lib
+    from posggym_baselines_b200.envs.env import Env
+
+    env = Env(model)
+    p = make_planner(model, seed=3, max_sims=6000, wave_size=32)
+    obs, _ = env.reset(seed=4)
+    p.reset()
+    a = p.step(obs["0"])
+    nodes_before = p._nodes_bound
+    obs, *_ = env.step({"0": a, "1": 0})
+    b, lib = p._b, _lib.lib()
+    key = np.ascontiguousarray(b.pack_obs(obs["0"]), dtype=np.uint64)
+    out4 = np.zeros(4, np.int32)
+    lib.posg_tree_advance(b._handle, _lib.ptr(p._arena), p._cap_nodes, p._cap_log, p._root, int(a), _lib.ptr(key), 0,
+                          _lib.ptr(out4), None)
+    child = int(out4[0])
+    assert child > 0, "the real observation was simulated at least once in 6000 simulations"
+    before = p._stats(child)
+    buf = torch.empty((1 << 16, 2), dtype=torch.int32, device=b.device)
+    cnt = np.zeros(1, np.int64)
+    lib.posg_tree_gather_belief(b._handle, _lib.ptr(p._arena), p._cap_nodes, p._cap_log, child, _lib.ptr(buf),
+                                buf.shape[0], _lib.ptr(cnt), None)
+    logged = set(map(tuple, buf[: int(cnt[0])].cpu().numpy().tolist()))
+    p.update(a, obs["0"])
+    assert p._root == 0 and p.tree_compactions == 1
+    after = p._stats(0)
+    for k in ("visits", "done", "total"):
+        assert (after[k] == before[k]).all(), k
+    assert after["node_visits"] == before["node_visits"]
+    assert 1 <= p._nodes_bound < nodes_before                      # siblings' subtrees were dropped
+    belief = set(map(tuple, p._root_particles.cpu().numpy().tolist()))
+    assert logged <= belief and p.root.belief.size() >= p.config.num_particles + p.config.extra_particles
+    # searching on from the kept subtree only adds to its statistics
+    p.get_action()
+    later = p._stats(0)
+    assert (later["done"] >= before["done"]).all() and later["done"].sum() == before["done"].sum() + 6000
+    p.close()
