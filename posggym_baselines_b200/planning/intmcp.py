@@ -135,6 +135,8 @@ class INTMCP:
             n1 = _lib.check(int(lib.posg_tree_arena_bytes(self._nested, self._cap_nodes, self._cap_log)))
             n0 = _lib.check(int(lib.posg_tree_arena_bytes(self._b._handle, self._cap_nodes, self._cap_log)))
             self._arena1 = torch.empty(n1, dtype=torch.uint8, device=self._b.device)
+            self._arena1_spare = torch.empty(n1, dtype=torch.uint8, device=self._b.device)
+            self._scratch = torch.empty(3 * self._cap_nodes, dtype=torch.int32, device=self._b.device)
             self._arena0 = torch.empty(n0, dtype=torch.uint8, device=self._b.device)
 
     def _stats(self, level: int, node: int):
@@ -237,6 +239,7 @@ class INTMCP:
             need = int((n0_h == u).sum())
             self._t0_beliefs[int(u)] = self._initial_belief(self._other, np.ascontiguousarray(obs_h[idx]), need)
         self._root1, self._root_t, self._absorbing = 0, 1, False
+        self._nodes1 = 1
 
     def _nested_update(self, action, obs):
         cfg, b, lib = self.config, self._b, _lib.lib()
@@ -274,6 +277,16 @@ class INTMCP:
                     _lib.ptr(rej), _lib.ptr(res), self._stream()))
             have += int(res[2])
         self._P1 = buf[:have]
+        # keep the level-1 subtree under the new root, drop the rest (intmcp.py:305-333 prunes the
+        # dead histories); the level-0 tree is append-only because level-1 particles index it
+        rr = np.zeros(2, np.int64)
+        with self._dev():
+            _lib.check(lib.posg_tree_reroot(self._nested, _lib.ptr(self._arena1), _lib.ptr(self._arena1_spare),
+                                            self._cap_nodes, self._cap_log, child, _lib.ptr(self._scratch),
+                                            _lib.ptr(rr), self._stream()))
+        self._arena1, self._arena1_spare = self._arena1_spare, self._arena1
+        self._root1 = 0
+        self._nodes1 = int(rr[0])
         # nested history distribution (intmcp.py:336-362) and the other tree's beliefs (278-304)
         n0 = self._P1[:, self._SW].contiguous()
         n0_h = n0.cpu().numpy()
@@ -378,7 +391,10 @@ class INTMCP:
                         wave = min(wave * 2, self.max_wave)
             n_sims_total += done
 
-        # ---- level 1: search the ego tree, the other agent acting by its tree
+        # ---- level 1: search the ego tree, the other agent acting by its tree.  This tree is
+        # compacted at every re-root, so its budget is whatever room is left in the arena.
+        if timed:
+            budget = max(1024, self._cap_nodes - self._nodes1 - 4096)
         wave, done, t_level = (self.wave_size or 32), 0, time.time()
         with self._dev():
             while done < budget and (not timed or time.time() - t_level < per_level):
@@ -395,6 +411,7 @@ class INTMCP:
         n_sims_total += done
 
         st = self._stats(1, self._root1)
+        self._nodes1 = int(min(st["node_count"], self._cap_nodes))
         self._min_value, self._max_value = st["min_value"], st["max_value"]
         self.step_statistics.update({
             "search_time": time.time() - start, "search_depth": int(st["max_depth"]), "num_sims": n_sims_total,
@@ -417,7 +434,7 @@ class INTMCP:
         if self._nested is not None and self._nested.value:
             _lib.lib().posg_model_destroy(self._nested)
             self._nested = None
-        self._arena1 = self._arena0 = None
+        self._arena1 = self._arena0 = self._arena1_spare = self._scratch = None
         self._P1 = None
         self._t0_beliefs = {}
 
