@@ -236,7 +236,7 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
             "config": "Driving-v1, nesting_level 1, discount 0.95, search_time_limit 0.2 s, ucb",
             "sims_per_decision_per_gpu": sum(isims) / max(1, len(isims)),
             "search_time_s": sum(itimes) / max(1, len(itimes)),
-            "note": "simulations per decision are capped by the tree arena budget (node_capacity / (step_limit + 2) per level)",
+            "note": "level-0 simulations per decision are budgeted (node_capacity / (step_limit + 2)): that tree is append-only",
             "reference_sims_per_decision_build_container": ref_sims,
             "reference_source": "unmodified reference INTMCP on the CPU oracle, 1 core, tests/golden/make_intmcp_golden.py"}
     except Exception as ex:
