@@ -169,6 +169,12 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
   }
   const float c = (float)P.c;
   const float prior = 1.0f / (float)A;  // RandomSearchPolicy.get_pi is uniform; so is the noise mix
+  // per-action exploration factors kept incrementally: only the chosen action's count changes
+  // between two consecutive virtual visits, so one rsqrt / one reciprocal per iteration
+  float rs[A];   // ucb: 1 / sqrt(n_a)      pucb: 1 / (1 + n_a)
+#pragma unroll
+  for (int a = 0; a < A; ++a)
+    rs[a] = (P.selection == SEL_PUCB) ? __frcp_rn(1.0f + n[a]) : (n[a] > 0.0f ? rsqrtf(n[a]) : 0.0f);
   int mine = 0;
   for (int s = 0; s < max_gsize; ++s) {
     const int N = n_base + s + (is_root ? 0 : 1);
@@ -178,25 +184,25 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
       // whole group agrees on it
       choice = (int)uniform_below(rnd_word * 0x9E3779B1u + (uint32_t)s * 0x85EBCA77u, (uint32_t)A);
     } else if (P.selection == SEL_UCB) {
-      const float logn = __logf((float)N);
+      // argmax_a  norm(Q_a) + c * sqrt(ln N / n_a), first unvisited action first (mcts.py:529-546)
+      const float cs = c * sqrtf(__logf((float)N));
       float best = -3.0e38f;
       bool unvisited = false;
 #pragma unroll
       for (int a = 0; a < A; ++a) {
-        if (!unvisited) {
-          if (n[a] == 0.0f) { choice = a; unvisited = true; }
-          else {
-            const float v = q[a] + c * sqrtf(logn / n[a]);
-            if (v > best) { best = v; choice = a; }
-          }
-        }
+        const bool zero = (n[a] == 0.0f);
+        const float v = q[a] + cs * rs[a];
+        const bool take = !unvisited && (zero || v > best);
+        choice = take ? a : choice;
+        best = take ? v : best;
+        unvisited = unvisited || zero;
       }
     } else if (P.selection == SEL_PUCB) {
-      const float sq = sqrtf((float)N);
+      const float cs = c * prior * sqrtf((float)N);
       float best = -3.0e38f;
 #pragma unroll
       for (int a = 0; a < A; ++a) {
-        const float v = (n[a] > 0.0f ? q[a] : 0.0f) + c * prior * (sq / (1.0f + n[a]));
+        const float v = (n[a] > 0.0f ? q[a] : 0.0f) + cs * rs[a];
         if (v > best) { best = v; choice = a; }
       }
     } else {
@@ -206,8 +212,16 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
         if (n[a] < best) { best = n[a]; choice = a; }
     }
     if (s == rank) mine = choice;
+    float nc = 0.0f;
 #pragma unroll
-    for (int a = 0; a < A; ++a) n[a] += (a == choice) ? 1.0f : 0.0f;
+    for (int a = 0; a < A; ++a) nc = (a == choice) ? n[a] : nc;
+    nc += 1.0f;
+    const float rc = (P.selection == SEL_PUCB) ? __frcp_rn(1.0f + nc) : rsqrtf(nc);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      n[a] = (a == choice) ? nc : n[a];
+      rs[a] = (a == choice) ? rc : rs[a];
+    }
   }
   return mine;
 }

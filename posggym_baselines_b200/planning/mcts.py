@@ -89,7 +89,7 @@ class MCTS:
         *,
         max_sims: Optional[int] = None,
         wave_size: Optional[int] = None,
-        max_wave: int = 65536,
+        max_wave: int = 262144,
         node_capacity: int = 1 << 25,
         log_capacity: int = 1 << 26,
         root_parallel: bool = False,
