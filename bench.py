@@ -270,6 +270,77 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
     return out
 
 
+def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
+    """``envs.step`` of the PPO rollout worker (ppo/worker.py:176-216) for 64 rollout steps
+    (exp_utils.py:81): one launch per step does model.step, TimeLimit, episode statistics,
+    auto-reset and the one-hot float32 flattening (300 floats per agent for LBF-v3)."""
+    import torch
+    import torch.distributed as dist
+
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.lbf import LBFModel
+    from posggym_baselines_b200.vector import BatchedVecEnv
+
+    peak, _ = load_peaks()
+    out = {"rollout_steps": 64}
+    for name, model, nact in (("LevelBasedForaging-v3", LBFModel(device=dev), 6), ("Driving-v1", DrivingModel(device=dev), 5)):
+        sec = {}
+        for label, nv in (("envs_8192_per_gpu", 8192), ("envs_1048576_per_gpu", 1 << 20)):
+            ve = BatchedVecEnv(model, nv, seed=seed, env_offset=rank * nv)
+            ve.reset()
+            acts = torch.randint(0, nact, (64, nv * 2), device=dev, dtype=torch.int64)
+            for k in range(8):
+                ve._global_step += 1
+                ve._launch(acts[k], 0)
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for k in range(64):
+                ve._global_step += 1
+                ve._launch(acts[k], 0)
+            v1.record()
+            barrier()
+            vms = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(vms, op=dist.ReduceOp.MAX)
+            # state r+w, int64 actions, f32 one-hot obs, f32 rewards, term, trunc, done, episode r / l
+            bytes_per = 8 + 8 + 16 + 2 * ve.flat_dim * 4 + 8 + 2 + 2 + 1 + 8 + 4
+            gbs = bytes_per * nv * 64 / (vms.item() / 1e3) / 1e9
+            sec[label] = {"env_steps_per_s": world * nv * 64 / (vms.item() / 1e3), "us_per_step": 1e3 * vms.item() / 64,
+                          "hbm_gbs": gbs, "hbm_frac": gbs / peak, "bytes_per_env_step": bytes_per}
+            sec["obs_dim"] = ve.flat_dim
+            del ve
+        out[name] = sec
+    if cpu:
+        # reference collector scale (BR checkpoints' config): 32 envs per worker stepped serially
+        # (ppo/worker.py:51); one worker on one core here.
+        from oracle import shims
+
+        shims.install()
+        import numpy as np
+
+        from oracle import vec_env as V
+        from oracle.lbf import LevelBasedForagingModel
+        from posggym_baselines_b200.envs.env import Env
+
+        def thunk():
+            m = LevelBasedForagingModel()
+            m.spec = type("S", (), {"max_episode_steps": 50, "id": "LevelBasedForaging-v3"})()
+            return V.FlattenObservations(Env(m, 50))
+
+        envs = V.StackEnv(V.RecordEpisodeStatistics(V.SyncVectorEnv([thunk] * 32)))
+        envs.reset(seed=0)
+        rng = np.random.default_rng(0)
+        t0, k = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 3.0:
+            envs.step(rng.integers(0, 6, size=64))
+            k += 1
+        out["cpu_reference"] = {"env_steps_per_s": 32 * k / (time.perf_counter() - t0), "cores": 1, "num_envs": 32,
+                                "what": "reference vec-env stack restated on the CPU oracle (oracle/vec_env.py), "
+                                        "LevelBasedForaging-v3, serial stepping as ppo/worker.py:51"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,39 +506,14 @@ def main():
                "sample": f"{r['env_steps']} env-steps of the same random-action depth-{DEPTH} Driving-v1 sweep in "
                          f"{r['seconds']:.1f} s, one Python process per core (the reference's model is pure Python)"}
 
-    # ---- PPO vector-env collection (configs[4] shape: 65 536 envs over 8 GPUs = 8 192 per GPU;
-    # also a large batch to show the HBM-bound regime).  LBF-v3 is not built yet: Driving-v1 here.
+    # ---- PPO vector-env collection (BASELINE.json configs[4]: LevelBasedForaging-v3, 65 536 envs over
+    # 8 GPUs = 8 192 per GPU, 64 rollout steps, uniform actions; plus a large batch that shows the
+    # HBM-bound regime, and Driving-v1 for comparison).
     vec = None
     try:
         if args.only_sweep:
             raise RuntimeError("skipped (--only-sweep)")
-        from posggym_baselines_b200.vector import BatchedVecEnv
-        from posggym_baselines_b200.envs.driving import DrivingModel as _DM
-
-        vm = _DM(device=dev)
-        vec = {"env": "Driving-v1 (LevelBasedForaging-v3 not built yet)", "obs_dim": 124, "rollout_steps": 64}
-        for label, nv in (("envs_8192_per_gpu", 8192), ("envs_1048576_per_gpu", 1 << 20)):
-            ve = BatchedVecEnv(vm, nv, seed=seed, env_offset=rank * nv)
-            ve.reset()
-            acts = torch.randint(0, 5, (64, nv * 2), device=dev, dtype=torch.int64)
-            for k in range(8):
-                ve._global_step += 1
-                ve._launch(acts[k], 0)
-            barrier()
-            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            v0.record()
-            for k in range(64):      # num_rollout_steps = 64 (exp_utils.py:81)
-                ve._global_step += 1
-                ve._launch(acts[k], 0)
-            v1.record()
-            barrier()
-            vms = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(vms, op=dist.ReduceOp.MAX)
-            bytes_per = 8 + 16 + 8 + 2 * 124 * 4 + 8 + 2 + 2 + 1 + 8 + 4
-            vec[label] = {"env_steps_per_s": world * nv * 64 / (vms.item() / 1e3), "us_per_step": 1e3 * vms.item() / 64,
-                          "hbm_gbs": bytes_per * nv * 64 / (vms.item() / 1e3) / 1e9, "bytes_per_env_step": bytes_per}
-            del ve
+        vec = bench_vec_env(dev, rank, world, seed, barrier, cpu=(rank == 0 and world == 1 and not args.no_cpu))
     except Exception as ex:
         vec = {"error": repr(ex)}
 

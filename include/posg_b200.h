@@ -147,6 +147,15 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
 int posg_pp_create(int grid_size, const char* block_rows, int num_predators, int num_prey,
                    int cooperative, int prey_strength, int obs_dim, posg_model_t* out);
 
+/* posggym LevelBasedForagingModel.__init__ (posggym.make("LevelBasedForaging-v3", ...),
+ * baseline_exps/env_data/LevelBasedForaging-v3/env_kwargs.yaml): static layout given as
+ * food cells and player start cells (x | y << 4).  State: 2 x uint32 (players + total food
+ * level spawned; eight 3-bit food levels); observation: 2 x uint64 per agent (the 30-entry
+ * tuple observation, 3-bit fields, see csrc/lbf.cuh); no step noise (one dummy word). */
+int posg_lbf_create(int size, int num_agents, int max_agent_level, int max_food, int sight,
+                    int force_coop, int normalize_reward, const uint8_t* food_xy,
+                    const uint8_t* player_xy, posg_model_t* out);
+
 /* model.sample_initial_state (mcts.py:191).  picks: explicit noise (uint8 per pick). */
 int posg_model_sample_initial_state(posg_model_t m, int64_t n, const uint8_t* picks, uint64_t seed,
                                     uint64_t particle_offset, uint32_t* state_out, void* stream);

@@ -107,3 +107,43 @@ def pp_rollout(model, state, ego: str, max_steps: int, discount: float, seed: in
         if ts.terminations[ego] or ts.truncations[ego] or ts.all_done:
             break
     return float(agent_return), k, state
+
+
+# ---- LevelBasedForaging-v3 conventions (LBFSim in posggym_baselines_b200/csrc/lbf.cuh) ----
+def lbf_step_noise(seed: int, particles, step: int):
+    """actions [n, 2]: block (particle, step, 0xA0) word x -> idx = floor(x * 36 / 2**32),
+    a0 = idx % 6, a1 = idx // 6.  The LBF transition itself takes no noise."""
+    particles = np.asarray(particles, dtype=np.uint64)
+    w = P.philox_block(seed, particles, step, P.STREAM_STEP)
+    idx = P.uniform_below(w[0], 36)
+    a1 = idx // 6
+    a0 = idx - 6 * a1
+    return np.stack([a0, a1], axis=-1)
+
+
+def lbf_initial_picks(model, seed: int, particles):
+    """Picks as the kernel derives them: block (particle, 0, 0xB0) words x, y -> player
+    levels, z, w -> foods 0, 1; block (.., 0xB1) -> foods 2..5; block (.., 0xB2) words x, y ->
+    foods 6, 7."""
+    particles = np.asarray(particles, dtype=np.uint64)
+    a = P.philox_block(seed, particles, 0, P.STREAM_INIT)
+    b = P.philox_block(seed, particles, 0, P.STREAM_INIT2)
+    c = P.philox_block(seed, particles, 0, 0xB2)
+    p0 = P.uniform_below(a[0], model.max_agent_level)
+    p1 = P.uniform_below(a[1], model.max_agent_level)
+    bound = np.ones_like(p0) if model.force_coop else p0 + p1 + 2
+    foods = [P.uniform_below(w, bound) for w in (a[2], a[3], b[0], b[1], b[2], b[3], c[0], c[1])]
+    return np.stack([p0, p1, *foods], axis=-1)
+
+
+def lbf_rollout(model, state, ego: str, max_steps: int, discount: float, seed: int, particle: int, step0: int = 0):
+    agent_return, k = 0, 0
+    while k < max_steps:
+        acts = lbf_step_noise(seed, np.asarray([particle], dtype=np.uint64), step0 + k)
+        ts = model.step_with_noise(state, {"0": int(acts[0, 0]), "1": int(acts[0, 1])}, None)
+        agent_return += discount**k * ts.rewards[ego]
+        state = ts.state
+        k += 1
+        if ts.terminations[ego] or ts.truncations[ego] or ts.all_done:
+            break
+    return float(agent_return), k, state

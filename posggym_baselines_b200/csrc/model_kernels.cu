@@ -9,6 +9,7 @@
 #include "common.h"
 #include "generic_kernels.cuh"
 #include "pp.cuh"
+#include "lbf.cuh"
 
 namespace posg {
 
@@ -94,6 +95,7 @@ using namespace posg;
 #define MODEL_DISPATCH(m, CALL)                                                   \
   switch ((m)->kind) {                                                            \
     case KIND_PREDATOR_PREY: { using M = PPSim; CALL; } break;                    \
+    case KIND_LBF: { using M = LBFSim; CALL; } break;                             \
     default: set_error("posg_model_*: unsupported model kind %d", (m)->kind);     \
              return POSG_E_UNSUPPORTED;                                           \
   }
@@ -113,6 +115,36 @@ int posg_pp_create(int grid_size, const char* block_rows, int num_predators, int
   cudaError_t e = cudaGetDevice(&m->device);
   if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, sizeof(pp::Blob));
   if (e == cudaSuccess) e = cudaMemcpy(m->d_blob, h, sizeof(pp::Blob), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { int rc = cuda_fail(e, "model upload"); posg_model_destroy(m); return rc; }
+  *out = m;
+  return POSG_OK;
+}
+
+int posg_lbf_create(int size, int num_agents, int max_agent_level, int max_food, int sight, int force_coop,
+                    int normalize_reward, const uint8_t* food_xy, const uint8_t* player_xy, posg_model_t* out) {
+  POSG_REQUIRE(out && food_xy && player_xy, "null argument");
+  if (num_agents != lbf::NPL || max_food != lbf::NF) {
+    set_error("the sm_100a kernels are specialised for 2 players and 8 foods");
+    return POSG_E_UNSUPPORTED;
+  }
+  if (size < 3 || size > 16 || sight != 2 || max_agent_level < 1 || max_agent_level > 3) {
+    set_error("unsupported LBF geometry (size 3..16, sight 2, max_agent_level 1..3)");
+    return POSG_E_UNSUPPORTED;
+  }
+  int ndev = posg_device_count();
+  if (ndev < 0) return ndev;
+  lbf::Blob* h = (lbf::Blob*)calloc(1, sizeof(lbf::Blob));
+  memset(h->food_at, 255, sizeof(h->food_at));
+  for (int k = 0; k < lbf::NF; ++k) { h->food_xy[k] = food_xy[k]; h->food_at[food_xy[k]] = (uint8_t)k; }
+  for (int i = 0; i < lbf::NPL; ++i) h->player_xy[i] = player_xy[i];
+  h->size = (uint8_t)size; h->sight = (uint8_t)sight; h->max_agent_level = (uint8_t)max_agent_level;
+  h->force_coop = force_coop ? 1 : 0; h->normalize_reward = normalize_reward ? 1 : 0;
+  posg_model* m = new posg_model();
+  m->kind = KIND_LBF; m->num_agents = num_agents; m->blob_bytes = (int)sizeof(lbf::Blob);
+  m->h_blob = h; m->d_blob = nullptr;
+  cudaError_t e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, sizeof(lbf::Blob));
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_blob, h, sizeof(lbf::Blob), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { int rc = cuda_fail(e, "model upload"); posg_model_destroy(m); return rc; }
   *out = m;
   return POSG_OK;

@@ -7,6 +7,7 @@
 #include "common.h"
 #include "driving_sim.cuh"
 #include "pp.cuh"
+#include "lbf.cuh"
 #include "nested_sim.cuh"
 #include "search.cuh"
 #include "stage.cuh"
@@ -250,6 +251,7 @@ static bool kind_info(const posg_model* m, KindInfo* k) {
   switch (m->kind) {
     case KIND_DRIVING: *k = {DrivingSim::A, DrivingSim::OW, DrivingSim::SW}; return true;
     case KIND_PREDATOR_PREY: *k = {PPSim::A, PPSim::OW, PPSim::SW}; return true;
+    case KIND_LBF: *k = {LBFSim::A, LBFSim::OW, LBFSim::SW}; return true;
     case KIND_NESTED | KIND_DRIVING: *k = {DrivingSim::A, DrivingSim::OW, DrivingSim::SW + 1}; return true;
     case KIND_NESTED | KIND_PREDATOR_PREY: *k = {PPSim::A, PPSim::OW, PPSim::SW + 1}; return true;
     default: return false;
@@ -398,6 +400,8 @@ static int search_common(posg_model_t m, void* arena, int64_t cap_nodes, int64_t
       launch_search<DrivingSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
     case KIND_PREDATOR_PREY:
       launch_search<PPSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
+    case KIND_LBF:
+      launch_search<LBFSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
   }
   POSG_CUDA(cudaGetLastError());
@@ -612,6 +616,7 @@ static int reinvigorate_common(posg_model_t m, void* other_arena, int64_t other_
   switch (m->kind) {
     case KIND_DRIVING: REINV(DrivingSim, NoCtx{}); break;
     case KIND_PREDATOR_PREY: REINV(PPSim, NoCtx{}); break;
+    case KIND_LBF: REINV(LBFSim, NoCtx{}); break;
     case KIND_NESTED | KIND_DRIVING: {
       NestedSim<DrivingSim>::Ctx ctx;
       rc = nested_ctx<DrivingSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
@@ -674,6 +679,11 @@ int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_ob
     case KIND_PREDATOR_PREY:
       initial_belief_kernel<PPSim><<<1, belief::CTA, m->blob_bytes, s>>>(
           (const PPSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, ego_agent, d_obs, (long long)n_needed,
+          (long long)max_attempts, seed, draw_id, out_states, d_res);
+      break;
+    case KIND_LBF:
+      initial_belief_kernel<LBFSim><<<1, belief::CTA, m->blob_bytes, s>>>(
+          (const LBFSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, ego_agent, d_obs, (long long)n_needed,
           (long long)max_attempts, seed, draw_id, out_states, d_res);
       break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;

@@ -4,6 +4,7 @@
 #include "common.h"
 #include "driving_sim.cuh"
 #include "pp.cuh"
+#include "lbf.cuh"
 #include "vec_env.cuh"
 
 namespace posg {
@@ -24,6 +25,20 @@ static std::vector<vec::FlatDesc> build_desc(const posg_model* m) {
     block(0, 48, 1, 2); block(0, 49, 1, 2);               // dest_reached, crashed
   } else if (m->kind == KIND_PREDATOR_PREY) {
     for (int c = 0; c < 25; ++c) block(0, 2 * c, 2, 4);
+  } else if (m->kind == KIND_LBF) {
+    const lbf::Blob* b = (const lbf::Blob*)m->h_blob;
+    const int pw = b->size + 1, fw = b->size + 2;    // Discrete(size+1, start=-1), Discrete(size+2, start=-1)
+    const int plv = b->max_agent_level + 1, flv = 2 * b->max_agent_level + 1;
+    // players: self, then the other agent (fields hold value + 1)
+    block(0, 0, 3, pw); block(0, 3, 3, pw); block(0, 6, 2, plv);
+    block(0, 8, 3, pw); block(0, 11, 3, pw); block(0, 14, 2, plv);
+    // food slots: 0 in w0 low half @16; 1..3 in w0 high half; 4..6 in w1 low half; 7 in w1 high half
+    for (int slot = 0; slot < 8; ++slot) {
+      const int word = slot < 4 ? 0 : 1;
+      const int base = slot == 0 ? 16 : ((slot >= 1 && slot <= 3) ? 32 + 9 * (slot - 1)
+                                   : (slot <= 6 ? 9 * (slot - 4) : 32));
+      block(word, base, 3, fw); block(word, base + 3, 3, fw); block(word, base + 6, 3, flv);
+    }
   }
   return d;
 }
@@ -87,6 +102,10 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
       return launch_vec<DrivingSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed,
                                     global_step, env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out,
                                     trunc_out, done_out, stat_r, stat_l, s);
+    case KIND_LBF:
+      return launch_vec<LBFSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed, global_step,
+                                env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out, trunc_out,
+                                done_out, stat_r, stat_l, s);
     case KIND_PREDATOR_PREY:
       return launch_vec<PPSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed, global_step,
                                env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out, trunc_out,

@@ -68,4 +68,8 @@ def make(env_id: str, **kwargs) -> Env:
         from posggym_baselines_b200.envs.predator_prey import PredatorPreyModel
 
         return Env(PredatorPreyModel(**kwargs), max_steps)
+    if env_id == "LevelBasedForaging-v3":
+        from posggym_baselines_b200.envs.lbf import LBFModel
+
+        return Env(LBFModel(**kwargs), max_steps)
     raise KeyError(f"{env_id!r} is not available in posggym_baselines_b200")

@@ -219,3 +219,102 @@ def test_oracle_reproduces_golden(driving):
     # the golden set exercises the interesting branches
     assert (g["reward"] == -1.0).any() and (g["reward"] > 0.5).any() and g["all_done"].any()
     assert ((g["reward"] < 0) & (g["reward"] > -1)).any()   # crash with progress in the same step
+
+
+# ---------------------------------------------------------------- LevelBasedForaging-v3
+@pytest.fixture(scope="module")
+def lbf(oracle_env):
+    from oracle.lbf import LevelBasedForagingModel
+
+    return LevelBasedForagingModel()
+
+
+def test_lbf_obs_width_and_actions(lbf, reference_fixtures):
+    from gymnasium import spaces
+
+    fx = reference_fixtures["LevelBasedForaging-v3"]
+    assert spaces.flatdim(lbf.observation_spaces["0"]) == fx["obs_dim"] == 300
+    assert lbf.action_spaces["0"].n == fx["num_actions"] == 6
+    assert fx["env_kwargs"]["static_layout"] is True and fx["env_kwargs"]["observation_mode"] == "tuple"
+
+
+def test_lbf_active_inputs_and_random_play(lbf, reference_fixtures):
+    """(1) the oracle never fires a one-hot input that never received gradient while the
+    shipped BR policies trained (Adam exp_avg_sq mask); (2) uniform-random joint play matches
+    div_results.csv (100 episodes there: 0.0597 +- 0.088 / 0.0158 +- 0.041)."""
+    from gymnasium import spaces
+
+    fx = reference_fixtures["LevelBasedForaging-v3"]
+    expected = np.array([c == "1" for c in fx["active_inputs"]])
+    sp = lbf.observation_spaces["0"]
+    seen = np.zeros(300, bool)
+    rng = random.Random(0)
+    lbf.seed(0)
+    rets = [[], []]
+    for _ in range(1500):
+        s = lbf.sample_initial_state()
+        o = lbf.sample_initial_obs(s)
+        r = [0.0, 0.0]
+        for t in range(50):
+            for i in lbf.possible_agents:
+                seen |= spaces.flatten(sp, o[i]).astype(bool)
+            ts = lbf.step(s, {i: rng.randrange(6) for i in lbf.possible_agents})
+            s, o = ts.state, ts.observations
+            r[0] += ts.rewards["0"]; r[1] += ts.rewards["1"]
+            if ts.all_done:
+                break
+        rets[0].append(r[0]); rets[1].append(r[1])
+    assert not (seen & ~expected).any(), np.nonzero(seen & ~expected)
+    # structure of the mask: self x / y one-hots fire only at value `sight` (index sight + 1)
+    assert list(np.nonzero(expected[0:11])[0]) == [3] and list(np.nonzero(expected[11:22])[0]) == [3]
+    assert (seen & expected).sum() >= 0.9 * expected.sum()
+    for k, ref in enumerate(fx["random_vs_random"]):
+        se = ref["episode_reward_std"] / 10
+        assert abs(np.mean(rets[k]) - ref["episode_reward_mean"]) < 3 * se, (k, np.mean(rets[k]))
+
+
+def test_lbf_reward_lattice(lbf, reference_fixtures):
+    """Episode returns are sums of level*food_level/(loader level sum * spawned): rationals in
+    [0, 1]; both agents together never collect more than 1 per episode, exactly 1 when every
+    food is loaded."""
+    from fractions import Fraction
+
+    from tests.golden.make_golden import lbf_greedy_action
+
+    fx = reference_fixtures["LevelBasedForaging-v3"]["lattice"]
+    assert fx["max_len"] == 50
+    assert all(0 < Fraction(r) <= 1 for r, _ in fx["top_returns"])
+    rng = random.Random(4)
+    lbf.seed(4)
+    finished = 0
+    for _ in range(150):
+        s = lbf.sample_initial_state()
+        tot = Fraction(0)
+        for t in range(200):
+            a = {i: lbf_greedy_action(lbf, s, int(i), rng) for i in lbf.possible_agents}
+            before = s
+            ts = lbf.step(s, a)
+            s = ts.state
+            for i in lbf.possible_agents:
+                if ts.rewards[i]:
+                    tot += Fraction(ts.rewards[i]).limit_denominator(10000)
+            assert s.food_spawned == before.food_spawned
+            if ts.all_done:
+                finished += 1
+                assert tot == 1
+                break
+        assert tot <= 1
+    assert finished > 20
+
+
+def test_lbf_oracle_reproduces_golden(lbf):
+    from tests.golden.make_golden import lbf_fields, lbf_state
+
+    g = golden("lbf_step.npz")
+    idx = np.random.default_rng(0).choice(len(g["state"]), 800, replace=False)
+    for i in idx:
+        ts = lbf.step(lbf_state(lbf, g["state"][i]), {"0": int(g["action"][i, 0]), "1": int(g["action"][i, 1])})
+        assert lbf_fields(ts.state) == g["next_state"][i].tolist()
+        assert [list(ts.observations[a]) for a in ("0", "1")] == g["obs"][i].tolist()
+        assert [ts.rewards[a] for a in ("0", "1")] == g["reward"][i].tolist()
+        assert ts.all_done == bool(g["all_done"][i])
