@@ -14,6 +14,16 @@ struct DrivingSim {
   static constexpr int NW = 1;   // explicit noise words per step (processing order)
   struct State { uint32_t w[SW]; };
 
+  // flattened-observation fields (gymnasium.spaces.flatten order of the observation tuple):
+  // 15 local cells, speed, x, y, dest x, dest y, dest_reached, crashed.  Returns
+  // 32-bit half of the packed observation | shift inside the half << 8 | bits << 16.
+  static constexpr int NFIELD = 22;
+  __host__ __device__ static constexpr uint32_t obs_field(int f) {
+    return f < 16 ? (0u | ((uint32_t)(2 * f) << 8) | (2u << 16))
+         : f < 20 ? (1u | ((uint32_t)(4 * (f - 16)) << 8) | (4u << 16))
+                  : (1u | ((uint32_t)(16 + (f - 20)) << 8) | (1u << 16));
+  }
+
   // ---- batch concept (generic_kernels.cuh / vec_env.cuh) ---------------------------
   __device__ static __forceinline__ void step_all(const Blob& B, State& s, const int (&act)[NAG],
                                                   const uint32_t (&noise)[NW], unsigned long long (&obs)[NAG][OW],

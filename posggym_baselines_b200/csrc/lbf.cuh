@@ -181,6 +181,20 @@ struct LBFSim {
   static constexpr int A = 6, OW = 2, SW = 2, NAG = 2, NW = 1, NPICK = 10;
   struct State { uint32_t w[SW]; };
 
+  // flattened-observation fields: (x, y, level) of self, the other player, then the eight
+  // food slots; coordinate fields hold value + 1 = the one-hot index of Discrete(.., start=-1)
+  // (see DrivingSim::obs_field for the encoding of the return value)
+  static constexpr int NFIELD = 30;
+  __host__ __device__ static constexpr uint32_t obs_field(int f) {
+    if (f < 6) {
+      const int sh = f == 0 ? 0 : f == 1 ? 3 : f == 2 ? 6 : f == 3 ? 8 : f == 4 ? 11 : 14;
+      return 0u | ((uint32_t)sh << 8) | ((f == 2 || f == 5 ? 2u : 3u) << 16);
+    }
+    const int slot = (f - 6) / 3, c = (f - 6) % 3;
+    const int half = slot == 0 ? 0 : (slot + 2) / 3, off = slot == 0 ? 16 : 9 * ((slot - 1) % 3);
+    return (uint32_t)half | ((uint32_t)(off + 3 * c) << 8) | (3u << 16);
+  }
+
   __device__ static __forceinline__ void step_all(const Blob& B, State& s, const int (&act)[NAG],
                                                   const uint32_t (&)[NW], unsigned long long (&obs)[NAG][OW],
                                                   double (&rew)[NAG], uint32_t& flags, bool& was_live) {

@@ -234,6 +234,12 @@ struct PPSim {
   static constexpr int A = 5, OW = 1, SW = 2, NAG = 2, NW = 3, NPICK = 5;
   struct State { uint32_t w[SW]; };
 
+  // flattened-observation fields: the 25 window cells, two bits each (see DrivingSim::obs_field)
+  static constexpr int NFIELD = 25;
+  __host__ __device__ static constexpr uint32_t obs_field(int f) {
+    return f < 16 ? (0u | ((uint32_t)(2 * f) << 8) | (2u << 16)) : (1u | ((uint32_t)(2 * (f - 16)) << 8) | (2u << 16));
+  }
+
   // explicit-noise joint step (model.step): obs / rewards for every agent
   __device__ static __forceinline__ void step_all(const Blob& B, State& s, const int (&act)[NAG],
                                                   const uint32_t (&noise)[NW],

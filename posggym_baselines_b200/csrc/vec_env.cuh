@@ -5,8 +5,14 @@
 //   model.step -> TimeLimit truncation -> episode statistics -> auto-reset of finished
 //   envs (the reset observation is returned) -> one-hot flattened float32 observations
 //   stacked env-major (row = env * num_agents + agent).
-// One thread steps one env; the CTA then expands its packed observations to one-hot
-// float rows cooperatively so that every global store is a coalesced 128-byte line.
+// A CTA of NT threads works on chunks of EPC envs.  Phase 1: one thread steps one env and
+// leaves the observation of each agent as a row of field bytes in shared memory.  Phase 2: all
+// threads expand the chunk's rows to one-hot floats, one 16-byte store per thread per iteration
+// (consecutive threads -> consecutive float4s: every warp store covers 512 contiguous bytes).
+// Large batches run <EPC = NT = 128> (every thread steps an env, no idle lanes in phase 1);
+// small, latency-bound batches run <16 or 32 envs, 256 threads> so that every SM gets work.
+// The output (2 x 300 floats per env for LevelBasedForaging-v3) is a pure write stream and the
+// kernel is HBM-write bound; the stores are streaming (st.global.cs).
 #pragma once
 #include <stdint.h>
 
@@ -16,18 +22,41 @@
 namespace posg {
 namespace vec {
 
-constexpr int THREADS = 128;
-constexpr int MAX_FLAT = 320;   // widest flattened per-agent observation supported
+constexpr int MAX_FLAT = 512;     // widest flattened per-agent observation supported (floats)
+constexpr int MAX_FIELDS = 32;    // observation fields (one byte each) per row
+constexpr int ROW_WORDS = 10;     // 32 field bytes + 8 bytes of padding (the gather reads two words)
 
-// one-hot descriptor of a flattened position: which packed word, shift, mask, hot value
-struct FlatDesc { uint8_t word, shift, mask, value; };
+// Descriptor of one float4 (4 consecutive flattened positions of a row):
+//   x = the four one-hot offsets inside their fields, one byte each
+//   y = first field word (field >> 2 of position 0) | PRMT selector of the four field bytes << 8
+struct Quad { uint32_t offs, ctrl; };
 
 template <class M>
-__global__ void __launch_bounds__(THREADS)
+__device__ __forceinline__ void field_bytes(const unsigned long long (&obs)[M::OW], uint32_t (&fw)[MAX_FIELDS / 4]) {
+  uint32_t h[2 * M::OW];
+#pragma unroll
+  for (int k = 0; k < M::OW; ++k) { h[2 * k] = (uint32_t)obs[k]; h[2 * k + 1] = (uint32_t)(obs[k] >> 32); }
+#pragma unroll
+  for (int w = 0; w < MAX_FIELDS / 4; ++w) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int f = 4 * w + b;
+      if (f < M::NFIELD) {
+        const uint32_t d = M::obs_field(f);
+        v |= ((h[d & 255u] >> ((d >> 8) & 255u)) & ((1u << (d >> 16)) - 1u)) << (8 * b);
+      }
+    }
+    fw[w] = v;
+  }
+}
+
+template <class M, int EPC, int NT>
+__global__ void __launch_bounds__(NT)
 vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
                 uint32_t* __restrict__ state, uint16_t* __restrict__ ep_t, double* __restrict__ ep_ret,
                 uint32_t* __restrict__ ep_count, const long long* __restrict__ actions,
-                const FlatDesc* __restrict__ desc, int flat_dim, uint64_t seed, uint32_t global_step,
+                const Quad* __restrict__ desc, int flat_dim, uint64_t seed, uint32_t global_step,
                 uint64_t env_offset, int max_episode_steps, int reset_only,
                 float* __restrict__ obs_out, float* __restrict__ rew_out, uint8_t* __restrict__ term_out,
                 uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out, float* __restrict__ stat_r,
@@ -35,28 +64,20 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
-  __shared__ unsigned long long s_obs[THREADS * NAG * OW];
-  __shared__ FlatDesc s_desc[MAX_FLAT];
-  for (int p = threadIdx.x; p < flat_dim; p += THREADS) s_desc[p] = desc[p];
+  static_assert(M::NFIELD <= MAX_FIELDS, "too many observation fields");
+  __shared__ uint32_t s_fields[EPC * NAG * ROW_WORDS];
+  __shared__ Quad s_desc[MAX_FLAT / 4];
+  const int Q = flat_dim >> 2;                 // float4s per row
+  for (int p = threadIdx.x; p < Q; p += NT) s_desc[p] = desc[p];
   stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
-  // per-lane descriptors of positions lane, lane + 32, ...: shift (mod 32) | mask << 8 |
-  // value << 16 | 32-bit half index (2 * word + (shift >= 32)) << 24
-  constexpr int MAXK = MAX_FLAT / 32;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int K = (flat_dim + 31) / 32;
-  uint32_t ldesc[MAXK];
-#pragma unroll
-  for (int k = 0; k < MAXK; ++k) {
-    const int p = lane + 32 * k;
-    const FlatDesc d = s_desc[p < flat_dim ? p : 0];
-    ldesc[k] = (uint32_t)(d.shift & 31) | ((uint32_t)d.mask << 8) | ((uint32_t)d.value << 16) |
-               ((uint32_t)(2 * d.word + (d.shift >> 5)) << 24);
-  }
+  const int tid = threadIdx.x;
+  const int row0 = tid / Q, q0 = tid - row0 * Q;      // this thread's first float4 of a chunk
+  const int dr = NT / Q, dq = NT - dr * Q;  // and its stride
 
-  for (int64_t base = (int64_t)blockIdx.x * THREADS; base < n; base += (int64_t)gridDim.x * THREADS) {
-    const int64_t i = base + threadIdx.x;
-    if (i < n) {
+  for (int64_t base = (int64_t)blockIdx.x * EPC; base < n; base += (int64_t)gridDim.x * EPC) {
+    const int64_t i = base + tid;
+    if (tid < EPC && i < n) {
       typename M::State s;
       unsigned long long obs[NAG][OW];
       const uint64_t env = env_offset + (uint64_t)i;
@@ -106,34 +127,32 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
 #pragma unroll
       for (int k = 0; k < SW; ++k) state[i * SW + k] = s.w[k];
 #pragma unroll
-      for (int a = 0; a < NAG; ++a)
+      for (int a = 0; a < NAG; ++a) {
+        uint32_t fw[MAX_FIELDS / 4];
+        field_bytes<M>(obs[a], fw);
+        uint32_t* dst = s_fields + (tid * NAG + a) * ROW_WORDS;
 #pragma unroll
-        for (int k = 0; k < OW; ++k) s_obs[(threadIdx.x * NAG + a) * OW + k] = obs[a][k];
+        for (int w = 0; w < (M::NFIELD + 3) / 4; ++w) dst[w] = fw[w];
+      }
     }
     __syncthreads();
-    // cooperative one-hot expansion: one warp per (env, agent) row, lane L owns positions
-    // L, L+32, ... (their descriptors are decoded once, above) -> every store instruction
-    // writes 32 consecutive floats
-    const int rows = (int)(((n - base) < THREADS ? (n - base) : THREADS) * NAG);
-    float* out = obs_out + base * NAG * flat_dim;
-    for (int row = warp; row < rows; row += THREADS / 32) {
-      uint32_t w32[2 * OW];
-#pragma unroll
-      for (int k = 0; k < OW; ++k) {
-        const unsigned long long w = s_obs[row * OW + k];
-        w32[2 * k] = (uint32_t)w; w32[2 * k + 1] = (uint32_t)(w >> 32);
-      }
-      float* orow = out + (int64_t)row * flat_dim + lane;
-#pragma unroll
-      for (int k = 0; k < MAXK; ++k) {
-        if (k < K && lane + 32 * k < flat_dim) {
-          const uint32_t d = ldesc[k];
-          uint32_t ww = w32[0];
-#pragma unroll
-          for (int h = 1; h < 2 * OW; ++h) ww = ((d >> 24) == (uint32_t)h) ? w32[h] : ww;
-          orow[32 * k] = (((ww >> (d & 31u)) & ((d >> 8) & 255u)) == ((d >> 16) & 255u)) ? 1.0f : 0.0f;
-        }
-      }
+    // one-hot expansion of the chunk: float4 j of the chunk = (row j / Q, quad j % Q)
+    const int64_t left = n - base;
+    const int total = (int)(left < EPC ? left : EPC) * NAG * Q;
+    float4* out4 = reinterpret_cast<float4*>(obs_out + base * NAG * flat_dim);
+    int row = row0, q = q0;
+    for (int j = tid; j < total; j += NT) {
+      const Quad d = s_desc[q];
+      const uint32_t* fr = s_fields + row * ROW_WORDS + (d.ctrl & 255u);
+      const uint32_t x = __byte_perm(fr[0], fr[1], d.ctrl >> 8) ^ d.offs;   // byte k == 0 <=> position k is hot
+      float4 o;
+      o.x = (x & 0x000000FFu) ? 0.0f : 1.0f;
+      o.y = (x & 0x0000FF00u) ? 0.0f : 1.0f;
+      o.z = (x & 0x00FF0000u) ? 0.0f : 1.0f;
+      o.w = (x & 0xFF000000u) ? 0.0f : 1.0f;
+      __stcs(out4 + j, o);
+      q += dq; row += dr;
+      if (q >= Q) { q -= Q; ++row; }
     }
     __syncthreads();
   }

@@ -9,67 +9,91 @@
 
 namespace posg {
 
-// gymnasium.spaces.flatten order of each model's per-agent observation (one-hot blocks)
-static std::vector<vec::FlatDesc> build_desc(const posg_model* m) {
-  std::vector<vec::FlatDesc> d;
-  auto block = [&](int word, int shift, int bits, int width) {
-    for (int v = 0; v < width; ++v)
-      d.push_back({(uint8_t)word, (uint8_t)shift, (uint8_t)((1u << bits) - 1u), (uint8_t)v});
-  };
+// One-hot widths of the flattened-observation fields (gymnasium.spaces.flatten order of each
+// model's per-agent observation tuple); field f's bits inside the packed observation are
+// M::obs_field(f).
+static std::vector<int> field_widths(const posg_model* m) {
+  std::vector<int> w;
   if (m->kind == KIND_DRIVING) {
     const driving::Blob* b = (const driving::Blob*)m->h_blob;
-    for (int c = 0; c < 15; ++c) block(0, 2 * c, 2, 4);  // local cells
-    block(0, 30, 2, 4);                                   // speed
-    block(0, 32, 4, b->width); block(0, 36, 4, b->height);   // current coord
-    block(0, 40, 4, b->width); block(0, 44, 4, b->height);   // destination coord
-    block(0, 48, 1, 2); block(0, 49, 1, 2);               // dest_reached, crashed
+    for (int c = 0; c < 15; ++c) w.push_back(4);          // local cells
+    w.push_back(4);                                        // speed
+    w.push_back(b->width); w.push_back(b->height);         // current coord
+    w.push_back(b->width); w.push_back(b->height);         // destination coord
+    w.push_back(2); w.push_back(2);                        // dest_reached, crashed
   } else if (m->kind == KIND_PREDATOR_PREY) {
-    for (int c = 0; c < 25; ++c) block(0, 2 * c, 2, 4);
+    for (int c = 0; c < 25; ++c) w.push_back(4);
   } else if (m->kind == KIND_LBF) {
     const lbf::Blob* b = (const lbf::Blob*)m->h_blob;
-    const int pw = b->size + 1, fw = b->size + 2;    // Discrete(size+1, start=-1), Discrete(size+2, start=-1)
-    const int plv = b->max_agent_level + 1, flv = 2 * b->max_agent_level + 1;
-    // players: self, then the other agent (fields hold value + 1)
-    block(0, 0, 3, pw); block(0, 3, 3, pw); block(0, 6, 2, plv);
-    block(0, 8, 3, pw); block(0, 11, 3, pw); block(0, 14, 2, plv);
-    // food slots: 0 in w0 low half @16; 1..3 in w0 high half; 4..6 in w1 low half; 7 in w1 high half
-    for (int slot = 0; slot < 8; ++slot) {
-      const int word = slot < 4 ? 0 : 1;
-      const int base = slot == 0 ? 16 : ((slot >= 1 && slot <= 3) ? 32 + 9 * (slot - 1)
-                                   : (slot <= 6 ? 9 * (slot - 4) : 32));
-      block(word, base, 3, fw); block(word, base + 3, 3, fw); block(word, base + 6, 3, flv);
-    }
+    // players: Discrete(size+1, start=-1) x 2, Discrete(max_agent_level+1);
+    // foods: Discrete(size+2, start=-1) x 2, Discrete(2*max_agent_level+1)
+    for (int i = 0; i < lbf::NPL; ++i) { w.push_back(b->size + 1); w.push_back(b->size + 1); w.push_back(b->max_agent_level + 1); }
+    for (int k = 0; k < lbf::NF; ++k) { w.push_back(b->size + 2); w.push_back(b->size + 2); w.push_back(2 * b->max_agent_level + 1); }
   }
-  return d;
+  return w;
 }
 
 static int ensure_desc(posg_model* m) {
   if (m->d_flat_desc) return POSG_OK;
-  std::vector<vec::FlatDesc> d = build_desc(m);
-  if (d.empty() || d.size() > (size_t)vec::MAX_FLAT) { set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED; }
-  POSG_CUDA(cudaMalloc(&m->d_flat_desc, d.size() * sizeof(vec::FlatDesc)));
-  POSG_CUDA(cudaMemcpy(m->d_flat_desc, d.data(), d.size() * sizeof(vec::FlatDesc), cudaMemcpyHostToDevice));
-  m->flat_dim = (int)d.size();
+  const std::vector<int> widths = field_widths(m);
+  std::vector<uint8_t> field, offs;    // per flattened position: its field and the one-hot offset in it
+  for (size_t f = 0; f < widths.size(); ++f)
+    for (int v = 0; v < widths[f]; ++v) { field.push_back((uint8_t)f); offs.push_back((uint8_t)v); }
+  const size_t flat = field.size();
+  if (flat == 0 || widths.size() > (size_t)vec::MAX_FIELDS) { set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED; }
+  if (flat % 4 != 0 || flat > (size_t)vec::MAX_FLAT) {
+    set_error("flattened observation width %d is not a multiple of 4 (or > %d): unsupported by the vec-env kernel",
+              (int)flat, vec::MAX_FLAT);
+    return POSG_E_UNSUPPORTED;
+  }
+  std::vector<vec::Quad> d(flat / 4);
+  for (size_t q = 0; q < d.size(); ++q) {
+    const uint32_t w0 = field[4 * q] >> 2;
+    uint32_t sel = 0, o = 0;
+    for (int k = 0; k < 4; ++k) {
+      sel |= (uint32_t)(field[4 * q + k] - 4 * w0) << (4 * k);   // PRMT nibble: byte index in {fr[0], fr[1]}
+      o |= (uint32_t)offs[4 * q + k] << (8 * k);
+    }
+    d[q] = {o, w0 | (sel << 8)};
+  }
+  POSG_CUDA(cudaMalloc(&m->d_flat_desc, d.size() * sizeof(vec::Quad)));
+  POSG_CUDA(cudaMemcpy(m->d_flat_desc, d.data(), d.size() * sizeof(vec::Quad), cudaMemcpyHostToDevice));
+  m->flat_dim = (int)flat;
   return POSG_OK;
 }
 
-template <class M>
-static int launch_vec(posg_model* m, int64_t n, uint32_t* state, uint16_t* ep_t, double* ep_ret, uint32_t* ep_count,
-                      const long long* actions, uint64_t seed, uint32_t global_step, uint64_t env_offset,
-                      int max_steps, int reset_only, float* obs_out, float* rew_out, uint8_t* term_out,
-                      uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int* stat_l, cudaStream_t s) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec::vec_step_kernel<M>, vec::THREADS, m->blob_bytes) !=
-          cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
-  const int64_t need = (n + vec::THREADS - 1) / vec::THREADS;
+template <class M, int EPC, int NT>
+static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* ep_t, double* ep_ret, uint32_t* ep_count,
+                          const long long* actions, uint64_t seed, uint32_t global_step, uint64_t env_offset,
+                          int max_steps, int reset_only, float* obs_out, float* rew_out, uint8_t* term_out,
+                          uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int* stat_l, cudaStream_t s) {
+  static int per_sm_cache[64] = {0};
+  int& per_sm = per_sm_cache[m->device & 63];
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec::vec_step_kernel<M, EPC, NT>, NT,
+                                                      m->blob_bytes) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError(); per_sm = 1;
+    }
+  }
+  const int64_t need = (n + EPC - 1) / EPC;
   const int64_t cap = (int64_t)sm_count() * per_sm;
   const int grid = (int)(need < cap ? need : cap);
-  vec::vec_step_kernel<M><<<grid, vec::THREADS, m->blob_bytes, s>>>(
+  vec::vec_step_kernel<M, EPC, NT><<<grid, NT, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, ep_t, ep_ret, ep_count, actions,
-      (const vec::FlatDesc*)m->d_flat_desc, m->flat_dim, seed, global_step, env_offset, max_steps, reset_only,
+      (const vec::Quad*)m->d_flat_desc, m->flat_dim, seed, global_step, env_offset, max_steps, reset_only,
       obs_out, rew_out, term_out, trunc_out, done_out, stat_r, stat_l);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
+}
+
+// Small batches (the 8 192 envs per GPU of the reference-scale collector) are latency bound:
+// 16 / 32 envs per chunk spread them over every SM; large batches step one env per thread.
+template <class M, class... Args>
+static int launch_vec(posg_model* m, int64_t n, Args... args) {
+  const int64_t sms = sm_count();
+  if (n <= sms * 16 * 4) return launch_vec_epc<M, 16, 256>(m, n, args...);
+  if (n <= sms * 32 * 8) return launch_vec_epc<M, 32, 256>(m, n, args...);
+  return launch_vec_epc<M, 128, 128>(m, n, args...);
 }
 
 }  // namespace posg
@@ -96,6 +120,7 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
   POSG_REQUIRE(reset_only || (actions && rew_out && term_out && trunc_out && done_out && stat_r && stat_l),
                "step needs actions and every output buffer");
   POSG_REQUIRE(max_episode_steps > 0 && max_episode_steps < 65535, "bad max_episode_steps");
+  POSG_REQUIRE(((uintptr_t)obs_out & 15u) == 0, "obs_out must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   switch (m->kind) {
     case KIND_DRIVING:

@@ -59,19 +59,34 @@ class BatchedVecEnv:
         self._stat_l = torch.zeros(n, dtype=torch.int32, device=dev)
         self._t0 = torch.zeros(n, dtype=torch.float64, device=dev)
         self._global_step = 0
+        self._args = None
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
 
     @property
     def single_observation_shape(self):
         return (self.flat_dim,)
 
     def _launch(self, actions, reset_only: int):
-        with torch.cuda.device(self._b.device):
-            _lib.check(_lib.lib().posg_vec_step(
-                self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._ep_t), _lib.ptr(self._ep_ret),
-                _lib.ptr(self._ep_count), _lib.ptr(actions), self.seed, self._global_step, self.env_offset,
-                self.max_episode_steps, reset_only, _lib.ptr(self._obs), _lib.ptr(self._rew), _lib.ptr(self._term),
-                _lib.ptr(self._trunc), _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l),
-                _lib.stream_ptr()))
+        # hot loop of the collector: buffer pointers are cached (the buffers live as long as the
+        # env), the device guard is only entered when another device is current
+        if self._args is None:
+            self._fn = _lib.lib().posg_vec_step
+            self._args = (
+                (self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._ep_t), _lib.ptr(self._ep_ret),
+                 _lib.ptr(self._ep_count)),
+                (_lib.ptr(self._obs), _lib.ptr(self._rew), _lib.ptr(self._term), _lib.ptr(self._trunc),
+                 _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l)))
+        head, tail = self._args
+        a = None if actions is None else actions.data_ptr()
+        if torch.cuda.current_device() == self._dev_index:
+            rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps, reset_only,
+                          *tail, torch.cuda.current_stream().cuda_stream or None)
+        else:
+            with torch.cuda.device(self._b.device):
+                rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps,
+                              reset_only, *tail, torch.cuda.current_stream().cuda_stream or None)
+        if rc < 0:
+            _lib.check(rc)
 
     def _out(self, t):
         return t.cpu().numpy() if self.as_numpy else t
