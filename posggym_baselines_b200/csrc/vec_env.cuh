@@ -9,8 +9,9 @@
 // leaves the observation of each agent as a row of field bytes in shared memory.  Phase 2: all
 // threads expand the chunk's rows to one-hot floats, one 16-byte store per thread per iteration
 // (consecutive threads -> consecutive float4s: every warp store covers 512 contiguous bytes).
-// Large batches run <EPC = NT = 128> (every thread steps an env, no idle lanes in phase 1);
-// small, latency-bound batches run <16 or 32 envs, 256 threads> so that every SM gets work.
+// Large batches run <EPC = NT = 256> (every thread steps an env, no idle lanes in phase 1) with
+// one CTA per chunk, so the hardware block scheduler balances the SMs; small, latency-bound
+// batches run <16 or 32 envs, 256 threads> so that every SM gets work.
 // The output (2 x 300 floats per env for LevelBasedForaging-v3) is a pure write stream and the
 // kernel is HBM-write bound; the stores are streaming (st.global.cs).
 #pragma once
@@ -51,8 +52,8 @@ __device__ __forceinline__ void field_bytes(const unsigned long long (&obs)[M::O
   }
 }
 
-template <class M, int EPC, int NT>
-__global__ void __launch_bounds__(NT)
+template <class M, int EPC, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
                 uint32_t* __restrict__ state, uint16_t* __restrict__ ep_t, double* __restrict__ ep_ret,
                 uint32_t* __restrict__ ep_count, const long long* __restrict__ actions,

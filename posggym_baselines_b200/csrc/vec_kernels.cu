@@ -1,4 +1,5 @@
 // Vector-env entry points of the C-ABI (PPO rollout collector path).
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
@@ -62,7 +63,7 @@ static int ensure_desc(posg_model* m) {
   return POSG_OK;
 }
 
-template <class M, int EPC, int NT>
+template <class M, int EPC, int NT, int MINB>
 static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* ep_t, double* ep_ret, uint32_t* ep_count,
                           const long long* actions, uint64_t seed, uint32_t global_step, uint64_t env_offset,
                           int max_steps, int reset_only, float* obs_out, float* rew_out, uint8_t* term_out,
@@ -70,15 +71,19 @@ static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* e
   static int per_sm_cache[64] = {0};
   int& per_sm = per_sm_cache[m->device & 63];
   if (per_sm == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec::vec_step_kernel<M, EPC, NT>, NT,
+    // static row buffer + the staged model blob can exceed the 48 KB default
+    POSG_CUDA(cudaFuncSetAttribute(vec::vec_step_kernel<M, EPC, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   m->blob_bytes > 65536 ? m->blob_bytes : 65536));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec::vec_step_kernel<M, EPC, NT, MINB>, NT,
                                                       m->blob_bytes) != cudaSuccess || per_sm < 1) {
       cudaGetLastError(); per_sm = 1;
     }
   }
   const int64_t need = (n + EPC - 1) / EPC;
-  const int64_t cap = (int64_t)sm_count() * per_sm;
+  static const bool persistent = getenv("POSG_VEC_PERSISTENT") != nullptr;   // dev A/B switch
+  const int64_t cap = persistent ? (int64_t)sm_count() * per_sm : (int64_t)1 << 30;
   const int grid = (int)(need < cap ? need : cap);
-  vec::vec_step_kernel<M, EPC, NT><<<grid, NT, m->blob_bytes, s>>>(
+  vec::vec_step_kernel<M, EPC, NT, MINB><<<grid, NT, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, ep_t, ep_ret, ep_count, actions,
       (const vec::Quad*)m->d_flat_desc, m->flat_dim, seed, global_step, env_offset, max_steps, reset_only,
       obs_out, rew_out, term_out, trunc_out, done_out, stat_r, stat_l);
@@ -91,9 +96,9 @@ static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* e
 template <class M, class... Args>
 static int launch_vec(posg_model* m, int64_t n, Args... args) {
   const int64_t sms = sm_count();
-  if (n <= sms * 16 * 4) return launch_vec_epc<M, 16, 256>(m, n, args...);
-  if (n <= sms * 32 * 8) return launch_vec_epc<M, 32, 256>(m, n, args...);
-  return launch_vec_epc<M, 128, 128>(m, n, args...);
+  if (n <= sms * 16 * 4) return launch_vec_epc<M, 16, 256, 4>(m, n, args...);
+  if (n <= sms * 32 * 8) return launch_vec_epc<M, 32, 256, 4>(m, n, args...);
+  return launch_vec_epc<M, 256, 256, 4>(m, n, args...);
 }
 
 }  // namespace posg
