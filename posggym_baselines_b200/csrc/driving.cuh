@@ -34,15 +34,22 @@ struct alignas(16) Blob {
   uint8_t n_agents, obs_front, obs_back, obs_side;
   uint8_t obstacle_collisions, pad_[7];
   uint8_t win_lut[4][64];            // [facing][(dy+3)*8 + (dx+3)] -> window cell 0..14, 15 = outside
-  // control table [action*16 + speed*4 + facing] -> next speed | facing<<2 | move dir<<4 | cells<<6
-  uint8_t ctrl[80];
+  // control table [action*16 + speed*4 + facing] -> next facing | next speed << 2 | move2 row
+  // (move dir * 3 + cells moved) << 4.  80 bytes = 20 words: bank-conflict free.
+  uint8_t ctrl2[80];
+  // step noise table [floor(word * 50 / 2^32)] -> first mover's action | second mover's action
+  // << 3 | (vehicle 1 moves first) << 6 | a0 << 7 | a1 << 10.  25 words: bank-conflict free.
+  uint16_t noise_lut[56];
   // reward table [(D0*3 + progress)*4 + kind], kind 0 plain, 1 destination reached, 2 crash,
   // 3 already done (0.0): base + 0.5 * (progress / D0)
   double reward_tab[MAX_D0 * 3 * 4];
   uint8_t dist[MAX_CELLS][256];      // dist[dest][y*16+x]; 255 = unreachable
-  // move table [dir*256 + y*16 + x] -> cell after 1 step | cell after 2 steps << 8 |
-  // blocked at step 1 << 16 | blocked at step 2 << 17
-  uint32_t move_tab[4 * 256];
+  // move table [(move dir * 3 + cells moved) * 256 + y*16 + x], walls already resolved:
+  //   bits 0..7   cell reached if no vehicle is in the way
+  //   bits 8..15  cell after the first step (= start cell if that step is not made)
+  //   bit 16 / 17 step 1 / step 2 enters a free road cell (a vehicle may be standing there)
+  //   bit 18 / 19 step 1 / step 2 runs into a wall AND obstacle collisions count as crashes
+  uint32_t move2[12 * 256];
   // 30-bit local-cell codes of a lone vehicle (walls, own destination, ego cell):
   // obs_base[(dest*4 + facing) * 256 + y*16 + x]
   uint32_t obs_base[1];
@@ -73,48 +80,46 @@ __host__ __device__ __forceinline__ uint32_t vpack(int x, int y, int dir, int sp
 
 // ---- transition -------------------------------------------------------------------
 // One vehicle's move.  `other` is the only other vehicle (its current cell blocks).
-// Speed / heading arithmetic and the wall tests are table lookups (shared memory); what
-// remains is the interaction with the other vehicle.
-__device__ __forceinline__ void move_vehicle(const Blob& B, uint32_t& me, uint32_t& other, int a) {
-  const bool active = !vdone(me);  // reached / crashed earlier, or hit earlier this step
-  const uint32_t c = B.ctrl[a * 16 + ((me >> 8) & 15u)];
-  uint32_t nsp = c & 3u;
-  const uint32_t ndir = (c >> 2) & 3u, mdir = (c >> 4) & 3u, nmoves = c >> 6;
+// Speed / heading arithmetic and the wall tests are two table lookups (shared memory); what
+// remains is the interaction with the other vehicle.  a16 = action << 4.
+__device__ __forceinline__ void move_vehicle(const Blob& B, uint32_t& me, uint32_t& other, uint32_t a16) {
+  const uint32_t c = B.ctrl2[a16 | ((me >> 8) & 15u)];
   const uint32_t xy0 = me & 255u, oxy = other & 255u;
-  const uint32_t e = B.move_tab[(mdir << 8) | xy0];
-  const uint32_t c1 = e & 255u, c2 = (e >> 8) & 255u;
-  const bool b1 = (e >> 16) & 1u, b2 = (e >> 17) & 1u;
-  const bool h1 = !b1 && (c1 == oxy);
-  const bool try1 = active && nmoves >= 1u;
-  const bool ok1 = try1 && !b1 && !h1;
-  const bool h2 = !b2 && (c2 == oxy);
-  const bool try2 = ok1 && nmoves == 2u;
-  const bool ok2 = try2 && !b2 && !h2;
-  const uint32_t xy = ok2 ? c2 : (ok1 ? c1 : xy0);
-  const bool obst = (try1 && b1) || (try2 && b2);
-  const bool hit = (try1 && h1) || (try2 && h2);
-  const bool crashed = hit || (obst && B.obstacle_collisions);
-  nsp = crashed ? (uint32_t)STOPPED : nsp;
-  const uint32_t dest = (me >> 12) & 7u;
-  const uint32_t d = B.dist[dest][xy];
+  const uint32_t e = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(B.move2) +
+                                                        (((c & 0xF0u) << 6) + (xy0 << 2)));
+  const uint32_t cf = e & 255u, c1 = (e >> 8) & 255u;
+  const bool active = (me & 0x18000u) == 0u;   // not reached / crashed earlier, nor hit earlier this step
+  const bool h1 = (e & 0x10000u) && (c1 == oxy);
+  const bool h2 = !h1 && (e & 0x20000u) && (cf == oxy);
+  const bool hit_any = h1 || h2;
+  const uint32_t xy = h1 ? xy0 : (h2 ? c1 : cf);
+  const bool crashed = hit_any || (e & 0x40000u) || (!h1 && (e & 0x80000u));
+  const uint32_t dirsp = crashed ? (((c & 3u) << 8) | ((uint32_t)STOPPED << 10)) : ((c & 15u) << 8);
+  const uint32_t d = *(reinterpret_cast<const unsigned char*>(B.dist) + (((me >> 4) & 0x700u) | xy));
   const uint32_t mind = min((me >> 17) & 127u, d);
-  const uint32_t reached = (d == 0u) ? 1u : 0u;   // distance 0 <=> on the own destination
-  const uint32_t moved = xy | (ndir << 8) | (nsp << 10) | (me & (7u << 12)) | (reached << 15) |
-                         ((crashed ? 1u : 0u) << 16) | (mind << 17) | (me & (127u << 24));
+  uint32_t moved = xy | dirsp | (me & 0x7F007000u) | (mind << 17);
+  moved |= (d == 0u) ? 0x8000u : 0u;           // distance 0 <=> on the own destination
+  moved |= crashed ? 0x10000u : 0u;
   me = active ? moved : me;
   // the vehicle that was run into: stopped + crashed
-  other = hit ? ((other & ~(3u << 10)) | ((uint32_t)STOPPED << 10) | (1u << 16)) : other;
+  other = (active && hit_any) ? ((other & ~(3u << 10)) | ((uint32_t)STOPPED << 10) | (1u << 16)) : other;
+}
+
+// joint transition with pre-shifted actions: af16 / as16 = action << 4 of the vehicle that moves
+// first / second, sw = vehicle 1 moves first
+__device__ __forceinline__ void transition16(const Blob& B, uint32_t& v0, uint32_t& v1, uint32_t af16, uint32_t as16,
+                                             bool sw) {
+  uint32_t first = sw ? v1 : v0, second = sw ? v0 : v1;
+  move_vehicle(B, first, second, af16);
+  move_vehicle(B, second, first, as16);
+  v0 = sw ? second : first; v1 = sw ? first : second;
 }
 
 // joint transition of both vehicles; order_idx 0 -> vehicle 0 first, 1 -> vehicle 1 first
 __device__ __forceinline__ void transition(const Blob& B, uint32_t& v0, uint32_t& v1, int a0, int a1,
                                            int order_idx) {
   const bool sw = order_idx != 0;
-  uint32_t first = sw ? v1 : v0, second = sw ? v0 : v1;
-  const int af = sw ? a1 : a0, as = sw ? a0 : a1;
-  move_vehicle(B, first, second, af);
-  move_vehicle(B, second, first, as);
-  v0 = sw ? second : first; v1 = sw ? first : second;
+  transition16(B, v0, v1, (uint32_t)(sw ? a1 : a0) << 4, (uint32_t)(sw ? a0 : a1) << 4, sw);
 }
 
 // Reward of a vehicle given its state before / after the transition.  For a vehicle that

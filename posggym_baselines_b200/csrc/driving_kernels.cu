@@ -152,6 +152,62 @@ step_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
   }
 }
 
+// Fast path of model.step for the random-action sweep (BASELINE.json configs[1]): actions and
+// processing order from Philox, particle_offset a multiple of four, whole blocks of 128 envs.
+// A warp owns 128 consecutive envs; lane L steps envs 32 j + L (j = 0..3), so every warp-level
+// global access is one contiguous run (state 256 B, observations / rewards 512 B per
+// instruction: the minimum number of L1 wavefronts).  The step noise keeps the convention of
+// the general kernel -- Philox block (particle >> 2), word (particle & 3): lane L computes the
+// block of envs 4 L .. 4 L + 3 and the words are transposed through 512 B of shared memory per
+// warp.  Same results as step_kernel (tests/test_driving_gpu.py).
+constexpr int WARP_ENVS = 128;
+
+template <bool WRITE_ACTIONS, bool COUNT_LIVE>
+__global__ void __launch_bounds__(THREADS, STEP_MIN_CTAS)
+step_fast_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nblocks,
+                 const uint2* __restrict__ state_in, uint64_t seed, uint32_t step_idx, uint64_t group_offset,
+                 uint2* __restrict__ state_out, ulonglong2* __restrict__ obs_out, double2* __restrict__ rewards_out,
+                 uint8_t* __restrict__ flags_out, uchar2* __restrict__ actions_out,
+                 unsigned long long* __restrict__ live_count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  __shared__ alignas(16) uint32_t s_words[THREADS / 32][WARP_ENVS];
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const Blob& B = *reinterpret_cast<const Blob*>(smem_raw);
+  unsigned live = 0;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t wstride = gridDim.x * (THREADS / 32);
+  for (uint32_t wb = blockIdx.x * (THREADS / 32) + warp; wb < nblocks; wb += wstride) {
+    const uint32_t e0 = wb * WARP_ENVS + lane;     // this lane's first env
+    uint2 sv[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) sv[j] = __ldg(state_in + e0 + 32 * j);
+    const uint4 blk = philox_block(seed, group_offset + (uint64_t)wb * 32u + lane, step_idx, STREAM_STEP);
+    __syncwarp();
+    *reinterpret_cast<uint4*>(&s_words[warp][4 * lane]) = blk;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const uint32_t nz = B.noise_lut[__umulhi(s_words[warp][32 * j + lane], 50u)];
+      uint32_t v0 = sv[j].x, v1 = sv[j].y;
+      const uint32_t b0 = v0, b1 = v1;
+      if (COUNT_LIVE) live += ((b0 & 0x18000u) && (b1 & 0x18000u)) ? 0u : 1u;
+      transition16(B, v0, v1, (nz << 4) & 0x70u, (nz << 1) & 0x70u, (nz & 0x40u) != 0u);
+      const uint32_t e = e0 + 32 * j;
+      state_out[e] = make_uint2(v0, v1);
+      const uint32_t t0 = (v0 & 0x18000u) ? 1u : 0u, t1 = (v1 & 0x18000u) ? 1u : 0u;
+      flags_out[e] = (uint8_t)(t0 | (t1 << 1) | ((t0 & t1) ? POSG_FLAG_ALL_DONE : 0u));
+      if (WRITE_ACTIONS) actions_out[e] = make_uchar2((unsigned char)((nz >> 7) & 7u), (unsigned char)((nz >> 10) & 7u));
+      obs_out[e] = make_ulonglong2(observe(B, v0, v1), observe(B, v1, v0));
+      rewards_out[e] = make_double2(reward(B, b0, v0), reward(B, b1, v1));
+    }
+  }
+  if (COUNT_LIVE) {
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
+    if (lane == 0 && live) atomicAdd(live_count, (unsigned long long)live);
+  }
+}
+
 // ------------------------------------------------------------------ observe / initial state
 __global__ void __launch_bounds__(THREADS)
 observe_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
@@ -387,23 +443,35 @@ static Blob* build_blob(const char* grid_rows, int num_agents, int obs_front, in
         const int mdir = rev ? ((dir + 2) & 3) : tdir;
         const int ndir = rev ? dir : tdir;   // a reversing vehicle keeps its facing
         const int nmoves = rev ? 1 : nsp - STOPPED;
-        out->ctrl[a * 16 + sp * 4 + dir] = (uint8_t)(nsp | (ndir << 2) | (mdir << 4) | (nmoves << 6));
+        out->ctrl2[a * 16 + sp * 4 + dir] = (uint8_t)(ndir | (nsp << 2) | ((mdir * 3 + nmoves) << 4));
       }
   // move table: up to two cells in a direction, stopping in front of walls / the grid edge
   for (int dir = 0; dir < 4; ++dir)
-    for (int y = 0; y < 16; ++y)
-      for (int x = 0; x < 16; ++x) {
-        const int dx = (dir == 1) - (dir == 3), dy = (dir == 2) - (dir == 0);
-        auto wall = [&](int cx, int cy) { return cx < 0 || cy < 0 || cx >= W || cy >= H || blk[cy][cx]; };
-        const int x1 = x + dx, y1 = y + dy;
-        const bool b1 = wall(x1, y1);
-        const int c1 = b1 ? (x | (y << 4)) : (x1 | (y1 << 4));
-        const int x2 = x1 + dx, y2 = y1 + dy;
-        const bool b2 = b1 || wall(x2, y2);
-        const int c2 = b2 ? c1 : (x2 | (y2 << 4));
-        out->move_tab[(dir << 8) | (y << 4) | x] =
-            (uint32_t)c1 | ((uint32_t)c2 << 8) | ((b1 ? 1u : 0u) << 16) | ((b2 ? 1u : 0u) << 17);
-      }
+    for (int nmoves = 0; nmoves < 3; ++nmoves)
+      for (int y = 0; y < 16; ++y)
+        for (int x = 0; x < 16; ++x) {
+          const int dx = (dir == 1) - (dir == 3), dy = (dir == 2) - (dir == 0);
+          auto wall = [&](int cx, int cy) { return cx < 0 || cy < 0 || cx >= W || cy >= H || blk[cy][cx]; };
+          const uint32_t c0 = (uint32_t)(x | (y << 4));
+          const int x1 = x + dx, y1 = y + dy, x2 = x1 + dx, y2 = y1 + dy;
+          const bool try1 = nmoves >= 1, b1 = wall(x1, y1);
+          const bool s1 = try1 && !b1, o1 = try1 && b1;
+          const bool try2 = s1 && nmoves == 2, b2 = wall(x2, y2);
+          const bool s2 = try2 && !b2, o2 = try2 && b2;
+          const uint32_t c1 = s1 ? (uint32_t)(x1 | (y1 << 4)) : c0;
+          const uint32_t cf = s2 ? (uint32_t)(x2 | (y2 << 4)) : c1;
+          const uint32_t oc = obstacle_collisions ? 1u : 0u;
+          out->move2[((dir * 3 + nmoves) << 8) | (y << 4) | x] =
+              cf | (c1 << 8) | ((s1 ? 1u : 0u) << 16) | ((s2 ? 1u : 0u) << 17) | ((o1 ? oc : 0u) << 18) |
+              ((o2 ? oc : 0u) << 19);
+        }
+  // step noise: the 50 (order, a0, a1) combinations (decode_step_noise)
+  for (uint32_t idx = 0; idx < 56; ++idx) {
+    const uint32_t i = idx < 50 ? idx : 49;
+    const uint32_t sw = i & 1u, r = i >> 1, a1 = r / 5u, a0 = r - 5u * a1;
+    const uint32_t af = sw ? a1 : a0, as = sw ? a0 : a1;
+    out->noise_lut[idx] = (uint16_t)(af | (as << 3) | (sw << 6) | (a0 << 7) | (a1 << 10));
+  }
   // window lookup: where inside the 5x3 window does the grid offset (dx, dy) fall?
   memset(out->win_lut, 15, sizeof(out->win_lut));
   for (int dir = 0; dir < 4; ++dir)
@@ -517,9 +585,37 @@ int posg_driving_step(posg_model_t m, int64_t n, const uint32_t* state_in, const
   int rc = check_driving(m); if (rc) return rc;
   if (n == 0) return POSG_OK;
   POSG_REQUIRE(n > 0 && state_in && state_out && obs_out && rewards_out && flags_out, "bad arguments");
-  step_kernel<<<grid_for(step_kernel, m->blob_bytes, (n + EPT - 1) / EPT), THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
-      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, actions_in, order_in, seed, step_idx,
-      particle_offset, state_out, obs_out, rewards_out, flags_out, actions_out, live_count);
+  cudaStream_t s = (cudaStream_t)stream;
+  const Blob* blob = (const Blob*)m->d_blob;
+  const uint32_t bb = (uint32_t)m->blob_bytes;
+  const bool aligned = (((uintptr_t)state_in | (uintptr_t)state_out | (uintptr_t)obs_out | (uintptr_t)rewards_out) & 15u) == 0 &&
+                       ((uintptr_t)flags_out & 3u) == 0 && ((uintptr_t)actions_out & 7u) == 0;
+  int64_t done = 0;
+  static const bool nofast = getenv("POSG_STEP_NOFAST") != nullptr;   // dev A/B switch
+  if (!nofast && !actions_in && !order_in && (particle_offset & 3ULL) == 0 && n >= WARP_ENVS && n < ((int64_t)1 << 31) && aligned) {
+    // whole blocks of 128 envs through the fast kernel; a ragged tail through the general one
+    const uint32_t nb = (uint32_t)(n / WARP_ENVS);
+    const int64_t items = (int64_t)nb * 32;   // threads needed
+#define POSG_STEP_FAST(WA, CL)                                                                                      \
+    step_fast_kernel<WA, CL><<<grid_for(step_fast_kernel<WA, CL>, m->blob_bytes, items), THREADS, m->blob_bytes, s>>>( \
+        blob, bb, nb, (const uint2*)state_in, seed, step_idx, particle_offset >> 2, (uint2*)state_out,               \
+        (ulonglong2*)obs_out, (double2*)rewards_out, flags_out, (uchar2*)actions_out, live_count)
+    if (actions_out && live_count) POSG_STEP_FAST(true, true);
+    else if (actions_out) POSG_STEP_FAST(true, false);
+    else if (live_count) POSG_STEP_FAST(false, true);
+    else POSG_STEP_FAST(false, false);
+#undef POSG_STEP_FAST
+    POSG_CUDA(cudaGetLastError());
+    done = (int64_t)nb * WARP_ENVS;
+  }
+  if (done < n) {
+    const int64_t r = n - done;
+    step_kernel<<<grid_for(step_kernel, m->blob_bytes, (r + EPT - 1) / EPT), THREADS, m->blob_bytes, s>>>(
+        blob, bb, r, state_in + 2 * done, actions_in ? actions_in + 2 * done : nullptr,
+        order_in ? order_in + done : nullptr, seed, step_idx, particle_offset + (uint64_t)done, state_out + 2 * done,
+        obs_out + 2 * done, rewards_out + 2 * done, flags_out + done, actions_out ? actions_out + 2 * done : nullptr,
+        live_count);
+  }
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }

@@ -107,6 +107,45 @@ def test_step_vs_oracle_live(env, oracle_env):
         cur = out.state
 
 
+def test_fast_path_vs_oracle_and_general_kernel(env, oracle_env):
+    """The random-action sweep runs whole 128-env blocks through step_fast_kernel (offset a
+    multiple of 4) and the ragged tail through the general kernel: compare every output with the
+    oracle, and with the general kernel driven by explicit actions / order on the same inputs."""
+    from oracle import rollout as R
+    from oracle.driving import DrivingModel
+
+    m = DrivingModel()
+    n, seed, off = 1000, 5, 4 * 777          # 7 full blocks + a 104-env tail
+    parts = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    st = env.sample_initial_state(n, seed=seed, particle_offset=off)
+    cpu_states = [m.initial_state_from_noise(p) for p in R.driving_initial_picks(m, seed, parts)]
+    live = torch.zeros(1, dtype=torch.int64, device=env.device)
+    cur, expect_live = st, 0
+    for step in range(20):
+        out = env.step(cur, seed=seed, step_idx=step, particle_offset=off, live_count=live)
+        acts, order = R.driving_step_noise(seed, parts, step, 2)
+        assert (out.actions.cpu().numpy() == acts).all()
+        ref = env.step(cur, torch.from_numpy(acts.astype(np.uint8)).to(env.device),
+                       torch.from_numpy(order.astype(np.uint8)).to(env.device))
+        assert torch.equal(out.state, ref.state) and torch.equal(out.obs, ref.obs)
+        assert torch.equal(out.rewards.view(torch.int64), ref.rewards.view(torch.int64)) and torch.equal(out.flags, ref.flags)
+        nolive = env.step(cur, seed=seed, step_idx=step, particle_offset=off, want_actions=False)
+        assert torch.equal(out.state, nolive.state) and torch.equal(out.obs, nolive.obs)
+        gs, go = env.unpack_state(out.state), env.unpack_obs(out.obs)
+        rew, flags = out.rewards.cpu().numpy(), out.flags.cpu().numpy()
+        for i in range(n):
+            expect_live += not all(v.dest_reached or v.crashed for v in cpu_states[i])
+            ts = m.step_with_noise(cpu_states[i], {"0": int(acts[i, 0]), "1": int(acts[i, 1])}, int(order[i]))
+            cpu_states[i] = ts.state
+            assert tuple(tuple(v) for v in gs[i]) == tuple(tuple(v) for v in ts.state), (step, i)
+            assert go[i] == (ts.observations["0"], ts.observations["1"]), (step, i)
+            assert rew[i, 0] == ts.rewards["0"] and rew[i, 1] == ts.rewards["1"]
+            assert bool(flags[i] & 0x80) == ts.all_done
+            assert (flags[i] & 3) == int(ts.terminations["0"]) + 2 * int(ts.terminations["1"])
+        cur = out.state
+    assert int(live.item()) == expect_live
+
+
 def test_edge_cases(env):
     dev = env.device
     # empty batch
