@@ -22,7 +22,8 @@
  *                     (n_agents == 2 -> one uint64 per env, vehicle 0 in the low word)
  *       bits  0-3 x | 4-7 y | 8-9 facing (N,E,S,W) | 10-11 speed (REV,STOP,SLOW,FAST)
  *       12-14 destination index | 15 dest_reached | 16 crashed
- *       17-23 min_dest_dist | 24-30 init_dest_dist
+ *       17-23 min_dest_dist | 24-29 init_dest_dist (1..63) | 30-31 zero (inputs with these
+ *       bits set are invalid; the kernels use them internally for the step's progress)
  *   Driving obs     : uint64 per agent, agents of one env adjacent
  *       bits 0-29 fifteen 2-bit cells (row-major 5x3 window, VEHICLE=0 WALL=1 EMPTY=2
  *       DESTINATION=3) | 30-31 speed | 32-35 x | 36-39 y | 40-43 dest x | 44-47 dest y

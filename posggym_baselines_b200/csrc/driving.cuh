@@ -40,9 +40,9 @@ struct alignas(16) Blob {
   // step noise table [floor(word * 50 / 2^32)] -> first mover's action | second mover's action
   // << 3 | (vehicle 1 moves first) << 6 | a0 << 7 | a1 << 10.  25 words: bank-conflict free.
   uint16_t noise_lut[56];
-  // reward table [(D0*3 + progress)*4 + kind], kind 0 plain, 1 destination reached, 2 crash,
-  // 3 already done (0.0): base + 0.5 * (progress / D0)
-  double reward_tab[MAX_D0 * 3 * 4];
+  // reward table [(D0 | progress << 6) * 4 + kind], kind 0 plain, 1 destination reached, 2 crash,
+  // 3 already done (0.0): base + 0.5 * (progress / D0); index = (raw state word >> 24) * 4 + kind
+  double reward_tab[MAX_D0 * 4 * 4];
   uint8_t dist[MAX_CELLS][256];      // dist[dest][y*16+x]; 255 = unreachable
   // move table [(move dir * 3 + cells moved) * 256 + y*16 + x], walls already resolved:
   //   bits 0..7   cell reached if no vehicle is in the way
@@ -96,8 +96,9 @@ __device__ __forceinline__ void move_vehicle(const Blob& B, uint32_t& me, uint32
   const bool crashed = hit_any || (e & 0x40000u) || (!h1 && (e & 0x80000u));
   const uint32_t dirsp = crashed ? (((c & 3u) << 8) | ((uint32_t)STOPPED << 10)) : ((c & 15u) << 8);
   const uint32_t d = *(reinterpret_cast<const unsigned char*>(B.dist) + (((me >> 4) & 0x700u) | xy));
-  const uint32_t mind = min((me >> 17) & 127u, d);
-  uint32_t moved = xy | dirsp | (me & 0x7F007000u) | (mind << 17);
+  const uint32_t mind0 = (me >> 17) & 127u, mind = min(mind0, d);
+  // bits 30..31 (transient, see STATE_MASK): progress made in this step, 0..2 cells
+  uint32_t moved = xy | dirsp | (me & 0x3F007000u) | (mind << 17) | ((mind0 - mind) << 30);
   moved |= (d == 0u) ? 0x8000u : 0u;           // distance 0 <=> on the own destination
   moved |= crashed ? 0x10000u : 0u;
   me = active ? moved : me;
@@ -105,8 +106,12 @@ __device__ __forceinline__ void move_vehicle(const Blob& B, uint32_t& me, uint32
   other = (active && hit_any) ? ((other & ~(3u << 10)) | ((uint32_t)STOPPED << 10) | (1u << 16)) : other;
 }
 
+// The words transition16 leaves behind carry the progress of the step in bits 30..31 (read by
+// reward_raw); the stored state is `word & STATE_MASK`.
+constexpr uint32_t STATE_MASK = 0x3FFFFFFFu;
+
 // joint transition with pre-shifted actions: af16 / as16 = action << 4 of the vehicle that moves
-// first / second, sw = vehicle 1 moves first
+// first / second, sw = vehicle 1 moves first.  Leaves RAW words (see STATE_MASK).
 __device__ __forceinline__ void transition16(const Blob& B, uint32_t& v0, uint32_t& v1, uint32_t af16, uint32_t as16,
                                              bool sw) {
   uint32_t first = sw ? v1 : v0, second = sw ? v0 : v1;
@@ -115,25 +120,22 @@ __device__ __forceinline__ void transition16(const Blob& B, uint32_t& v0, uint32
   v0 = sw ? second : first; v1 = sw ? first : second;
 }
 
-// joint transition of both vehicles; order_idx 0 -> vehicle 0 first, 1 -> vehicle 1 first
-__device__ __forceinline__ void transition(const Blob& B, uint32_t& v0, uint32_t& v1, int a0, int a1,
-                                           int order_idx) {
+// joint transition of both vehicles; order_idx 0 -> vehicle 0 first, 1 -> vehicle 1 first.
+// Leaves RAW words (see STATE_MASK).
+__device__ __forceinline__ void transition_raw(const Blob& B, uint32_t& v0, uint32_t& v1, int a0, int a1,
+                                               int order_idx) {
   const bool sw = order_idx != 0;
   transition16(B, v0, v1, (uint32_t)(sw ? a1 : a0) << 4, (uint32_t)(sw ? a0 : a1) << 4, sw);
 }
 
-// Reward of a vehicle given its state before / after the transition.  For a vehicle that
-// was not done before, the crashed bit after the step is set exactly when it crashed in
-// this step -- as the mover (vehicle collision, or obstacle collision if those count) or as
-// the vehicle that was run into -- which is the reference's crash-reward condition.
-__device__ __forceinline__ double reward(const Blob& B, uint32_t before, uint32_t after) {
-  const uint32_t fl = (after >> 15) & 3u;                 // bit 0 reached, bit 1 crashed
-  const uint32_t kind = vdone(before) ? 3u : (fl > 2u ? 2u : fl);
-  int p = vmindist(before) - vmindist(after);
-  p = p < 0 ? 0 : (p > 2 ? 2 : p);
-  int d0 = vinitdist(before);
-  d0 = d0 < 1 ? 1 : (d0 >= MAX_D0 ? MAX_D0 - 1 : d0);
-  return B.reward_tab[(d0 * 3 + p) * 4 + kind];
+// Reward of a vehicle given its state before the transition and its RAW word after it.  For a
+// vehicle that was not done before, the crashed bit after the step is set exactly when it
+// crashed in this step -- as the mover (vehicle collision, or obstacle collision if those
+// count) or as the vehicle that was run into -- which is the reference's crash-reward condition.
+__device__ __forceinline__ double reward_raw(const Blob& B, uint32_t before, uint32_t after_raw) {
+  const uint32_t fl = min((after_raw >> 15) & 3u, 2u);            // 0 plain, 1 reached, 2 crashed (wins)
+  const uint32_t kind = (before & 0x18000u) ? 3u : fl;
+  return B.reward_tab[((after_raw >> 24) << 2) | kind];
 }
 
 // ---- observation --------------------------------------------------------------------

@@ -32,13 +32,14 @@ struct EnvOut { uint32_t v0, v1; uint64_t o0, o1; double r0, r1; uint32_t flags;
 
 __device__ __forceinline__ EnvOut step_env(const Blob& B, uint32_t v0, uint32_t v1, int a0, int a1, int order_idx) {
   const uint32_t b0 = v0, b1 = v1;
-  transition(B, v0, v1, a0, a1, order_idx);
+  transition_raw(B, v0, v1, a0, a1, order_idx);
   EnvOut e;
+  e.r0 = reward_raw(B, b0, v0);
+  e.r1 = reward_raw(B, b1, v1);
+  v0 &= STATE_MASK; v1 &= STATE_MASK;
   e.v0 = v0; e.v1 = v1;
   e.o0 = observe(B, v0, v1);
   e.o1 = observe(B, v1, v0);
-  e.r0 = reward(B, b0, v0);
-  e.r1 = reward(B, b1, v1);
   const uint32_t t0 = vdone(v0) ? 1u : 0u, t1 = vdone(v1) ? 1u : 0u;
   e.flags = t0 | (t1 << 1) | ((t0 & t1) ? POSG_FLAG_ALL_DONE : 0u);
   return e;
@@ -194,12 +195,13 @@ step_fast_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nb
       if (COUNT_LIVE) live += ((b0 & 0x18000u) && (b1 & 0x18000u)) ? 0u : 1u;
       transition16(B, v0, v1, (nz << 4) & 0x70u, (nz << 1) & 0x70u, (nz & 0x40u) != 0u);
       const uint32_t e = e0 + 32 * j;
+      rewards_out[e] = make_double2(reward_raw(B, b0, v0), reward_raw(B, b1, v1));
+      v0 &= STATE_MASK; v1 &= STATE_MASK;
       state_out[e] = make_uint2(v0, v1);
       const uint32_t t0 = (v0 & 0x18000u) ? 1u : 0u, t1 = (v1 & 0x18000u) ? 1u : 0u;
       flags_out[e] = (uint8_t)(t0 | (t1 << 1) | ((t0 & t1) ? POSG_FLAG_ALL_DONE : 0u));
       if (WRITE_ACTIONS) actions_out[e] = make_uchar2((unsigned char)((nz >> 7) & 7u), (unsigned char)((nz >> 10) & 7u));
       obs_out[e] = make_ulonglong2(observe(B, v0, v1), observe(B, v1, v0));
-      rewards_out[e] = make_double2(reward(B, b0, v0), reward(B, b1, v1));
     }
   }
   if (COUNT_LIVE) {
@@ -309,9 +311,10 @@ rollout_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
         int a0, a1, order_idx;
         sample_step_noise(seed, particle_offset + (uint64_t)item, step0 + (uint32_t)k, a0, a1, order_idx);
         const uint32_t before = ego ? v1 : v0;
-        transition(B, v0, v1, a0, a1, order_idx);
+        transition_raw(B, v0, v1, a0, a1, order_idx);
+        const double r = reward_raw(B, before, ego ? v1 : v0);
+        v0 &= STATE_MASK; v1 &= STATE_MASK;
         const uint32_t after = ego ? v1 : v0;
-        const double r = reward(B, before, after);
         ret = __dadd_rn(ret, __dmul_rn(sdisc[k], r));
         ++k; ++executed;
         finished = vdone(after) || (vdone(v0) && vdone(v1)) || (k >= max_steps);
@@ -416,16 +419,16 @@ static Blob* build_blob(const char* grid_rows, int num_agents, int obs_front, in
         if (nx < 0 || ny < 0 || nx >= W || ny >= H || blk[ny][nx]) continue;
         const int k = nx | (ny << 4);
         if (out->dist[d][k] != 255) continue;
-        if (out->dist[d][c] + 1 >= 127) { set_error("shortest path longer than 126"); free(out); return nullptr; }
+        if (out->dist[d][c] + 1 >= MAX_D0) { set_error("shortest path longer than %d", MAX_D0 - 1); free(out); return nullptr; }
         out->dist[d][k] = (uint8_t)(out->dist[d][c] + 1); q.push(k);
       }
     }
   }
   for (int d0 = 0; d0 < MAX_D0; ++d0)
-    for (int p = 0; p < 3; ++p) {
+    for (int p = 0; p < 4; ++p) {
       // r = base; r += R_PROGRESS * (progress / D0)   (base: step cost 0, destination 0.5, crash -1)
-      const double prog = 0.5 * ((double)p / (double)(d0 < 1 ? 1 : d0));
-      double* r = out->reward_tab + (d0 * 3 + p) * 4;
+      const double prog = 0.5 * ((double)(p > 2 ? 2 : p) / (double)(d0 < 1 ? 1 : d0));
+      double* r = out->reward_tab + (d0 | (p << 6)) * 4;
       r[0] = 0.0 + prog; r[1] = 0.5 + prog; r[2] = -1.0 + prog; r[3] = 0.0;
     }
   // control table: (action, speed, facing) -> next speed, next facing, move direction, cells moved

@@ -30,11 +30,12 @@ struct DrivingSim {
                                                   double (&rew)[NAG], uint32_t& flags, bool& was_live) {
     const uint32_t b0 = s.w[0], b1 = s.w[1];
     was_live = !(driving::vdone(b0) && driving::vdone(b1));
-    driving::transition(B, s.w[0], s.w[1], act[0], act[1], (int)(noise[0] & 1u));
+    driving::transition_raw(B, s.w[0], s.w[1], act[0], act[1], (int)(noise[0] & 1u));
+    rew[0] = driving::reward_raw(B, b0, s.w[0]);
+    rew[1] = driving::reward_raw(B, b1, s.w[1]);
+    s.w[0] &= driving::STATE_MASK; s.w[1] &= driving::STATE_MASK;
     obs[0][0] = driving::observe(B, s.w[0], s.w[1]);
     obs[1][0] = driving::observe(B, s.w[1], s.w[0]);
-    rew[0] = driving::reward(B, b0, s.w[0]);
-    rew[1] = driving::reward(B, b1, s.w[1]);
     const uint32_t t0 = driving::vdone(s.w[0]) ? 1u : 0u, t1 = driving::vdone(s.w[1]) ? 1u : 0u;
     flags = t0 | (t1 << 1) | ((t0 & t1) ? 0x80u : 0u);
   }
@@ -62,10 +63,11 @@ struct DrivingSim {
     driving::decode_step_noise(word, a0, a1, ord);
     if (ego == 0) a0 = ego_action; else a1 = ego_action;
     const uint32_t before = ego ? s.w[1] : s.w[0];
-    driving::transition(B, s.w[0], s.w[1], a0, a1, ord);
+    driving::transition_raw(B, s.w[0], s.w[1], a0, a1, ord);
+    r = driving::reward_raw(B, before, ego ? s.w[1] : s.w[0]);
+    s.w[0] &= driving::STATE_MASK; s.w[1] &= driving::STATE_MASK;
     const uint32_t after = ego ? s.w[1] : s.w[0];
     const uint32_t other = ego ? s.w[0] : s.w[1];
-    r = driving::reward(B, before, after);
     obs[0] = driving::observe(B, after, other);
     done = driving::vdone(after) || (driving::vdone(s.w[0]) && driving::vdone(s.w[1]));
   }
@@ -76,9 +78,10 @@ struct DrivingSim {
     int a0, a1, ord;
     driving::decode_step_noise(word, a0, a1, ord);
     const uint32_t before = ego ? s.w[1] : s.w[0];
-    driving::transition(B, s.w[0], s.w[1], a0, a1, ord);
+    driving::transition_raw(B, s.w[0], s.w[1], a0, a1, ord);
+    r = driving::reward_raw(B, before, ego ? s.w[1] : s.w[0]);
+    s.w[0] &= driving::STATE_MASK; s.w[1] &= driving::STATE_MASK;
     const uint32_t after = ego ? s.w[1] : s.w[0];
-    r = driving::reward(B, before, after);
     done = driving::vdone(after) || (driving::vdone(s.w[0]) && driving::vdone(s.w[1]));
   }
 

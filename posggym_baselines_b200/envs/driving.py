@@ -207,6 +207,8 @@ class BatchedDriving:
         for i, st in enumerate(states):
             for a, v in enumerate(st):
                 dest = self.dest_coords.index(tuple(v.dest_coord))
+                if not 0 < int(v.init_dest_dist) < 64:
+                    raise ValueError("init_dest_dist must be in 1..63 (6-bit field of the packed state)")
                 out[i, a] = (
                     v.coord[0] | (v.coord[1] << 4) | (int(v.facing_dir) << 8) | (int(v.speed) << 10)
                     | (dest << 12) | (int(v.dest_reached) << 15) | (int(v.crashed) << 16)
@@ -222,7 +224,7 @@ class BatchedDriving:
                 VehicleState(
                     (int(v & 15), int((v >> 4) & 15)), int((v >> 8) & 3), int((v >> 10) & 3),
                     self.dest_coords[int((v >> 12) & 7)], int((v >> 15) & 1), int((v >> 16) & 1),
-                    int((v >> 17) & 127), int((v >> 24) & 127),
+                    int((v >> 17) & 127), int((v >> 24) & 63),
                 )
                 for v in row
             ))
