@@ -139,16 +139,29 @@ __device__ __forceinline__ double reward_raw(const Blob& B, uint32_t before, uin
 }
 
 // ---- observation --------------------------------------------------------------------
-__device__ __forceinline__ uint64_t observe(const Blob& B, uint32_t me, uint32_t other) {
-  const int dir = vdir(me), dest = vdest(me);
-  uint32_t cells = B.obs_base[((dest * 4 + dir) << 8) | vxy(me)];
-  const int dx = vx(other) - vx(me) + 3, dy = vy(other) - vy(me) + 3;
-  const bool inside = ((unsigned)dx < 7u) && ((unsigned)dy < 7u);
-  const int cidx = B.win_lut[dir][inside ? (dy * 8 + dx) : 63];   // 15 = outside the window
+// `cidx` = window cell (0..14) the other vehicle occupies, 15 = outside the window
+__device__ __forceinline__ uint64_t observe_with(const Blob& B, uint32_t me, int cidx) {
+  const int dest = vdest(me);
+  uint32_t cells = B.obs_base[(((me >> 10) & 0x1Cu) | ((me >> 8) & 3u)) << 8 | (me & 255u)];
   cells &= ~(3u << (2 * cidx));                                    // VEHICLE = 0 (shift 30: no-op)
   const uint32_t lo = cells | ((uint32_t)vspeed(me) << 30);
   const uint32_t hi = (uint32_t)vxy(me) | ((uint32_t)B.dest_xy[dest] << 8) | (((me >> 15) & 3u) << 16);
   return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+__device__ __forceinline__ uint64_t observe(const Blob& B, uint32_t me, uint32_t other) {
+  const int dx = vx(other) - vx(me) + 3, dy = vy(other) - vy(me) + 3;
+  const bool inside = ((unsigned)dx < 7u) && ((unsigned)dy < 7u);
+  return observe_with(B, me, B.win_lut[vdir(me)][inside ? (dy * 8 + dx) : 63]);
+}
+
+// both vehicles' observations: the grid offset is computed once (vehicle 1 sees the negated one)
+__device__ __forceinline__ void observe_pair(const Blob& B, uint32_t v0, uint32_t v1, uint64_t& o0, uint64_t& o1) {
+  const int dx = vx(v1) - vx(v0), dy = vy(v1) - vy(v0);
+  const bool inside = ((unsigned)(dx + 3) < 7u) && ((unsigned)(dy + 3) < 7u);
+  const int t = dy * 8 + dx;
+  o0 = observe_with(B, v0, B.win_lut[vdir(v0)][inside ? 27 + t : 63]);
+  o1 = observe_with(B, v1, B.win_lut[vdir(v1)][inside ? 27 - t : 63]);
 }
 
 // ---- initial state --------------------------------------------------------------------

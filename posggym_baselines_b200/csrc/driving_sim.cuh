@@ -34,8 +34,9 @@ struct DrivingSim {
     rew[0] = driving::reward_raw(B, b0, s.w[0]);
     rew[1] = driving::reward_raw(B, b1, s.w[1]);
     s.w[0] &= driving::STATE_MASK; s.w[1] &= driving::STATE_MASK;
-    obs[0][0] = driving::observe(B, s.w[0], s.w[1]);
-    obs[1][0] = driving::observe(B, s.w[1], s.w[0]);
+    uint64_t o0, o1;
+    driving::observe_pair(B, s.w[0], s.w[1], o0, o1);
+    obs[0][0] = o0; obs[1][0] = o1;
     const uint32_t t0 = driving::vdone(s.w[0]) ? 1u : 0u, t1 = driving::vdone(s.w[1]) ? 1u : 0u;
     flags = t0 | (t1 << 1) | ((t0 & t1) ? 0x80u : 0u);
   }
@@ -50,8 +51,9 @@ struct DrivingSim {
     noise[0] = word >> 31;
   }
   __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
-    obs[0][0] = driving::observe(B, s.w[0], s.w[1]);
-    obs[1][0] = driving::observe(B, s.w[1], s.w[0]);
+    uint64_t o0, o1;
+    driving::observe_pair(B, s.w[0], s.w[1], o0, o1);
+    obs[0][0] = o0; obs[1][0] = o1;
   }
 
   // model.step with the ego action fixed and the other vehicle uniform random
