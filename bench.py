@@ -426,6 +426,8 @@ def main():
     launch_ms = ms / launches
     peak, peak_src = load_peaks()
     achieved = BYTES_PER_ENV_STEP * n / (launch_ms / 1e3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu capture
+    # (profiles/step_kernel_traffic.json), scaled to this batch size
     traffic = None
     tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(tp):
@@ -538,7 +540,7 @@ def main():
                        "counted": "env-steps executed on not-yet-all-done particles", "padded_env_steps_per_s": padded / (ms / 1e3)},
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "posg::driving::step_kernel<2>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                         "traffic": traffic, "kernel": "posg::driving::step_fast_kernel<true, true>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "launch_ms": launch_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "pomcp": pomcp, "vec_env": vec,
         }

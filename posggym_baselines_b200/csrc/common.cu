@@ -61,6 +61,7 @@ int posg_model_destroy(posg_model_t m) {
     free(m->h_blob);
   }
   if (m->d_flat_desc) cudaFree(m->d_flat_desc);
+  if (m->host_stage && m->host_stage_free) m->host_stage_free(m->host_stage);
   delete m;
   return POSG_OK;
 }

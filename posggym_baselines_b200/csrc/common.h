@@ -44,4 +44,8 @@ struct posg_model {
   void* d_flat_desc = nullptr;  // one-hot descriptors of the flattened observation (vec env)
   int flat_dim = 0;
   int borrowed = 0;             // blob pointers belong to another handle (posg_nested_create)
+  // staging of the *_host entry points: device slices + streams, created on first use and
+  // reused by later calls (guarded by a mutex: one host-buffer call per handle at a time)
+  void* host_stage = nullptr;
+  void (*host_stage_free)(void*) = nullptr;
 };

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <queue>
 #include <string>
 #include <vector>
@@ -533,6 +534,31 @@ static int grid_for(K kernel, size_t smem, int64_t work_items) {
 using namespace posg;
 using namespace posg::driving;
 
+// staging context of posg_driving_sweep_host (see posg_model::host_stage)
+struct HostStage {
+  static constexpr int NSLOT = 3;
+  std::mutex mu;
+  unsigned char* d_base[NSLOT] = {nullptr, nullptr, nullptr};
+  size_t bytes[NSLOT] = {0, 0, 0};
+  cudaStream_t st[NSLOT] = {nullptr, nullptr, nullptr};
+  unsigned long long* d_live = nullptr;
+};
+static void host_stage_free(void* p) {
+  HostStage* hs = (HostStage*)p;
+  for (int i = 0; i < HostStage::NSLOT; ++i) {
+    if (hs->st[i]) { cudaStreamSynchronize(hs->st[i]); cudaStreamDestroy(hs->st[i]); }
+    cudaFree(hs->d_base[i]);
+  }
+  cudaFree(hs->d_live);
+  delete hs;
+}
+static HostStage* host_stage_of(posg_model* m) {
+  static std::mutex create_mu;
+  std::lock_guard<std::mutex> lock(create_mu);
+  if (!m->host_stage) { m->host_stage = new HostStage(); m->host_stage_free = host_stage_free; }
+  return (HostStage*)m->host_stage;
+}
+
 static int check_driving(posg_model_t m) {
   if (!m || m->kind != KIND_DRIVING) { set_error("not a Driving model handle"); return POSG_E_INVALID; }
   return POSG_OK;
@@ -705,31 +731,32 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
   int rc = check_driving(m); if (rc) return rc;
   if (n == 0) return POSG_OK;
   POSG_REQUIRE(n > 0 && state_in_host && num_steps >= 1, "bad arguments");
-  constexpr int NSTREAM = 2;
-  // slices are multiples of 4 envs so that every slice keeps the 16-byte fast path and
-  // the Philox word grouping (particle >> 2) of the monolithic call
-  int64_t chunk = ((n + 7) / 8 + 3) & ~(int64_t)3;
-  if (chunk < 1 << 16) chunk = (n + 3) & ~(int64_t)3;
+  // Slices are multiples of 128 envs (whole fast-kernel blocks; also keeps the Philox word
+  // grouping of the monolithic call).  Three slots: while one slice computes, the previous one
+  // drains to the host and the next one is uploaded (PCIe is full duplex).
+  HostStage* hs = host_stage_of(m);
+  std::lock_guard<std::mutex> lock(hs->mu);
+  int64_t chunk = ((n + 15) / 16 + 127) & ~(int64_t)127;
+  if (chunk < (1 << 16)) chunk = (n + 127) & ~(int64_t)127;
   const size_t per_env = 8 + 16 + 16 + 1 + 2;
-  unsigned char* d_base[NSTREAM] = {nullptr, nullptr};
-  cudaStream_t st[NSTREAM] = {nullptr, nullptr};
-  unsigned long long* d_live = nullptr;
-  auto cleanup = [&]() {
-    for (int i = 0; i < NSTREAM; ++i) { if (st[i]) cudaStreamDestroy(st[i]); cudaFree(d_base[i]); }
-    cudaFree(d_live);
-  };
-#define SWEEP_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #call); } } while (0)
-  SWEEP_CUDA(cudaMalloc((void**)&d_live, 8));
-  SWEEP_CUDA(cudaMemset(d_live, 0, 8));
-  for (int i = 0; i < NSTREAM; ++i) {
-    SWEEP_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    SWEEP_CUDA(cudaMalloc((void**)&d_base[i], (size_t)chunk * per_env + 512));
+  const size_t slot_bytes = (size_t)chunk * per_env + 1024;
+#define SWEEP_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return cuda_fail(_e, #call); } while (0)
+  for (int i = 0; i < HostStage::NSLOT; ++i) {
+    if (!hs->st[i]) SWEEP_CUDA(cudaStreamCreateWithFlags(&hs->st[i], cudaStreamNonBlocking));
+    if (hs->bytes[i] < slot_bytes) {
+      if (hs->d_base[i]) { SWEEP_CUDA(cudaStreamSynchronize(hs->st[i])); cudaFree(hs->d_base[i]); hs->d_base[i] = nullptr; hs->bytes[i] = 0; }
+      SWEEP_CUDA(cudaMalloc((void**)&hs->d_base[i], slot_bytes));
+      hs->bytes[i] = slot_bytes;
+    }
   }
+  if (!hs->d_live) SWEEP_CUDA(cudaMalloc((void**)&hs->d_live, 8));
+  SWEEP_CUDA(cudaMemsetAsync(hs->d_live, 0, 8, hs->st[0]));
+  SWEEP_CUDA(cudaStreamSynchronize(hs->st[0]));
   int slot = 0;
-  for (int64_t off = 0; off < n && rc == POSG_OK; off += chunk, slot ^= 1) {
+  for (int64_t off = 0; off < n && rc == POSG_OK; off += chunk, slot = (slot + 1) % HostStage::NSLOT) {
     const int64_t c = (n - off < chunk) ? (n - off) : chunk;
-    cudaStream_t s = st[slot];
-    unsigned char* base = d_base[slot];
+    cudaStream_t s = hs->st[slot];
+    unsigned char* base = hs->d_base[slot];
     uint32_t* d_state = (uint32_t*)base;
     uint64_t* d_obs = (uint64_t*)(base + (size_t)chunk * 8);
     double* d_rew = (double*)(base + (size_t)chunk * 24);
@@ -738,19 +765,19 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
     SWEEP_CUDA(cudaMemcpyAsync(d_state, state_in_host + 2 * off, (size_t)c * 8, cudaMemcpyHostToDevice, s));
     for (int k = 0; k < num_steps && rc == POSG_OK; ++k)
       rc = posg_driving_step(m, c, d_state, nullptr, nullptr, seed, (uint32_t)k, particle_offset + (uint64_t)off,
-                             d_state, d_obs, d_rew, d_flags, d_act, d_live, s);
+                             d_state, d_obs, d_rew, d_flags, d_act, hs->d_live, s);
     if (rc != POSG_OK) break;
     if (state_out_host) SWEEP_CUDA(cudaMemcpyAsync(state_out_host + 2 * off, d_state, (size_t)c * 8, cudaMemcpyDeviceToHost, s));
     if (obs_out_host) SWEEP_CUDA(cudaMemcpyAsync(obs_out_host + 2 * off, d_obs, (size_t)c * 16, cudaMemcpyDeviceToHost, s));
     if (rewards_out_host) SWEEP_CUDA(cudaMemcpyAsync(rewards_out_host + 2 * off, d_rew, (size_t)c * 16, cudaMemcpyDeviceToHost, s));
     if (flags_out_host) SWEEP_CUDA(cudaMemcpyAsync(flags_out_host + off, d_flags, (size_t)c, cudaMemcpyDeviceToHost, s));
   }
-  if (rc == POSG_OK) {
-    for (int i = 0; i < NSTREAM; ++i) SWEEP_CUDA(cudaStreamSynchronize(st[i]));
-    if (live_count_host) SWEEP_CUDA(cudaMemcpy(live_count_host, d_live, 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < HostStage::NSLOT; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(hs->st[i]);
+    if (e != cudaSuccess && rc == POSG_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
   }
+  if (rc == POSG_OK && live_count_host) SWEEP_CUDA(cudaMemcpy(live_count_host, hs->d_live, 8, cudaMemcpyDeviceToHost));
 #undef SWEEP_CUDA
-  cleanup();
   return rc;
 }
 
