@@ -114,14 +114,27 @@ __device__ __forceinline__ bool obs_eq(const unsigned long long* a, const unsign
 // Child obs node of action node `anode` with observation `obs`; created when missing
 // (action_node.has_child / _add_obs_node, mcts.py:358-369).  Lock-free prepend to the
 // action node's child list; returns -1 when the arena is full.
+// `reserved` >= 0: node id set aside for the caller (one per simulation, see simulate) -- the new
+// node is then born EXPANDED (flag bit 0 set before it is linked): its creator evaluates it.
+// `reserved` == -2: the caller's reservation failed (arena full).  -1: allocate here.
 template <int A, int OW>
-__device__ int find_or_insert(const Tree& T, int anode, const unsigned long long (&obs)[OW], int t, bool& created) {
+__device__ int find_or_insert(const Tree& T, int anode, const unsigned long long (&obs)[OW], int t, bool& created,
+                              int reserved = -1) {
   created = false;
   int head = *((volatile int*)&T.an_first[anode]);
   int stop = -1, mine = -1;
   while (true) {
     for (int c = head; c >= 0 && c != stop; c = *((volatile int*)&T.node_next[c]))
       if (obs_eq<OW>(T.node_obs + (size_t)c * OW, obs)) return c;  // (a spare `mine` stays unused)
+    if (mine < 0 && reserved != -1) {
+      if (reserved < 0) { atomicAdd(&T.ctr->overflow, 1u); return -1; }
+      mine = reserved;
+#pragma unroll
+      for (int w = 0; w < OW; ++w) T.node_obs[(size_t)mine * OW + w] = obs[w];
+      T.node_t[mine] = (unsigned char)t;
+      T.node_parent[mine] = anode;
+      atomicOr((unsigned int*)(T.node_flags + (mine & ~3)), 1u << (8 * (mine & 3)));
+    }
     if (mine < 0) {
       // the last RESERVE slots are kept for the re-root (posg_tree_advance)
       if (*((volatile unsigned long long*)&T.ctr->node_count) + RESERVE >= (unsigned long long)T.cap_nodes) {
@@ -156,8 +169,13 @@ template <int A>
 __device__ int select_action(const Tree& T, const Params& P, int node, bool is_root, unsigned grp, int rank,
                              int max_gsize, int n_base, uint32_t rnd_word) {
   float n[A], q[A];
-  const double mn = dunkey(*((volatile unsigned long long*)&T.ctr->min_key));
-  const double mx = dunkey(*((volatile unsigned long long*)&T.ctr->max_key));
+  // MinMaxStats.normalize (utils.py:34-39) in single precision: the scores are compared as floats
+  // anyway, and ten double divisions per tree level cost more than the rest of the selection
+  const float mn = (float)dunkey(*((volatile unsigned long long*)&T.ctr->min_key));
+  const float mx = (float)dunkey(*((volatile unsigned long long*)&T.ctr->max_key));
+  const bool ranged = mx > mn;
+  const float inv_range = ranged ? __frcp_rn(mx - mn) : 1.0f;
+  const float shift = ranged ? mn : 0.0f;
 #pragma unroll
   for (int a = 0; a < A; ++a) {
     const int an = node * A + a;
@@ -165,7 +183,7 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
     const int done = *((volatile int*)&T.an_done[an]);
     const double tot = *((volatile double*)&T.an_total[an]);
     n[a] = (float)vis;
-    q[a] = done > 0 ? (float)normalize(tot / (double)done, mn, mx) : 0.0f;
+    q[a] = done > 0 ? (__fdividef((float)tot, (float)done) - shift) * inv_range : 0.0f;
   }
   const float c = (float)P.c;
   const float prior = 1.0f / (float)A;  // RandomSearchPolicy.get_pi is uniform; so is the noise mix
@@ -175,9 +193,20 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
 #pragma unroll
   for (int a = 0; a < A; ++a)
     rs[a] = (P.selection == SEL_PUCB) ? __frcp_rn(1.0f + n[a]) : (n[a] > 0.0f ? rsqrtf(n[a]) : 0.0f);
+  // c * sqrt(ln N) over the group's consecutive visit counts N0 .. N0 + max_gsize - 1: exact per
+  // iteration while N is small, linear in between the two ends once N0 >= 256 (relative error of the
+  // interpolation < (max_gsize / N0)^2 / 8 < 2e-3 of a term that itself changes by < 1 %)
+  const int N0 = n_base + (is_root ? 0 : 1);
+  const bool interp = (P.selection == SEL_UCB) && N0 >= 256;
+  float cs_lo = 0.0f, cs_step = 0.0f;
+  if (interp) {
+    cs_lo = c * sqrtf(__logf((float)N0));
+    const float cs_hi = c * sqrtf(__logf((float)(N0 + max_gsize)));
+    cs_step = (cs_hi - cs_lo) * __frcp_rn((float)max_gsize);
+  }
   int mine = 0;
   for (int s = 0; s < max_gsize; ++s) {
-    const int N = n_base + s + (is_root ? 0 : 1);
+    const int N = N0 + s;
     int choice = 0;
     if (N == 0) {
       // obs_node.visits == 0: random action (mcts.py:496,531); derived from the node so the
@@ -185,7 +214,7 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
       choice = (int)uniform_below(rnd_word * 0x9E3779B1u + (uint32_t)s * 0x85EBCA77u, (uint32_t)A);
     } else if (P.selection == SEL_UCB) {
       // argmax_a  norm(Q_a) + c * sqrt(ln N / n_a), first unvisited action first (mcts.py:529-546)
-      const float cs = c * sqrtf(__logf((float)N));
+      const float cs = interp ? fmaf((float)s, cs_step, cs_lo) : c * sqrtf(__logf((float)N));
       float best = -3.0e38f;
       bool unvisited = false;
 #pragma unroll
@@ -257,6 +286,8 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
   double leaf = 0.0;
   bool descending = active;
   bool virtual_leaf = false;  // arena full: the state just reached is evaluated but not stored
+  bool need_rollout = false;  // this lane expanded a leaf: evaluate it after the warp's descent
+  int roll_depth = 0, roll_t = 0;
   if (active) {
     const uint4 w = philox_block(P.seed, sim_id, 0xFFFFu, STREAM_BELIEF);
     long long pi;
@@ -271,6 +302,27 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
     for (int k = 0; k < SW; ++k) st.w[k] = __ldg(root_particles + pi * SW + k);
     node = root;
   }
+  // A simulation adds at most one node (the node it creates is born expanded and evaluated by its
+  // creator), so the warp reserves one id per simulation with ONE atomic: a wave of 2^18 simulations
+  // bumping the node counter one by one serialises in L2.  Ids of simulations that end without
+  // creating a node stay unlinked (zeroed) holes; the re-root compaction drops them.
+  int reserved = -2;
+  {
+    const unsigned am = __ballot_sync(full, active);
+    if (am) {
+      const int ldr = __ffs(am) - 1, cnt = __popc(am);
+      unsigned long long base = 0;
+      if ((int)lane == ldr) {
+        base = ~0ULL;   // arena full (the last RESERVE slots are kept for the re-root)
+        if (*((volatile unsigned long long*)&T.ctr->node_count) + RESERVE + 32 < (unsigned long long)T.cap_nodes)
+          base = atomicAdd(&T.ctr->node_count, (unsigned long long)cnt);
+      }
+      base = __shfl_sync(full, base, ldr);
+      const unsigned long long id = base + (unsigned long long)__popc(am & ((1u << lane) - 1u));
+      if (active && base != ~0ULL && id + RESERVE / 2 < (unsigned long long)T.cap_nodes) reserved = (int)id;
+    }
+  }
+  bool created_here = false;  // this lane created (and therefore expands) the node it stands on
 
   while (__any_sync(full, descending)) {
     // ---- stop conditions / leaf expansion ------------------------------------------
@@ -280,6 +332,9 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
       if (depth > P.depth_limit || t_rule > P.step_limit || depth >= MAX_DEPTH - 1) {
         descending = false;  // returns 0 (mcts.py:315-316)
       } else if (virtual_leaf) {
+        expand = true;
+        descending = false;
+      } else if (created_here) {
         expand = true;
         descending = false;
       } else {
@@ -292,22 +347,10 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
         if (expand) descending = false;
       }
     }
-    if (expand) {
-      // MCTS._rollout (mcts.py:405-452): uniform random joint actions until done / limits
-      int d = depth, tt = t, k = 0;
-      double ret = 0.0;
-      uint4 blk = make_uint4(0, 0, 0, 0);
-      while (d <= P.depth_limit && tt <= P.step_limit && k < MAX_DEPTH) {
-        if ((k & 3) == 0) blk = philox_block(P.seed, sim_id, 0x10000u + (uint32_t)(k >> 2), STREAM_TREE);
-        const uint32_t word = (k & 3) == 0 ? blk.x : (k & 3) == 1 ? blk.y : (k & 3) == 2 ? blk.z : blk.w;
-        double r; bool done;
-        M::rollout_step(B, ctx, st, P.ego, word, r, done);
-        ret = __dadd_rn(ret, __dmul_rn(P.disc_pow[k], r));
-        if (done) break;
-        ++d; ++tt; ++k;
-      }
-      leaf = ret;
-    }
+    // The leaf rollout is deferred until every lane of the warp has finished its descent, so that
+    // the lanes roll out side by side instead of one tree level after the other (the rollout only
+    // reads the lane's own state and its own Philox counters: the result is the same).
+    if (expand) { need_rollout = true; roll_depth = depth; roll_t = t; }
     if (!__any_sync(full, descending)) break;
 
     // ---- action selection (water-filling among lanes sharing the node) ---------------
@@ -325,11 +368,13 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
     }
     // group-consistent random word: the group leader's
     const uint32_t rnd = __shfl_sync(full, w.z, __ffs(grp) - 1);
-    if (descending) {
-      action = select_action<A>(T, P, node, node == root, grp, rank, max_g, n_base, rnd ^ (uint32_t)node);
-      atomicAdd(&T.an_visits[node * A + action], 1);
+    if (descending) action = select_action<A>(T, P, node, node == root, grp, rank, max_g, n_base, rnd ^ (uint32_t)node);
+    {
+      // virtual visit, one atomic per distinct action node of the warp: near the root thousands of
+      // simulations per wave hit the same few counters, and same-address atomics serialise in L2
+      const unsigned va = __match_any_sync(full, descending ? node * A + action : -1 - (int)lane);
+      if (descending && (int)lane == __ffs(va) - 1) atomicAdd(&T.an_visits[node * A + action], __popc(va));
     }
-    __syncwarp(full);
 
     // ---- model step, child lookup, particle log ---------------------------------------
     unsigned long long obs[OW];
@@ -350,7 +395,8 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
     int child = -1;
     if (descending && (int)lane == leader) {
       bool created;
-      child = find_or_insert<A, OW>(T, anode, obs, t + 1, created);
+      child = find_or_insert<A, OW>(T, anode, obs, t + 1, created, reserved);
+      created_here = created;
       if (child >= 0) {
         atomicAdd(&T.node_visits[child], __popc(same));
         // child_obs_node.is_absorbing = ego_done (mcts.py:370)
@@ -389,18 +435,63 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
     }
   }
 
+  // ---- leaf evaluation: MCTS._rollout (mcts.py:405-452), uniform random joint actions until
+  // done / limits; all expanding lanes of the warp together
+  if (need_rollout) {
+    int d = roll_depth, tt = roll_t, k = 0;
+    double ret = 0.0;
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    while (d <= P.depth_limit && tt <= P.step_limit && k < MAX_DEPTH) {
+      if ((k & 3) == 0) blk = philox_block(P.seed, sim_id, 0x10000u + (uint32_t)(k >> 2), STREAM_TREE);
+      const uint32_t word = (k & 3) == 0 ? blk.x : (k & 3) == 1 ? blk.y : (k & 3) == 2 ? blk.z : blk.w;
+      double r; bool done;
+      M::rollout_step(B, ctx, st, P.ego, word, r, done);
+      ret = __dadd_rn(ret, __dmul_rn(P.disc_pow[k], r));
+      if (done) break;
+      ++d; ++tt; ++k;
+    }
+    leaf = ret;
+  }
+
   // ---- backup (mcts.py:378-381; node.py:166-178) --------------------------------------
-  if (active) {
+  // Warp-synchronous and aggregated: at path position i the lanes that share an action node add
+  // their returns with ONE atomicAdd (same-address atomics serialise in L2, and near the root a wave
+  // of simulations shares a handful of nodes).  MinMaxStats sees the node's mean after the group's
+  // update (the reference: after each single update).
+  {
     double G = leaf;
     for (int i = npath - 1; i >= 0; --i) {
       G = __dadd_rn(path_r[i], __dmul_rn(P.discount, G));
-      const int an = path_an[i];
-      const double old_tot = atomicAdd(&T.an_total[an], G);
-      const int old_done = atomicAdd(&T.an_done[an], 1);
-      const unsigned long long vk = dkey((old_tot + G) / (double)(old_done + 1));
-      // MinMaxStats.update (utils.py:29-32); the atomics fire only when the bound moves
-      if (vk < *((volatile unsigned long long*)&T.ctr->min_key)) atomicMin(&T.ctr->min_key, vk);
-      if (vk > *((volatile unsigned long long*)&T.ctr->max_key)) atomicMax(&T.ctr->max_key, vk);
+      path_r[i] = G;
+    }
+    const int max_np = __reduce_max_sync(full, active ? npath : 0);
+    for (int i = 0; i < max_np; ++i) {
+      const bool on = active && i < npath;
+      const int an = on ? path_an[i] : -1 - (int)lane;
+      const double g = on ? path_r[i] : 0.0;
+      const unsigned m = __match_any_sync(full, an);
+      const int cnt = __popc(m);
+      const int max_cnt = __reduce_max_sync(full, on ? cnt : 1);
+      double sum = g;
+      if (max_cnt > 1) {
+        // every lane sums its own group (itself included) in lane order
+        sum = 0.0;
+        unsigned rest = m;
+        for (int k = 0; k < max_cnt; ++k) {
+          const int src = rest ? __ffs(rest) - 1 : (int)lane;
+          const double v = __shfl_sync(full, g, src);
+          if (rest) sum += v;
+          rest &= rest - 1u;
+        }
+      }
+      if (on && (int)lane == __ffs(m) - 1) {
+        const double old_tot = atomicAdd(&T.an_total[an], sum);
+        const int old_done = atomicAdd(&T.an_done[an], cnt);
+        const unsigned long long vk = dkey((old_tot + sum) / (double)(old_done + cnt));
+        // MinMaxStats.update (utils.py:29-32); the atomics fire only when the bound moves
+        if (vk < *((volatile unsigned long long*)&T.ctr->min_key)) atomicMin(&T.ctr->min_key, vk);
+        if (vk > *((volatile unsigned long long*)&T.ctr->max_key)) atomicMax(&T.ctr->max_key, vk);
+      }
     }
   }
   const unsigned act = __ballot_sync(full, active);

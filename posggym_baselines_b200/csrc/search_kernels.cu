@@ -14,10 +14,16 @@
 
 namespace posg {
 
-constexpr int SEARCH_THREADS = 128;
+#ifndef POSG_SEARCH_THREADS
+#define POSG_SEARCH_THREADS 256
+#endif
+#ifndef POSG_SEARCH_MIN_CTAS
+#define POSG_SEARCH_MIN_CTAS 4
+#endif
+constexpr int SEARCH_THREADS = POSG_SEARCH_THREADS;
 
 template <class M>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+__global__ void __launch_bounds__(SEARCH_THREADS, POSG_SEARCH_MIN_CTAS)
 search_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, search::Tree T,
               const __grid_constant__ search::Params P, const __grid_constant__ typename M::Ctx ctx, int root,
               int root_t, const uint32_t* __restrict__ particles, long long n_particles, search::RootSelect sel,
