@@ -151,7 +151,9 @@ __device__ int find_or_insert(const Tree& T, int anode, const unsigned long long
       // visits / flags / action-node arrays were zeroed (an_first: -1) by posg_tree_reset
     }
     T.node_next[mine] = head;
-    __threadfence();
+    // publish the node's fields before it becomes reachable (release; lighter than the
+    // sequentially consistent fence of __threadfence())
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     const int old = atomicCAS(&T.an_first[anode], head, mine);
     if (old == head) { created = true; return mine; }
     stop = head;
@@ -465,6 +467,10 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
       path_r[i] = G;
     }
     const int max_np = __reduce_max_sync(full, active ? npath : 0);
+    // MinMaxStats bounds, read once: the lane's own updates are folded into the local copy (another
+    // warp's concurrent update can only make the atomics below redundant, never wrong)
+    unsigned long long kmin = *((volatile unsigned long long*)&T.ctr->min_key);
+    unsigned long long kmax = *((volatile unsigned long long*)&T.ctr->max_key);
     for (int i = 0; i < max_np; ++i) {
       const bool on = active && i < npath;
       const int an = on ? path_an[i] : -1 - (int)lane;
@@ -489,8 +495,8 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
         const int old_done = atomicAdd(&T.an_done[an], cnt);
         const unsigned long long vk = dkey((old_tot + sum) / (double)(old_done + cnt));
         // MinMaxStats.update (utils.py:29-32); the atomics fire only when the bound moves
-        if (vk < *((volatile unsigned long long*)&T.ctr->min_key)) atomicMin(&T.ctr->min_key, vk);
-        if (vk > *((volatile unsigned long long*)&T.ctr->max_key)) atomicMax(&T.ctr->max_key, vk);
+        if (vk < kmin) { atomicMin(&T.ctr->min_key, vk); kmin = vk; }
+        if (vk > kmax) { atomicMax(&T.ctr->max_key, vk); kmax = vk; }
       }
     }
   }
