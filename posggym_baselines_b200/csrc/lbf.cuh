@@ -22,154 +22,167 @@ enum : int { NONE = 0, NORTH = 1, SOUTH = 2, WEST = 3, EAST = 4, LOAD = 5 };
 struct alignas(16) Blob {
   uint8_t food_xy[NF];        // x | y << 4 (static layout)
   uint8_t player_xy[4];       // start cells
-  uint8_t size, sight, max_agent_level, force_coop, normalize_reward, pad_[11];
-  uint8_t food_at[256];       // food index at cell y*16+x, 255 = none
+  uint8_t size, sight, max_agent_level, force_coop, normalize_reward, pad_[3];
+  int8_t move_delta[8];       // cell-index delta (x | y << 4 arithmetic) of NONE, N, S, W, E, LOAD
+  // 3 * k of the food whose cell is x | y << 4, 24 if there is none: level = (w1 >> shift) & 7
+  // (w1 holds 24 level bits, so shift 24 reads 0)
+  uint8_t food_sh[256];
+  // food_sh of the N, S, W, E neighbours of cell x | y << 4 (one byte each; 24 = none / outside)
+  uint32_t adj_sh[256];
+  // what a player standing on cell x | y << 4 can see: bits 0..7 food k within sight;
+  // bits 8 + 6 k .. 13 + 6 k: (dx + sight + 1) | (dy + sight + 1) << 3 of food k
+  unsigned long long vis[256];
 };
 static_assert(sizeof(Blob) % 16 == 0, "blob must be a multiple of 16 B");
 
-struct Ents {
-  int px[NPL], py[NPL], pl[NPL];
-  int fl[NF];
-  int spawned;
-};
+// host side: fill the tables from food_xy / size / sight
+inline void build_tables(Blob* b) {
+  const int8_t md[8] = {0, -16, 16, -1, 1, 0, 0, 0};
+  for (int k = 0; k < 8; ++k) b->move_delta[k] = md[k];
+  for (int c = 0; c < 256; ++c) b->food_sh[c] = 24;
+  for (int k = 0; k < NF; ++k) b->food_sh[b->food_xy[k]] = (uint8_t)(3 * k);
+  const int size = b->size, s = b->sight;
+  for (int y = 0; y < 16; ++y)
+    for (int x = 0; x < 16; ++x) {
+      auto sh = [&](int cx, int cy) -> uint32_t {
+        return (cx < 0 || cy < 0 || cx >= size || cy >= size) ? 24u : (uint32_t)b->food_sh[cx | (cy << 4)];
+      };
+      b->adj_sh[x | (y << 4)] = sh(x, y - 1) | (sh(x, y + 1) << 8) | (sh(x - 1, y) << 16) | (sh(x + 1, y) << 24);
+      unsigned long long v = 0;
+      for (int k = 0; k < NF; ++k) {
+        const int dx = (b->food_xy[k] & 15) - x, dy = (b->food_xy[k] >> 4) - y;
+        if (dx >= -s && dx <= s && dy >= -s && dy <= s) {
+          v |= 1ULL << k;
+          v |= (unsigned long long)((dx + s + 1) | ((dy + s + 1) << 3)) << (8 + 6 * k);
+        }
+      }
+      b->vis[x | (y << 4)] = v;
+    }
+}
 
-__device__ __forceinline__ void unpack(uint32_t w0, uint32_t w1, Ents& e) {
+// shift (3 * food index) of the first uncollected food next to `cell` in the order N, S, W, E; 24 if none
+__device__ __forceinline__ uint32_t adjacent_food(const Blob& B, uint32_t w1, uint32_t cell) {
+  const uint32_t a = B.adj_sh[cell];
+  const uint32_t sn = a & 255u, ss = (a >> 8) & 255u, sw = (a >> 16) & 255u, se = a >> 24;
+  uint32_t sh = ((w1 >> se) & 7u) ? se : 24u;
+  sh = ((w1 >> sw) & 7u) ? sw : sh;
+  sh = ((w1 >> ss) & 7u) ? ss : sh;
+  sh = ((w1 >> sn) & 7u) ? sn : sh;
+  return sh;
+}
+
+// Joint transition on the packed words (see the header of this file); rew[] per player; returns
+// all_done.  Moves are branch-free table lookups; only the (rare) loading resolution branches.
+__device__ __forceinline__ bool transition(const Blob& B, uint32_t& w0, uint32_t& w1, const int (&act)[NPL],
+                                           double (&rew)[NPL]) {
+  const uint32_t size = B.size;
+  uint32_t cell[NPL], lvl[NPL], tgt[NPL], load_sh[NPL];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     const uint32_t p = (w0 >> (10 * i)) & 1023u;
-    e.px[i] = p & 15; e.py[i] = (p >> 4) & 15; e.pl[i] = (p >> 8) & 3;
-  }
-  e.spawned = (w0 >> 20) & 63;
-#pragma unroll
-  for (int k = 0; k < NF; ++k) e.fl[k] = (w1 >> (3 * k)) & 7;
-}
-__device__ __forceinline__ void pack(const Ents& e, uint32_t& w0, uint32_t& w1) {
-  w0 = (uint32_t)e.spawned << 20; w1 = 0;
-#pragma unroll
-  for (int i = 0; i < NPL; ++i)
-    w0 |= ((uint32_t)e.px[i] | ((uint32_t)e.py[i] << 4) | ((uint32_t)e.pl[i] << 8)) << (10 * i);
-#pragma unroll
-  for (int k = 0; k < NF; ++k) w1 |= (uint32_t)e.fl[k] << (3 * k);
-}
-
-// index of the (uncollected) food at (x, y), -1 if none / outside
-__device__ __forceinline__ int food_at(const Blob& B, const Ents& e, int x, int y) {
-  if ((unsigned)x >= (unsigned)B.size || (unsigned)y >= (unsigned)B.size) return -1;
-  const int k = B.food_at[x | (y << 4)];
-  int lvl = 0;
-#pragma unroll
-  for (int j = 0; j < NF; ++j) lvl = (j == k) ? e.fl[j] : lvl;
-  return (k != 255 && lvl > 0) ? k : -1;
-}
-// first adjacent food in the order N, S, W, E
-__device__ __forceinline__ int adjacent_food(const Blob& B, const Ents& e, int x, int y) {
-  int k = food_at(B, e, x, y - 1);
-  if (k < 0) k = food_at(B, e, x, y + 1);
-  if (k < 0) k = food_at(B, e, x - 1, y);
-  if (k < 0) k = food_at(B, e, x + 1, y);
-  return k;
-}
-
-// joint transition; rew[] per player; returns all_done
-__device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&act)[NPL], double (&rew)[NPL]) {
-  int tx[NPL], ty[NPL];
-  bool loading[NPL];
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
+    cell[i] = p & 255u; lvl[i] = p >> 8;
     const int a = act[i];
-    tx[i] = e.px[i]; ty[i] = e.py[i]; loading[i] = false;
-    if (a >= NORTH && a <= EAST) {
-      const int nx = e.px[i] + (a == EAST) - (a == WEST), ny = e.py[i] + (a == SOUTH) - (a == NORTH);
-      const bool inside = (unsigned)nx < (unsigned)B.size && (unsigned)ny < (unsigned)B.size;
-      if (inside && food_at(B, e, nx, ny) < 0) { tx[i] = nx; ty[i] = ny; }
-    } else if (a == LOAD) {
-      loading[i] = adjacent_food(B, e, e.px[i], e.py[i]) >= 0;
-    }
+    const uint32_t nc = cell[i] + (uint32_t)(int)B.move_delta[a & 7];
+    // inside the field: row in range (a step off the top wraps to a huge value) and column in range
+    // (a step off the left edge borrows: column nibble 15)
+    const bool inside = (nc < (size << 4)) && ((nc & 15u) < size);
+    const bool food = ((w1 >> B.food_sh[nc & 255u]) & 7u) != 0u;
+    tgt[i] = (inside && !food) ? nc : cell[i];     // NONE / LOAD: nc == cell
+    load_sh[i] = (a == LOAD) ? adjacent_food(B, w1, cell[i]) : 24u;
   }
   // players whose target cell is claimed by more than one player stay
-  const bool clash = (tx[0] == tx[1]) && (ty[0] == ty[1]);
-  if (!clash) {
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) { e.px[i] = tx[i]; e.py[i] = ty[i]; }
-  }
+  const bool clash = tgt[0] == tgt[1];
+  cell[0] = clash ? cell[0] : tgt[0];
+  cell[1] = clash ? cell[1] : tgt[1];
+  w0 = (w0 & 0xFFF00000u) | cell[0] | (lvl[0] << 8) | ((cell[1] | (lvl[1] << 8)) << 10);
   rew[0] = 0.0; rew[1] = 0.0;
-  // loading, in player index order; a group = the pending loaders adjacent to the same food
-  bool pending[NPL] = {loading[0], loading[1]};
+  if (load_sh[0] != 24u || load_sh[1] != 24u) {   // somebody loads
+    const double spawned = (double)((w0 >> 20) & 63u);
+    bool pending[NPL] = {load_sh[0] != 24u, load_sh[1] != 24u};
+    // loading, in player index order; a group = the pending loaders adjacent to the same food
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    if (!pending[i]) continue;
-    pending[i] = false;
-    const int k = adjacent_food(B, e, e.px[i], e.py[i]);
-    if (k < 0) continue;
-    const int fx = B.food_xy[k] & 15, fy = B.food_xy[k] >> 4;
-    bool in_group[NPL] = {false, false};
-    in_group[i] = true;
-    int level_sum = e.pl[i];
+    for (int i = 0; i < NPL; ++i) {
+      if (!pending[i]) continue;
+      pending[i] = false;
+      // a loader did not move; the food it faced may have been taken by the previous group
+      const uint32_t sh = (i == 0) ? load_sh[0] : adjacent_food(B, w1, cell[i]);
+      if (sh == 24u) continue;
+      const uint32_t fxy = B.food_xy[(sh * 11u) >> 5];   // sh / 3 for sh in {0, 3, .., 21}
+      const int fx = fxy & 15, fy = fxy >> 4;
+      bool in_group[NPL] = {false, false};
+      in_group[i] = true;
+      uint32_t level_sum = lvl[i];
 #pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-      if (j == i || !pending[j]) continue;
-      if (abs(e.px[j] - fx) + abs(e.py[j] - fy) == 1) { in_group[j] = true; pending[j] = false; level_sum += e.pl[j]; }
+      for (int j = 0; j < NPL; ++j) {
+        if (j == i || !pending[j]) continue;
+        if (abs((int)(cell[j] & 15u) - fx) + abs((int)(cell[j] >> 4) - fy) == 1) {
+          in_group[j] = true; pending[j] = false; level_sum += lvl[j];
+        }
+      }
+      const uint32_t flevel = (w1 >> sh) & 7u;
+      if (level_sum < flevel) continue;
+#pragma unroll
+      for (int j = 0; j < NPL; ++j) {
+        if (!in_group[j]) continue;
+        double r = (double)(lvl[j] * flevel);
+        if (B.normalize_reward) r = __ddiv_rn(r, __dmul_rn((double)level_sum, spawned));
+        rew[j] = __dadd_rn(rew[j], r);
+      }
+      w1 &= ~(7u << sh);
     }
-    int flevel = 0;
-#pragma unroll
-    for (int f = 0; f < NF; ++f) flevel = (f == k) ? e.fl[f] : flevel;
-    if (level_sum < flevel) continue;
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-      if (!in_group[j]) continue;
-      double r = (double)(e.pl[j] * flevel);
-      if (B.normalize_reward) r = __ddiv_rn(r, (double)(level_sum * e.spawned));
-      rew[j] = __dadd_rn(rew[j], r);
-    }
-#pragma unroll
-    for (int f = 0; f < NF; ++f) e.fl[f] = (f == k) ? 0 : e.fl[f];
   }
-  bool all_done = true;
-#pragma unroll
-  for (int f = 0; f < NF; ++f) all_done &= (e.fl[f] == 0);
-  return all_done;
+  return w1 == 0u;
 }
 
 // tuple observation of player i as two packed words
-__device__ __forceinline__ void observe(const Blob& B, const Ents& e, int i, unsigned long long (&obs)[2]) {
-  const int s = B.sight, o = 1 - i;
-  uint32_t h[4] = {0, 0, 0, 0};   // w0 lo, w0 hi, w1 lo, w1 hi
-  h[0] = (uint32_t)(s + 1) | ((uint32_t)(s + 1) << 3) | ((uint32_t)e.pl[i] << 6);
+__device__ __forceinline__ void observe(const Blob& B, uint32_t w0, uint32_t w1, int i, unsigned long long (&obs)[2]) {
+  const uint32_t s = B.sight;
+  const uint32_t me = (w0 >> (10 * i)) & 1023u, ot = (w0 >> (10 * (1 - i))) & 1023u;
+  uint32_t h0 = (s + 1u) | ((s + 1u) << 3) | ((me >> 8) << 6);
   {
-    const int dx = e.px[o] - e.px[i], dy = e.py[o] - e.py[i];
-    if (abs(dx) <= s && abs(dy) <= s)
-      h[0] |= ((uint32_t)(dx + s + 1) << 8) | ((uint32_t)(dy + s + 1) << 11) | ((uint32_t)e.pl[o] << 14);
+    const uint32_t dx = (ot & 15u) - (me & 15u) + s, dy = ((ot >> 4) & 15u) - ((me >> 4) & 15u) + s;
+    if (dx <= 2u * s && dy <= 2u * s) h0 |= ((dx + 1u) << 8) | ((dy + 1u) << 11) | ((ot >> 8) << 14);
   }
-  int slot = 0;
+  // visible foods, packed into consecutive 9-bit slots of a 72-bit stream (slot 7 straddles)
+  const unsigned long long V = B.vis[me & 255u];
+  unsigned long long lo = 0;
+  uint32_t hi = 0, slot9 = 0;   // slot9 = 9 * slot
 #pragma unroll
   for (int k = 0; k < NF; ++k) {
-    const int dx = (B.food_xy[k] & 15) - e.px[i], dy = (B.food_xy[k] >> 4) - e.py[i];
-    if (e.fl[k] > 0 && abs(dx) <= s && abs(dy) <= s) {
-      const uint32_t f = (uint32_t)(dx + s + 1) | ((uint32_t)(dy + s + 1) << 3) | ((uint32_t)e.fl[k] << 6);
-      // slot 0 -> h[0] @16; slots 1..3 -> h[1] @0,9,18; 4..6 -> h[2]; 7 -> h[3] @0
-      const int half = slot == 0 ? 0 : (slot + 2) / 3, off = slot == 0 ? 16 : 9 * ((slot - 1) % 3);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) h[q] |= (q == half) ? (f << off) : 0u;
-      ++slot;
-    }
+    const uint32_t lv = (w1 >> (3 * k)) & 7u;
+    const bool seen = ((V >> k) & 1ULL) && lv;
+    const unsigned long long code = (unsigned long long)(((uint32_t)(V >> (8 + 6 * k)) & 63u) | (lv << 6));
+    const unsigned long long put = seen ? code : 0ULL;
+    lo |= put << slot9;
+    if (k == NF - 1) hi = (slot9 == 63u) ? (uint32_t)(put >> 1) : 0u;
+    slot9 += seen ? 9u : 0u;
   }
-  obs[0] = (unsigned long long)h[0] | ((unsigned long long)h[1] << 32);
-  obs[1] = (unsigned long long)h[2] | ((unsigned long long)h[3] << 32);
+  // stream -> layout: slot 0 at w0 lo bit 16; slots 1..3 in w0 hi; 4..6 in w1 lo; 7 in w1 hi
+  h0 |= ((uint32_t)lo & 511u) << 16;
+  const uint32_t h1 = (uint32_t)(lo >> 9) & 0x7FFFFFFu, h2 = (uint32_t)(lo >> 36) & 0x7FFFFFFu;
+  const uint32_t h3 = ((uint32_t)(lo >> 63) | (hi << 1)) & 511u;
+  obs[0] = (unsigned long long)h0 | ((unsigned long long)h1 << 32);
+  obs[1] = (unsigned long long)h2 | ((unsigned long long)h3 << 32);
 }
 
-__device__ __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NPL + NF], Ents& e) {
-  int max_level = 0;
+__device__ __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NPL + NF], uint32_t& w0,
+                                                   uint32_t& w1) {
+  uint32_t max_level = 0;
+  w0 = 0; w1 = 0;
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
-    e.px[i] = B.player_xy[i] & 15; e.py[i] = B.player_xy[i] >> 4; e.pl[i] = picks[i] + 1;
-    max_level += e.pl[i];
+    const uint32_t l = (uint32_t)picks[i] + 1u;
+    w0 |= ((uint32_t)B.player_xy[i] | (l << 8)) << (10 * i);
+    max_level += l;
   }
-  e.spawned = 0;
+  uint32_t spawned = 0;
 #pragma unroll
   for (int k = 0; k < NF; ++k) {
-    e.fl[k] = B.force_coop ? max_level : picks[NPL + k] + 1;
-    e.spawned += e.fl[k];
+    const uint32_t l = B.force_coop ? max_level : (uint32_t)picks[NPL + k] + 1u;
+    w1 |= l << (3 * k);
+    spawned += l;
   }
+  w0 |= spawned << 20;
 }
 
 }  // namespace lbf
@@ -198,22 +211,16 @@ struct LBFSim {
   __device__ static __forceinline__ void step_all(const Blob& B, State& s, const int (&act)[NAG],
                                                   const uint32_t (&)[NW], unsigned long long (&obs)[NAG][OW],
                                                   double (&rew)[NAG], uint32_t& flags, bool& was_live) {
-    lbf::Ents e;
-    lbf::unpack(s.w[0], s.w[1], e);
     was_live = s.w[1] != 0u;
-    const bool all_done = lbf::transition(B, e, act, rew);
-    lbf::pack(e, s.w[0], s.w[1]);
-    lbf::observe(B, e, 0, obs[0]);
-    lbf::observe(B, e, 1, obs[1]);
+    const bool all_done = lbf::transition(B, s.w[0], s.w[1], act, rew);
+    lbf::observe(B, s.w[0], s.w[1], 0, obs[0]);
+    lbf::observe(B, s.w[0], s.w[1], 1, obs[1]);
     flags = all_done ? (0x80u | 3u) : 0u;
   }
   __device__ static __forceinline__ void step_noobs(const Blob& B, State& s, const int (&act)[NAG],
                                                     const uint32_t (&)[NW], double (&rew)[NAG], uint32_t& term,
                                                     bool& all_done) {
-    lbf::Ents e;
-    lbf::unpack(s.w[0], s.w[1], e);
-    all_done = lbf::transition(B, e, act, rew);
-    lbf::pack(e, s.w[0], s.w[1]);
+    all_done = lbf::transition(B, s.w[0], s.w[1], act, rew);
     term = all_done ? 3u : 0u;
   }
   // uniform joint action from one Philox word: idx = floor(w * 36 / 2^32), a0 = idx % 6, a1 = idx / 6
@@ -230,15 +237,11 @@ struct LBFSim {
   }
   __device__ static __forceinline__ void noise_from_word(uint32_t, uint32_t (&noise)[NW]) { noise[0] = 0u; }
   __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
-    lbf::Ents e;
-    lbf::unpack(s.w[0], s.w[1], e);
-    lbf::observe(B, e, 0, obs[0]);
-    lbf::observe(B, e, 1, obs[1]);
+    lbf::observe(B, s.w[0], s.w[1], 0, obs[0]);
+    lbf::observe(B, s.w[0], s.w[1], 1, obs[1]);
   }
   __device__ static __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NPICK], State& s) {
-    lbf::Ents e;
-    lbf::initial_from_picks(B, picks, e);
-    lbf::pack(e, s.w[0], s.w[1]);
+    lbf::initial_from_picks(B, picks, s.w[0], s.w[1]);
   }
   // picks from Philox: block (particle, 0, 0xB0): x, y -> player levels, z, w -> foods 0, 1;
   // block (.., 0xB1): foods 2..5; block (.., 0xB2): x, y -> foods 6, 7
@@ -264,29 +267,21 @@ struct LBFSim {
     const int other = (int)uniform_below(word, 6u);
     act[0] = ego == 0 ? ego_action : other;
     act[1] = ego == 1 ? ego_action : other;
-    lbf::Ents e;
-    lbf::unpack(s.w[0], s.w[1], e);
     double rew[NAG];
-    done = lbf::transition(B, e, act, rew);
-    lbf::pack(e, s.w[0], s.w[1]);
+    done = lbf::transition(B, s.w[0], s.w[1], act, rew);
     r = rew[ego];
-    lbf::observe(B, e, ego, obs);
+    lbf::observe(B, s.w[0], s.w[1], ego, obs);
   }
   __device__ static __forceinline__ void rollout_step(const Blob& B, const Ctx&, State& s, int ego, uint32_t word,
                                                       double& r, bool& done) {
     int act[NAG];
     actions_from_word(word, act);
-    lbf::Ents e;
-    lbf::unpack(s.w[0], s.w[1], e);
     double rew[NAG];
-    done = lbf::transition(B, e, act, rew);
-    lbf::pack(e, s.w[0], s.w[1]);
+    done = lbf::transition(B, s.w[0], s.w[1], act, rew);
     r = rew[ego];
   }
   __device__ static __forceinline__ void observe(const Blob& B, const State& s, int ego, unsigned long long (&obs)[OW]) {
-    lbf::Ents e;
-    lbf::unpack(s.w[0], s.w[1], e);
-    lbf::observe(B, e, ego, obs);
+    lbf::observe(B, s.w[0], s.w[1], ego, obs);
   }
 };
 

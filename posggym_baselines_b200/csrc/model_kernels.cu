@@ -127,18 +127,18 @@ int posg_lbf_create(int size, int num_agents, int max_agent_level, int max_food,
     set_error("the sm_100a kernels are specialised for 2 players and 8 foods");
     return POSG_E_UNSUPPORTED;
   }
-  if (size < 3 || size > 16 || sight != 2 || max_agent_level < 1 || max_agent_level > 3) {
-    set_error("unsupported LBF geometry (size 3..16, sight 2, max_agent_level 1..3)");
+  if (size < 3 || size > 15 || sight != 2 || max_agent_level < 1 || max_agent_level > 3) {
+    set_error("unsupported LBF geometry (size 3..15, sight 2, max_agent_level 1..3)");
     return POSG_E_UNSUPPORTED;
   }
   int ndev = posg_device_count();
   if (ndev < 0) return ndev;
   lbf::Blob* h = (lbf::Blob*)calloc(1, sizeof(lbf::Blob));
-  memset(h->food_at, 255, sizeof(h->food_at));
-  for (int k = 0; k < lbf::NF; ++k) { h->food_xy[k] = food_xy[k]; h->food_at[food_xy[k]] = (uint8_t)k; }
+  for (int k = 0; k < lbf::NF; ++k) h->food_xy[k] = food_xy[k];
   for (int i = 0; i < lbf::NPL; ++i) h->player_xy[i] = player_xy[i];
   h->size = (uint8_t)size; h->sight = (uint8_t)sight; h->max_agent_level = (uint8_t)max_agent_level;
   h->force_coop = force_coop ? 1 : 0; h->normalize_reward = normalize_reward ? 1 : 0;
+  lbf::build_tables(h);
   posg_model* m = new posg_model();
   m->kind = KIND_LBF; m->num_agents = num_agents; m->blob_bytes = (int)sizeof(lbf::Blob);
   m->h_blob = h; m->d_blob = nullptr;
