@@ -28,8 +28,13 @@ step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int6
   const int64_t stride = (int64_t)gridDim.x * THREADS;
   for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += stride) {
     typename M::State s;
+    if constexpr (SW == 2) {   // one 8-byte load / store per env (cudaMalloc'ed arrays are aligned)
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(state_in) + i);
+      s.w[0] = v.x; s.w[1] = v.y;
+    } else {
 #pragma unroll
-    for (int k = 0; k < SW; ++k) s.w[k] = __ldg(state_in + i * SW + k);
+      for (int k = 0; k < SW; ++k) s.w[k] = __ldg(state_in + i * SW + k);
+    }
     int act[NAG];
     uint32_t noise[NW];
     if (actions_in == nullptr || noise_in == nullptr)
@@ -48,14 +53,27 @@ step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int6
     bool was_live;
     M::step_all(B, s, act, noise, obs, rew, flags, was_live);
     live += was_live ? 1u : 0u;
+    if constexpr (SW == 2) {
+      reinterpret_cast<uint2*>(state_out)[i] = make_uint2(s.w[0], s.w[1]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < SW; ++k) state_out[i * SW + k] = s.w[k];
+      for (int k = 0; k < SW; ++k) state_out[i * SW + k] = s.w[k];
+    }
+    if constexpr (NAG == 2 && (OW == 1 || OW == 2)) {
+      // 16-byte stores: both agents' words (OW == 1) or one agent's two words (OW == 2) at a time
+      ulonglong2* o = reinterpret_cast<ulonglong2*>(obs_out) + i * OW;
+      if constexpr (OW == 1) { o[0] = make_ulonglong2(obs[0][0], obs[1][0]); }
+      else { o[0] = make_ulonglong2(obs[0][0], obs[0][1]); o[1] = make_ulonglong2(obs[1][0], obs[1][1]); }
+      reinterpret_cast<double2*>(rewards_out)[i] = make_double2(rew[0], rew[1]);
+      if (actions_out) reinterpret_cast<uchar2*>(actions_out)[i] = make_uchar2((unsigned char)act[0], (unsigned char)act[1]);
+    } else {
 #pragma unroll
-    for (int a = 0; a < NAG; ++a) {
+      for (int a = 0; a < NAG; ++a) {
 #pragma unroll
-      for (int k = 0; k < OW; ++k) obs_out[(i * NAG + a) * OW + k] = obs[a][k];
-      rewards_out[i * NAG + a] = rew[a];
-      if (actions_out) actions_out[i * NAG + a] = (uint8_t)act[a];
+        for (int k = 0; k < OW; ++k) obs_out[(i * NAG + a) * OW + k] = obs[a][k];
+        rewards_out[i * NAG + a] = rew[a];
+        if (actions_out) actions_out[i * NAG + a] = (uint8_t)act[a];
+      }
     }
     flags_out[i] = (uint8_t)flags;
   }

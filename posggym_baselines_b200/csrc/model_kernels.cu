@@ -180,6 +180,9 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
   POSG_REQUIRE(m, "null model");
   if (n == 0) return POSG_OK;
   POSG_REQUIRE(n > 0 && state_in && state_out && obs_out && rewards_out && flags_out, "bad arguments");
+  POSG_REQUIRE((((uintptr_t)state_in | (uintptr_t)state_out) & 7u) == 0 &&
+               (((uintptr_t)obs_out | (uintptr_t)rewards_out) & 15u) == 0 && ((uintptr_t)actions_out & 1u) == 0,
+               "state buffers must be 8-byte, obs / rewards buffers 16-byte aligned");
   MODEL_DISPATCH(m, (generic::step_kernel<M><<<persistent_grid(generic::step_kernel<M>, m->blob_bytes, n),
                      generic::THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
                      (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, actions_in, noise_in, seed,
