@@ -85,6 +85,7 @@ static pp::Blob* build_pp_blob(int size, const char* blocks, int num_predators, 
         }
       b->obs_base[x | (y << 4)] = cells;
     }
+  pp::build_tables(b);
   return b;
 }
 

@@ -25,7 +25,29 @@ struct alignas(16) Blob {
   double per_prey_reward;
   double pad2_;
   unsigned long long obs_base[256];  // wall cells of the window centred at (x, y)
+  uint8_t wall4[256];                // bit k: neighbour k (N, E, S, W) of cell x | y << 4 is blocked / outside
+  uint8_t nth_lut[32 * 8];           // [mask5 * 8 + n] -> index of the n-th set bit of mask5 (bits 0..4)
+  int8_t nb_delta[8];                // cell-index delta of N, E, S, W, stay
+  uint8_t pad3_[8];
 };
+
+// host side: fill the lookup tables from rows[] (walls)
+inline void build_tables(Blob* b) {
+  for (int y = 0; y < 16; ++y)
+    for (int x = 0; x < 16; ++x) {
+      const int nx[4] = {x, x + 1, x, x - 1}, ny[4] = {y - 1, y, y + 1, y};
+      uint8_t m = 0;
+      for (int k = 0; k < 4; ++k) m |= (uint8_t)(((b->rows[ny[k] + PAD] >> (nx[k] + PAD)) & 1u) << k);
+      b->wall4[x | (y << 4)] = m;
+    }
+  for (int m = 0; m < 32; ++m) {
+    int n = 0;
+    for (int bit = 0; bit < 5; ++bit) if ((m >> bit) & 1) b->nth_lut[m * 8 + n++] = (uint8_t)bit;
+    for (; n < 8; ++n) b->nth_lut[m * 8 + n] = 4;
+  }
+  const int8_t d[8] = {-16, 1, 16, -1, 0, 0, 0, 0};
+  for (int k = 0; k < 8; ++k) b->nb_delta[k] = d[k];
+}
 static_assert(sizeof(Blob) % 16 == 0, "blob must be a multiple of 16 B");
 
 __device__ __forceinline__ bool blocked(const Blob& B, int x, int y) {
@@ -51,95 +73,94 @@ __device__ __forceinline__ void pack(const Ents& e, uint32_t& w0, uint32_t& w1) 
   w1 = (uint32_t)e.prey[0] | ((uint32_t)e.prey[1] << 8) | ((uint32_t)e.prey[2] << 16);
 }
 
-// free = inside, not a block, not occupied by a predator or an uncaught prey (cur[] =
-// positions with the moves made so far applied)
-__device__ __forceinline__ bool cell_free(const Blob& B, const Ents& e, const int (&cur)[NQ], int x, int y) {
-  if (blocked(B, x, y)) return false;
-  const int c = x | (y << 4);
-  bool occ = (c == e.pred[0]) || (c == e.pred[1]);
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) occ |= (!((e.caught >> j) & 1u)) && (cur[j] == c);
-  return !occ;
-}
+__device__ __forceinline__ uint32_t swapnib(uint32_t c) { return ((c << 4) & 0xF0u) | ((c >> 4) & 15u); }
 
-// flee from the closest of `threats` (index order) if within obs_dim; returns -1 if none in sight
-__device__ __forceinline__ int move_away(const Blob& B, const Ents& e, const int (&cur)[NQ], int coord,
-                                         const int* threats, int nthreats, uint32_t word) {
-  int dmin = 1 << 20, nclose = 0;
-  for (int k = 0; k < nthreats; ++k) { const int d = mdist(coord, threats[k]); dmin = d < dmin ? d : dmin; }
-  if (nthreats == 0 || dmin > (int)B.obs_dim) return -1;
-  for (int k = 0; k < nthreats; ++k) nclose += (mdist(coord, threats[k]) == dmin);
-  const int want = (int)pick_index(word, (uint32_t)nclose);
-  int threat = threats[0], seen = 0;
-  for (int k = 0; k < nthreats; ++k)
-    if (mdist(coord, threats[k]) == dmin) { if (seen == want) threat = threats[k]; ++seen; }
-  // current cell, then neighbours N, E, S, W; keep the max of (dist, x, y)
-  int best = coord, bd = mdist(coord, threat);
-  const int x = coord & 15, y = coord >> 4;
-  const int nx[4] = {x, x + 1, x, x - 1}, ny[4] = {y - 1, y, y + 1, y};
+// One prey move (PredatorPreyModel._move_away / the random move of _get_next_prey_state), branch
+// free: flee = keep the free option (staying included) with the largest (distance to `threat`, x, y);
+// otherwise the pick_index(word)-th of the free neighbours N, E, S, W followed by staying.
+// occ[] = cells of the predators and of the uncaught prey (moves made so far applied; -1 = none).
+__device__ __forceinline__ int prey_move(const Blob& B, int coord, bool flee, int threat, uint32_t word,
+                                         const int (&occ)[NP + NQ]) {
+  const uint32_t w4 = B.wall4[coord];
+  const int dx = (threat & 15) - (coord & 15), dy = (threat >> 4) - (coord >> 4);
+  const int adx = abs(dx), ady = abs(dy);
+  const int nb[4] = {coord - 16, coord + 1, coord + 16, coord - 1};
+  const int dist[4] = {adx + abs(dy + 1), abs(dx - 1) + ady, adx + abs(dy - 1), abs(dx + 1) + ady};
+  uint32_t free4 = 0, best = ((uint32_t)(adx + ady) << 8) | swapnib((uint32_t)coord);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (!cell_free(B, e, cur, nx[k], ny[k])) continue;
-    const int c = nx[k] | (ny[k] << 4);
-    const int d = mdist(c, threat);
-    const bool better = d > bd || (d == bd && (nx[k] > (best & 15) || (nx[k] == (best & 15) && ny[k] > (best >> 4))));
-    if (better) { best = c; bd = d; }
+    bool taken = false;
+#pragma unroll
+    for (int j = 0; j < NP + NQ; ++j) taken |= (nb[k] == occ[j]);
+    const bool fr = !((w4 >> k) & 1u) && !taken;
+    free4 |= (fr ? 1u : 0u) << k;
+    const uint32_t key = fr ? (((uint32_t)dist[k] << 8) | swapnib((uint32_t)nb[k] & 255u)) : 0u;
+    best = max(best, key);
   }
-  return best;
+  const int flee_cell = (int)swapnib(best & 255u);
+  const uint32_t m5 = free4 | 16u;
+  const uint32_t sel = B.nth_lut[m5 * 8u + pick_index(word, (uint32_t)__popc(m5))];
+  const int rnd_cell = coord + (int)B.nb_delta[sel];
+  return flee ? flee_cell : rnd_cell;
 }
 
 // joint transition; rew[] per predator; returns all_done
 __device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&act)[NP], const uint32_t (&words)[NQ],
                                            double (&rew)[NP]) {
-  int cur[NQ];
-  bool moved[NQ];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) { cur[i] = e.prey[i]; moved[i] = (e.caught >> i) & 1u; }
-  // 1. flee from predators
+  const int od = (int)B.obs_dim;
+  const int n_unc = NQ - __popc(e.caught);
+  // Which rule moves each prey is a function of the state before the step: 0 flee from the closest
+  // predator in sight, 1 keep away from the closest other prey in sight, 2 random move, 3 caught.
+  // The moves are then made in (rule, index) order, as the reference's three passes do.
+  uint32_t info[NQ], key[NQ];   // info: cell | threat << 8 | flee << 16
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
-    if (moved[i]) continue;
-    const int nxt = move_away(B, e, cur, e.prey[i], e.pred, NP, words[i]);
-    if (nxt >= 0) { cur[i] = nxt; moved[i] = true; }
+    const int c = e.prey[i];
+    const bool caught = (e.caught >> i) & 1u;
+    const bool hi = (words[i] >> 31) != 0u;            // pick_index(word, 2)
+    const int d0 = mdist(c, e.pred[0]), d1 = mdist(c, e.pred[1]);
+    const bool ph1 = min(d0, d1) <= od;
+    const int t1 = d0 < d1 ? e.pred[0] : (d1 < d0 ? e.pred[1] : (hi ? e.pred[1] : e.pred[0]));
+    const int j1 = i == 0 ? 1 : 0, j2 = i == 2 ? 1 : 2;
+    const int f1 = ((e.caught >> j1) & 1u) ? (1 << 20) : mdist(c, e.prey[j1]);
+    const int f2 = ((e.caught >> j2) & 1u) ? (1 << 20) : mdist(c, e.prey[j2]);
+    const bool ph2 = !ph1 && n_unc > 1 && min(f1, f2) <= od;
+    const int t2 = f1 < f2 ? e.prey[j1] : (f2 < f1 ? e.prey[j2] : (hi ? e.prey[j2] : e.prey[j1]));
+    const uint32_t rule = caught ? 3u : (ph1 ? 0u : (ph2 ? 1u : 2u));
+    info[i] = (uint32_t)c | ((uint32_t)(ph1 ? t1 : t2) << 8) | ((ph1 || ph2) ? 0x10000u : 0u);
+    key[i] = rule * 4u + (uint32_t)i;
   }
-  // 2. keep away from other prey (their positions before this step)
-  if (NQ - __popc(e.caught) > 1) {
+  // sort the three keys
+  uint32_t k0 = min(key[0], key[1]), k1 = max(key[0], key[1]), k2 = key[2];
+  { const uint32_t t = min(k1, k2); k2 = max(k1, k2); k1 = t; }
+  { const uint32_t t = min(k0, k1); k1 = max(k0, k1); k0 = t; }
+  const uint32_t order[NQ] = {k0, k1, k2};
+  int cur[NQ] = {e.prey[0], e.prey[1], e.prey[2]};
+  int occ[NP + NQ] = {e.pred[0], e.pred[1], (e.caught & 1u) ? -1 : cur[0], (e.caught & 2u) ? -1 : cur[1],
+                      (e.caught & 4u) ? -1 : cur[2]};
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-      if (moved[i]) continue;
-      int others[NQ], no = 0;
+  for (int k = 0; k < NQ; ++k) {
+    const uint32_t i = order[k] & 3u;
+    const bool live = order[k] < 12u;
+    const uint32_t inf = i == 0u ? info[0] : (i == 1u ? info[1] : info[2]);
+    const uint32_t word = i == 0u ? words[0] : (i == 1u ? words[1] : words[2]);
+    const int nxt = prey_move(B, (int)(inf & 255u), (inf >> 16) != 0u, (int)((inf >> 8) & 255u), word, occ);
 #pragma unroll
-      for (int j = 0; j < NQ; ++j)
-        if (j != i && !((e.caught >> j) & 1u)) others[no++] = e.prey[j];
-      const int nxt = move_away(B, e, cur, e.prey[i], others, no, words[i]);
-      if (nxt >= 0) { cur[i] = nxt; moved[i] = true; }
+    for (int j = 0; j < NQ; ++j) {
+      const bool mine = live && i == (uint32_t)j;
+      cur[j] = mine ? nxt : cur[j];
+      occ[NP + j] = mine ? nxt : occ[NP + j];
     }
-  }
-  // 3. random move among free neighbours (N, E, S, W) and staying
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) {
-    if (moved[i]) continue;
-    const int x = e.prey[i] & 15, y = e.prey[i] >> 4;
-    const int nx[4] = {x, x + 1, x, x - 1}, ny[4] = {y - 1, y, y + 1, y};
-    int cands[5], nc = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (cell_free(B, e, cur, nx[k], ny[k])) cands[nc++] = nx[k] | (ny[k] << 4);
-    cands[nc++] = e.prey[i];
-    cur[i] = cands[pick_index(words[i], (uint32_t)nc)];
-    moved[i] = true;
   }
   // predators: simultaneous moves; prey cells and shared targets block
   int pot[NP];
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    const int a = act[i], x = e.pred[i] & 15, y = e.pred[i] >> 4;
-    const int dx = (a == 4) - (a == 3), dy = (a == 2) - (a == 1);
-    int c = e.pred[i];
-    if (a != 0 && !blocked(B, x + dx, y + dy)) c = (x + dx) | ((y + dy) << 4);
-    bool on_prey = false;
-#pragma unroll
-    for (int j = 0; j < NQ; ++j) on_prey |= (!((e.caught >> j) & 1u)) && (cur[j] == c);
+    const int a = act[i];
+    const uint32_t dir = (0x13200u >> (4 * a)) & 3u;   // UP, DOWN, LEFT, RIGHT -> N, S, W, E
+    const bool moves = a != 0 && !((B.wall4[e.pred[i]] >> dir) & 1u);
+    const int c = moves ? e.pred[i] + (int)B.nb_delta[dir] : e.pred[i];
+    const bool on_prey = (c == occ[NP]) || (c == occ[NP + 1]) || (c == occ[NP + 2]);
     pot[i] = on_prey ? e.pred[i] : c;
   }
   const bool clash = pot[0] == pot[1];
@@ -148,23 +169,20 @@ __device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&a
   uint32_t newly = 0;
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    if ((e.caught >> j) & 1u) continue;
     const int adj = (mdist(cur[j], p0) <= 1) + (mdist(cur[j], p1) <= 1);
-    if (adj >= (int)B.prey_strength) newly |= 1u << j;
+    newly |= (!((e.caught >> j) & 1u) && adj >= (int)B.prey_strength) ? (1u << j) : 0u;
   }
   rew[0] = 0.0; rew[1] = 0.0;
-  if (newly) {
-    if (B.cooperative) {
-      rew[0] = rew[1] = B.reward_k[__popc(newly)];
-    } else {
+  if (B.cooperative) {
+    rew[0] = rew[1] = B.reward_k[__popc(newly)];   // reward_k[0] == 0.0
+  } else if (newly) {
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) {
-        if (!((newly >> j) & 1u)) continue;
-        const bool i0 = mdist(cur[j], p0) <= 1, i1 = mdist(cur[j], p1) <= 1;
-        const double share = __ddiv_rn(B.per_prey_reward, (double)((int)i0 + (int)i1));
-        if (i0) rew[0] = __dadd_rn(rew[0], share);
-        if (i1) rew[1] = __dadd_rn(rew[1], share);
-      }
+    for (int j = 0; j < NQ; ++j) {
+      if (!((newly >> j) & 1u)) continue;
+      const bool i0 = mdist(cur[j], p0) <= 1, i1 = mdist(cur[j], p1) <= 1;
+      const double share = __ddiv_rn(B.per_prey_reward, (double)((int)i0 + (int)i1));
+      if (i0) rew[0] = __dadd_rn(rew[0], share);
+      if (i1) rew[1] = __dadd_rn(rew[1], share);
     }
   }
   e.pred[0] = p0; e.pred[1] = p1;
