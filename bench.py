@@ -118,7 +118,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
@@ -341,7 +341,30 @@ def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
     return out
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Library chatter (e.g. "NCCL version ..." with NCCL_DEBUG=VERSION) must not share stdout with
+    the ONE JSON line: fd 1 is pointed at stderr for the whole run, the line goes to the saved fd."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -544,7 +567,7 @@ def main():
                          "launch_ms": launch_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "pomcp": pomcp, "vec_env": vec,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
