@@ -246,3 +246,36 @@ def test_pomcp_on_lbf():
         if done:
             break
     planner.close()
+
+
+def test_edge_cases(env):
+    """Empty batch, a single env, stepping a terminal state (all food loaded) and LOAD next to a
+    food that is too heavy: nothing changes, nothing is paid."""
+    from posggym_baselines_b200.envs.lbf import Food, LBFState, Player
+
+    dev = env.device
+    empty = torch.empty((0, 2), dtype=torch.int32, device=dev)
+    out = env.step(empty, seed=1)
+    assert out.state.shape == (0, 2) and out.obs.shape == (0, 2, 2)
+    ret, steps, _ = env.rollout(empty, 0, 50, 0.95)
+    assert ret.shape == (0,)
+    one = env.sample_initial_state(1, seed=3)
+    assert env.step(one, seed=3).state.shape == (1, 2)
+    fc = env.food_coords
+    # terminal state: every food collected
+    done = LBFState((Player(0, (0, 9), 2), Player(1, (9, 0), 3)), tuple(Food(c, 0) for c in fc), 20)
+    # player 0 (level 1) next to food 0 (level 3): a failed load
+    heavy = LBFState((Player(0, (fc[0][0] - 1, fc[0][1]), 1), Player(1, (9, 0), 1)),
+                     tuple(Food(c, 3 if k == 0 else 0) for k, c in enumerate(fc)), 3)
+    # both players next to food 0 (level 3), levels 1 + 2: a joint load that pays 1/3 and 2/3
+    joint = LBFState((Player(0, (fc[0][0] - 1, fc[0][1]), 1), Player(1, (fc[0][0], fc[0][1] - 1), 2)),
+                     tuple(Food(c, 3 if k == 0 else 0) for k, c in enumerate(fc)), 3)
+    packed = torch.from_numpy(env.pack_state([done, heavy, joint])).to(dev)
+    acts = torch.tensor([[5, 5], [5, 0], [5, 5]], dtype=torch.uint8, device=dev)
+    out = env.step(packed, acts, torch.zeros((3, 1), dtype=torch.int32, device=dev))
+    st = env.unpack_state(out.state)
+    rew, flags = out.rewards.cpu().numpy(), out.flags.cpu().numpy()
+    assert st[0] == done and (rew[0] == 0).all() and flags[0] == 0x83
+    assert st[1] == heavy and (rew[1] == 0).all() and flags[1] == 0
+    assert all(f.level == 0 for f in st[2].food) and flags[2] == 0x83
+    assert rew[2, 0] == 1 * 3 / (3 * 3) and rew[2, 1] == 2 * 3 / (3 * 3)
