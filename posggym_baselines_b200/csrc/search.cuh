@@ -169,7 +169,7 @@ __device__ __forceinline__ double normalize(double v, double mn, double mx) {
 // `grp` = mask of those lanes.  Every lane of a group runs the same arithmetic.
 template <int A>
 __device__ int select_action(const Tree& T, const Params& P, int node, bool is_root, unsigned grp, int rank,
-                             int max_gsize, int n_base, uint32_t rnd_word) {
+                             int max_gsize, int n_base, uint32_t rnd_word, unsigned desc_mask) {
   float n[A], q[A];
   // MinMaxStats.normalize (utils.py:34-39) in single precision: the scores are compared as floats
   // anyway, and ten double divisions per tree level cost more than the rest of the selection
@@ -195,6 +195,62 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
 #pragma unroll
   for (int a = 0; a < A; ++a)
     rs[a] = (P.selection == SEL_PUCB) ? __frcp_rn(1.0f + n[a]) : (n[a] > 0.0f ? rsqrtf(n[a]) : 0.0f);
+  // Large groups (near the root a whole warp shares a node): the g sequential UCB picks with frozen
+  // values are the g largest "marginals" m_a(i) = Q_a + cs / sqrt(n_a + i) (m_a decreases in i, so
+  // greedy == top-g; ties go to the lower action index).  The lane of rank r evaluates the
+  // candidates (a, r) and counts in closed form how many marginals precede each: (a, r) is taken
+  // iff fewer than g do.  O(A^2) per lane instead of O(g * A); cs is frozen at the group's middle
+  // visit count.  Only the per-action COUNTS matter (lanes are exchangeable), so lane r then takes
+  // the action whose cumulative count first exceeds r.  Warp-uniform switch; max_gsize < 8 (and
+  // wave size 1, the reference's sequential search) keeps the exact loop below.
+  if (P.selection == SEL_UCB && max_gsize >= 8) {
+    const int g = __popc(grp);
+    const int Nmid = n_base + (is_root ? 0 : 1) + (g >> 1);
+    const float csm = c * sqrtf(__logf((float)(Nmid > 1 ? Nmid : 1)));
+    int k[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const float na = n[a] + (float)rank;
+      const bool inf_a = na <= 0.0f;                 // an unvisited action's first visit: +inf
+      const float v = q[a] + csm * rsqrtf(fmaxf(na, 1.0f));
+      float before = (float)rank;                    // (a, 0..rank-1)
+#pragma unroll
+      for (int b = 0; b < A; ++b) {
+        if (b == a) continue;
+        float cnt;
+        if (inf_a) {
+          cnt = (n[b] <= 0.0f && b < a) ? 1.0f : 0.0f;
+        } else {
+          const float diff = v - q[b];
+          const float ratio = __fdividef(csm, diff);
+          const float X = ratio * ratio;             // m_b(i) > v  <=>  n_b + i < X
+          const float t = X - n[b], ti = rintf(t);
+          const bool tie = fabsf(t - ti) <= fmaxf(1e-3f, 4e-5f * X);
+          cnt = fmaxf(tie ? ti + (b < a ? 1.0f : 0.0f) : ceilf(t), 0.0f);
+          cnt = diff > 0.0f ? cnt : 1e9f;            // Q_b >= v: every marginal of b precedes
+        }
+        before += cnt;
+      }
+      k[a] = __popc(__ballot_sync(desc_mask, before < (float)g) & grp);
+    }
+    int cum = 0, mine = -1;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      mine = (mine < 0 && rank < cum + k[a]) ? a : mine;
+      cum += k[a];
+    }
+    if (mine < 0) {
+      // rounding left fewer than g candidates: the next best marginal
+      float best = -3.0e38f;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        const float nn = n[a] + (float)k[a];
+        const float v = nn > 0.0f ? q[a] + csm * rsqrtf(nn) : 3.0e38f;
+        if (v > best) { best = v; mine = a; }
+      }
+    }
+    return mine;
+  }
   // c * sqrt(ln N) over the group's consecutive visit counts N0 .. N0 + max_gsize - 1: exact per
   // iteration while N is small, linear in between the two ends once N0 >= 256 (relative error of the
   // interpolation < (max_gsize / N0)^2 / 8 < 2e-3 of a term that itself changes by < 1 %)
@@ -370,7 +426,9 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
     }
     // group-consistent random word: the group leader's
     const uint32_t rnd = __shfl_sync(full, w.z, __ffs(grp) - 1);
-    if (descending) action = select_action<A>(T, P, node, node == root, grp, rank, max_g, n_base, rnd ^ (uint32_t)node);
+    const unsigned desc_mask = __ballot_sync(full, descending);
+    if (descending)
+      action = select_action<A>(T, P, node, node == root, grp, rank, max_g, n_base, rnd ^ (uint32_t)node, desc_mask);
     {
       // virtual visit, one atomic per distinct action node of the warp: near the root thousands of
       // simulations per wave hit the same few counters, and same-address atomics serialise in L2
