@@ -163,8 +163,15 @@ step_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
 // warp.  Same results as step_kernel (tests/test_driving_gpu.py).
 constexpr int WARP_ENVS = 128;
 
+// Software pipeline (A/B switch): the next block's states are loaded and its Philox rounds
+// issued one iteration ahead, so neither the DRAM latency nor the ten dependent multiply rounds
+// sit in front of the first env of a block.  Measured share of the HBM roofline, CTAs/SM:
+// without the pipeline 3: 71.7 %, 4: 72.4 %, 5: 69.5 %; with it 3: 76.9 % (80 registers), 4: 72.8 %.
+#ifndef STEP_FAST_PREFETCH
+#define STEP_FAST_PREFETCH 1
+#endif
 #ifndef STEP_FAST_MIN_CTAS
-#define STEP_FAST_MIN_CTAS 4  // 64 registers, no spills; measured 3: 71.7 %, 4: 72.4 %, 5: 69.5 % of the HBM roofline
+#define STEP_FAST_MIN_CTAS 3
 #endif
 
 template <bool WRITE_ACTIONS, bool COUNT_LIVE>
@@ -182,18 +189,52 @@ step_fast_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nb
   unsigned live = 0;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t wstride = gridDim.x * (THREADS / 32);
-  for (uint32_t wb = blockIdx.x * (THREADS / 32) + warp; wb < nblocks; wb += wstride) {
+  uint32_t wb = blockIdx.x * (THREADS / 32) + warp;
+#if STEP_FAST_PREFETCH
+  // software pipeline: the next block's states are requested before this block is computed, so
+  // the DRAM latency of the only global loads of the loop is hidden behind ~1000 instructions
+  uint2 nxt[EPT];
+#pragma unroll
+  for (int j = 0; j < EPT; ++j) nxt[j] = wb < nblocks ? __ldg(state_in + wb * WARP_ENVS + lane + 32 * j) : make_uint2(0u, 0u);
+#endif
+#if STEP_FAST_PREFETCH
+  uint4 blk_next = philox_block(seed, group_offset + (uint64_t)wb * 32u + lane, step_idx, STREAM_STEP);
+#endif
+  for (; wb < nblocks; wb += wstride) {
     const uint32_t e0 = wb * WARP_ENVS + lane;     // this lane's first env
     uint2 sv[EPT];
+#if STEP_FAST_PREFETCH
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) sv[j] = nxt[j];
+    if (wb + wstride < nblocks) {
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) nxt[j] = __ldg(state_in + (wb + wstride) * WARP_ENVS + lane + 32 * j);
+    }
+#else
 #pragma unroll
     for (int j = 0; j < EPT; ++j) sv[j] = __ldg(state_in + e0 + 32 * j);
+#endif
+#if STEP_FAST_PREFETCH
+    __syncwarp();
+    *reinterpret_cast<uint4*>(&s_words[warp][4 * lane]) = blk_next;
+    __syncwarp();
+    uint32_t nzw[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) nzw[j] = s_words[warp][32 * j + lane];
+    // the next block's Philox rounds are independent of everything below: the scheduler overlaps them
+    blk_next = philox_block(seed, group_offset + (uint64_t)(wb + wstride) * 32u + lane, step_idx, STREAM_STEP);
+#else
     const uint4 blk = philox_block(seed, group_offset + (uint64_t)wb * 32u + lane, step_idx, STREAM_STEP);
     __syncwarp();
     *reinterpret_cast<uint4*>(&s_words[warp][4 * lane]) = blk;
     __syncwarp();
+    uint32_t nzw[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) nzw[j] = s_words[warp][32 * j + lane];
+#endif
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
-      const uint32_t nz = B.noise_lut[__umulhi(s_words[warp][32 * j + lane], 50u)];
+      const uint32_t nz = B.noise_lut[__umulhi(nzw[j], 50u)];
       uint32_t v0 = sv[j].x, v1 = sv[j].y;
       const uint32_t b0 = v0, b1 = v1;
       if (COUNT_LIVE) live += ((b0 & 0x18000u) && (b1 & 0x18000u)) ? 0u : 1u;
