@@ -290,14 +290,12 @@ def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
             ve.reset()
             acts = torch.randint(0, nact, (64, nv * 2), device=dev, dtype=torch.int64)
             for k in range(8):
-                ve._global_step += 1
-                ve._launch(acts[k], 0)
+                ve.step(acts[k])
             barrier()
             v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             v0.record()
-            for k in range(64):
-                ve._global_step += 1
-                ve._launch(acts[k], 0)
+            for k in range(64):          # the public call: envs.step(actions) -> (obs, rew, term, trunc, dones, infos)
+                ve.step(acts[k])
             v1.record()
             barrier()
             vms = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)

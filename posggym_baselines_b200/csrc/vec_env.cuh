@@ -61,7 +61,7 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
                 uint64_t env_offset, int max_episode_steps, int reset_only,
                 float* __restrict__ obs_out, float* __restrict__ rew_out, uint8_t* __restrict__ term_out,
                 uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out, float* __restrict__ stat_r,
-                int* __restrict__ stat_l) {
+                int* __restrict__ stat_l, double now, double* __restrict__ ep_t0, double* __restrict__ stat_t) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
@@ -87,6 +87,7 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
         M::initial_state(B, seed, env, s);  // episode 0 of this env: Philox step field 0
         M::observe_all(B, s, obs);
         ep_t[i] = 0; ep_count[i] = 0;
+        if (ep_t0 != nullptr) ep_t0[i] = now;
 #pragma unroll
         for (int a = 0; a < NAG; ++a) ep_ret[i * NAG + a] = 0.0;
       } else {
@@ -114,6 +115,12 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
         }
         stat_l[i] = done ? t : 0;
         done_out[i] = done ? 1 : 0;
+        if (ep_t0 != nullptr) {
+          // RecordEpisodeStatistics "t": wall time of the episode that ends with this step
+          const double t0 = ep_t0[i];
+          stat_t[i] = done ? now - t0 : 0.0;
+          if (done) ep_t0[i] = now;
+        }
         if (done) {
           // auto-reset (SyncVectorEnv): the observation returned is the new episode's first
           const uint32_t ep = ep_count[i] + 1;

@@ -11,7 +11,9 @@ observations, ``reward`` / ``terminated`` / ``truncated`` the same number of row
 one entry per env, ``infos[agent_id]["episode"]`` holds ``r``, ``l``, ``t`` arrays indexed by
 env on the steps where some episode ended.  Finished envs are auto-reset in the same call
 (the worker never calls ``reset`` again).  Everything is computed by one kernel launch
-(posg_vec_step); tensors stay on the GPU unless ``as_numpy=True``.
+(posg_vec_step) without a host synchronisation; tensors stay on the GPU unless ``as_numpy=True``
+and are views of buffers that the next call overwrites (the worker copies them into its rollout
+buffers right away, ppo/worker.py:141-146,176-195).
 
 Sharding: ``env_offset`` gives this shard's first global env index (Philox counters are
 global env indices, so a 65 536-env job split over 8 GPUs is the same job).
@@ -55,11 +57,16 @@ class BatchedVecEnv:
         self._term = torch.zeros(n * a, dtype=torch.uint8, device=dev)
         self._trunc = torch.zeros(n * a, dtype=torch.uint8, device=dev)
         self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        # bool views of the kernel's byte flags (the kernel writes exactly 0 / 1)
+        self._term_b, self._trunc_b, self._done_b = (
+            self._term.view(torch.bool), self._trunc.view(torch.bool), self._done.view(torch.bool))
         self._stat_r = torch.zeros((n, a), dtype=torch.float32, device=dev)
         self._stat_l = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._t0 = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._t0 = torch.zeros(n, dtype=torch.float64, device=dev)      # start time of the running episode
+        self._stat_t = torch.zeros(n, dtype=torch.float64, device=dev)  # wall time of the episode just ended
         self._global_step = 0
         self._args = None
+        self._ret = None
         self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
 
     @property
@@ -75,16 +82,18 @@ class BatchedVecEnv:
                 (self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._ep_t), _lib.ptr(self._ep_ret),
                  _lib.ptr(self._ep_count)),
                 (_lib.ptr(self._obs), _lib.ptr(self._rew), _lib.ptr(self._term), _lib.ptr(self._trunc),
-                 _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l)))
-        head, tail = self._args
+                 _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l)),
+                (_lib.ptr(self._t0), _lib.ptr(self._stat_t)))
+        head, tail, clock = self._args
         a = None if actions is None else actions.data_ptr()
+        now = time.perf_counter()
         if torch.cuda.current_device() == self._dev_index:
             rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps, reset_only,
-                          *tail, torch.cuda.current_stream().cuda_stream or None)
+                          *tail, now, *clock, torch.cuda.current_stream().cuda_stream or None)
         else:
             with torch.cuda.device(self._b.device):
                 rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps,
-                              reset_only, *tail, torch.cuda.current_stream().cuda_stream or None)
+                              reset_only, *tail, now, *clock, torch.cuda.current_stream().cuda_stream or None)
         if rc < 0:
             _lib.check(rc)
 
@@ -96,28 +105,34 @@ class BatchedVecEnv:
             self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._global_step = 0
         self._launch(None, 1)
-        self._t0.fill_(time.perf_counter())
         return self._out(self._obs), {i: {} for i in self.possible_agents}
 
     def step(self, actions):
-        """``actions``: flat integer array / tensor of ``num_envs * num_agents`` entries, env-major."""
+        """``actions``: flat integer array / tensor of ``num_envs * num_agents`` entries, env-major.
+
+        One kernel launch and no host synchronisation: ``infos[agent]["episode"]`` is present on
+        every step (the worker only reads it at the envs whose ``dones`` entry is set,
+        ppo/worker.py:196-216); ``r`` / ``l`` / ``t`` are zero at the other envs, like the arrays
+        ``RecordEpisodeStatistics`` builds on the steps where some episode ended."""
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions))
-        actions = actions.to(device=self._b.device, dtype=torch.int64).reshape(-1).contiguous()
+        if actions.dtype != torch.int64 or actions.device != self._b.device or not actions.is_contiguous():
+            actions = actions.to(device=self._b.device, dtype=torch.int64).contiguous()
         assert actions.numel() == self.num_envs * self.num_agents
         self._global_step += 1
         self._launch(actions, 0)
-        infos: Dict[str, dict] = {i: {} for i in self.possible_agents}
-        dones = self._done.bool()
-        if bool(dones.any()):  # one sync per step, as cheap as the worker's own `for env_done in dones`
-            now = time.perf_counter()
-            el = torch.where(dones, now - self._t0, torch.zeros_like(self._t0))
-            self._t0 = torch.where(dones, torch.full_like(self._t0, now), self._t0)
-            for k, i in enumerate(self.possible_agents):
-                infos[i]["episode"] = {"r": self._out(self._stat_r[:, k]), "l": self._out(self._stat_l),
-                                       "t": self._out(el)}
-        return (self._out(self._obs), self._out(self._rew), self._out(self._term.bool()),
-                self._out(self._trunc.bool()), self._out(dones), infos)
+        if not self.as_numpy:
+            if self._ret is None:   # views of the persistent buffers: built once
+                infos = {i: {"episode": {"r": self._stat_r[:, k], "l": self._stat_l, "t": self._stat_t}}
+                         for k, i in enumerate(self.possible_agents)}
+                self._ret = (self._obs, self._rew, self._term_b, self._trunc_b, self._done_b, infos)
+            return self._ret
+        infos: Dict[str, dict] = {}
+        for k, i in enumerate(self.possible_agents):
+            infos[i] = {"episode": {"r": self._out(self._stat_r[:, k]), "l": self._out(self._stat_l),
+                                    "t": self._out(self._stat_t)}}
+        return (self._out(self._obs), self._out(self._rew), self._out(self._term_b), self._out(self._trunc_b),
+                self._out(self._done_b), infos)
 
     def close(self):
         pass

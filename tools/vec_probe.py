@@ -21,14 +21,12 @@ for name, model, nact in (("lbf", LBFModel(device=dev), 6), ("driving", DrivingM
         ve.reset()
         acts = torch.randint(0, nact, (64, nv * 2), device=dev, dtype=torch.int64)
         for k in range(8):
-            ve._global_step += 1
-            ve._launch(acts[k], 0)
+            ve.step(acts[k])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(64):
-            ve._global_step += 1
-            ve._launch(acts[k], 0)
+            ve.step(acts[k])
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 64
