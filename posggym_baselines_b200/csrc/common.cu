@@ -3,6 +3,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace posg {
 
@@ -32,6 +35,18 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+void smem_optin_impl(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> granted;   // (kernel, device) -> bytes opted in
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int& have = granted[std::make_pair(kernel, dev)];
+  if (have >= bytes) return;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess) have = bytes;
+  else cudaGetLastError();   // the launch that follows reports the failure
 }
 
 }  // namespace posg

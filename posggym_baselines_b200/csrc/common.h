@@ -30,6 +30,14 @@ int cuda_fail(cudaError_t e, const char* what);
 // SM count of the current device (cached per device).
 int sm_count();
 
+// Dynamic shared memory above the 48 KB default needs a per-kernel opt-in (the Driving blob with
+// its 64-bit observation table is ~56 KB).  Remembered per (kernel, device); call before a launch.
+void smem_optin_impl(const void* kernel, int bytes);
+template <typename K>
+inline void smem_optin(K kernel, int bytes) {
+  if (bytes > 48 * 1024) smem_optin_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 enum ModelKind : int { KIND_DRIVING = 1, KIND_PREDATOR_PREY = 2, KIND_LBF = 3, KIND_NESTED = 0x100 };
 
 }  // namespace posg

@@ -559,6 +559,7 @@ static Blob* build_blob(const char* grid_rows, int num_agents, int obs_front, in
 // persistent grid: every resident CTA slot of every SM gets exactly one CTA
 template <typename K>
 static int grid_for(K kernel, size_t smem, int64_t work_items) {
+  smem_optin(kernel, (int)smem);
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();

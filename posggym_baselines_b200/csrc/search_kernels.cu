@@ -386,6 +386,7 @@ static void launch_search(const posg_model* m, const search::Tree& T, const sear
                           long long n_particles, const search::RootSelect& sel, long long n_sims,
                           unsigned long long sim_id0, cudaStream_t s) {
   const int grid = (int)((n_sims + SEARCH_THREADS - 1) / SEARCH_THREADS);
+  smem_optin(search_kernel<M>, m->blob_bytes);
   search_kernel<M><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, ctx, root, root_t, particles, n_particles,
       sel, n_sims, sim_id0);
@@ -615,6 +616,7 @@ static int reinvigorate_common(posg_model_t m, void* other_arena, int64_t other_
   unsigned long long* d_obs; long long* d_res;
   int rc = belief_common(m, k.obs_words, target_obs_host, s, &d_obs, &d_res); if (rc) return rc;
 #define REINV(MODEL, CTX)                                                                                   \
+  smem_optin(reinvigorate_kernel<MODEL>, m->blob_bytes);                                                    \
   reinvigorate_kernel<MODEL><<<1, belief::CTA, m->blob_bytes, s>>>(                                         \
       (const MODEL::Blob*)m->d_blob, (uint32_t)m->blob_bytes, CTX, parent_particles, (long long)n_parent,   \
       ego_agent, action, d_obs, (long long)n_needed, (long long)max_attempts, seed, draw_id, out_states,    \
@@ -678,6 +680,7 @@ int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_ob
   int rc = belief_common(m, k.obs_words, target_obs_host, s, &d_obs, &d_res); if (rc) return rc;
   switch (m->kind) {
     case KIND_DRIVING:
+      smem_optin(initial_belief_kernel<DrivingSim>, m->blob_bytes);
       initial_belief_kernel<DrivingSim><<<1, belief::CTA, m->blob_bytes, s>>>(
           (const DrivingSim::Blob*)m->d_blob, (uint32_t)m->blob_bytes, ego_agent, d_obs, (long long)n_needed,
           (long long)max_attempts, seed, draw_id, out_states, d_res);
