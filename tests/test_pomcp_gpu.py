@@ -247,3 +247,70 @@ def test_pucb_and_uniform_selection_match_reference(model):
         assert (np.abs(vis.mean(0) - np.array(scen["visit_frac_mean"])) < 4 * se_n + 0.03).all(), (scen["mode"], vis.mean(0))
         if scen["mode"] == "uniform":       # min-visit search: counts differ by at most one
             assert (np.abs(vis * scen["n_sims"] - scen["n_sims"] / 5) <= 1.0 + 1e-9).all()
+
+
+# ---- PredatorPrey-v0 / LevelBasedForaging-v3 against the unmodified reference planner ----------
+@pytest.fixture(scope="module")
+def gold_envs():
+    with open(os.path.join(GOLDEN, "planner_envs.json")) as f:
+        return json.load(f)
+
+
+def _env_model(env_id, kwargs):
+    from posggym_baselines_b200.envs.env import make
+
+    return make(env_id, **kwargs).model
+
+
+@pytest.mark.parametrize("env_id", ["LevelBasedForaging-v3", "PredatorPrey-v0"])
+@pytest.mark.parametrize("wave", [1, 32])
+def test_root_statistics_match_reference_other_envs(gold_envs, env_id, wave):
+    """As test_root_statistics_match_reference, for the models of BASELINE.json configs[2] and
+    configs[4]: root action values after 192 simulations from a first observation within 4
+    standard errors + 0.003 of the unmodified reference planner's (values are 0.002 .. 0.05 here),
+    visit shares within 0.03, and the reference's clearly best action (LBF, env seed 9: NORTH,
+    towards the food in sight) is the CUDA planner's best action."""
+    from posggym_baselines_b200.planning import POMCP, MCTSConfig, RandomSearchPolicy
+
+    g = gold_envs[env_id]
+    model = _env_model(env_id, gold_envs["env_kwargs"][env_id])
+    for scen in g["root_stats"]:
+        reps, vals, vis = 60, [], []
+        for rep in range(reps):
+            cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb",
+                             seed=rep)
+            p = POMCP(model, "0", cfg, RandomSearchPolicy(model, "0"), max_sims=scen["n_sims"], wave_size=wave,
+                      node_capacity=1 << 18, log_capacity=1 << 21)
+            p.reset()
+            p.update(None, tuple(scen["ego_obs"]))
+            p.get_action()
+            st = p._last_root_stats
+            vals.append(np.where(st["done"] > 0, st["total"] / np.maximum(st["done"], 1), 0.0))
+            vis.append(st["done"] / st["done"].sum())
+            p.close()
+        vals, vis = np.array(vals), np.array(vis)
+        ref_mean, ref_std = np.array(scen["value_mean"]), np.array(scen["value_std"])
+        se = np.sqrt(ref_std**2 / scen["reps"] + vals.std(0) ** 2 / reps)
+        assert (np.abs(vals.mean(0) - ref_mean) < 4 * se + 0.003).all(), (env_id, vals.mean(0), ref_mean, se)
+        assert (np.abs(vis.mean(0) - np.array(scen["visit_frac_mean"])) < 0.03).all(), (vis.mean(0), scen["visit_frac_mean"])
+        order = np.argsort(ref_mean)
+        if ref_mean[order[-1]] - ref_mean[order[-2]] > 4 * se.max() + 0.003:
+            assert int(np.argmax(vals.mean(0))) == int(order[-1])
+
+
+@pytest.mark.parametrize("env_id", ["LevelBasedForaging-v3", "PredatorPrey-v0"])
+def test_rollout_return_distribution_ks_other_envs(gold_envs, env_id):
+    """KS two-sample test of the fused rollout kernel's returns against the reference's
+    MCTS._rollout (its own RNG streams) from the same state: not rejected at p > 0.001."""
+    from tests.test_lbf_gpu import to_states as lbf_states
+    from tests.test_pp_gpu import to_states as pp_states
+
+    scen = gold_envs[env_id]["rollouts"]
+    b = _env_model(env_id, gold_envs["env_kwargs"][env_id]).batched
+    f = np.array([scen["state"]])
+    st = lbf_states(b, f) if env_id.startswith("Level") else pp_states(f)
+    packed = torch.from_numpy(np.repeat(b.pack_state(st), 100_000, axis=0)).to(b.device)
+    max_steps = min(scen["depth_limit"] + 1, scen["step_limit"] - 1 + 1)
+    ret, _, _ = b.rollout(packed, 0, max_steps, scen["discount"], seed=321)
+    d, p = ks_2samp(ret.cpu().numpy(), np.array(scen["returns_sorted"]))
+    assert p > 0.001, (env_id, d, p)
