@@ -73,12 +73,17 @@ __device__ __forceinline__ void pack(const Ents& e, uint32_t& w0, uint32_t& w1) 
   w1 = (uint32_t)e.prey[0] | ((uint32_t)e.prey[1] << 8) | ((uint32_t)e.prey[2] << 16);
 }
 
-__device__ __forceinline__ uint32_t swapnib(uint32_t c) { return ((c << 4) & 0xF0u) | ((c >> 4) & 15u); }
+// |ax - bx| + |ay - by| in two instructions (VABSDIFF with accumulate) on unpacked coordinates
+__device__ __forceinline__ int mdist_xy(int ax, int ay, int bx, int by) {
+  return (int)__sad(ax, bx, __sad(ay, by, 0u));
+}
 
 // One prey move (PredatorPreyModel._move_away / the random move of _get_next_prey_state), branch
 // free: flee = keep the free option (staying included) with the largest (distance to `threat`, x, y);
 // otherwise the pick_index(word)-th of the free neighbours N, E, S, W followed by staying.
 // occ[] = cells of the predators and of the uncaught prey (moves made so far applied; -1 = none).
+// The (x, y) tie-break among equally distant options is a fixed priority of the five options:
+// E (x+1) > S (y+1) > stay > N (y-1) > W (x-1).
 __device__ __forceinline__ int prey_move(const Blob& B, int coord, bool flee, int threat, uint32_t word,
                                          const int (&occ)[NP + NQ]) {
   const uint32_t w4 = B.wall4[coord];
@@ -86,7 +91,8 @@ __device__ __forceinline__ int prey_move(const Blob& B, int coord, bool flee, in
   const int adx = abs(dx), ady = abs(dy);
   const int nb[4] = {coord - 16, coord + 1, coord + 16, coord - 1};
   const int dist[4] = {adx + abs(dy + 1), abs(dx - 1) + ady, adx + abs(dy - 1), abs(dx + 1) + ady};
-  uint32_t free4 = 0, best = ((uint32_t)(adx + ady) << 8) | swapnib((uint32_t)coord);
+  constexpr uint32_t PRIO[4] = {1u, 4u, 3u, 0u};       // N, E, S, W; staying = 2
+  uint32_t free4 = 0, best = ((uint32_t)(adx + ady) << 3) | 2u;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     bool taken = false;
@@ -94,14 +100,13 @@ __device__ __forceinline__ int prey_move(const Blob& B, int coord, bool flee, in
     for (int j = 0; j < NP + NQ; ++j) taken |= (nb[k] == occ[j]);
     const bool fr = !((w4 >> k) & 1u) && !taken;
     free4 |= (fr ? 1u : 0u) << k;
-    const uint32_t key = fr ? (((uint32_t)dist[k] << 8) | swapnib((uint32_t)nb[k] & 255u)) : 0u;
-    best = max(best, key);
+    best = max(best, fr ? (((uint32_t)dist[k] << 3) | PRIO[k]) : 0u);
   }
-  const int flee_cell = (int)swapnib(best & 255u);
+  // priority -> option index (W, N, stay, S, E -> 3, 0, 4, 2, 1), packed three bits each
+  const uint32_t flee_sel = (0x1503u >> (3u * (best & 7u))) & 7u;
   const uint32_t m5 = free4 | 16u;
-  const uint32_t sel = B.nth_lut[m5 * 8u + pick_index(word, (uint32_t)__popc(m5))];
-  const int rnd_cell = coord + (int)B.nb_delta[sel];
-  return flee ? flee_cell : rnd_cell;
+  const uint32_t rnd_sel = B.nth_lut[m5 * 8u + pick_index(word, (uint32_t)__popc(m5))];
+  return coord + (int)B.nb_delta[flee ? flee_sel : rnd_sel];
 }
 
 // joint transition; rew[] per predator; returns all_done
@@ -113,17 +118,24 @@ __device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&a
   // predator in sight, 1 keep away from the closest other prey in sight, 2 random move, 3 caught.
   // The moves are then made in (rule, index) order, as the reference's three passes do.
   uint32_t info[NQ], key[NQ];   // info: cell | threat << 8 | flee << 16
+  const int px[NP] = {e.pred[0] & 15, e.pred[1] & 15}, py[NP] = {e.pred[0] >> 4, e.pred[1] >> 4};
+  const int qx[NQ] = {e.prey[0] & 15, e.prey[1] & 15, e.prey[2] & 15};
+  const int qy[NQ] = {e.prey[0] >> 4, e.prey[1] >> 4, e.prey[2] >> 4};
+  // the three prey-prey distances, shared by both ends
+  const int qq01 = mdist_xy(qx[0], qy[0], qx[1], qy[1]), qq02 = mdist_xy(qx[0], qy[0], qx[2], qy[2]);
+  const int qq12 = mdist_xy(qx[1], qy[1], qx[2], qy[2]);
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
     const int c = e.prey[i];
     const bool caught = (e.caught >> i) & 1u;
     const bool hi = (words[i] >> 31) != 0u;            // pick_index(word, 2)
-    const int d0 = mdist(c, e.pred[0]), d1 = mdist(c, e.pred[1]);
+    const int d0 = mdist_xy(qx[i], qy[i], px[0], py[0]), d1 = mdist_xy(qx[i], qy[i], px[1], py[1]);
     const bool ph1 = min(d0, d1) <= od;
     const int t1 = d0 < d1 ? e.pred[0] : (d1 < d0 ? e.pred[1] : (hi ? e.pred[1] : e.pred[0]));
     const int j1 = i == 0 ? 1 : 0, j2 = i == 2 ? 1 : 2;
-    const int f1 = ((e.caught >> j1) & 1u) ? (1 << 20) : mdist(c, e.prey[j1]);
-    const int f2 = ((e.caught >> j2) & 1u) ? (1 << 20) : mdist(c, e.prey[j2]);
+    const int e1 = i == 0 ? qq01 : (i == 1 ? qq01 : qq02), e2 = i == 0 ? qq02 : (i == 1 ? qq12 : qq12);
+    const int f1 = ((e.caught >> j1) & 1u) ? (1 << 20) : e1;
+    const int f2 = ((e.caught >> j2) & 1u) ? (1 << 20) : e2;
     const bool ph2 = !ph1 && n_unc > 1 && min(f1, f2) <= od;
     const int t2 = f1 < f2 ? e.prey[j1] : (f2 < f1 ? e.prey[j2] : (hi ? e.prey[j2] : e.prey[j1]));
     const uint32_t rule = caught ? 3u : (ph1 ? 0u : (ph2 ? 1u : 2u));
@@ -168,8 +180,11 @@ __device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&a
   // captures
   uint32_t newly = 0;
 #pragma unroll
+  const int p0x = p0 & 15, p0y = p0 >> 4, p1x = p1 & 15, p1y = p1 >> 4;
+#pragma unroll
   for (int j = 0; j < NQ; ++j) {
-    const int adj = (mdist(cur[j], p0) <= 1) + (mdist(cur[j], p1) <= 1);
+    const int cx = cur[j] & 15, cy = cur[j] >> 4;
+    const int adj = (mdist_xy(cx, cy, p0x, p0y) <= 1) + (mdist_xy(cx, cy, p1x, p1y) <= 1);
     newly |= (!((e.caught >> j) & 1u) && adj >= (int)B.prey_strength) ? (1u << j) : 0u;
   }
   rew[0] = 0.0; rew[1] = 0.0;
