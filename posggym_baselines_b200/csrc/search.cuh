@@ -200,19 +200,22 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
   // greedy == top-g; ties go to the lower action index).  The lane of rank r evaluates the
   // candidates (a, r) and counts in closed form how many marginals precede each: (a, r) is taken
   // iff fewer than g do.  O(A^2) per lane instead of O(g * A); cs is frozen at the group's middle
-  // visit count.  Only the per-action COUNTS matter (lanes are exchangeable), so lane r then takes
+  // visit count.  PUCB (the default action_selection) has the same structure with 1 / (1 + n).  Only the per-action COUNTS matter (lanes are exchangeable), so lane r then takes
   // the action whose cumulative count first exceeds r.  Warp-uniform switch; max_gsize < 8 (and
   // wave size 1, the reference's sequential search) keeps the exact loop below.
-  if (P.selection == SEL_UCB && max_gsize >= 8) {
+  if ((P.selection == SEL_UCB || P.selection == SEL_PUCB) && max_gsize >= 8) {
+    const bool pucb = P.selection == SEL_PUCB;
     const int g = __popc(grp);
     const int Nmid = n_base + (is_root ? 0 : 1) + (g >> 1);
-    const float csm = c * sqrtf(__logf((float)(Nmid > 1 ? Nmid : 1)));
+    const float fN = (float)(Nmid > 1 ? Nmid : 1);
+    // exploration scale: ucb  m_a(i) = Q_a + csm / sqrt(n_a + i);  pucb  m_a(i) = Q_a + csm / (1 + n_a + i)
+    const float csm = pucb ? c * prior * sqrtf(fN) : c * sqrtf(__logf(fN));
     int k[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) {
       const float na = n[a] + (float)rank;
-      const bool inf_a = na <= 0.0f;                 // an unvisited action's first visit: +inf
-      const float v = q[a] + csm * rsqrtf(fmaxf(na, 1.0f));
+      const bool inf_a = !pucb && na <= 0.0f;        // ucb: an unvisited action's first visit is +inf
+      const float v = q[a] + csm * (pucb ? __frcp_rn(1.0f + na) : rsqrtf(fmaxf(na, 1.0f)));
       float before = (float)rank;                    // (a, 0..rank-1)
 #pragma unroll
       for (int b = 0; b < A; ++b) {
@@ -223,9 +226,10 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
         } else {
           const float diff = v - q[b];
           const float ratio = __fdividef(csm, diff);
-          const float X = ratio * ratio;             // m_b(i) > v  <=>  n_b + i < X
+          // m_b(i) > v  <=>  n_b + i < X (ucb: X = ratio^2; pucb: X = ratio - 1)
+          const float X = pucb ? ratio - 1.0f : ratio * ratio;
           const float t = X - n[b], ti = rintf(t);
-          const bool tie = fabsf(t - ti) <= fmaxf(1e-3f, 4e-5f * X);
+          const bool tie = fabsf(t - ti) <= fmaxf(1e-3f, 4e-5f * fabsf(X));
           cnt = fmaxf(tie ? ti + (b < a ? 1.0f : 0.0f) : ceilf(t), 0.0f);
           cnt = diff > 0.0f ? cnt : 1e9f;            // Q_b >= v: every marginal of b precedes
         }
@@ -245,7 +249,7 @@ __device__ int select_action(const Tree& T, const Params& P, int node, bool is_r
 #pragma unroll
       for (int a = 0; a < A; ++a) {
         const float nn = n[a] + (float)k[a];
-        const float v = nn > 0.0f ? q[a] + csm * rsqrtf(nn) : 3.0e38f;
+        const float v = pucb ? q[a] + csm * __frcp_rn(1.0f + nn) : (nn > 0.0f ? q[a] + csm * rsqrtf(nn) : 3.0e38f);
         if (v > best) { best = v; mine = a; }
       }
     }

@@ -219,17 +219,19 @@ def test_reroot_keeps_the_subtree(model):
     p.close()
 
 
-def test_pucb_and_uniform_selection_match_reference(model):
+@pytest.mark.parametrize("wave", [1, 32])
+def test_pucb_and_uniform_selection_match_reference(model, wave):
     """action_selection = pucb (PUCB search, max-visit final choice) and uniform (min-visit
     search): root values and visit shares at equal simulation counts vs the reference planner
-    (golden: tests/golden/make_planner_modes_golden.py), within 4 SE + 0.02 / + 0.03."""
+    (golden: tests/golden/make_planner_modes_golden.py), within 4 SE + 0.02 / + 0.03.  Wave 32
+    exercises the closed-form group selection."""
     with open(os.path.join(GOLDEN, "planner_modes_driving.json")) as f:
         modes = json.load(f)["modes"]
     for scen in modes:
         reps = 50
         vals, vis = [], []
         for rep in range(reps):
-            p = make_planner(model, seed=rep, max_sims=scen["n_sims"], wave_size=1, action_selection=scen["mode"],
+            p = make_planner(model, seed=rep, max_sims=scen["n_sims"], wave_size=wave, action_selection=scen["mode"],
                              c=scen["c"], pucb_exploration_fraction=0.5)
             p.reset()
             p.update(None, fields_to_obs(scen["ego_obs"]))
@@ -245,7 +247,7 @@ def test_pucb_and_uniform_selection_match_reference(model):
         se_n = np.sqrt(np.array(scen["visit_frac_std"]) ** 2 / scen["reps"] + vis.std(0) ** 2 / reps)
         assert (np.abs(vals.mean(0) - np.array(scen["value_mean"])) < 4 * se_v + 0.02).all(), (scen["mode"], vals.mean(0))
         assert (np.abs(vis.mean(0) - np.array(scen["visit_frac_mean"])) < 4 * se_n + 0.03).all(), (scen["mode"], vis.mean(0))
-        if scen["mode"] == "uniform":       # min-visit search: counts differ by at most one
+        if scen["mode"] == "uniform" and wave == 1:   # min-visit search: counts differ by at most one
             assert (np.abs(vis * scen["n_sims"] - scen["n_sims"] / 5) <= 1.0 + 1e-9).all()
 
 
