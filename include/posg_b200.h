@@ -302,6 +302,17 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
                   float* rew_out, uint8_t* term_out, uint8_t* trunc_out, uint8_t* done_out,
                   float* stat_r, int32_t* stat_l, double now, double* ep_t0, double* stat_t, void* stream);
 
+/* First trunk layer of the PPO policy on the PACKED observation: what
+ * PPOLSTMModel.trunk[0:2] = nn.Linear(input_size, trunk_sizes[0]) + nn.Tanh (ppo/network.py:171-178)
+ * computes from the one-hot rows the worker feeds it (ppo/worker.py:143-163), without writing or
+ * reading those rows: out[env * A + agent, :] = act(bias + sum over observation fields f of
+ * wT[offset_f + value_f, :]).  state [n, SW] u32 (the vec env's carried state: the observation is
+ * recomputed from it); wT [flat_dim, hidden] f32 row-major (= trunk.0.weight transposed); bias
+ * [hidden]; hidden <= 128; out [n * A, hidden] f32.  Pass obs_out = NULL to posg_vec_step to skip
+ * the one-hot rows altogether. */
+int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const float* wT, const float* bias,
+                   int hidden, int apply_tanh, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,7 +35,9 @@ int sm_count();
 void smem_optin_impl(const void* kernel, int bytes);
 template <typename K>
 inline void smem_optin(K kernel, int bytes) {
-  if (bytes > 48 * 1024) smem_optin_impl(reinterpret_cast<const void*>(kernel), bytes);
+  // static + dynamic shared memory together must stay under 48 KB without the opt-in; the kernels
+  // here hold up to ~22 KB of static arrays, so opt in from 24 KB of dynamic memory on
+  if (bytes > 24 * 1024) smem_optin_impl(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 enum ModelKind : int { KIND_DRIVING = 1, KIND_PREDATOR_PREY = 2, KIND_LBF = 3, KIND_NESTED = 0x100 };

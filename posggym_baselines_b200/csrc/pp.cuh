@@ -179,7 +179,6 @@ __device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&a
   const int p0 = clash ? e.pred[0] : pot[0], p1 = clash ? e.pred[1] : pot[1];
   // captures
   uint32_t newly = 0;
-#pragma unroll
   const int p0x = p0 & 15, p0y = p0 >> 4, p1x = p1 & 15, p1y = p1 >> 4;
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {

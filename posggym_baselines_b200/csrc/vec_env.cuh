@@ -146,7 +146,7 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
     __syncthreads();
     // one-hot expansion of the chunk: float4 j of the chunk = (row j / Q, quad j % Q)
     const int64_t left = n - base;
-    const int total = (int)(left < EPC ? left : EPC) * NAG * Q;
+    const int total = obs_out == nullptr ? 0 : (int)(left < EPC ? left : EPC) * NAG * Q;   // no one-hot rows wanted
     float4* out4 = reinterpret_cast<float4*>(obs_out + base * NAG * flat_dim);
     int row = row0, q = q0;
     for (int j = tid; j < total; j += NT) {
@@ -161,6 +161,74 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
       __stcs(out4 + j, o);
       q += dq; row += dr;
       if (q >= Q) { q -= Q; ++row; }
+    }
+    __syncthreads();
+  }
+}
+
+// First trunk layer of the PPO network applied to the flattened one-hot observation WITHOUT
+// materialising it (ppo/network.py:171-178: nn.Linear(input_size, trunk_sizes[0]) + nn.Tanh, fed by
+// the worker at ppo/worker.py:143-163): a one-hot row times W is the sum of one weight column per
+// observation field, so  hidden[row] = act(bias + sum_f wT[offset_f + value_f]).  Per env-step this
+// reads 30 x 256 B of (L1-resident) weights and writes H floats per agent instead of writing and
+// re-reading 300 floats per agent.  Phase 1 as in vec_step_kernel (observation -> field bytes in
+// shared memory), phase 2: one warp per row, lane j owns hidden units j, j + 32, ...
+constexpr int EMB_THREADS = 256, EMB_EPC = 128, EMB_MAX_H = 128;
+
+template <class M>
+__global__ void __launch_bounds__(EMB_THREADS)
+vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+                 const uint32_t* __restrict__ state, const uint16_t* __restrict__ field_offset,
+                 const float* __restrict__ wT, const float* __restrict__ bias, int H, int apply_tanh,
+                 float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NF = M::NFIELD;
+  __shared__ uint32_t s_fields[EMB_EPC * NAG * ROW_WORDS];
+  __shared__ uint16_t s_off[MAX_FIELDS];
+  if (threadIdx.x < MAX_FIELDS) s_off[threadIdx.x] = threadIdx.x < NF ? field_offset[threadIdx.x] : 0;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KH = (H + 31) >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * EMB_EPC; base < n; base += (int64_t)gridDim.x * EMB_EPC) {
+    const int64_t i = base + tid;
+    if (tid < EMB_EPC && i < n) {
+      typename M::State s;
+#pragma unroll
+      for (int k = 0; k < SW; ++k) s.w[k] = __ldg(state + i * SW + k);
+      unsigned long long obs[NAG][OW];
+      M::observe_all(B, s, obs);
+#pragma unroll
+      for (int a = 0; a < NAG; ++a) {
+        uint32_t fw[MAX_FIELDS / 4];
+        field_bytes<M>(obs[a], fw);
+        uint32_t* dst = s_fields + (tid * NAG + a) * ROW_WORDS;
+#pragma unroll
+        for (int w = 0; w < (NF + 3) / 4; ++w) dst[w] = fw[w];
+      }
+    }
+    __syncthreads();
+    const int64_t left = n - base;
+    const int rows = (int)(left < EMB_EPC ? left : EMB_EPC) * NAG;
+    for (int row = warp; row < rows; row += EMB_THREADS / 32) {
+      // lane f holds the weight row of field f: offset_f + value_f
+      const unsigned char* fb = reinterpret_cast<const unsigned char*>(s_fields + row * ROW_WORDS);
+      const int my = lane < NF ? (int)s_off[lane] + (int)fb[lane] : 0;
+      float acc[EMB_MAX_H / 32];
+#pragma unroll
+      for (int k = 0; k < EMB_MAX_H / 32; ++k) acc[k] = (k < KH && lane + 32 * k < H) ? __ldg(bias + lane + 32 * k) : 0.0f;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float* wr = wT + (int64_t)__shfl_sync(0xffffffffu, my, f) * H + lane;
+#pragma unroll
+        for (int k = 0; k < EMB_MAX_H / 32; ++k)
+          if (k < KH && lane + 32 * k < H) acc[k] = __fadd_rn(acc[k], __ldg(wr + 32 * k));
+      }
+      float* orow = out + (base * NAG + row) * H + lane;
+#pragma unroll
+      for (int k = 0; k < EMB_MAX_H / 32; ++k)
+        if (k < KH && lane + 32 * k < H) orow[32 * k] = apply_tanh ? tanhf(acc[k]) : acc[k];
     }
     __syncthreads();
   }

@@ -57,9 +57,26 @@ static int ensure_desc(posg_model* m) {
     }
     d[q] = {o, w0 | (sel << 8)};
   }
-  POSG_CUDA(cudaMalloc(&m->d_flat_desc, d.size() * sizeof(vec::Quad)));
-  POSG_CUDA(cudaMemcpy(m->d_flat_desc, d.data(), d.size() * sizeof(vec::Quad), cudaMemcpyHostToDevice));
+  // one allocation: the quad descriptors, then the flattened offset of every field (uint16)
+  std::vector<uint16_t> off(vec::MAX_FIELDS, 0);
+  for (size_t f = 0, o = 0; f < widths.size(); o += (size_t)widths[f], ++f) off[f] = (uint16_t)o;
+  const size_t qbytes = d.size() * sizeof(vec::Quad);
+  POSG_CUDA(cudaMalloc(&m->d_flat_desc, qbytes + off.size() * sizeof(uint16_t)));
+  POSG_CUDA(cudaMemcpy(m->d_flat_desc, d.data(), qbytes, cudaMemcpyHostToDevice));
+  POSG_CUDA(cudaMemcpy((char*)m->d_flat_desc + qbytes, off.data(), off.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   m->flat_dim = (int)flat;
+  return POSG_OK;
+}
+
+template <class M>
+static int launch_embed(posg_model* m, int64_t n, const uint32_t* state, const float* wT, const float* bias, int H,
+                        int apply_tanh, float* out, cudaStream_t s) {
+  smem_optin(vec::vec_embed_kernel<M>, m->blob_bytes);
+  const int64_t need = (n + vec::EMB_EPC - 1) / vec::EMB_EPC;
+  const uint16_t* off = (const uint16_t*)((const char*)m->d_flat_desc + (size_t)(m->flat_dim / 4) * sizeof(vec::Quad));
+  vec::vec_embed_kernel<M><<<(int)(need < (1 << 30) ? need : (1 << 30)), vec::EMB_THREADS, m->blob_bytes, s>>>(
+      (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, off, wT, bias, H, apply_tanh, out);
+  POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
 
@@ -122,7 +139,7 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
   POSG_REQUIRE(m, "null model");
   int rc = ensure_desc(m); if (rc) return rc;
   if (n_envs == 0) return POSG_OK;
-  POSG_REQUIRE(n_envs > 0 && state && ep_t && ep_ret && ep_count && obs_out, "bad arguments");
+  POSG_REQUIRE(n_envs > 0 && state && ep_t && ep_ret && ep_count, "bad arguments");   // obs_out may be NULL (posg_vec_embed)
   POSG_REQUIRE(reset_only || (actions && rew_out && term_out && trunc_out && done_out && stat_r && stat_l),
                "step needs actions and every output buffer");
   POSG_REQUIRE(max_episode_steps > 0 && max_episode_steps < 65535, "bad max_episode_steps");
@@ -142,6 +159,22 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
       return launch_vec<PPSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed, global_step,
                                env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out, trunc_out,
                                done_out, stat_r, stat_l, now, ep_t0, stat_t, s);
+    default: set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED;
+  }
+}
+
+int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const float* wT, const float* bias,
+                   int hidden, int apply_tanh, float* out, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  int rc = ensure_desc(m); if (rc) return rc;
+  if (n_envs == 0) return POSG_OK;
+  POSG_REQUIRE(n_envs > 0 && state && wT && bias && out, "bad arguments");
+  POSG_REQUIRE(hidden >= 1 && hidden <= vec::EMB_MAX_H, "hidden size outside [1, 128]");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (m->kind) {
+    case KIND_DRIVING: return launch_embed<DrivingSim>(m, n_envs, state, wT, bias, hidden, apply_tanh, out, s);
+    case KIND_LBF: return launch_embed<LBFSim>(m, n_envs, state, wT, bias, hidden, apply_tanh, out, s);
+    case KIND_PREDATOR_PREY: return launch_embed<PPSim>(m, n_envs, state, wT, bias, hidden, apply_tanh, out, s);
     default: set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED;
   }
 }

@@ -31,7 +31,7 @@ from posggym_baselines_b200 import _lib
 
 class BatchedVecEnv:
     def __init__(self, model, num_envs: int, max_episode_steps: Optional[int] = None, seed: int = 0,
-                 env_offset: int = 0, as_numpy: bool = False):
+                 env_offset: int = 0, as_numpy: bool = False, write_obs: bool = True):
         self.model = model
         self._b = model.batched
         self.num_envs = int(num_envs)
@@ -52,7 +52,10 @@ class BatchedVecEnv:
         self._ep_t = torch.zeros(n, dtype=torch.int16, device=dev)
         self._ep_ret = torch.zeros((n, a), dtype=torch.float64, device=dev)
         self._ep_count = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._obs = torch.empty((n * a, self.flat_dim), dtype=torch.float32, device=dev)
+        # write_obs=False: no one-hot rows (the policy consumes the packed observation through embed())
+        self.write_obs = bool(write_obs)
+        self._obs = torch.empty((n * a, self.flat_dim), dtype=torch.float32, device=dev) if write_obs else None
+        self._wT, self._wT_key = None, None
         self._rew = torch.zeros(n * a, dtype=torch.float32, device=dev)
         self._term = torch.zeros(n * a, dtype=torch.uint8, device=dev)
         self._trunc = torch.zeros(n * a, dtype=torch.uint8, device=dev)
@@ -81,7 +84,8 @@ class BatchedVecEnv:
             self._args = (
                 (self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._ep_t), _lib.ptr(self._ep_ret),
                  _lib.ptr(self._ep_count)),
-                (_lib.ptr(self._obs), _lib.ptr(self._rew), _lib.ptr(self._term), _lib.ptr(self._trunc),
+                (_lib.ptr(self._obs) if self.write_obs else None, _lib.ptr(self._rew), _lib.ptr(self._term),
+                 _lib.ptr(self._trunc),
                  _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l)),
                 (_lib.ptr(self._t0), _lib.ptr(self._stat_t)))
         head, tail, clock = self._args
@@ -98,6 +102,8 @@ class BatchedVecEnv:
             _lib.check(rc)
 
     def _out(self, t):
+        if t is None:    # write_obs=False
+            return None
         return t.cpu().numpy() if self.as_numpy else t
 
     def reset(self, seed: Optional[int] = None, options=None):
@@ -133,6 +139,28 @@ class BatchedVecEnv:
                                     "t": self._out(self._stat_t)}}
         return (self._out(self._obs), self._out(self._rew), self._out(self._term_b), self._out(self._trunc_b),
                 self._out(self._done_b), infos)
+
+    def embed(self, weight, bias, tanh: bool = True, out=None):
+        """First trunk layer of the PPO policy on the CURRENT observations without the one-hot rows:
+        ``tanh(F.linear(obs, weight, bias))`` for ``weight`` = ``trunk.0.weight`` ``[hidden, obs_dim]``
+        and ``bias`` = ``trunk.0.bias`` of ``PPOLSTMModel`` / ``PPOMLPModel`` (ppo/network.py:171-178),
+        computed as a sum of one weight column per observation field (posg_vec_embed).  Returns
+        ``[num_envs * num_agents, hidden]`` float32.  Construct the env with ``write_obs=False`` to
+        make ``reset`` / ``step`` skip the one-hot rows altogether."""
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        if self._wT_key != key:   # transposed copy: one contiguous row of `hidden` floats per one-hot input
+            assert weight.shape[1] == self.flat_dim, (tuple(weight.shape), self.flat_dim)
+            self._wT = weight.detach().to(device=self._b.device, dtype=torch.float32).t().contiguous()
+            self._wT_key = key
+        b = bias.detach().to(device=self._b.device, dtype=torch.float32).contiguous()
+        h = self._wT.shape[1]
+        if out is None:
+            out = torch.empty((self.num_envs * self.num_agents, h), dtype=torch.float32, device=self._b.device)
+        with torch.cuda.device(self._b.device):
+            _lib.check(_lib.lib().posg_vec_embed(
+                self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._wT), _lib.ptr(b), h, int(tanh),
+                _lib.ptr(out), _lib.stream_ptr()))
+        return out
 
     def close(self):
         pass

@@ -127,3 +127,38 @@ def test_predator_prey_vec_env_and_sharding():
         c = hi.step(act[n:])
         for k in range(5):
             assert torch.equal(a[k], torch.cat([b[k], c[k]])), k
+
+
+@pytest.mark.parametrize("env_id,nact", [("LevelBasedForaging-v3", 6), ("Driving-v1", 5), ("PredatorPrey-v0", 5)])
+def test_embed_matches_torch_linear_on_one_hot_rows(env_id, nact):
+    """posg_vec_embed == tanh(F.linear(one_hot_obs, W, b)) of the first trunk layer
+    (ppo/network.py:171-178) in float32: the one-hot product is a sum of one weight column per
+    observation field.  Tolerance 2e-6 absolute (float32 sums of <= 31 terms in a different order),
+    written here because this is the one floating-point kernel of the path.  Also: an env built
+    with write_obs=False steps identically and never writes the one-hot rows."""
+    from posggym_baselines_b200.vector import load_vec_env
+
+    n, hidden = 3000, 64
+    envs = load_vec_env(env_id, num_envs=n, seed=11)
+    lean = load_vec_env(env_id, num_envs=n, seed=11)
+    lean.write_obs, lean._obs, lean._args = False, None, None
+    g = torch.Generator().manual_seed(3)
+    w = (torch.randn(hidden, envs.flat_dim, generator=g) * 0.3).cuda()
+    b = (torch.randn(hidden, generator=g) * 0.1).cuda()
+    obs = envs.reset()[0]
+    assert lean.reset()[0] is None
+    for step in range(12):
+        ref = torch.tanh(torch.nn.functional.linear(obs, w, b))
+        got, got_lean = envs.embed(w, b), lean.embed(w, b)
+        assert got.shape == (2 * n, hidden) and got.dtype == torch.float32
+        assert (got - ref).abs().max().item() < 2e-6, (step, (got - ref).abs().max().item())
+        assert torch.equal(got, got_lean)
+        raw = envs.embed(w, b, tanh=False)
+        assert (raw - torch.nn.functional.linear(obs, w, b)).abs().max().item() < 5e-6
+        act = torch.randint(0, nact, (2 * n,), generator=g)
+        obs, rew, *_ = envs.step(act)
+        o2, rew2, *_ = lean.step(act)
+        assert o2 is None and torch.equal(rew, rew2)
+    # a hidden size that is not a multiple of 32
+    w2, b2 = w[:40].contiguous(), b[:40].contiguous()
+    assert (envs.embed(w2, b2) - torch.tanh(torch.nn.functional.linear(obs, w2, b2))).abs().max().item() < 2e-6
