@@ -308,6 +308,44 @@ def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
                           "hbm_gbs": gbs, "hbm_frac": gbs / peak, "bytes_per_env_step": bytes_per}
             sec["obs_dim"] = ve.flat_dim
             del ve
+        if name == "LevelBasedForaging-v3":
+            # SURVEY 8(f) N1, first half: envs.step + the policy's first trunk layer (Linear(300, 64) + Tanh,
+            # ppo/network.py:171-178).  A: one-hot rows + torch (cuBLAS sgemm + tanh); B: no one-hot rows,
+            # posg_vec_embed sums one weight column per observation field.
+            sec["step_plus_trunk0"] = {}
+            w = torch.randn(64, 300, device=dev) * 0.1
+            bia = torch.zeros(64, device=dev)
+            for label, nv in (("envs_8192_per_gpu", 8192), ("envs_1048576_per_gpu", 1 << 20)):
+                res = {}
+                for mode in ("one_hot_plus_torch_linear", "packed_embed"):
+                    ve = BatchedVecEnv(model, nv, seed=seed, env_offset=rank * nv, write_obs=(mode != "packed_embed"))
+                    ve.reset()
+                    acts = torch.randint(0, nact, (32, nv * 2), device=dev, dtype=torch.int64)
+                    hid = torch.empty((nv * 2, 64), dtype=torch.float32, device=dev)
+
+                    def one(k):
+                        o = ve.step(acts[k])[0]
+                        if mode == "packed_embed":
+                            ve.embed(w, bia, out=hid)
+                        else:
+                            torch.tanh(torch.nn.functional.linear(o, w, bia), out=hid)
+
+                    for k in range(6):
+                        one(k)
+                    barrier()
+                    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    v0.record()
+                    for k in range(32):
+                        one(k)
+                    v1.record()
+                    barrier()
+                    vms = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(vms, op=dist.ReduceOp.MAX)
+                    res[mode] = {"us_per_step": 1e3 * vms.item() / 32, "env_steps_per_s": world * nv * 32 / (vms.item() / 1e3)}
+                    del ve
+                res["speedup"] = res["one_hot_plus_torch_linear"]["us_per_step"] / res["packed_embed"]["us_per_step"]
+                sec["step_plus_trunk0"][label] = res
         out[name] = sec
     if cpu:
         # reference collector scale (BR checkpoints' config): 32 envs per worker stepped serially

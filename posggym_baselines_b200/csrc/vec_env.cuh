@@ -175,7 +175,9 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
 // shared memory), phase 2: one warp per row, lane j owns hidden units j, j + 32, ...
 constexpr int EMB_THREADS = 256, EMB_EPC = 128, EMB_MAX_H = 128;
 
-template <class M>
+// LPR = lanes per row (each lane owns four consecutive hidden units: one 16-byte weight load per
+// field); H = 4 * LPR in {32, 64, 128}.  LPR == 0: any H <= 128, one warp per row, scalar loads.
+template <class M, int LPR>
 __global__ void __launch_bounds__(EMB_THREADS)
 vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
                  const uint32_t* __restrict__ state, const uint16_t* __restrict__ field_offset,
@@ -184,13 +186,13 @@ vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NF = M::NFIELD;
-  __shared__ uint32_t s_fields[EMB_EPC * NAG * ROW_WORDS];
+  // per row: the weight-row index offset_f + value_f of every field
+  __shared__ uint16_t s_idx[EMB_EPC * NAG][MAX_FIELDS];
   __shared__ uint16_t s_off[MAX_FIELDS];
   if (threadIdx.x < MAX_FIELDS) s_off[threadIdx.x] = threadIdx.x < NF ? field_offset[threadIdx.x] : 0;
   stage_blob(smem_raw, gblob, blob_size, &mbar);
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int KH = (H + 31) >> 5;
   for (int64_t base = (int64_t)blockIdx.x * EMB_EPC; base < n; base += (int64_t)gridDim.x * EMB_EPC) {
     const int64_t i = base + tid;
     if (tid < EMB_EPC && i < n) {
@@ -203,32 +205,51 @@ vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
       for (int a = 0; a < NAG; ++a) {
         uint32_t fw[MAX_FIELDS / 4];
         field_bytes<M>(obs[a], fw);
-        uint32_t* dst = s_fields + (tid * NAG + a) * ROW_WORDS;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_idx[tid * NAG + a][0]);
 #pragma unroll
-        for (int w = 0; w < (NF + 3) / 4; ++w) dst[w] = fw[w];
+        for (int f = 0; f < NF; f += 2) {
+          const uint32_t v0 = (fw[f >> 2] >> (8 * (f & 3))) & 255u;
+          const uint32_t v1 = f + 1 < NF ? (fw[(f + 1) >> 2] >> (8 * ((f + 1) & 3))) & 255u : 0u;
+          dst[f >> 1] = (v0 + s_off[f]) | ((v1 + (f + 1 < NF ? s_off[f + 1] : 0u)) << 16);
+        }
       }
     }
     __syncthreads();
     const int64_t left = n - base;
     const int rows = (int)(left < EMB_EPC ? left : EMB_EPC) * NAG;
-    for (int row = warp; row < rows; row += EMB_THREADS / 32) {
-      // lane f holds the weight row of field f: offset_f + value_f
-      const unsigned char* fb = reinterpret_cast<const unsigned char*>(s_fields + row * ROW_WORDS);
-      const int my = lane < NF ? (int)s_off[lane] + (int)fb[lane] : 0;
-      float acc[EMB_MAX_H / 32];
+    if constexpr (LPR > 0) {
+      constexpr int RPW = 32 / LPR;                 // rows per warp iteration
+      const int sub = lane / LPR, col = (lane % LPR) * 4;
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      for (int row = warp * RPW + sub; row < rows; row += (EMB_THREADS / 32) * RPW) {
+        float4 acc = b4;
 #pragma unroll
-      for (int k = 0; k < EMB_MAX_H / 32; ++k) acc[k] = (k < KH && lane + 32 * k < H) ? __ldg(bias + lane + 32 * k) : 0.0f;
+        for (int f = 0; f < NF; ++f) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(wT + (int)s_idx[row][f] * (4 * LPR) + col));
+          acc.x = __fadd_rn(acc.x, w.x); acc.y = __fadd_rn(acc.y, w.y);
+          acc.z = __fadd_rn(acc.z, w.z); acc.w = __fadd_rn(acc.w, w.w);
+        }
+        if (apply_tanh) { acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w); }
+        *reinterpret_cast<float4*>(out + (base * NAG + row) * (4 * LPR) + col) = acc;
+      }
+    } else {
+      const int KH = (H + 31) >> 5;
+      for (int row = warp; row < rows; row += EMB_THREADS / 32) {
+        float acc[EMB_MAX_H / 32];
 #pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const float* wr = wT + (int64_t)__shfl_sync(0xffffffffu, my, f) * H + lane;
+        for (int k = 0; k < EMB_MAX_H / 32; ++k) acc[k] = (k < KH && lane + 32 * k < H) ? __ldg(bias + lane + 32 * k) : 0.0f;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          const float* wr = wT + (int64_t)s_idx[row][f] * H + lane;
+#pragma unroll
+          for (int k = 0; k < EMB_MAX_H / 32; ++k)
+            if (k < KH && lane + 32 * k < H) acc[k] = __fadd_rn(acc[k], __ldg(wr + 32 * k));
+        }
+        float* orow = out + (base * NAG + row) * H + lane;
 #pragma unroll
         for (int k = 0; k < EMB_MAX_H / 32; ++k)
-          if (k < KH && lane + 32 * k < H) acc[k] = __fadd_rn(acc[k], __ldg(wr + 32 * k));
+          if (k < KH && lane + 32 * k < H) orow[32 * k] = apply_tanh ? tanhf(acc[k]) : acc[k];
       }
-      float* orow = out + (base * NAG + row) * H + lane;
-#pragma unroll
-      for (int k = 0; k < EMB_MAX_H / 32; ++k)
-        if (k < KH && lane + 32 * k < H) orow[32 * k] = apply_tanh ? tanhf(acc[k]) : acc[k];
     }
     __syncthreads();
   }

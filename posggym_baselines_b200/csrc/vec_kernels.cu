@@ -68,16 +68,26 @@ static int ensure_desc(posg_model* m) {
   return POSG_OK;
 }
 
-template <class M>
-static int launch_embed(posg_model* m, int64_t n, const uint32_t* state, const float* wT, const float* bias, int H,
-                        int apply_tanh, float* out, cudaStream_t s) {
-  smem_optin(vec::vec_embed_kernel<M>, m->blob_bytes);
+template <class M, int LPR>
+static int launch_embed_lpr(posg_model* m, int64_t n, const uint32_t* state, const float* wT, const float* bias, int H,
+                            int apply_tanh, float* out, cudaStream_t s) {
+  smem_optin(vec::vec_embed_kernel<M, LPR>, m->blob_bytes);
   const int64_t need = (n + vec::EMB_EPC - 1) / vec::EMB_EPC;
   const uint16_t* off = (const uint16_t*)((const char*)m->d_flat_desc + (size_t)(m->flat_dim / 4) * sizeof(vec::Quad));
-  vec::vec_embed_kernel<M><<<(int)(need < (1 << 30) ? need : (1 << 30)), vec::EMB_THREADS, m->blob_bytes, s>>>(
+  vec::vec_embed_kernel<M, LPR><<<(int)(need < (1 << 30) ? need : (1 << 30)), vec::EMB_THREADS, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, off, wT, bias, H, apply_tanh, out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
+}
+
+template <class M>
+static int launch_embed(posg_model* m, int64_t n, const uint32_t* state, const float* wT, const float* bias, int H,
+                        int apply_tanh, float* out, cudaStream_t s) {
+  const bool vec4 = ((((uintptr_t)wT | (uintptr_t)bias | (uintptr_t)out) & 15u) == 0);
+  if (vec4 && H == 64) return launch_embed_lpr<M, 16>(m, n, state, wT, bias, H, apply_tanh, out, s);
+  if (vec4 && H == 32) return launch_embed_lpr<M, 8>(m, n, state, wT, bias, H, apply_tanh, out, s);
+  if (vec4 && H == 128) return launch_embed_lpr<M, 32>(m, n, state, wT, bias, H, apply_tanh, out, s);
+  return launch_embed_lpr<M, 0>(m, n, state, wT, bias, H, apply_tanh, out, s);
 }
 
 template <class M, int EPC, int NT, int MINB>

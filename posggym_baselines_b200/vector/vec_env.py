@@ -147,12 +147,13 @@ class BatchedVecEnv:
         computed as a sum of one weight column per observation field (posg_vec_embed).  Returns
         ``[num_envs * num_agents, hidden]`` float32.  Construct the env with ``write_obs=False`` to
         make ``reset`` / ``step`` skip the one-hot rows altogether."""
-        key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+        key = (weight.data_ptr(), weight._version, tuple(weight.shape), bias.data_ptr(), bias._version)
         if self._wT_key != key:   # transposed copy: one contiguous row of `hidden` floats per one-hot input
             assert weight.shape[1] == self.flat_dim, (tuple(weight.shape), self.flat_dim)
             self._wT = weight.detach().to(device=self._b.device, dtype=torch.float32).t().contiguous()
             self._wT_key = key
-        b = bias.detach().to(device=self._b.device, dtype=torch.float32).contiguous()
+            self._bias = bias.detach().to(device=self._b.device, dtype=torch.float32).contiguous().clone()
+        b = self._bias
         h = self._wT.shape[1]
         if out is None:
             out = torch.empty((self.num_envs * self.num_agents, h), dtype=torch.float32, device=self._b.device)
