@@ -313,6 +313,14 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
 int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const float* wT, const float* bias,
                    int hidden, int apply_tanh, float* out, void* stream);
 
+/* Generalised advantage estimation of the PPO learner (ppo/core.py:226-244): the
+ * backward loop over seq_len steps of PPOTrainer.update in one launch.  rewards [T, n_cols] f32,
+ * dones / values [T + 1, n_cols] f32 (the extra final row as the worker collects it), outputs
+ * advantages / returns [T, n_cols] f32 (returns = advantages + values[:-1]).  Bit-identical to the
+ * reference's float32 tensor expressions.  Advantage normalisation (norm_adv) stays with the caller. */
+int posg_gae(int T, int64_t n_cols, const float* rewards, const float* dones, const float* values, double gamma,
+             double gae_lambda, float* advantages, float* returns, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

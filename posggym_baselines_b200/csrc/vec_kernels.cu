@@ -129,6 +129,33 @@ static int launch_vec(posg_model* m, int64_t n, Args... args) {
   return launch_vec_epc<M, 256, 256, 4>(m, n, args...);
 }
 
+// Generalised advantage estimation of the PPO learner (ppo/core.py:226-244) for a whole rollout
+// batch in one launch: one thread per (env, agent) column scans the T steps backwards.  The
+// float32 operations and their order are those of the reference's tensor expressions (the Python
+// scalars gamma and gamma * gae_lambda are rounded to float32 once, as PyTorch does for float32
+// tensors; the library is compiled with --fmad=false), so the result is bit-identical.
+__global__ void gae_kernel(int T, int64_t N, const float* __restrict__ rewards, const float* __restrict__ dones,
+                           const float* __restrict__ values, float gamma, float gamma_lambda,
+                           float* __restrict__ advantages, float* __restrict__ returns) {
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x) {
+    float last = 0.0f;
+    float next_value = values[(int64_t)T * N + c], next_done = dones[(int64_t)T * N + c];
+    for (int t = T - 1; t >= 0; --t) {
+      const int64_t i = (int64_t)t * N + c;
+      const float v = values[i];
+      const float nonterminal = __fsub_rn(1.0f, next_done);
+      // delta = rewards[t] + gamma * nextvalues * nextnonterminal - values[t]
+      const float delta = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(__fmul_rn(gamma, next_value), nonterminal)), v);
+      // lastgaelam = delta + gamma * gae_lambda * nextnonterminal * lastgaelam
+      last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lambda, nonterminal), last));
+      advantages[i] = last;
+      returns[i] = __fadd_rn(last, v);
+      next_value = v;
+      next_done = dones[i];
+    }
+  }
+}
+
 }  // namespace posg
 
 using namespace posg;
@@ -187,6 +214,20 @@ int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const 
     case KIND_PREDATOR_PREY: return launch_embed<PPSim>(m, n_envs, state, wT, bias, hidden, apply_tanh, out, s);
     default: set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED;
   }
+}
+
+int posg_gae(int T, int64_t n_cols, const float* rewards, const float* dones, const float* values, double gamma,
+             double gae_lambda, float* advantages, float* returns, void* stream) {
+  if (T <= 0 || n_cols == 0) return POSG_OK;
+  POSG_REQUIRE(n_cols > 0 && rewards && dones && values && advantages && returns, "bad arguments");
+  int ndev = posg_device_count();
+  if (ndev < 0) return ndev;
+  const int64_t need = (n_cols + 127) / 128;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  gae_kernel<<<(int)(need < cap ? need : cap), 128, 0, (cudaStream_t)stream>>>(
+      T, n_cols, rewards, dones, values, (float)gamma, (float)(gamma * gae_lambda), advantages, returns);
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
 }
 
 }  // extern "C"
