@@ -1,5 +1,5 @@
 // Driving-v1 kernels + C-ABI.  Persistent CTAs (grid = k x SM count) stage the model
-// blob (wall bitmap, distance tables, observation base table, reward table; ~20 KB)
+// blob (wall bitmap, distance / move / observation base / reward tables; ~40 KB)
 // into shared memory once via one TMA bulk copy and then grid-stride over the batch
 // with coalesced 16-byte loads and stores.
 #include <cmath>
