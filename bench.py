@@ -307,6 +307,25 @@ def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
             sec[label] = {"env_steps_per_s": world * nv * 64 / (vms.item() / 1e3), "us_per_step": 1e3 * vms.item() / 64,
                           "hbm_gbs": gbs, "hbm_frac": gbs / peak, "bytes_per_env_step": bytes_per}
             sec["obs_dim"] = ve.flat_dim
+            if nv == 8192:
+                # the same 64 steps with envs.step captured in a CUDA graph (the call rate of the eager
+                # path is bound by the ~16 us a Python -> ctypes launch costs, not by the 8 us kernel)
+                buf, replay = ve.capture_step()
+                for k in range(8):
+                    buf.copy_(acts[k]); replay()
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for k in range(64):
+                    buf.copy_(acts[k])
+                    replay()
+                g1.record()
+                barrier()
+                gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+                sec[label]["cuda_graph"] = {"us_per_step": 1e3 * gms.item() / 64,
+                                            "env_steps_per_s": world * nv * 64 / (gms.item() / 1e3)}
             del ve
         if name == "LevelBasedForaging-v3":
             # SURVEY 8(f) N1, first half: envs.step + the policy's first trunk layer (Linear(300, 64) + Tanh,

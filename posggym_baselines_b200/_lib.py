@@ -63,7 +63,7 @@ SIGNATURES = {
         _int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _int, _int, _vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
     "posg_vec_flat_dim": (_int, [_vp]),
     "posg_vec_step": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _int, _int, _vp, _vp, _vp, _vp,
-                              _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
+                              _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     "posg_vec_embed": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp]),
     "posg_gae": (_int, [_int, _i64, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp, _vp]),
     "posg_model_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),

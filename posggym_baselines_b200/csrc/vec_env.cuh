@@ -61,7 +61,8 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
                 uint64_t env_offset, int max_episode_steps, int reset_only,
                 float* __restrict__ obs_out, float* __restrict__ rew_out, uint8_t* __restrict__ term_out,
                 uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out, float* __restrict__ stat_r,
-                int* __restrict__ stat_l, double now, double* __restrict__ ep_t0, double* __restrict__ stat_t) {
+                int* __restrict__ stat_l, double now, double* __restrict__ ep_t0, double* __restrict__ stat_t,
+                const uint32_t* __restrict__ step_counter) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
@@ -72,6 +73,8 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
   for (int p = threadIdx.x; p < Q; p += NT) s_desc[p] = desc[p];
   stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  // CUDA-graph replays bake the scalar arguments: the step index then comes from device memory
+  if (step_counter != nullptr) global_step = *step_counter;
   const int tid = threadIdx.x;
   const int row0 = tid / Q, q0 = tid - row0 * Q;      // this thread's first float4 of a chunk
   const int dr = NT / Q, dq = NT - dr * Q;  // and its stride

@@ -95,7 +95,7 @@ static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* e
                           const long long* actions, uint64_t seed, uint32_t global_step, uint64_t env_offset,
                           int max_steps, int reset_only, float* obs_out, float* rew_out, uint8_t* term_out,
                           uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int* stat_l, double now, double* ep_t0,
-                          double* stat_t, cudaStream_t s) {
+                          double* stat_t, const uint32_t* step_counter, cudaStream_t s) {
   static int per_sm_cache[64] = {0};
   int& per_sm = per_sm_cache[m->device & 63];
   if (per_sm == 0) {
@@ -114,7 +114,7 @@ static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* e
   vec::vec_step_kernel<M, EPC, NT, MINB><<<grid, NT, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, ep_t, ep_ret, ep_count, actions,
       (const vec::Quad*)m->d_flat_desc, m->flat_dim, seed, global_step, env_offset, max_steps, reset_only,
-      obs_out, rew_out, term_out, trunc_out, done_out, stat_r, stat_l, now, ep_t0, stat_t);
+      obs_out, rew_out, term_out, trunc_out, done_out, stat_r, stat_l, now, ep_t0, stat_t, step_counter);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
@@ -172,7 +172,7 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
                   uint32_t* ep_count, const int64_t* actions, uint64_t seed, uint32_t global_step,
                   uint64_t env_offset, int max_episode_steps, int reset_only, float* obs_out, float* rew_out,
                   uint8_t* term_out, uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int32_t* stat_l,
-                  double now, double* ep_t0, double* stat_t, void* stream) {
+                  double now, double* ep_t0, double* stat_t, const uint32_t* step_counter, void* stream) {
   POSG_REQUIRE(m, "null model");
   int rc = ensure_desc(m); if (rc) return rc;
   if (n_envs == 0) return POSG_OK;
@@ -187,15 +187,15 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
     case KIND_DRIVING:
       return launch_vec<DrivingSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed,
                                     global_step, env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out,
-                                    trunc_out, done_out, stat_r, stat_l, now, ep_t0, stat_t, s);
+                                    trunc_out, done_out, stat_r, stat_l, now, ep_t0, stat_t, step_counter, s);
     case KIND_LBF:
       return launch_vec<LBFSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed, global_step,
                                 env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out, trunc_out,
-                                done_out, stat_r, stat_l, now, ep_t0, stat_t, s);
+                                done_out, stat_r, stat_l, now, ep_t0, stat_t, step_counter, s);
     case KIND_PREDATOR_PREY:
       return launch_vec<PPSim>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed, global_step,
                                env_offset, max_episode_steps, reset_only, obs_out, rew_out, term_out, trunc_out,
-                               done_out, stat_r, stat_l, now, ep_t0, stat_t, s);
+                               done_out, stat_r, stat_l, now, ep_t0, stat_t, step_counter, s);
     default: set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED;
   }
 }

@@ -68,6 +68,8 @@ class BatchedVecEnv:
         self._t0 = torch.zeros(n, dtype=torch.float64, device=dev)      # start time of the running episode
         self._stat_t = torch.zeros(n, dtype=torch.float64, device=dev)  # wall time of the episode just ended
         self._global_step = 0
+        self._step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)   # device copy for captured graphs
+        self._ctr_shadow = 0
         self._args = None
         self._ret = None
         self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -76,7 +78,7 @@ class BatchedVecEnv:
     def single_observation_shape(self):
         return (self.flat_dim,)
 
-    def _launch(self, actions, reset_only: int):
+    def _launch(self, actions, reset_only: int, graphed: bool = False):
         # hot loop of the collector: buffer pointers are cached (the buffers live as long as the
         # env), the device guard is only entered when another device is current
         if self._args is None:
@@ -91,13 +93,17 @@ class BatchedVecEnv:
         head, tail, clock = self._args
         a = None if actions is None else actions.data_ptr()
         now = time.perf_counter()
+        if graphed:   # captured launch: step index from the device counter, no wall-clock bookkeeping
+            clock, ctr = (None, None), self._step_ctr.data_ptr()
+        else:
+            ctr = None
         if torch.cuda.current_device() == self._dev_index:
             rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps, reset_only,
-                          *tail, now, *clock, torch.cuda.current_stream().cuda_stream or None)
+                          *tail, now, *clock, ctr, torch.cuda.current_stream().cuda_stream or None)
         else:
             with torch.cuda.device(self._b.device):
                 rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps,
-                              reset_only, *tail, now, *clock, torch.cuda.current_stream().cuda_stream or None)
+                              reset_only, *tail, now, *clock, ctr, torch.cuda.current_stream().cuda_stream or None)
         if rc < 0:
             _lib.check(rc)
 
@@ -113,13 +119,19 @@ class BatchedVecEnv:
         self._launch(None, 1)
         return self._out(self._obs), {i: {} for i in self.possible_agents}
 
-    def step(self, actions):
+    def step(self, actions, _replay_only: bool = False):
         """``actions``: flat integer array / tensor of ``num_envs * num_agents`` entries, env-major.
 
         One kernel launch and no host synchronisation: ``infos[agent]["episode"]`` is present on
         every step (the worker only reads it at the envs whose ``dones`` entry is set,
         ppo/worker.py:196-216); ``r`` / ``l`` / ``t`` are zero at the other envs, like the arrays
         ``RecordEpisodeStatistics`` builds on the steps where some episode ended."""
+        if _replay_only:   # capture_step: just the tuple of persistent views
+            if self.as_numpy:
+                raise _lib.PosgB200Error("capture_step needs as_numpy=False")
+            infos = {i: {"episode": {"r": self._stat_r[:, k], "l": self._stat_l, "t": self._stat_t}}
+                     for k, i in enumerate(self.possible_agents)}
+            return (self._obs, self._rew, self._term_b, self._trunc_b, self._done_b, infos)
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions))
         if actions.dtype != torch.int64 or actions.device != self._b.device or not actions.is_contiguous():
@@ -139,6 +151,36 @@ class BatchedVecEnv:
                                     "t": self._out(self._stat_t)}}
         return (self._out(self._obs), self._out(self._rew), self._out(self._term_b), self._out(self._trunc_b),
                 self._out(self._done_b), infos)
+
+    def capture_step(self):
+        """Capture ``envs.step`` in a CUDA graph (the collector's inner loop is launch bound at the
+        reference's batch sizes: ~16 us per Python call against an 8 us kernel at 8 192 envs).
+        Returns ``(actions, replay)``: write the step's actions into the static int64 tensor
+        ``actions`` (``num_envs * num_agents`` entries), call ``replay()`` -- it returns the same
+        tuple as ``step`` (views of the same persistent buffers).  The step index of the Philox
+        counter lives in device memory and is bumped by a node of the graph; episode wall times
+        (``infos[agent]["episode"]["t"]``) are not tracked in this mode."""
+        dev = self._b.device
+        actions = torch.zeros(self.num_envs * self.num_agents, dtype=torch.int64, device=dev)
+        self._step_ctr.fill_(self._global_step)
+        self._ctr_shadow = self._global_step
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):      # recorded, not executed: the envs do not move here
+            self._step_ctr.add_(1)
+            self._launch(actions, 0, graphed=True)
+        ret = self.step(None, _replay_only=True)
+
+        def replay():
+            if self._ctr_shadow != self._global_step:   # eager step() / reset() calls in between
+                self._step_ctr.fill_(self._global_step)
+            self._global_step += 1
+            self._ctr_shadow = self._global_step
+            graph.replay()
+            return ret
+
+        self._graph = graph   # keep alive
+        return actions, replay
 
     def embed(self, weight, bias, tanh: bool = True, out=None):
         """First trunk layer of the PPO policy on the CURRENT observations without the one-hot rows:

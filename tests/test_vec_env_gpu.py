@@ -162,3 +162,29 @@ def test_embed_matches_torch_linear_on_one_hot_rows(env_id, nact):
     # a hidden size that is not a multiple of 32
     w2, b2 = w[:40].contiguous(), b[:40].contiguous()
     assert (envs.embed(w2, b2) - torch.tanh(torch.nn.functional.linear(obs, w2, b2))).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("env_id,nact", [("Driving-v1", 5), ("LevelBasedForaging-v3", 6)])
+def test_captured_step_equals_eager_step(env_id, nact):
+    """envs.step captured in a CUDA graph (step index read from device memory) == the eager call,
+    also when eager steps are mixed in; Driving's processing-order noise depends on the step index."""
+    from posggym_baselines_b200.vector import load_vec_env
+
+    n = 4096
+    eager = load_vec_env(env_id, num_envs=n, seed=21)
+    graphed = load_vec_env(env_id, num_envs=n, seed=21)
+    assert torch.equal(eager.reset()[0], graphed.reset()[0])
+    actions, replay = graphed.capture_step()
+    g = torch.Generator().manual_seed(5)
+    for step in range(80):
+        act = torch.randint(0, nact, (2 * n,), generator=g).cuda()
+        a = eager.step(act)
+        if step in (20, 21, 50):       # an eager step in between must not desynchronise the counter
+            b = graphed.step(act)
+        else:
+            actions.copy_(act)
+            b = replay()
+        for k in range(5):
+            assert torch.equal(a[k], b[k]), (step, k)
+        assert torch.equal(a[5]["0"]["episode"]["r"], b[5]["0"]["episode"]["r"])
+        assert torch.equal(a[5]["1"]["episode"]["l"], b[5]["1"]["episode"]["l"])
