@@ -308,24 +308,32 @@ def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
                           "hbm_gbs": gbs, "hbm_frac": gbs / peak, "bytes_per_env_step": bytes_per}
             sec["obs_dim"] = ve.flat_dim
             if nv == 8192:
-                # the same 64 steps with envs.step captured in a CUDA graph (the call rate of the eager
-                # path is bound by the ~16 us a Python -> ctypes launch costs, not by the 8 us kernel)
-                buf, replay = ve.capture_step()
-                for k in range(8):
-                    buf.copy_(acts[k]); replay()
+                # the same 64 steps captured in ONE CUDA graph (envs.step_device; the step index lives
+                # on the device): the eager call rate is bound by the ~16 us a Python -> ctypes launch
+                # costs, the replay by the 8 us kernel.  A collector would capture its policy's kernels
+                # between the steps in the same way.
+                ve.enable_device_counter()
+                for k in range(4):
+                    ve.step_device(acts[k])
+                barrier()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for k in range(64):
+                        ve.step_device(acts[k])
+                graph.replay()
                 barrier()
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 g0.record()
-                for k in range(64):
-                    buf.copy_(acts[k])
-                    replay()
+                for _ in range(4):
+                    graph.replay()
                 g1.record()
                 barrier()
-                gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+                gms = torch.tensor([g0.elapsed_time(g1) / 4], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-                sec[label]["cuda_graph"] = {"us_per_step": 1e3 * gms.item() / 64,
-                                            "env_steps_per_s": world * nv * 64 / (gms.item() / 1e3)}
+                sec[label]["cuda_graph_rollout"] = {"us_per_step": 1e3 * gms.item() / 64,
+                                                    "env_steps_per_s": world * nv * 64 / (gms.item() / 1e3)}
+                del graph
             del ve
         if name == "LevelBasedForaging-v3":
             # SURVEY 8(f) N1, first half: envs.step + the policy's first trunk layer (Linear(300, 64) + Tanh,

@@ -294,9 +294,10 @@ int posg_belief_reinvigorate_nested(posg_model_t nested, void* other_arena, int6
  *   Optional episode wall time (RecordEpisodeStatistics' "t"): `now` = the caller's clock in
  *   seconds, ep_t0 [n] f64 (carried: start time of the running episode), stat_t [n] f64
  *   (elapsed time of the episode that just ended, 0 elsewhere); pass NULL for both to skip.
- *   step_counter (device, optional): when not NULL the step index of the Philox counter is read
- *   from it instead of global_step -- a CUDA graph replays the launch with its scalar arguments
- *   baked in, so a captured collector loop bumps this counter with a graph node of its own.
+ *   step_counter (device, 2 x u32, optional): when not NULL the step index of the Philox counter is
+ *   step_counter[0] + 1 instead of global_step, and the launch stores it back when its last CTA
+ *   finishes (step_counter[1] = scratch, must be 0) -- a CUDA graph replays the launch with its
+ *   scalar arguments baked in, so a captured collector loop keeps its step index on the device.
  * Step noise: Philox counter (env_offset + i, global_step); reset_only != 0 = envs.reset(). */
 int posg_vec_flat_dim(posg_model_t m);
 int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_t, double* ep_ret,
@@ -304,7 +305,7 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
                   uint64_t env_offset, int max_episode_steps, int reset_only, float* obs_out,
                   float* rew_out, uint8_t* term_out, uint8_t* trunc_out, uint8_t* done_out,
                   float* stat_r, int32_t* stat_l, double now, double* ep_t0, double* stat_t,
-                  const uint32_t* step_counter, void* stream);
+                  uint32_t* step_counter, void* stream);
 
 /* First trunk layer of the PPO policy on the PACKED observation: what
  * PPOLSTMModel.trunk[0:2] = nn.Linear(input_size, trunk_sizes[0]) + nn.Tanh (ppo/network.py:171-178)

@@ -62,7 +62,7 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
                 float* __restrict__ obs_out, float* __restrict__ rew_out, uint8_t* __restrict__ term_out,
                 uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out, float* __restrict__ stat_r,
                 int* __restrict__ stat_l, double now, double* __restrict__ ep_t0, double* __restrict__ stat_t,
-                const uint32_t* __restrict__ step_counter) {
+                uint32_t* __restrict__ step_counter) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
@@ -73,8 +73,10 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
   for (int p = threadIdx.x; p < Q; p += NT) s_desc[p] = desc[p];
   stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
-  // CUDA-graph replays bake the scalar arguments: the step index then comes from device memory
-  if (step_counter != nullptr) global_step = *step_counter;
+  // CUDA-graph replays bake the scalar arguments: the step index then comes from device memory,
+  // step_counter[0] + 1; the last CTA to finish publishes it for the next replay (every CTA has read
+  // the counter before it can finish; step_counter[1] counts the finished CTAs)
+  if (step_counter != nullptr) global_step = *((volatile uint32_t*)step_counter) + 1u;
   const int tid = threadIdx.x;
   const int row0 = tid / Q, q0 = tid - row0 * Q;      // this thread's first float4 of a chunk
   const int dr = NT / Q, dq = NT - dr * Q;  // and its stride
@@ -166,6 +168,14 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
       if (q >= Q) { q -= Q; ++row; }
     }
     __syncthreads();
+  }
+  if (step_counter != nullptr && !reset_only && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(step_counter + 1, 1u) == gridDim.x - 1u) {
+      step_counter[1] = 0u;
+      step_counter[0] = global_step;
+      __threadfence();
+    }
   }
 }
 

@@ -95,7 +95,7 @@ static int launch_vec_epc(posg_model* m, int64_t n, uint32_t* state, uint16_t* e
                           const long long* actions, uint64_t seed, uint32_t global_step, uint64_t env_offset,
                           int max_steps, int reset_only, float* obs_out, float* rew_out, uint8_t* term_out,
                           uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int* stat_l, double now, double* ep_t0,
-                          double* stat_t, const uint32_t* step_counter, cudaStream_t s) {
+                          double* stat_t, uint32_t* step_counter, cudaStream_t s) {
   static int per_sm_cache[64] = {0};
   int& per_sm = per_sm_cache[m->device & 63];
   if (per_sm == 0) {
@@ -172,7 +172,7 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
                   uint32_t* ep_count, const int64_t* actions, uint64_t seed, uint32_t global_step,
                   uint64_t env_offset, int max_episode_steps, int reset_only, float* obs_out, float* rew_out,
                   uint8_t* term_out, uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int32_t* stat_l,
-                  double now, double* ep_t0, double* stat_t, const uint32_t* step_counter, void* stream) {
+                  double now, double* ep_t0, double* stat_t, uint32_t* step_counter, void* stream) {
   POSG_REQUIRE(m, "null model");
   int rc = ensure_desc(m); if (rc) return rc;
   if (n_envs == 0) return POSG_OK;

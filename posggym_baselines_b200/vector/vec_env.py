@@ -68,8 +68,8 @@ class BatchedVecEnv:
         self._t0 = torch.zeros(n, dtype=torch.float64, device=dev)      # start time of the running episode
         self._stat_t = torch.zeros(n, dtype=torch.float64, device=dev)  # wall time of the episode just ended
         self._global_step = 0
-        self._step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)   # device copy for captured graphs
-        self._ctr_shadow = 0
+        self._step_ctr = torch.zeros(2, dtype=torch.int32, device=dev)   # [step index, CTA scratch] for captured graphs
+        self._device_counter = False
         self._args = None
         self._ret = None
         self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -93,10 +93,11 @@ class BatchedVecEnv:
         head, tail, clock = self._args
         a = None if actions is None else actions.data_ptr()
         now = time.perf_counter()
-        if graphed:   # captured launch: step index from the device counter, no wall-clock bookkeeping
-            clock, ctr = (None, None), self._step_ctr.data_ptr()
-        else:
-            ctr = None
+        # device-counter mode (capture_step / enable_device_counter): the step index lives on the
+        # device for eager and captured launches alike; a captured launch has no wall clock
+        ctr = self._step_ctr.data_ptr() if self._device_counter else None
+        if graphed:
+            clock = (None, None)
         if torch.cuda.current_device() == self._dev_index:
             rc = self._fn(*head, a, self.seed, self._global_step, self.env_offset, self.max_episode_steps, reset_only,
                           *tail, now, *clock, ctr, torch.cuda.current_stream().cuda_stream or None)
@@ -116,6 +117,8 @@ class BatchedVecEnv:
         if seed is not None:
             self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self._global_step = 0
+        if self._device_counter:
+            self._step_ctr.zero_()
         self._launch(None, 1)
         return self._out(self._obs), {i: {} for i in self.possible_agents}
 
@@ -152,30 +155,42 @@ class BatchedVecEnv:
         return (self._out(self._obs), self._out(self._rew), self._out(self._term_b), self._out(self._trunc_b),
                 self._out(self._done_b), infos)
 
+    def enable_device_counter(self):
+        """Keep the step index of the Philox counter in device memory (advanced by the kernel) from
+        now on, for eager and captured launches alike -- the precondition for capturing
+        ``step_device`` in a CUDA graph, where scalar arguments are frozen."""
+        if not self._device_counter:
+            self._step_ctr.zero_()
+            self._step_ctr[0] = self._global_step
+            self._device_counter = True
+
+    def step_device(self, actions: torch.Tensor):
+        """Graph-capturable ``envs.step``: ``actions`` must be an int64 CUDA tensor of
+        ``num_envs * num_agents`` entries; no host-side conversion, clock or synchronisation.  Call
+        it inside ``torch.cuda.graph(...)`` (after ``enable_device_counter()``) together with the
+        policy's kernels to replay a whole rollout with one launch.  Returns the same tuple of
+        persistent views as ``step``; episode wall times are not tracked in captured launches."""
+        self.enable_device_counter() if not torch.cuda.is_current_stream_capturing() else None
+        assert self._device_counter, "call enable_device_counter() before capturing"
+        self._global_step += 1
+        self._launch(actions, 0, graphed=torch.cuda.is_current_stream_capturing())
+        return self.step(None, _replay_only=True)
+
     def capture_step(self):
-        """Capture ``envs.step`` in a CUDA graph (the collector's inner loop is launch bound at the
-        reference's batch sizes: ~16 us per Python call against an 8 us kernel at 8 192 envs).
-        Returns ``(actions, replay)``: write the step's actions into the static int64 tensor
-        ``actions`` (``num_envs * num_agents`` entries), call ``replay()`` -- it returns the same
-        tuple as ``step`` (views of the same persistent buffers).  The step index of the Philox
-        counter lives in device memory and is bumped by a node of the graph; episode wall times
-        (``infos[agent]["episode"]["t"]``) are not tracked in this mode."""
+        """Capture one ``envs.step`` in a CUDA graph.  Returns ``(actions, replay)``: write the step's
+        actions into the static int64 tensor ``actions``, call ``replay()`` -- it returns the same
+        tuple as ``step`` (views of the same persistent buffers)."""
         dev = self._b.device
         actions = torch.zeros(self.num_envs * self.num_agents, dtype=torch.int64, device=dev)
-        self._step_ctr.fill_(self._global_step)
-        self._ctr_shadow = self._global_step
+        self.enable_device_counter()
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):      # recorded, not executed: the envs do not move here
-            self._step_ctr.add_(1)
-            self._launch(actions, 0, graphed=True)
-        ret = self.step(None, _replay_only=True)
+            ret = self.step_device(actions)
+        self._global_step -= 1             # the recorded launch was not a step
 
         def replay():
-            if self._ctr_shadow != self._global_step:   # eager step() / reset() calls in between
-                self._step_ctr.fill_(self._global_step)
             self._global_step += 1
-            self._ctr_shadow = self._global_step
             graph.replay()
             return ret
 

@@ -188,3 +188,20 @@ def test_captured_step_equals_eager_step(env_id, nact):
             assert torch.equal(a[k], b[k]), (step, k)
         assert torch.equal(a[5]["0"]["episode"]["r"], b[5]["0"]["episode"]["r"])
         assert torch.equal(a[5]["1"]["episode"]["l"], b[5]["1"]["episode"]["l"])
+    # a whole rollout in one graph (step_device), replayed twice, against eager steps
+    acts = torch.randint(0, nact, (16, 2 * n), generator=g).cuda()
+    roll = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(roll):
+        for k in range(16):
+            out = graphed.step_device(acts[k])
+    for rep in range(2):
+        roll.replay()
+        for k in range(16):
+            ref = eager.step(acts[k])
+        for k in range(5):
+            assert torch.equal(ref[k], out[k]), (rep, k)
+    # reset() restarts the device counter as well
+    assert torch.equal(eager.reset()[0], graphed.reset()[0])
+    a, b = eager.step(acts[0]), graphed.step(acts[0])
+    for k in range(5):
+        assert torch.equal(a[k], b[k])
