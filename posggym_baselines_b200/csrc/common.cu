@@ -37,6 +37,28 @@ int sm_count() {
   return cached[dev];
 }
 
+// The planner's host entry points take a few bytes of scratch with cudaMallocAsync.  By default the
+// pool gives its memory back to the driver at every synchronisation and maps it again at the next
+// allocation (milliseconds each; the very first allocation creates the pool: ~0.5 s).  Keep freed
+// blocks cached and pay the pool creation when the model is built, not inside planner.update().
+void async_pool_init() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return; }
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[dev]) return;
+  done[dev] = true;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, 256, 0) == cudaSuccess) { cudaFreeAsync(p, 0); cudaStreamSynchronize(0); }
+  }
+  cudaGetLastError();
+}
+
 void smem_optin_impl(const void* kernel, int bytes) {
   static std::mutex mu;
   static std::map<std::pair<const void*, int>, int> granted;   // (kernel, device) -> bytes opted in

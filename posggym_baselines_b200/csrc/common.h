@@ -30,6 +30,9 @@ int cuda_fail(cudaError_t e, const char* what);
 // SM count of the current device (cached per device).
 int sm_count();
 
+// Configure (once per device) the stream-ordered allocator used for the host entry points' scratch.
+void async_pool_init();
+
 // Dynamic shared memory above the 48 KB default needs a per-kernel opt-in (the Driving blob with
 // its 64-bit observation table is ~56 KB).  Remembered per (kernel, device); call before a launch.
 void smem_optin_impl(const void* kernel, int bytes);

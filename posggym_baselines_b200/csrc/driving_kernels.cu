@@ -617,6 +617,7 @@ int posg_driving_create(const char* grid_rows, int num_agents, int obs_front, in
   }
   int ndev = posg_device_count();
   if (ndev < 0) return ndev;
+  async_pool_init();
   if (num_agents != NA) {
     set_error("num_agents %d unsupported: the sm_100a kernels are specialised for 2 vehicles", num_agents);
     return POSG_E_UNSUPPORTED;

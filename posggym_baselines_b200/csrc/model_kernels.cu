@@ -108,6 +108,7 @@ int posg_pp_create(int grid_size, const char* block_rows, int num_predators, int
   POSG_REQUIRE(out, "null argument");
   int ndev = posg_device_count();
   if (ndev < 0) return ndev;
+  async_pool_init();
   pp::Blob* h = build_pp_blob(grid_size, block_rows, num_predators, num_prey, cooperative, prey_strength, obs_dim);
   if (!h) return POSG_E_UNSUPPORTED;
   posg_model* m = new posg_model();
@@ -134,6 +135,7 @@ int posg_lbf_create(int size, int num_agents, int max_agent_level, int max_food,
   }
   int ndev = posg_device_count();
   if (ndev < 0) return ndev;
+  async_pool_init();
   lbf::Blob* h = (lbf::Blob*)calloc(1, sizeof(lbf::Blob));
   for (int k = 0; k < lbf::NF; ++k) h->food_xy[k] = food_xy[k];
   for (int i = 0; i < lbf::NPL; ++i) h->player_xy[i] = player_xy[i];
