@@ -49,8 +49,8 @@ _SELECTION = {"ucb": 0, "pucb": 1, "uniform": 2}
 class INTMCP:
     def __init__(self, model, agent_id: str, config: MCTSConfig, nesting_level: int,
                  other_agent_policies: Optional[Dict[str, "INTMCP"]], search_policies: Dict[str, SearchPolicy], *,
-                 max_sims_per_level: Optional[int] = None, wave_size: Optional[int] = None, max_wave: int = 65536,
-                 node_capacity: int = 1 << 23, log_capacity: int = 1 << 25, belief_cap: int = 4096,
+                 max_sims_per_level: Optional[int] = None, wave_size: Optional[int] = None, max_wave: int = 262144,
+                 node_capacity: int = 1 << 25, log_capacity: int = 1 << 27, belief_cap: int = 4096,
                  max_histories: int = 64, history_belief_cap: int = 256):
         if nesting_level != 1 or len(model.possible_agents) != 2:
             raise NotImplementedError("the B200 I-NTMCP supports nesting_level=1 with two agents")
