@@ -111,11 +111,13 @@ def pp_rollout(model, state, ego: str, max_steps: int, discount: float, seed: in
 
 # ---- LevelBasedForaging-v3 conventions (LBFSim in posggym_baselines_b200/csrc/lbf.cuh) ----
 def lbf_step_noise(seed: int, particles, step: int):
-    """actions [n, 2]: block (particle, step, 0xA0) word x -> idx = floor(x * 36 / 2**32),
+    """actions [n, 2]: ONE 32-bit Philox word per env-step, as for Driving -- block = counter
+    (particle >> 2, step, stream 0xA0), word = particle & 3; idx = floor(word * 36 / 2**32),
     a0 = idx % 6, a1 = idx // 6.  The LBF transition itself takes no noise."""
     particles = np.asarray(particles, dtype=np.uint64)
-    w = P.philox_block(seed, particles, step, P.STREAM_STEP)
-    idx = P.uniform_below(w[0], 36)
+    w = P.philox_block(seed, particles >> np.uint64(2), step, P.STREAM_STEP)
+    word = np.choose((particles & np.uint64(3)).astype(np.int64), w)
+    idx = P.uniform_below(word, 36)
     a1 = idx // 6
     a0 = idx - 6 * a1
     return np.stack([a0, a1], axis=-1)

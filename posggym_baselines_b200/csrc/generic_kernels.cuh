@@ -4,6 +4,7 @@
 #pragma once
 #include <stdint.h>
 
+#include "philox.cuh"
 #include "stage.cuh"
 
 namespace posg {
@@ -80,6 +81,87 @@ step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int6
   if (live_count != nullptr) {
     for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
     if ((threadIdx.x & 31) == 0 && live) atomicAdd(live_count, (unsigned long long)live);
+  }
+}
+
+// Fast path of model.step for models whose step noise is ONE Philox word per env (M::ONE_WORD_NOISE:
+// block = particle >> 2, word = particle & 3), random actions, particle_offset a multiple of four and
+// whole blocks of 128 envs -- the design of driving::step_fast_kernel: a warp owns 128 consecutive
+// envs, lane L steps envs 32 j + L (every warp-level global access is one contiguous run), lane L
+// computes the Philox block of envs 4 L .. 4 L + 3 and the words are transposed through shared
+// memory; the next block's states and Philox rounds are issued one iteration ahead.
+constexpr int FAST_WARP_ENVS = 128, FAST_EPT = 4;
+
+template <class M, bool WRITE_ACTIONS, bool COUNT_LIVE>
+__global__ void __launch_bounds__(THREADS, 3)
+step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nblocks,
+                 const uint2* __restrict__ state_in, uint64_t seed, uint32_t step_idx, uint64_t group_offset,
+                 uint2* __restrict__ state_out, ulonglong2* __restrict__ obs_out, double2* __restrict__ rewards_out,
+                 uint8_t* __restrict__ flags_out, uchar2* __restrict__ actions_out,
+                 unsigned long long* __restrict__ live_count) {
+  static_assert(M::SW == 2 && M::NAG == 2 && (M::OW == 1 || M::OW == 2) && M::ONE_WORD_NOISE, "unsupported model");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  __shared__ alignas(16) uint32_t s_words[THREADS / 32][FAST_WARP_ENVS];
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  constexpr int OW = M::OW, NAG = M::NAG, NW = M::NW;
+  unsigned live = 0;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t wstride = gridDim.x * (THREADS / 32);
+  uint32_t wb = blockIdx.x * (THREADS / 32) + warp;
+  uint2 nxt[FAST_EPT];
+#pragma unroll
+  for (int j = 0; j < FAST_EPT; ++j)
+    nxt[j] = wb < nblocks ? __ldg(state_in + wb * FAST_WARP_ENVS + lane + 32 * j) : make_uint2(0u, 0u);
+  uint4 blk_next = philox_block(seed, group_offset + (uint64_t)wb * 32u + lane, step_idx, STREAM_STEP);
+  for (; wb < nblocks; wb += wstride) {
+    const uint32_t e0 = wb * FAST_WARP_ENVS + lane;
+    uint2 sv[FAST_EPT];
+#pragma unroll
+    for (int j = 0; j < FAST_EPT; ++j) sv[j] = nxt[j];
+    if (wb + wstride < nblocks) {
+#pragma unroll
+      for (int j = 0; j < FAST_EPT; ++j) nxt[j] = __ldg(state_in + (wb + wstride) * FAST_WARP_ENVS + lane + 32 * j);
+    }
+    __syncwarp();
+    *reinterpret_cast<uint4*>(&s_words[warp][4 * lane]) = blk_next;
+    __syncwarp();
+    uint32_t word[FAST_EPT];
+#pragma unroll
+    for (int j = 0; j < FAST_EPT; ++j) word[j] = s_words[warp][32 * j + lane];
+    blk_next = philox_block(seed, group_offset + (uint64_t)(wb + wstride) * 32u + lane, step_idx, STREAM_STEP);
+#pragma unroll
+    for (int j = 0; j < FAST_EPT; ++j) {
+      typename M::State s;
+      s.w[0] = sv[j].x; s.w[1] = sv[j].y;
+      int act[NAG];
+      uint32_t noise[NW];
+      M::actions_from_word(word[j], act);
+#pragma unroll
+      for (int k = 0; k < NW; ++k) noise[k] = 0u;
+      unsigned long long obs[NAG][OW];
+      double rew[NAG];
+      uint32_t flags;
+      bool was_live;
+      M::step_all(B, s, act, noise, obs, rew, flags, was_live);
+      if (COUNT_LIVE) live += was_live ? 1u : 0u;
+      const uint32_t e = e0 + 32 * j;
+      state_out[e] = make_uint2(s.w[0], s.w[1]);
+      flags_out[e] = (uint8_t)flags;
+      if (WRITE_ACTIONS) actions_out[e] = make_uchar2((unsigned char)act[0], (unsigned char)act[1]);
+      if constexpr (OW == 1) {
+        obs_out[e] = make_ulonglong2(obs[0][0], obs[1][0]);
+      } else {
+        obs_out[2 * e] = make_ulonglong2(obs[0][0], obs[0][1]);
+        obs_out[2 * e + 1] = make_ulonglong2(obs[1][0], obs[1][1]);
+      }
+      rewards_out[e] = make_double2(rew[0], rew[1]);
+    }
+  }
+  if (COUNT_LIVE) {
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_down_sync(0xffffffffu, live, o);
+    if (lane == 0 && live) atomicAdd(live_count, (unsigned long long)live);
   }
 }
 

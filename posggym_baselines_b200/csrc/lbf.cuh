@@ -223,6 +223,7 @@ struct LBFSim {
     all_done = lbf::transition(B, s.w[0], s.w[1], act, rew);
     term = all_done ? 3u : 0u;
   }
+  static constexpr bool ONE_WORD_NOISE = true;   // the whole step noise is one Philox word (step_fast_kernel)
   // uniform joint action from one Philox word: idx = floor(w * 36 / 2^32), a0 = idx % 6, a1 = idx / 6
   __device__ static __forceinline__ void actions_from_word(uint32_t word, int (&act)[NAG]) {
     const uint32_t idx = uniform_below(word, 36u);
@@ -231,8 +232,11 @@ struct LBFSim {
   }
   __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
                                                            int (&act)[NAG], uint32_t (&noise)[NW]) {
-    const uint4 w = philox_block(seed, particle, step, STREAM_STEP);
-    actions_from_word(w.x, act);
+    // one 32-bit word per env-step: block (particle >> 2, step), word particle & 3 (four consecutive
+    // envs share a block; generic::step_fast_kernel computes it once for the four)
+    const uint4 w = philox_block(seed, particle >> 2, step, STREAM_STEP);
+    const unsigned which = (unsigned)(particle & 3ULL);
+    actions_from_word(which == 0 ? w.x : which == 1 ? w.y : which == 2 ? w.z : w.w, act);
     noise[0] = 0u;
   }
   __device__ static __forceinline__ void noise_from_word(uint32_t, uint32_t (&noise)[NW]) { noise[0] = 0u; }

@@ -186,11 +186,47 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
   POSG_REQUIRE((((uintptr_t)state_in | (uintptr_t)state_out) & 7u) == 0 &&
                (((uintptr_t)obs_out | (uintptr_t)rewards_out) & 15u) == 0 && ((uintptr_t)actions_out & 1u) == 0,
                "state buffers must be 8-byte, obs / rewards buffers 16-byte aligned");
-  MODEL_DISPATCH(m, (generic::step_kernel<M><<<persistent_grid(generic::step_kernel<M>, m->blob_bytes, n),
-                     generic::THREADS, m->blob_bytes, (cudaStream_t)stream>>>(
-                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, actions_in, noise_in, seed,
-                     step_idx, particle_offset, state_out, obs_out, rewards_out, flags_out, actions_out, live_count)));
-  POSG_CUDA(cudaGetLastError());
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t done = 0;
+  if (m->kind == KIND_LBF && !actions_in && !noise_in && (particle_offset & 3ULL) == 0 &&
+      n >= generic::FAST_WARP_ENVS && n < ((int64_t)1 << 31)) {
+    // whole blocks of 128 envs through the fast kernel; a ragged tail through the general one
+    using M = LBFSim;
+    const uint32_t nb = (uint32_t)(n / generic::FAST_WARP_ENVS);
+#define POSG_FAST(WA, CL)                                                                                        \
+    generic::step_fast_kernel<M, WA, CL><<<persistent_grid(generic::step_fast_kernel<M, WA, CL>, m->blob_bytes,   \
+                                                           (int64_t)nb * 32), generic::THREADS, m->blob_bytes, s>>>( \
+        (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, seed, step_idx,           \
+        particle_offset >> 2, (uint2*)state_out, (ulonglong2*)obs_out, (double2*)rewards_out, flags_out,          \
+        (uchar2*)actions_out, live_count)
+    if (actions_out && live_count) POSG_FAST(true, true);
+    else if (actions_out) POSG_FAST(true, false);
+    else if (live_count) POSG_FAST(false, true);
+    else POSG_FAST(false, false);
+#undef POSG_FAST
+    POSG_CUDA(cudaGetLastError());
+    done = (int64_t)nb * generic::FAST_WARP_ENVS;
+  }
+  if (done < n) {
+    const int64_t r = n - done;
+    int n_act = 0, ow = 0, sw = 0;
+    int rc = posg_model_info(m, &n_act, &ow, &sw); if (rc) return rc;
+    const int na = m->num_agents;
+    const uint32_t* sin = state_in + done * sw;
+    uint32_t* sout = state_out + done * sw;
+    uint64_t* oout = obs_out + done * na * ow;
+    double* rout = rewards_out + done * na;
+    uint8_t* fout = flags_out + done;
+    const uint8_t* ain = actions_in ? actions_in + done * na : nullptr;
+    uint8_t* aout = actions_out ? actions_out + done * na : nullptr;
+    const uint64_t off = particle_offset + (uint64_t)done;
+    MODEL_DISPATCH(m, (generic::step_kernel<M><<<persistent_grid(generic::step_kernel<M>, m->blob_bytes, r),
+                       generic::THREADS, m->blob_bytes, s>>>(
+                       (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, r, sin, ain,
+                       noise_in /* explicit noise excludes the fast path: done == 0 */, seed, step_idx, off, sout, oout,
+                       rout, fout, aout, live_count)));
+    POSG_CUDA(cudaGetLastError());
+  }
   return POSG_OK;
 }
 

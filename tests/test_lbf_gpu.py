@@ -110,6 +110,43 @@ def test_step_vs_oracle_live(env, oracle_env):
         cur = out.state
 
 
+def test_fast_path_vs_oracle_and_general_kernel(env, oracle_env):
+    """The random-action sweep runs whole 128-env blocks through generic::step_fast_kernel (offset a
+    multiple of 4) and the ragged tail through the general kernel: every output against the oracle
+    and against the general kernel driven with the same explicit actions."""
+    from oracle import rollout as R
+    from oracle.lbf import LevelBasedForagingModel
+
+    m = LevelBasedForagingModel(**KW)
+    n, seed, off = 1000, 6, 4 * 321          # 7 full blocks + a 104-env tail
+    parts = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    st = env.sample_initial_state(n, seed=seed, particle_offset=off)
+    cpu = [m.initial_state_from_noise([int(v) for v in pk]) for pk in R.lbf_initial_picks(m, seed, parts)]
+    live = torch.zeros(1, dtype=torch.int64, device=env.device)
+    cur, expect_live = st, 0
+    zero_noise = torch.zeros((n, 1), dtype=torch.int32, device=env.device)
+    for step in range(30):
+        out = env.step(cur, seed=seed, step_idx=step, particle_offset=off, live_count=live)
+        acts = R.lbf_step_noise(seed, parts, step)
+        assert (out.actions.cpu().numpy() == acts).all()
+        ref = env.step(cur, torch.from_numpy(acts.astype(np.uint8)).to(env.device), zero_noise)
+        assert torch.equal(out.state, ref.state) and torch.equal(out.obs, ref.obs) and torch.equal(out.flags, ref.flags)
+        assert torch.equal(out.rewards.view(torch.int64), ref.rewards.view(torch.int64))
+        lean = env.step(cur, seed=seed, step_idx=step, particle_offset=off, want_actions=False)
+        assert torch.equal(out.state, lean.state) and torch.equal(out.obs, lean.obs)
+        go, rew, flags = env.unpack_obs(out.obs), out.rewards.cpu().numpy(), out.flags.cpu().numpy()
+        for i in range(n):
+            expect_live += any(f.level > 0 for f in cpu[i].food)
+            ts = m.step(cpu[i], {"0": int(acts[i, 0]), "1": int(acts[i, 1])})
+            cpu[i] = ts.state
+            assert go[i] == (ts.observations["0"], ts.observations["1"]), (step, i)
+            assert rew[i, 0] == ts.rewards["0"] and rew[i, 1] == ts.rewards["1"]
+            assert bool(flags[i] & 0x80) == ts.all_done
+        assert fields(env.unpack_state(out.state)).tolist() == fields(cpu).tolist(), step
+        cur = out.state
+    assert int(live.item()) == expect_live
+
+
 def test_sweep_equals_rollout_at_scale(env):
     """Full-size property: the fused rollout equals a 50-launch step sweep, and a shard by
     particle offset equals the monolithic run (2 M particles x 50 steps)."""
