@@ -199,8 +199,9 @@ vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NF = M::NFIELD;
-  // per row: the weight-row index offset_f + value_f of every field
-  __shared__ uint16_t s_idx[EMB_EPC * NAG][MAX_FIELDS];
+  // per row: the weight-row index offset_f + value_f of every field.  Row stride 17 words: the env
+  // threads of phase 1 store to consecutive rows, which then fall into consecutive banks
+  __shared__ uint16_t s_idx[EMB_EPC * NAG][MAX_FIELDS + 2];
   __shared__ uint16_t s_off[MAX_FIELDS];
   if (threadIdx.x < MAX_FIELDS) s_off[threadIdx.x] = threadIdx.x < NF ? field_offset[threadIdx.x] : 0;
   stage_blob(smem_raw, gblob, blob_size, &mbar);
