@@ -170,10 +170,12 @@ class BatchedVecEnv:
         it inside ``torch.cuda.graph(...)`` (after ``enable_device_counter()``) together with the
         policy's kernels to replay a whole rollout with one launch.  Returns the same tuple of
         persistent views as ``step``; episode wall times are not tracked in captured launches."""
-        self.enable_device_counter() if not torch.cuda.is_current_stream_capturing() else None
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.enable_device_counter()
         assert self._device_counter, "call enable_device_counter() before capturing"
-        self._global_step += 1
-        self._launch(actions, 0, graphed=torch.cuda.is_current_stream_capturing())
+        self._global_step += 1    # informational in this mode: the device counter is authoritative
+        self._launch(actions, 0, graphed=capturing)
         return self.step(None, _replay_only=True)
 
     def capture_step(self):
