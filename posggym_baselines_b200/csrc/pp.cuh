@@ -217,16 +217,17 @@ __device__ __forceinline__ unsigned long long observe(const Blob& B, const Ents&
   const int p = e.pred[i];
   unsigned long long cells = B.obs_base[p];
   const int od = B.obs_dim;
-  // prey first, predators after (a predator takes priority; cells never coincide anyway)
+  // Entities stand on free cells (EMPTY = 0 in the wall-only base) and never share a cell -- moves
+  // into occupied cells are rejected by the transition -- so each one is a single OR.
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     const int k = ((e.caught >> j) & 1u) ? -1 : window_cell(p, e.prey[j], od);
-    if (k >= 0) cells = (cells & ~(3ULL << (2 * k))) | ((unsigned long long)PREY << (2 * k));
+    cells |= k >= 0 ? ((unsigned long long)PREY << (2 * k)) : 0ULL;
   }
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const int k = window_cell(p, e.pred[j], od);
-    if (k >= 0) cells = (cells & ~(3ULL << (2 * k))) | ((unsigned long long)PREDATOR << (2 * k));
+    cells |= k >= 0 ? ((unsigned long long)PREDATOR << (2 * k)) : 0ULL;
   }
   return cells;
 }
