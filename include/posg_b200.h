@@ -176,6 +176,19 @@ int posg_model_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, int 
                        uint64_t particle_offset, double* returns_out, uint8_t* steps_out,
                        uint32_t* state_out, unsigned long long* live_count, void* stream);
 
+/* ------------------------------------------------------------------ sweep checksum
+ * Per-particle 64-bit rolling hash over the outputs of a model.step sweep ("every
+ * step's (state, obs, r, term, trunc, all_done) compared bit-exact ... by 64-bit rolling hash for larger
+ * N").  One call folds ONE step's outputs of n particles into hash_inout[i]:
+ *     h <- init ? (particle_offset + i + 1) * 0xD6E8FEB86659FD93 : hash_inout[i]
+ *     for w in [state words (each zero-extended), obs words (agent-major), reward bit patterns,
+ *               flags | a0 << 8 | a1 << 16 ...]:   h <- (h ^ w) * 0x9E3779B97F4A7C15;  h <- h ^ (h >> 32)
+ * state == NULL: only the initialisation is stored.  The CPU oracles (oracle/c/oracle_common.h) compute the
+ * same value from their own restatement of the model; equal hashes certify the whole trace. */
+int posg_trace_hash(int64_t n, uint64_t* hash_inout, int init, uint64_t particle_offset, const uint32_t* state,
+                    int state_words, const uint64_t* obs, int obs_words, const double* rewards, int num_agents,
+                    const uint8_t* flags, const uint8_t* actions, void* stream);
+
 /* ------------------------------------------------------------------ POMCP search tree
  * The tree (obs nodes, per-action statistics, child lists, particle log) lives in one
  * caller-owned device arena; see posggym_baselines_b200/csrc/search.cuh for the layout.

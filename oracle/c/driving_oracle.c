@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "oracle_common.h"
+
 #define MAXC 8
 #define NF 10 /* fields per vehicle */
 enum { REVERSE = 0, STOPPED = 1, FORWARD_SLOW = 2, FORWARD_FAST = 3 };
@@ -194,21 +196,10 @@ void drv_step(int64_t n, const int* state, const uint8_t* actions, const uint8_t
   }
 }
 
-/* ---- Philox4x32-10 and the kernels' noise conventions (include/posg_b200.h) ------------- */
-static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-static uint32_t below(uint32_t w, uint32_t n) { return (uint32_t)(((uint64_t)w * n) >> 32); }
-
+/* ---- the kernels' noise conventions (include/posg_b200.h); Philox in oracle_common.h ---- */
 static void initial_state(uint64_t seed, uint64_t particle, Veh* s) {
   uint32_t w[4];
-  philox((uint32_t)particle, (uint32_t)(particle >> 32), 0u, 0xB0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  philox_block(seed, particle, 0u, STREAM_INIT, w);
   int used_s[MAXC] = {0}, used_d[MAXC] = {0};
   for (int i = 0; i < 2; ++i) {
     int navail = 0, sel = 0, k = 0;
@@ -235,7 +226,7 @@ static void initial_state(uint64_t seed, uint64_t particle, Veh* s) {
 static void step_noise(uint64_t seed, uint64_t particle, uint32_t step, int* act, int* order) {
   uint32_t w[4];
   const uint64_t blk = particle >> 2;
-  philox((uint32_t)blk, (uint32_t)(blk >> 32), step, 0xA0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  philox_block(seed, blk, step, STREAM_STEP, w);
   const uint32_t idx = below(w[particle & 3], 50u);
   *order = (int)(idx & 1u);
   const uint32_t r = idx >> 1;
@@ -295,4 +286,54 @@ int64_t drv_sweep(uint64_t seed, int depth, int64_t budget_steps) {
     ++particle;
   }
   return executed;
+}
+
+/* ---- packed words of include/posg_b200.h (what the kernels read and write) and the trace hash ---- */
+static uint32_t pack_vehicle(const Veh* v) {
+  return (uint32_t)v->x | ((uint32_t)v->y << 4) | ((uint32_t)v->dir << 8) | ((uint32_t)v->speed << 10) |
+         ((uint32_t)dest_index(v->dx, v->dy) << 12) | ((uint32_t)v->reached << 15) | ((uint32_t)v->crashed << 16) |
+         ((uint32_t)v->mind << 17) | ((uint32_t)v->d0 << 24);
+}
+static uint64_t pack_obs(const int* o) {
+  uint64_t w = 0;
+  for (int c = 0; c < 15; ++c) w |= (uint64_t)o[c] << (2 * c);
+  w |= (uint64_t)o[15] << 30;
+  w |= (uint64_t)o[16] << 32; w |= (uint64_t)o[17] << 36; w |= (uint64_t)o[18] << 40; w |= (uint64_t)o[19] << 44;
+  w |= (uint64_t)o[20] << 48; w |= (uint64_t)o[21] << 49;
+  return w;
+}
+
+/* BASELINE.json configs[1]: the random-action model.step sweep from Philox-drawn initial states, every
+ * particle stepped `depth` times whether or not it is done (terminal states are absorbing), for
+ * particles [p0, p0 + n).  hash_out[i] = rolling hash over every step's packed outputs
+ * (oracle_common.h); the optional arrays receive the full per-step trace, [depth][n][..].
+ * Returns the env-steps executed on particles that were not yet all-done. */
+int64_t drv_trace(uint64_t seed, uint64_t p0, int64_t n, int depth, uint64_t* hash_out, uint32_t* state_tr,
+                  uint64_t* obs_tr, double* rew_tr, uint8_t* flags_tr, uint8_t* act_tr) {
+  const TraceOut tr = {state_tr, obs_tr, rew_tr, flags_tr, act_tr};
+  int64_t live = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t particle = p0 + (uint64_t)i;
+    Veh s[2], ns[2];
+    initial_state(seed, particle, s);
+    uint64_t h = trace_hash_init(particle);
+    for (int k = 0; k < depth; ++k) {
+      int act[2], order, coll[2], o[44];
+      double rew[2];
+      live += !((s[0].reached || s[0].crashed) && (s[1].reached || s[1].crashed));
+      step_noise(seed, particle, (uint32_t)k, act, &order);
+      step2(s, act, order, ns, rew, coll);
+      observe(ns, 0, o); observe(ns, 1, o + 22);
+      const int t0 = ns[0].reached || ns[0].crashed, t1 = ns[1].reached || ns[1].crashed;
+      const uint8_t flags = (uint8_t)(t0 | (t1 << 1) | ((t0 && t1) ? 0x80 : 0));
+      const uint32_t sw[2] = {pack_vehicle(&ns[0]), pack_vehicle(&ns[1])};
+      const uint64_t ow[2] = {pack_obs(o), pack_obs(o + 22)};
+      const uint8_t a8[2] = {(uint8_t)act[0], (uint8_t)act[1]};
+      h = trace_hash_step(h, sw, 2, ow, 2, rew, 2, flags, a8);
+      trace_record(&tr, n, i, k, sw, 2, ow, 2, rew, 2, flags, a8);
+      s[0] = ns[0]; s[1] = ns[1];
+    }
+    hash_out[i] = h;
+  }
+  return live;
 }

@@ -71,9 +71,47 @@ void smem_optin_impl(const void* kernel, int bytes) {
   else cudaGetLastError();   // the launch that follows reports the failure
 }
 
+// posg_trace_hash: one thread per particle; every pointer is read once, coalesced.
+__global__ void __launch_bounds__(256)
+trace_hash_kernel(int64_t n, unsigned long long* __restrict__ hash, int init, uint64_t particle_offset,
+                  const uint32_t* __restrict__ state, int sw, const unsigned long long* __restrict__ obs, int ow,
+                  const unsigned long long* __restrict__ rew_bits, int nag, const uint8_t* __restrict__ flags,
+                  const uint8_t* __restrict__ actions) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned long long h = init ? (particle_offset + (uint64_t)i + 1ULL) * 0xD6E8FEB86659FD93ULL : hash[i];
+    auto mix = [&h](unsigned long long w) { h = (h ^ w) * 0x9E3779B97F4A7C15ULL; h ^= h >> 32; };
+    if (state != nullptr) {
+      for (int k = 0; k < sw; ++k) mix((unsigned long long)__ldg(state + i * sw + k));
+      for (int k = 0; k < ow; ++k) mix(__ldg(obs + i * ow + k));
+      for (int k = 0; k < nag; ++k) mix(__ldg(rew_bits + i * nag + k));
+      unsigned long long tail = __ldg(flags + i);
+      for (int k = 0; k < nag; ++k) tail |= (unsigned long long)__ldg(actions + i * nag + k) << (8 * (k + 1));
+      mix(tail);
+    }
+    hash[i] = h;
+  }
+}
+
 }  // namespace posg
 
 extern "C" {
+
+int posg_trace_hash(int64_t n, uint64_t* hash_inout, int init, uint64_t particle_offset, const uint32_t* state,
+                    int state_words, const uint64_t* obs, int obs_words, const double* rewards, int num_agents,
+                    const uint8_t* flags, const uint8_t* actions, void* stream) {
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(n > 0 && hash_inout, "bad arguments");
+  POSG_REQUIRE(state == nullptr || (obs && rewards && flags && actions && state_words > 0 && obs_words > 0 &&
+                                    num_agents > 0 && num_agents <= 7),
+               "posg_trace_hash: every output array of the step is needed");
+  const int64_t blocks = (n + 255) / 256, cap = (int64_t)posg::sm_count() * 8;
+  posg::trace_hash_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+      n, (unsigned long long*)hash_inout, init, particle_offset, state, state_words, (const unsigned long long*)obs,
+      obs_words, (const unsigned long long*)rewards, num_agents, flags, actions);
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
 
 const char* posg_last_error(void) { return posg::g_err; }
 

@@ -42,6 +42,21 @@ def to_numpy(t) -> np.ndarray:
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
 
+def trace_hash(hashes, out=None, init: bool = False, particle_offset: int = 0):
+    """Folds one step's outputs (a ``StepOut`` of any model, with actions) into the per-particle rolling
+    hash ``hashes`` (int64 [n], device) -- ``posg_trace_hash`` (include/posg_b200.h).  ``out=None`` with
+    ``init=True`` only initialises."""
+    n = hashes.shape[0]
+    if out is None:
+        args = (None, 0, None, 0, None, 0, None, None)
+    else:
+        args = (_lib.ptr(out.state), out.state.shape[1], _lib.ptr(out.obs), out.obs.numel() // max(n, 1),
+                _lib.ptr(out.rewards), out.rewards.shape[1], _lib.ptr(out.flags), _lib.ptr(out.actions))
+    with torch.cuda.device(hashes.device):
+        _lib.check(_lib.lib().posg_trace_hash(n, _lib.ptr(hashes), int(init), particle_offset, *args, _lib.stream_ptr()))
+    return hashes
+
+
 class BatchedModel:
     """Subclasses set ``num_agents``, ``state_words``, ``obs_words``, ``noise_words``,
     ``num_picks`` and create ``self._handle``."""
