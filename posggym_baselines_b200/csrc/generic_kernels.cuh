@@ -84,22 +84,26 @@ step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int6
   }
 }
 
-// Fast path of model.step for models whose step noise is ONE Philox word per env (M::ONE_WORD_NOISE:
-// block = particle >> 2, word = particle & 3), random actions, particle_offset a multiple of four and
-// whole blocks of 128 envs -- the design of driving::step_fast_kernel: a warp owns 128 consecutive
+// Fast path of model.step for random actions, particle_offset a multiple of four and whole blocks of 128
+// envs.  Models whose step noise is ONE Philox word per env (M::ONE_WORD_NOISE: block = particle >> 2,
+// word = particle & 3) share a block between four envs; the others (PredatorPrey: four words per env)
+// compute one block per env in place -- the design of driving::step_fast_kernel: a warp owns 128 consecutive
 // envs, lane L steps envs 32 j + L (every warp-level global access is one contiguous run), lane L
 // computes the Philox block of envs 4 L .. 4 L + 3 and the words are transposed through shared
 // memory; the next block's states and Philox rounds are issued one iteration ahead.
 constexpr int FAST_WARP_ENVS = 128, FAST_EPT = 4;
 
+#ifndef GENERIC_FAST_MIN_CTAS
+#define GENERIC_FAST_MIN_CTAS 3
+#endif
 template <class M, bool WRITE_ACTIONS, bool COUNT_LIVE>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, GENERIC_FAST_MIN_CTAS)
 step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nblocks,
                  const uint2* __restrict__ state_in, uint64_t seed, uint32_t step_idx, uint64_t group_offset,
                  uint2* __restrict__ state_out, ulonglong2* __restrict__ obs_out, double2* __restrict__ rewards_out,
                  uint8_t* __restrict__ flags_out, uchar2* __restrict__ actions_out,
                  unsigned long long* __restrict__ live_count) {
-  static_assert(M::SW == 2 && M::NAG == 2 && (M::OW == 1 || M::OW == 2) && M::ONE_WORD_NOISE, "unsupported model");
+  static_assert(M::SW == 2 && M::NAG == 2 && (M::OW == 1 || M::OW == 2), "unsupported model");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   __shared__ alignas(16) uint32_t s_words[THREADS / 32][FAST_WARP_ENVS];
@@ -114,7 +118,8 @@ step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
 #pragma unroll
   for (int j = 0; j < FAST_EPT; ++j)
     nxt[j] = wb < nblocks ? __ldg(state_in + wb * FAST_WARP_ENVS + lane + 32 * j) : make_uint2(0u, 0u);
-  uint4 blk_next = philox_block(seed, group_offset + (uint64_t)wb * 32u + lane, step_idx, STREAM_STEP);
+  uint4 blk_next = make_uint4(0u, 0u, 0u, 0u);
+  if constexpr (M::ONE_WORD_NOISE) blk_next = philox_block(seed, group_offset + (uint64_t)wb * 32u + lane, step_idx, STREAM_STEP);
   for (; wb < nblocks; wb += wstride) {
     const uint32_t e0 = wb * FAST_WARP_ENVS + lane;
     uint2 sv[FAST_EPT];
@@ -124,22 +129,29 @@ step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
 #pragma unroll
       for (int j = 0; j < FAST_EPT; ++j) nxt[j] = __ldg(state_in + (wb + wstride) * FAST_WARP_ENVS + lane + 32 * j);
     }
-    __syncwarp();
-    *reinterpret_cast<uint4*>(&s_words[warp][4 * lane]) = blk_next;
-    __syncwarp();
     uint32_t word[FAST_EPT];
+    if constexpr (M::ONE_WORD_NOISE) {
+      __syncwarp();
+      *reinterpret_cast<uint4*>(&s_words[warp][4 * lane]) = blk_next;
+      __syncwarp();
 #pragma unroll
-    for (int j = 0; j < FAST_EPT; ++j) word[j] = s_words[warp][32 * j + lane];
-    blk_next = philox_block(seed, group_offset + (uint64_t)(wb + wstride) * 32u + lane, step_idx, STREAM_STEP);
+      for (int j = 0; j < FAST_EPT; ++j) word[j] = s_words[warp][32 * j + lane];
+      blk_next = philox_block(seed, group_offset + (uint64_t)(wb + wstride) * 32u + lane, step_idx, STREAM_STEP);
+    }
 #pragma unroll
     for (int j = 0; j < FAST_EPT; ++j) {
       typename M::State s;
       s.w[0] = sv[j].x; s.w[1] = sv[j].y;
       int act[NAG];
       uint32_t noise[NW];
-      M::actions_from_word(word[j], act);
+      if constexpr (M::ONE_WORD_NOISE) {
+        M::actions_from_word(word[j], act);
 #pragma unroll
-      for (int k = 0; k < NW; ++k) noise[k] = 0u;
+        for (int k = 0; k < NW; ++k) noise[k] = 0u;
+      } else {
+        // one Philox block per env: counter = global particle index (the general kernel's convention)
+        M::noise_from_philox(seed, group_offset * 4u + (uint64_t)(e0 + 32 * j), step_idx, act, noise);
+      }
       unsigned long long obs[NAG][OW];
       double rew[NAG];
       uint32_t flags;

@@ -93,9 +93,14 @@ static pp::Blob* build_pp_blob(int size, const char* blocks, int num_predators, 
 
 using namespace posg;
 
+// PredatorPrey: the table-driven adapter where its tables are exact (grids up to 10x10), else the general one
+static inline bool pp_lut(const posg_model* m) { return ((const pp::Blob*)m->h_blob)->lut_ok != 0; }
+
 #define MODEL_DISPATCH(m, CALL)                                                   \
   switch ((m)->kind) {                                                            \
-    case KIND_PREDATOR_PREY: { using M = PPSim; CALL; } break;                    \
+    case KIND_PREDATOR_PREY:                                                      \
+      if (pp_lut(m)) { using M = PPSimLut; CALL; } else { using M = PPSim; CALL; } \
+      break;                                                                      \
     case KIND_LBF: { using M = LBFSim; CALL; } break;                             \
     default: set_error("posg_model_*: unsupported model kind %d", (m)->kind);     \
              return POSG_E_UNSUPPORTED;                                           \
@@ -188,10 +193,11 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
                "state buffers must be 8-byte, obs / rewards buffers 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   int64_t done = 0;
-  if (m->kind == KIND_LBF && !actions_in && !noise_in && (particle_offset & 3ULL) == 0 &&
+  static const bool nofast = getenv("POSG_STEP_NOFAST") != nullptr;   // dev A/B switch
+  const bool fast_kind = m->kind == KIND_LBF || (m->kind == KIND_PREDATOR_PREY && pp_lut(m));
+  if (!nofast && fast_kind && !actions_in && !noise_in && (particle_offset & 3ULL) == 0 &&
       n >= generic::FAST_WARP_ENVS && n < ((int64_t)1 << 31)) {
     // whole blocks of 128 envs through the fast kernel; a ragged tail through the general one
-    using M = LBFSim;
     const uint32_t nb = (uint32_t)(n / generic::FAST_WARP_ENVS);
 #define POSG_FAST(WA, CL)                                                                                        \
     generic::step_fast_kernel<M, WA, CL><<<persistent_grid(generic::step_fast_kernel<M, WA, CL>, m->blob_bytes,   \
@@ -199,10 +205,14 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
         (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, seed, step_idx,           \
         particle_offset >> 2, (uint2*)state_out, (ulonglong2*)obs_out, (double2*)rewards_out, flags_out,          \
         (uchar2*)actions_out, live_count)
-    if (actions_out && live_count) POSG_FAST(true, true);
-    else if (actions_out) POSG_FAST(true, false);
-    else if (live_count) POSG_FAST(false, true);
-    else POSG_FAST(false, false);
+#define POSG_FAST_ALL()                                 \
+    if (actions_out && live_count) POSG_FAST(true, true); \
+    else if (actions_out) POSG_FAST(true, false);         \
+    else if (live_count) POSG_FAST(false, true);          \
+    else POSG_FAST(false, false)
+    if (m->kind == KIND_LBF) { using M = LBFSim; POSG_FAST_ALL(); }
+    else { using M = PPSimLut; POSG_FAST_ALL(); }
+#undef POSG_FAST_ALL
 #undef POSG_FAST
     POSG_CUDA(cudaGetLastError());
     done = (int64_t)nb * generic::FAST_WARP_ENVS;

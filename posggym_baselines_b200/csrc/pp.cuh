@@ -24,12 +24,35 @@ struct alignas(16) Blob {
   double reward_k[4];              // k * (1 / num_prey), k newly caught prey (cooperative)
   double per_prey_reward;
   double pad2_;
+  double share_k[4];               // per_prey_reward / k, k predators involved in a capture (non-cooperative)
   unsigned long long obs_base[256];  // wall cells of the window centred at (x, y)
   uint8_t wall4[256];                // bit k: neighbour k (N, E, S, W) of cell x | y << 4 is blocked / outside
   uint8_t nth_lut[32 * 8];           // [mask5 * 8 + n] -> index of the n-th set bit of mask5 (bits 0..4)
   int8_t nb_delta[8];                // cell-index delta of N, E, S, W, stay
-  uint8_t pad3_[8];
+  uint8_t lut_ok, pad3_[7];          // 1: the relative-offset tables below are exact for this grid (size <= 10)
+  // ---- relative-offset tables, index REL0 + (b - a) for packed cells a, b (x | y << 4).  The offset
+  // dx + 16 dy is unique for |dx| <= 2 on grids up to 14 wide; caught prey are given the cell SENT,
+  // which on grids up to 10x10 is "far" from every cell under every table (no select per use).
+  uint8_t rel_nb[512];               // bit k: b is the N / E / S / W neighbour of a
+  // threat score of b for a prey at a: 4 * Manhattan + 2 within obs_dim, else THR_FAR (the caller adds +-1 to
+  // the second of two candidates -- the tie pick -- and THR_PREY to prey candidates, then takes a minimum
+  // together with the score THR_RND of "nobody in sight: random move")
+  uint8_t rel_thr[512];
+  // cell delta of a prey's move, [row * 16 + free-neighbour mask (N, E, S, W)]: rows MOVE_FLEE0 + d = flee
+  // (_move_away) from a threat at offset d; rows MOVE_RND + picks8 = random move with picks8 = p2 | p3 << 1 |
+  // p4 << 3 | p5 << 5, p_n = pick_index(word, n)
+  int8_t move_delta[(80 + 256) * 16];
+  uint8_t pred_move[5 * 256];        // [action * 256 + cell] -> the predator's target cell (walls resolved)
+  uint32_t caught_mask[8];           // bytes 0xFF at the prey whose caught bit is set
+  // observation pieces: window cells that are outside the grid by column (+ the centre PREDATOR) / by row,
+  // and the PREY code at the window cell of an entity at offset u = (dx + od) + 16 (dy + od), u < 80
+  unsigned long long win_col[16], win_row[16];
+  unsigned long long win_obs[80];
 };
+constexpr int REL0 = 256, SENT = 0xCC, THR_FAR = 66, THR_PREY = 32, THR_RND = 64;
+// move_delta rows are addressed in the biased offset space REL0 + d of the candidate keys: flee rows sit at
+// REL0 + d - MOVE_BASE (|d| <= 34), the random rows behind them
+constexpr int MOVE_BASE = REL0 - 40, MOVE_RND = 80;
 
 // host side: fill the lookup tables from rows[] (walls)
 inline void build_tables(Blob* b) {
@@ -47,6 +70,69 @@ inline void build_tables(Blob* b) {
   }
   const int8_t d[8] = {-16, 1, 16, -1, 0, 0, 0, 0};
   for (int k = 0; k < 8; ++k) b->nb_delta[k] = d[k];
+  for (int k = 0; k < 4; ++k) b->share_k[k] = b->per_prey_reward / (double)(k < 1 ? 1 : k);
+  // relative-offset tables
+  const int od = b->obs_dim, w = 2 * od + 1;
+  bool blocks = false;
+  for (int y = 0; y < b->size; ++y)
+    for (int x = 0; x < b->size; ++x) blocks |= ((b->rows[y + PAD] >> (x + PAD)) & 1u) != 0;
+  b->lut_ok = (b->size <= 10 && od == 2 && !blocks) ? 1 : 0;
+  for (int i = 0; i < 512; ++i) { b->rel_nb[i] = 0; b->rel_thr[i] = (uint8_t)THR_FAR; }
+  for (int i = 0; i < 80; ++i) b->win_obs[i] = 0;
+  for (int dy = -od; dy <= od; ++dy)
+    for (int dx = -od; dx <= od; ++dx) {
+      const int i = REL0 + dx + 16 * dy, man = abs(dx) + abs(dy);
+      if (man <= od && man > 0) b->rel_thr[i] = (uint8_t)(4 * man + 2);
+      if (man == 1) b->rel_nb[i] = (uint8_t)(dy == -1 ? 1 : dx == 1 ? 2 : dy == 1 ? 4 : 8);
+      b->win_obs[(dx + od) + 16 * (dy + od)] = (unsigned long long)PREY << (2 * ((dx + od) * w + (dy + od)));
+    }
+  for (int v = 0; v < 16; ++v) {
+    unsigned long long col = (unsigned long long)PREDATOR << (2 * (od * w + od)), row = 0;
+    for (int k = 0; k < w; ++k) {
+      const int g = v + k - od;   // grid column (row) shown in window column (row) k
+      if (g >= 0 && g < b->size) continue;
+      for (int m = 0; m < w; ++m) {
+        col |= (unsigned long long)WALL << (2 * (k * w + m));
+        row |= (unsigned long long)WALL << (2 * (m * w + k));
+      }
+    }
+    b->win_col[v] = col; b->win_row[v] = row;
+  }
+  for (int c = 0; c < 8; ++c)
+    b->caught_mask[c] = ((c & 1) ? 0xFFu : 0u) | ((c & 2) ? 0xFF00u : 0u) | ((c & 4) ? 0xFF0000u : 0u);
+  // prey moves.  Flee: keep the free option (staying included) with the largest (distance to the threat, x, y)
+  const int ox[5] = {0, 1, 0, -1, 0}, oy[5] = {-1, 0, 1, 0, 0};
+  for (int i = 0; i < (80 + 256) * 16; ++i) b->move_delta[i] = 0;
+  for (int dy = -od; dy <= od; ++dy)
+    for (int dx = -od; dx <= od; ++dx) {
+      if (abs(dx) + abs(dy) > od) continue;
+      for (int f = 0; f < 16; ++f) {
+        int best = 4, bd = abs(dx) + abs(dy);
+        for (int k = 0; k < 4; ++k) {
+          if (!((f >> k) & 1)) continue;
+          const int dd = abs(dx - ox[k]) + abs(dy - oy[k]);
+          const bool better = dd > bd || (dd == bd && (ox[k] > ox[best] || (ox[k] == ox[best] && oy[k] > oy[best])));
+          if (better) { best = k; bd = dd; }
+        }
+        b->move_delta[(REL0 + dx + 16 * dy - MOVE_BASE) * 16 + f] = d[best];
+      }
+    }
+  // random move: the pick-th of the free neighbours N, E, S, W followed by staying
+  for (int picks = 0; picks < 256; ++picks)
+    for (int f = 0; f < 16; ++f) {
+      const int pk[6] = {0, 0, picks & 1, (picks >> 1) & 3, (picks >> 3) & 3, (picks >> 5) & 7};
+      const int m5 = f | 16;
+      int cnt = 0;
+      for (int bit = 0; bit < 5; ++bit) cnt += (m5 >> bit) & 1;
+      b->move_delta[(MOVE_RND + picks) * 16 + f] = d[b->nth_lut[m5 * 8 + (pk[cnt] < cnt ? pk[cnt] : cnt - 1)]];
+    }
+  // predator targets
+  for (int a = 0; a < 5; ++a)
+    for (int c = 0; c < 256; ++c) {
+      const int dir = a == 1 ? 0 : a == 2 ? 2 : a == 3 ? 3 : a == 4 ? 1 : 4;   // UP, DOWN, LEFT, RIGHT -> N, S, W, E
+      const bool blocked = dir < 4 && ((b->wall4[c] >> dir) & 1);
+      b->pred_move[a * 256 + c] = (uint8_t)(c + ((dir == 4 || blocked) ? 0 : (int)d[dir]));
+    }
 }
 static_assert(sizeof(Blob) % 16 == 0, "blob must be a multiple of 16 B");
 
@@ -232,6 +318,155 @@ __device__ __forceinline__ unsigned long long observe(const Blob& B, const Ents&
   return cells;
 }
 
+
+// i == 0 ? a : (i == 1 ? b : c) as two selects (left to itself the compiler branches around them)
+__device__ __forceinline__ uint32_t sel3(uint32_t i, uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.u32 p0, %1, 0;\n\tsetp.eq.u32 p1, %1, 1;\n\t"
+      "selp.b32 %0, %3, %4, p1;\n\tselp.b32 %0, %2, %0, p0;\n\t}" : "=r"(r) : "r"(i), "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+// ---- table-driven transition (block-free grids up to 10x10: Blob::lut_ok) ---------------------
+// Same semantics as transition() above, on the packed words, balanced between the two units that bound
+// these kernels: the integer ALU pipe and the shared-memory data pipe (a random byte lookup costs ~2-5
+// wavefronts of bank conflicts = as much as 4-10 ALU instructions, so tables are used only where they
+// replace more than that):
+//  * neighbour bits / threat scores are byte lookups on the packed-cell difference; caught prey sit on the
+//    cell SENT, which is far from everything, has no free neighbour and is adjacent to nothing, so nothing
+//    below needs a "caught" select (a caught prey "moves" by 0 and is "captured" never);
+//  * a prey's rule, threat and move-table row are ONE minimum over five candidate keys score << 10 | row
+//    (closest predator, else closest other prey -- the tie pick folded into the score as +-1 --, else the
+//    random-move row holding its pick for every possible number of options);
+//  * the sort key of a prey carries rule class, index, cell and that row, so the move is
+//    move_delta[row * 16 + free-neighbour mask] with no dynamic select;
+//  * adjacency for the captures is arithmetic: the packed difference d of two cells on a grid this small
+//    has d * d in {0, 1, 256} exactly when they are within Manhattan distance 1.
+// occ[] returns the cells of the prey after the step with SENT for every caught one (observe_lut).
+__device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint32_t& w1, const int (&act)[NP],
+                                               const uint32_t (&words)[NQ], double (&rew)[NP], int (&occ)[NQ]) {
+  const uint8_t* __restrict__ THR = B.rel_thr + REL0;
+  const uint8_t* __restrict__ NB = B.rel_nb + REL0;
+  const int8_t* __restrict__ MOVE = B.move_delta - MOVE_BASE * 16;
+  const int p0 = (int)(w0 & 255u), p1 = (int)((w0 >> 8) & 255u);
+  const uint32_t caught = (w0 >> 16) & 7u;
+  const uint32_t cmask = B.caught_mask[caught];
+  const uint32_t cells = (w1 & ~cmask) | ((uint32_t)SENT * 0x010101u & cmask);
+  occ[0] = (int)__byte_perm(cells, 0u, 0x4440); occ[1] = (int)__byte_perm(cells, 0u, 0x4441);
+  occ[2] = (int)__byte_perm(cells, 0u, 0x4442);
+  // prey-prey threat scores, shared by both ends
+  const int t01 = THR[occ[1] - occ[0]], t02 = THR[occ[2] - occ[0]], t12 = THR[occ[2] - occ[1]];
+  uint32_t key[NQ];   // (class * 4 + index) << 24 | cell << 16 | move-table row: moves are made in ascending order
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int c = occ[i], rc = REL0 - c;
+    const int sgn = (int)words[i] >> 31;                 // -pick_index(word, 2): the tie pick
+    const int j1 = i == 0 ? 1 : 0, j2 = i == 2 ? 1 : 2;
+    const int f1 = i == 2 ? t02 : t01, f2 = i == 0 ? t02 : t12;
+    // candidate keys score << 10 | biased offset: the second of a pair wins a tie iff the pick says so
+    // (score - 1 instead of + 1)
+    const int second = 2048 * sgn + 1024;
+    const int d0 = p0 + rc, d1 = p1 + rc, e1 = occ[j1] + rc, e2 = occ[j2] + rc;
+    const int k0 = THR[d0 - REL0] * 1024 + d0;
+    const int k1 = THR[d1 - REL0] * 1024 + (second + d1);
+    const int k2 = f1 * 1024 + (THR_PREY * 1024 + e1);
+    const int k3 = f2 * 1024 + (THR_PREY * 1024 + second + e2);
+    // pick_index(word, n) for n = 2..5 options, packed: the random-move row
+    const int k4 = (((int)__umulhi(words[i], 5u) * 4 + (int)(words[i] >> 30)) * 4 + (int)__umulhi(words[i], 3u)) * 2 +
+                   (THR_RND * 1024 + MOVE_BASE + MOVE_RND - sgn);
+    const int best = min(min(min(k0, k1), min(k2, k3)), k4);
+    // class = score >> 5: 0 predator in sight, 1 prey in sight, 2 random
+    key[i] = (uint32_t)((best >> 15) * (4 << 24) + (c * 65536 + ((best & 1023) + (i << 24))));
+  }
+  uint32_t k0 = min(key[0], key[1]), k1 = max(key[0], key[1]), k2 = key[2];
+  { const uint32_t t = min(k1, k2); k2 = max(k1, k2); k1 = t; }
+  { const uint32_t t = min(k0, k1); k1 = max(k0, k1); k0 = t; }
+  const uint32_t order[NQ] = {k0, k1, k2};
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const int c = (int)__byte_perm(order[k], 0u, 0x4442);
+    const int row = (int)(order[k] & 0xFFFFu);
+    // a prey is no neighbour of itself (offset 0), so all five entities go through the table
+    const uint32_t taken = NB[p0 - c] | NB[p1 - c] | NB[occ[0] - c] | NB[occ[1] - c] | NB[occ[2] - c];
+    const uint32_t free4 = ~((uint32_t)B.wall4[c] | taken) & 15u;
+    const int nxt = c + (int)MOVE[row * 16 + (int)free4];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) occ[j] = (((order[k] >> 24) & 3u) == (uint32_t)j) ? nxt : occ[j];
+  }
+  // predators: simultaneous moves; prey cells and shared targets block
+  int pot[NP];
+  const int pc[NP] = {p0, p1};
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int c = (int)B.pred_move[act[i] * 256 + pc[i]];
+    const bool on_prey = (c == occ[0]) || (c == occ[1]) || (c == occ[2]);
+    pot[i] = on_prey ? pc[i] : c;
+  }
+  const bool clash = pot[0] == pot[1];
+  const int n0 = clash ? p0 : pot[0], n1 = clash ? p1 : pot[1];
+  // captures (SENT is adjacent to nothing): within Manhattan distance 1 <=> d * d in {0, 1, 256}
+  uint32_t sq[NQ][NP];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const int da = n0 - occ[j], db = n1 - occ[j];
+    sq[j][0] = (uint32_t)(da * da); sq[j][1] = (uint32_t)(db * db);
+  }
+  uint32_t newly;
+  if (B.prey_strength >= 2)   // uniform: both predators adjacent
+    newly = ((((sq[0][0] | sq[0][1]) & 0xFFFFFEFEu) == 0u) ? 1u : 0u) | ((((sq[1][0] | sq[1][1]) & 0xFFFFFEFEu) == 0u) ? 2u : 0u) |
+            ((((sq[2][0] | sq[2][1]) & 0xFFFFFEFEu) == 0u) ? 4u : 0u);
+  else                        // a product with a zero factor: one of them adjacent
+    newly = (((sq[0][0] & 0xFFFFFEFEu) * (sq[0][1] & 0xFFFFFEFEu) == 0u) ? 1u : 0u) |
+            (((sq[1][0] & 0xFFFFFEFEu) * (sq[1][1] & 0xFFFFFEFEu) == 0u) ? 2u : 0u) |
+            (((sq[2][0] & 0xFFFFFEFEu) * (sq[2][1] & 0xFFFFFEFEu) == 0u) ? 4u : 0u);
+  rew[0] = 0.0; rew[1] = 0.0;
+  if (B.cooperative) {
+    rew[0] = rew[1] = B.reward_k[__popc(newly)];   // reward_k[0] == 0.0
+  } else if (newly) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      if (!((newly >> j) & 1u)) continue;
+      const int da = n0 - occ[j], db = n1 - occ[j];
+      const bool i0 = ((uint32_t)(da * da) & 0xFFFFFEFEu) == 0u, i1 = ((uint32_t)(db * db) & 0xFFFFFEFEu) == 0u;
+      const double share = B.share_k[(int)i0 + (int)i1];
+      if (i0) rew[0] = __dadd_rn(rew[0], share);
+      if (i1) rew[1] = __dadd_rn(rew[1], share);
+    }
+  }
+  // caught prey keep the cell they had; newly caught ones the cell they were caught on
+  const uint32_t moved = (uint32_t)occ[0] + ((uint32_t)occ[1] * 256u + (uint32_t)occ[2] * 65536u);
+  const uint32_t all = caught | newly;
+  w0 = (uint32_t)n0 + ((uint32_t)n1 * 256u + all * 65536u);
+  w1 = (w1 & cmask) | (moved & ~cmask);
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) occ[j] = ((newly >> j) & 1u) ? SENT : occ[j];
+  return all == 7u;
+}
+
+// observation of predator i: out-of-grid columns / rows (and the own cell) from two 16-entry tables; another
+// entity contributes the table entry of its offset, looked up only by the lanes that have it in the window
+// (a predicated-off lane makes no shared-memory access, so the lookup costs a wavefront or two, not six)
+__device__ __forceinline__ unsigned long long observe_lut(const Blob& B, uint32_t w0, const int (&occ)[NQ], int i) {
+  const uint32_t p = (w0 >> (8 * i)) & 255u, o = (w0 >> (8 * (1 - i))) & 255u;
+  unsigned long long cells = B.win_col[p & 15u] | B.win_row[p >> 4];
+  const uint32_t bias = 2u * 17u - p;     // obs_dim = 2: u = (dx + 2) + 16 (dy + 2)
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    const uint32_t u = (uint32_t)occ[j] + bias;
+    if ((u & 15u) <= 4u && u < 80u) cells |= B.win_obs[u];
+  }
+  {
+    const uint32_t u = o + bias;
+    // PREDATOR (2) = PREY (3) with the low bit of the cell cleared
+    if ((u & 15u) <= 4u && u < 80u) cells |= B.win_obs[u] & 0xAAAAAAAAAAAAAAAAULL;
+  }
+  return cells;
+}
+__device__ __forceinline__ void occ_of(uint32_t w0, uint32_t w1, int (&occ)[NQ]) {
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) occ[j] = ((w0 >> (16 + j)) & 1u) ? SENT : (int)((w1 >> (8 * j)) & 255u);
+}
+
 __device__ __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NP + NQ], Ents& e) {
   uint32_t used = 0;
   for (int i = 0; i < NP; ++i) {
@@ -260,12 +495,16 @@ __device__ __forceinline__ void initial_from_picks(const Blob& B, const int (&pi
 
 }  // namespace pp
 
-// Adapter for the generic batch / search / belief kernels.
-struct PPSim {
+// Adapter for the generic batch / search / belief kernels.  LUT = true: the table-driven transition /
+// observation (Blob::lut_ok; the host picks the instantiation), same results.
+template <bool LUT>
+struct PPSimT {
   using Blob = pp::Blob;
   using Ctx = NoCtx;
   static constexpr int A = 5, OW = 1, SW = 2, NAG = 2, NW = 3, NPICK = 5;
+  static constexpr bool ONE_WORD_NOISE = false;   // four Philox words per env-step
   struct State { uint32_t w[SW]; };
+  __device__ static __forceinline__ void actions_from_word(uint32_t, int (&)[NAG]) {}
 
   // flattened-observation fields: the 25 window cells, two bits each (see DrivingSim::obs_field)
   static constexpr int NFIELD = 25;
@@ -278,23 +517,37 @@ struct PPSim {
                                                   const uint32_t (&noise)[NW],
                                                   unsigned long long (&obs)[NAG][OW], double (&rew)[NAG],
                                                   uint32_t& flags, bool& was_live) {
-    pp::Ents e;
-    pp::unpack(s.w[0], s.w[1], e);
-    was_live = e.caught != 7u;
-    const bool all_done = pp::transition(B, e, act, noise, rew);
-    pp::pack(e, s.w[0], s.w[1]);
-    obs[0][0] = pp::observe(B, e, 0);
-    obs[1][0] = pp::observe(B, e, 1);
-    flags = all_done ? (0x80u | 3u) : 0u;
+    if constexpr (LUT) {
+      was_live = ((s.w[0] >> 16) & 7u) != 7u;
+      int occ[pp::NQ];
+      const bool all_done = pp::transition_lut(B, s.w[0], s.w[1], act, noise, rew, occ);
+      obs[0][0] = pp::observe_lut(B, s.w[0], occ, 0);
+      obs[1][0] = pp::observe_lut(B, s.w[0], occ, 1);
+      flags = all_done ? (0x80u | 3u) : 0u;
+    } else {
+      pp::Ents e;
+      pp::unpack(s.w[0], s.w[1], e);
+      was_live = e.caught != 7u;
+      const bool all_done = pp::transition(B, e, act, noise, rew);
+      pp::pack(e, s.w[0], s.w[1]);
+      obs[0][0] = pp::observe(B, e, 0);
+      obs[1][0] = pp::observe(B, e, 1);
+      flags = all_done ? (0x80u | 3u) : 0u;
+    }
   }
   // the same without observations (rollouts); term = per-agent terminated bits
   __device__ static __forceinline__ void step_noobs(const Blob& B, State& s, const int (&act)[NAG],
                                                     const uint32_t (&noise)[NW], double (&rew)[NAG],
                                                     uint32_t& term, bool& all_done) {
-    pp::Ents e;
-    pp::unpack(s.w[0], s.w[1], e);
-    all_done = pp::transition(B, e, act, noise, rew);
-    pp::pack(e, s.w[0], s.w[1]);
+    if constexpr (LUT) {
+      int occ[pp::NQ];
+      all_done = pp::transition_lut(B, s.w[0], s.w[1], act, noise, rew, occ);
+    } else {
+      pp::Ents e;
+      pp::unpack(s.w[0], s.w[1], e);
+      all_done = pp::transition(B, e, act, noise, rew);
+      pp::pack(e, s.w[0], s.w[1]);
+    }
     term = all_done ? 3u : 0u;
   }
   // uniform joint action + prey words from one Philox block (particle, step, STREAM_STEP)
@@ -311,10 +564,17 @@ struct PPSim {
     noise[0] = w.x; noise[1] = w.y; noise[2] = w.z;
   }
   __device__ static __forceinline__ void observe_all(const Blob& B, const State& s, unsigned long long (&obs)[NAG][OW]) {
-    pp::Ents e;
-    pp::unpack(s.w[0], s.w[1], e);
-    obs[0][0] = pp::observe(B, e, 0);
-    obs[1][0] = pp::observe(B, e, 1);
+    if constexpr (LUT) {
+      int occ[pp::NQ];
+      pp::occ_of(s.w[0], s.w[1], occ);
+      obs[0][0] = pp::observe_lut(B, s.w[0], occ, 0);
+      obs[1][0] = pp::observe_lut(B, s.w[0], occ, 1);
+    } else {
+      pp::Ents e;
+      pp::unpack(s.w[0], s.w[1], e);
+      obs[0][0] = pp::observe(B, e, 0);
+      obs[1][0] = pp::observe(B, e, 1);
+    }
   }
   __device__ static __forceinline__ void initial_from_picks(const Blob& B, const int (&picks)[NPICK], State& s) {
     pp::Ents e;
@@ -346,13 +606,19 @@ struct PPSim {
     act[0] = ego == 0 ? ego_action : other;
     act[1] = ego == 1 ? ego_action : other;
     const uint32_t noise[NW] = {w.x, w.y, w.z};
-    pp::Ents e;
-    pp::unpack(s.w[0], s.w[1], e);
     double rew[NAG];
-    done = pp::transition(B, e, act, noise, rew);
-    pp::pack(e, s.w[0], s.w[1]);
+    if constexpr (LUT) {
+      int occ[pp::NQ];
+      done = pp::transition_lut(B, s.w[0], s.w[1], act, noise, rew, occ);
+      obs[0] = pp::observe_lut(B, s.w[0], occ, ego);
+    } else {
+      pp::Ents e;
+      pp::unpack(s.w[0], s.w[1], e);
+      done = pp::transition(B, e, act, noise, rew);
+      pp::pack(e, s.w[0], s.w[1]);
+      obs[0] = pp::observe(B, e, ego);
+    }
     r = rew[ego];
-    obs[0] = pp::observe(B, e, ego);
   }
   __device__ static __forceinline__ void rollout_step(const Blob& B, const Ctx&, State& s, int ego, uint32_t word,
                                                       double& r, bool& done) {
@@ -362,18 +628,31 @@ struct PPSim {
     act[1] = (int)(idx / 5u);
     act[0] = (int)(idx - 5u * (uint32_t)act[1]);
     const uint32_t noise[NW] = {w.x, w.y, w.z};
-    pp::Ents e;
-    pp::unpack(s.w[0], s.w[1], e);
     double rew[NAG];
-    done = pp::transition(B, e, act, noise, rew);
-    pp::pack(e, s.w[0], s.w[1]);
+    if constexpr (LUT) {
+      int occ[pp::NQ];
+      done = pp::transition_lut(B, s.w[0], s.w[1], act, noise, rew, occ);
+    } else {
+      pp::Ents e;
+      pp::unpack(s.w[0], s.w[1], e);
+      done = pp::transition(B, e, act, noise, rew);
+      pp::pack(e, s.w[0], s.w[1]);
+    }
     r = rew[ego];
   }
   __device__ static __forceinline__ void observe(const Blob& B, const State& s, int ego, unsigned long long (&obs)[OW]) {
-    pp::Ents e;
-    pp::unpack(s.w[0], s.w[1], e);
-    obs[0] = pp::observe(B, e, ego);
+    if constexpr (LUT) {
+      int occ[pp::NQ];
+      pp::occ_of(s.w[0], s.w[1], occ);
+      obs[0] = pp::observe_lut(B, s.w[0], occ, ego);
+    } else {
+      pp::Ents e;
+      pp::unpack(s.w[0], s.w[1], e);
+      obs[0] = pp::observe(B, e, ego);
+    }
   }
 };
+using PPSim = PPSimT<false>;
+using PPSimLut = PPSimT<true>;
 
 }  // namespace posg
