@@ -30,6 +30,24 @@ BYTES_PER_ENV_STEP = 51  # 8 B state in; 8 state + 16 obs + 16 r
 DEPTH = 50
 
 
+def workload_config(n: int, seed: int = 2026) -> dict:
+    """``config`` of the JSON line -- identical for this repo's arm and the reference arm."""
+    return {"workload": f"Driving-v1 14x14RoundAbout, 2 agents, obs_dim (3,1,1): random-action model.step sweep, "
+                        f"{n} particles per GPU x depth {DEPTH} (BASELINE.json configs[1])",
+            "particles_per_gpu": n, "depth": DEPTH, "seed": seed,
+            "l2": f"per-launch working set {n * BYTES_PER_ENV_STEP / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)",
+            "counted": "env-steps executed on not-yet-all-done particles"}
+
+
+def load_counters() -> dict:
+    """Per-kernel counters distilled from the committed ncu captures (profiles/kernel_counters.json)."""
+    p = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -107,14 +125,13 @@ def run_reference(args):
         vals.append(r["env_steps_per_s"])
         secs += r["seconds"]
     v = sum(vals) / len(vals)
-    sample = f"{budget:.1f} s of Driving-v1 random-action depth-{DEPTH} episodes per step on each of {cores} processes (Python oracle port)"
+    sample = (f"bounded sample of the workload: {budget:.1f} s of Driving-v1 random-action depth-{DEPTH} episodes per step "
+              f"on each of {cores} processes (Python oracle port of the model; the reference's model is pure Python)")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"Driving-v1 14x14RoundAbout, 2 agents, obs_dim (3,1,1): random-action model.step sweep, "
-                               f"{args.particles} particles per GPU x depth {DEPTH} (BASELINE.json configs[1])",
-                   "sample": sample},
+        "config": workload_config(args.particles),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -142,12 +159,14 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
     rng = random.Random(rank)
     obs, _ = env.reset(seed=100 + rank)
     planner.reset()
-    sims, times = [], []
+    sims, times, upd, infos = [], [], [], []
     for d in range(decisions + 1):
         a = planner.step(obs["0"])
         if d > 0 and planner.step_statistics["num_sims"] == planner.step_statistics["num_sims"]:  # skip warm-up / NaN
             sims.append(planner.step_statistics["num_sims"])
             times.append(planner.step_statistics["search_time"])
+            upd.append(planner.step_statistics["update_time"])
+            infos.append(dict(planner.search_info))
         obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
         if done:
             obs, _ = env.reset()
@@ -162,7 +181,15 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
            "sims_per_decision_per_gpu": tot[0].item() / max(1.0, tot[1].item()),
            "sims_per_decision_all_gpus": world * tot[0].item() / max(1.0, tot[1].item()),
            "sims_per_s_all_gpus": world * tot[0].item() / max(1.0, tot[1].item()) / max(1e-9, tmax.item()),
-           "search_time_s": tmax.item(), "trees": world}
+           "search_time_s": tmax.item(), "trees": world,
+           # planner.update (re-root + belief + reinvigoration) runs outside the search budget, like the reference's
+           # update_time; the next four say how much of the search still grew the tree (rank 0's tree)
+           "update_time_s": sum(upd) / max(1, len(upd)),
+           "overflow_share": sum(i["overflow_share"] for i in infos) / max(1, len(infos)),
+           "nodes_created_per_decision": sum(i["nodes_created"] for i in infos) / max(1, len(infos)),
+           "arena_fill_max": max([i["arena_fill"] for i in infos] or [0.0]),
+           "waves_per_decision": sum(i["waves"] for i in infos) / max(1, len(infos)),
+           "node_capacity": planner._cap_nodes}
     # BASELINE.json configs[2]: root-parallel POMCP on PredatorPrey-v0 -- every rank grows its own
     # tree from the same root belief; root visit counts and value sums merged by ONE allreduce
     # per decision (NCCL); every rank then takes the same action.
@@ -267,6 +294,100 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
         out["cpu_reference_sims_per_decision"] = sum(c_sims) / max(1, len(c_sims))
         out["cpu_reference"] = "oracle/pomcp.py (restated reference planner, pure Python, 1 core), same config"
         out["ratio"] = out["sims_per_decision_per_gpu"] / max(1e-9, out["cpu_reference_sims_per_decision"])
+    return out
+
+
+def bench_models(dev, rank, world, seed, barrier, steps: int):
+    """``model.step`` of the two other in-scope models as roofline-shaped sections: the same random-action
+    depth-50 sweep (Philox initial states / joint actions, every output written) at 2^22 envs per GPU --
+    per-launch working set 214 / 281 MB, larger than the 126 MB L2."""
+    import torch
+    import torch.distributed as dist
+
+    from posggym_baselines_b200.envs.lbf import BatchedLBF
+    from posggym_baselines_b200.envs.predator_prey import BatchedPredatorPrey
+
+    peak, peak_src = load_peaks()
+    counters = load_counters()
+    n = 1 << 22
+    out = {}
+    for name, env, kernel in (("PredatorPrey-v0", BatchedPredatorPrey(device=dev), "posg::generic::step_fast_kernel<posg::PPSimT<true>, true, true>"),
+                              ("LevelBasedForaging-v3", BatchedLBF(device=dev), "posg::generic::step_fast_kernel<posg::LBFSim, true, true>")):
+        bytes_per = 8 + 8 + 16 * env.obs_words + 16 + 1 + 2   # state in; state, obs, f64 rewards, flags, actions out
+        st0 = env.sample_initial_state(n, seed=seed, particle_offset=rank * n)
+        live = torch.zeros(1, dtype=torch.int64, device=dev)
+        bufs = [env.step(st0, seed=seed, step_idx=0, particle_offset=rank * n, live_count=live) for _ in range(2)]
+
+        def sweep():
+            cur = st0
+            for k in range(DEPTH):
+                o = bufs[k & 1]
+                env.step(cur, seed=seed, step_idx=k, particle_offset=rank * n, out=o, live_count=live)
+                cur = o.state
+
+        for _ in range(3):
+            sweep()
+        barrier()
+        live.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            sweep()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        lv = live.clone()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lv, op=dist.ReduceOp.SUM)
+        launch_ms = ms.item() / (steps * DEPTH)
+        achieved = bytes_per * n / (launch_ms / 1e3) / 1e9
+        c = counters.get(kernel, {})
+        out[name] = {
+            "env_steps_per_s": int(lv.item()) / (ms.item() / 1e3), "padded_env_steps_per_s": world * n * DEPTH * steps / (ms.item() / 1e3),
+            "envs_per_gpu": n, "depth": DEPTH,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (c.get("dram_bytes_per_env_step") * n) if c.get("dram_bytes_per_env_step") else None,
+                         "kernel": kernel, "bytes_per_env_step": bytes_per, "launch_ms": launch_ms, "peak_source": peak_src,
+                         "thread_instructions_per_env_step": c.get("thread_instructions_per_env_step"),
+                         "limiter": c.get("limiter")}}
+        del bufs, st0
+    return out
+
+
+def bench_particle_sweep(env, dev, rank, seed, barrier):
+    """BASELINE.json configs[1]: the Driving-v1 sweep from 1 K to 16 M particles (depth 50, one GPU's share).
+    Below ~1 M particles the 50 launches are bound by the launch rate and the working set sits in L2."""
+    import torch
+
+    out = []
+    for log2n in range(10, 25, 2):
+        n = 1 << log2n
+        st0 = env.sample_initial_state(n, seed=seed, particle_offset=rank * n)
+        bufs = [env.step(st0, seed=seed, step_idx=0, particle_offset=rank * n) for _ in range(2)]
+        reps = max(2, min(40, (1 << 22) // n))
+
+        def sweep():
+            cur = st0
+            for k in range(DEPTH):
+                o = bufs[k & 1]
+                env.step(cur, seed=seed, step_idx=k, particle_offset=rank * n, out=o)
+                cur = o.state
+
+        sweep()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            sweep()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out.append({"particles": n, "ms_per_sweep": ms, "us_per_launch": 1e3 * ms / DEPTH,
+                    "padded_env_steps_per_s": n * DEPTH / (ms / 1e3),
+                    "algorithmic_gbs": BYTES_PER_ENV_STEP * n * DEPTH / (ms / 1e3) / 1e9,
+                    "working_set_mb": n * BYTES_PER_ENV_STEP / 1e6})
+        del bufs, st0
     return out
 
 
@@ -541,10 +662,24 @@ def main():
     if world > 1:
         dist.all_reduce(rms, op=dist.ReduceOp.MAX)
         dist.all_reduce(rl_live, op=dist.ReduceOp.SUM)
-    rl = {"rollouts_per_s": n * world * args.steps / (rms.item() / 1e3),
+    rl_steps = 1 if args.only_sweep else args.steps
+    rl = {"rollouts_per_s": n * world * rl_steps / (rms.item() / 1e3),
           "env_steps_per_s": int(rl_live.item()) / (rms.item() / 1e3),
-          "ms_per_batch": rms.item() / args.steps, "depth": DEPTH, "ego_agent": 0,
+          "ms_per_batch": rms.item() / rl_steps, "depth": DEPTH, "ego_agent": 0,
           "note": "fused MCTS._rollout kernel: stops at ego termination; issue-bound, ~16 B of HBM per rollout"}
+    # this kernel moves ~0.4 B of HBM per env-step; its bound is the issue rate (148 SMs x 4
+    # schedulers x SM clock warp-instructions/s).  Warp-instructions per env-step come from the committed ncu
+    # capture of this kernel (profiles/kernel_counters.json); the rate is measured here.
+    rc = load_counters().get("posg::driving::rollout_kernel", {})
+    if rc.get("warp_instructions_per_env_step"):
+        sm_hz = (rc.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = 148 * 4 * sm_hz
+        issue_ach = rc["warp_instructions_per_env_step"] * rl["env_steps_per_s"] / max(1, world)
+        rl["roofline"] = {"bound": "issue", "achieved": issue_ach, "peak": issue_peak, "unit": "warp-instructions/s",
+                          "frac": issue_ach / issue_peak, "kernel": "posg::driving::rollout_kernel",
+                          "warp_instructions_per_env_step": rc["warp_instructions_per_env_step"],
+                          "lanes_active": rc.get("avg_active_threads_per_warp"),
+                          "traffic": rc.get("dram_bytes_per_launch")}
 
     # ---- e2e: C-ABI with pinned HOST buffers, copies inside the timed region ----
     e2e = None
@@ -605,6 +740,17 @@ def main():
     except Exception as ex:
         vec = {"error": repr(ex)}
 
+    # ---- the other two models' step kernels and the particle sweep of configs[1] ----
+    models, psweep = None, None
+    try:
+        if args.only_sweep:
+            raise RuntimeError("skipped (--only-sweep)")
+        models = bench_models(dev, rank, world, seed, barrier, max(2, min(args.steps, 4)))
+        if world == 1:
+            psweep = bench_particle_sweep(env, dev, rank, seed, barrier)
+    except Exception as ex:
+        models = {"error": repr(ex)}
+
     # ---- POMCP simulations per 0.1 s decision (second half of BASELINE.json's metric) ----
     pomcp = None
     try:
@@ -619,16 +765,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"Driving-v1 14x14RoundAbout, 2 agents, obs_dim (3,1,1): random-action model.step sweep, "
-                                   f"{n} particles per GPU x depth {DEPTH} (BASELINE.json configs[1])",
-                       "particles_per_gpu": n, "depth": DEPTH, "seed": seed,
-                       "l2": f"per-launch working set {n * BYTES_PER_ENV_STEP / 1e6:.0f} MB >> 126 MB L2 (inputs larger than L2)",
-                       "counted": "env-steps executed on not-yet-all-done particles", "padded_env_steps_per_s": padded / (ms / 1e3)},
+            "config": workload_config(n, seed), "padded_env_steps_per_s": padded / (ms / 1e3),
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "posg::driving::step_fast_kernel<true, true>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "launch_ms": launch_ms, "peak_source": peak_src},
-            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "pomcp": pomcp, "vec_env": vec,
+            "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "models": models, "particle_sweep": psweep,
+            "pomcp": pomcp, "vec_env": vec,
         }
         emit(line)
     if world > 1:

@@ -207,6 +207,9 @@ typedef struct posg_search_params {
   int ego_agent;
   int intmcp_depth_rule;            /* 1: INTMCP._simulate's stop rule node.t + depth > step_limit (intmcp.py:450-453) */
   uint64_t seed;
+  int n_waves;                      /* posg_search_multi / posg_search_nested: > 1 = that many consecutive waves of n_sims
+                                       simulations each in one call (see posg_search_waves); 0 or 1 = one wave */
+  int pad_;
 } posg_search_params;
 
 /* ego action count, 64-bit words per observation key, 32-bit words per packed state */
@@ -221,11 +224,25 @@ int posg_tree_reset(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_
 int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
                 const uint32_t* particles, int64_t n_particles, int64_t n_sims, uint64_t sim_id0,
                 const posg_search_params* p, void* stream);
+/* n_waves consecutive waves of wave_size simulations each (wave w uses Philox counters sim_id0 + w * wave_size ..),
+ * every wave seeing all backups of the one before -- the same as n_waves posg_search calls, in one launch for
+ * waves of up to 1024 simulations.  Simulations of ONE wave see each other's visit counts but not each other's
+ * returns, so equivalence with the reference's sequential loop (mcts.py:285-290) needs waves that are small
+ * beside the root's visit count (posggym_baselines_b200/planning/mcts.py: wave_growth). */
+int posg_search_waves(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
+                      const uint32_t* particles, int64_t n_particles, int64_t wave_size, int n_waves, uint64_t sim_id0,
+                      const posg_search_params* p, void* stream);
 /* Copies to HOST: visits[A], completed[A], total_value[A] of the node's action children
  * (ActionNode.visits / total_value, node.py:138-140) then node visits, node count, log
- * count, max search depth, min value, max value, overflow count, sims done, node flags. */
+ * count, max search depth, min value, max value, overflow count, sims done, node flags, obs nodes created
+ * since the last reset / re-root (3 * A + 10 doubles). */
 int posg_tree_node_stats(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
                          double* out_host, void* stream);
+/* The same completed[A], total_value[A] as doubles written to DEVICE memory (2 * A doubles): the buffer
+ * of the root-parallel allreduce (ActionNode.visits / total_value summed over the ranks' trees, one
+ * collective per decision), so the merge needs no host round trip before the collective. */
+int posg_tree_root_stats_device(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
+                                double* out_device, void* stream);
 /* MCTS._update re-rooting (mcts.py:229-263): child of (root, action) with observation
  * obs (HOST words); out_host = {node or -1, created, flags, t}. */
 int posg_tree_advance(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root,

@@ -71,7 +71,9 @@ SIGNATURES = {
     "posg_tree_arena_bytes": (_i64, [_vp, _i64, _i64]),
     "posg_tree_reset": (_int, [_vp, _vp, _i64, _i64, _int, _dbl, _dbl, _vp]),
     "posg_search": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _u64, _vp, _vp]),
+    "posg_search_waves": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _int, _u64, _vp, _vp]),
     "posg_tree_node_stats": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
+    "posg_tree_root_stats_device": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "posg_tree_advance": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _int, _vp, _vp]),
     "posg_tree_reroot": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "posg_tree_gather_belief": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _i64, _vp, _vp]),
@@ -88,6 +90,7 @@ class SearchParams(C.Structure):
         ("discount", _dbl), ("c", _dbl), ("known_min", _dbl), ("known_max", _dbl),
         ("pucb_exploration_fraction", _dbl), ("depth_limit", _int), ("step_limit", _int),
         ("selection", _int), ("ego_agent", _int), ("intmcp_depth_rule", _int), ("seed", _u64),
+        ("n_waves", _int), ("pad_", _int),
     ]
 
 _lib: Optional[C.CDLL] = None

@@ -347,7 +347,6 @@ __device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint
                                                const uint32_t (&words)[NQ], double (&rew)[NP], int (&occ)[NQ]) {
   const uint8_t* __restrict__ THR = B.rel_thr + REL0;
   const uint8_t* __restrict__ NB = B.rel_nb + REL0;
-  const int8_t* __restrict__ MOVE = B.move_delta - MOVE_BASE * 16;
   const int p0 = (int)(w0 & 255u), p1 = (int)((w0 >> 8) & 255u);
   const uint32_t caught = (w0 >> 16) & 7u;
   const uint32_t cmask = B.caught_mask[caught];
@@ -389,7 +388,7 @@ __device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint
     // a prey is no neighbour of itself (offset 0), so all five entities go through the table
     const uint32_t taken = NB[p0 - c] | NB[p1 - c] | NB[occ[0] - c] | NB[occ[1] - c] | NB[occ[2] - c];
     const uint32_t free4 = ~((uint32_t)B.wall4[c] | taken) & 15u;
-    const int nxt = c + (int)MOVE[row * 16 + (int)free4];
+    const int nxt = c + (int)B.move_delta[(row - MOVE_BASE) * 16 + (int)free4];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) occ[j] = (((order[k] >> 24) & 3u) == (uint32_t)j) ? nxt : occ[j];
   }

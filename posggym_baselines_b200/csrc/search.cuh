@@ -30,9 +30,13 @@ struct Counters {               // first 64 bytes of the arena
   unsigned int max_depth;
   unsigned int overflow;        // simulations that could not expand (arena full)
   unsigned long long sims_done;
-  unsigned long long pad_[2];
+  unsigned long long nodes_created;   // obs nodes the searches linked into the tree (node_count also counts reserved ids)
+  // order-preserving keys of the smallest / largest single return backed up so far: a node's mean lies between
+  // them, which bounds what a torn (total, visits) pair of a concurrent backup can feed to min_key / max_key
+  unsigned long long gmin_key, gmax_key;
+  unsigned long long pad_[7];
 };
-static_assert(sizeof(Counters) == 64, "counter block is 64 bytes");
+static_assert(sizeof(Counters) == 128, "counter block is 128 bytes");
 
 struct Params {
   double discount;
@@ -533,10 +537,17 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
     // warp's concurrent update can only make the atomics below redundant, never wrong)
     unsigned long long kmin = *((volatile unsigned long long*)&T.ctr->min_key);
     unsigned long long kmax = *((volatile unsigned long long*)&T.ctr->max_key);
+    unsigned long long gmin = *((volatile unsigned long long*)&T.ctr->gmin_key);
+    unsigned long long gmax = *((volatile unsigned long long*)&T.ctr->gmax_key);
     for (int i = 0; i < max_np; ++i) {
       const bool on = active && i < npath;
       const int an = on ? path_an[i] : -1 - (int)lane;
       const double g = on ? path_r[i] : 0.0;
+      if (on) {
+        const unsigned long long gk = dkey(g);
+        if (gk < gmin) { atomicMin(&T.ctr->gmin_key, gk); gmin = gk; }
+        if (gk > gmax) { atomicMax(&T.ctr->gmax_key, gk); gmax = gk; }
+      }
       const unsigned m = __match_any_sync(full, an);
       const int cnt = __popc(m);
       const int max_cnt = __reduce_max_sync(full, on ? cnt : 1);
@@ -555,7 +566,12 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
       if (on && (int)lane == __ffs(m) - 1) {
         const double old_tot = atomicAdd(&T.an_total[an], sum);
         const int old_done = atomicAdd(&T.an_done[an], cnt);
-        const unsigned long long vk = dkey((old_tot + sum) / (double)(old_done + cnt));
+        // (old_tot, old_done) come from two atomics: another warp's backup of the same node can fall between
+        // them.  A mean is never outside the range of the single returns, so clamp to it (a no-op for wave 1).
+        unsigned long long vk = dkey((old_tot + sum) / (double)(old_done + cnt));
+        const unsigned long long mk = dkey(sum / (double)cnt);   // the group's own mean is inside that range too
+        const unsigned long long lo = gmin < mk ? gmin : mk, hi = gmax > mk ? gmax : mk;
+        vk = vk < lo ? lo : (vk > hi ? hi : vk);
         // MinMaxStats.update (utils.py:29-32); the atomics fire only when the bound moves
         if (vk < kmin) { atomicMin(&T.ctr->min_key, vk); kmin = vk; }
         if (vk > kmax) { atomicMax(&T.ctr->max_key, vk); kmax = vk; }
@@ -567,6 +583,8 @@ __device__ void simulate(const typename M::Blob& B, const typename M::Ctx& ctx, 
   // self.root.visits += 1 per simulation (mcts.py:288); lanes may have different roots
   const unsigned same_root = __match_any_sync(full, active ? root : -1 - (int)lane);
   if (active && (int)lane == __ffs(same_root) - 1) atomicAdd(&T.node_visits[root], __popc(same_root));
+  const unsigned cr = __ballot_sync(full, active && created_here);
+  if (cr && (int)lane == __ffs(cr) - 1) atomicAdd(&T.ctr->nodes_created, (unsigned long long)__popc(cr));
   if (act && (int)lane == __ffs(act) - 1) {
     atomicAdd(&T.ctr->sims_done, (unsigned long long)__popc(act));
     if (dmax > *((volatile unsigned int*)&T.ctr->max_depth)) atomicMax(&T.ctr->max_depth, dmax);

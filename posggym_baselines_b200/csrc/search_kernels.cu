@@ -1,5 +1,7 @@
 // Search-tree and particle-belief entry points of the C-ABI (model-generic; dispatched
 // on the model kind).  See search.cuh / belief.cuh for the algorithms.
+#include <cooperative_groups.h>
+
 #include <cmath>
 #include <cstring>
 
@@ -11,6 +13,8 @@
 #include "nested_sim.cuh"
 #include "search.cuh"
 #include "stage.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace posg {
 
@@ -35,6 +39,30 @@ search_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, se
   const long long i = (long long)blockIdx.x * SEARCH_THREADS + threadIdx.x;
   // whole warps enter (warp collectives inside); lanes past n_sims are inactive
   search::simulate<M>(B, ctx, T, P, root, root_t, particles, n_particles, sel, sim_id0 + (unsigned long long)i, i < n_sims);
+}
+
+// n_waves consecutive waves of up to 1024 simulations in ONE launch: a single CTA runs wave after wave with a
+// block barrier in between, so wave w + 1 sees every backup of wave w exactly as separate launches would --
+// without the launch + host synchronisation per wave that dominates small waves (a 32-simulation wave is one
+// warp and ~40 us of dependent work).  Small waves are what keeps the search equivalent to the reference's
+// sequential loop (tests/test_pomcp_gpu.py: a wave may be ~1/2048 of the root's visits).
+template <class M>
+__global__ void __launch_bounds__(1024, 1)
+search_waves_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, search::Tree T,
+                    const __grid_constant__ search::Params P, const __grid_constant__ typename M::Ctx ctx, int root,
+                    int root_t, const uint32_t* __restrict__ particles, long long n_particles, search::RootSelect sel,
+                    int wave_size, int n_waves, unsigned long long sim_id0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  for (int w = 0; w < n_waves; ++w) {
+    search::simulate<M>(B, ctx, T, P, root, root_t, particles, n_particles, sel,
+                        sim_id0 + (unsigned long long)w * (unsigned long long)wave_size + threadIdx.x,
+                        (int)threadIdx.x < wave_size);
+    __threadfence();
+    __syncthreads();
+  }
 }
 
 template <class M>
@@ -75,7 +103,8 @@ __global__ void tree_init_kernel(search::Tree T, int n_actions, int root_t, doub
     const bool known = known_min <= known_max;
     T.ctr->min_key = known ? search::dkey(known_min) : search::KEY_POS_INF;
     T.ctr->max_key = known ? search::dkey(known_max) : search::KEY_NEG_INF;
-    T.ctr->max_depth = 0; T.ctr->overflow = 0; T.ctr->sims_done = 0;
+    T.ctr->max_depth = 0; T.ctr->overflow = 0; T.ctr->sims_done = 0; T.ctr->nodes_created = 0;
+    T.ctr->gmin_key = search::KEY_POS_INF; T.ctr->gmax_key = search::KEY_NEG_INF;
     T.node_t[0] = (unsigned char)root_t;
     T.node_parent[0] = -1;
   }
@@ -83,26 +112,59 @@ __global__ void tree_init_kernel(search::Tree T, int n_actions, int root_t, doub
 
 
 // ---- re-rooting: keep the subtree under the new root (MCTS._update, mcts.py:229-263: "remove
-// reference to parent, effectively pruning dead branches") by copying it, renumbered, into a
-// second arena.  Breadth-first marking, one launch per tree level.
-__global__ void reroot_expand_kernel(search::Tree S, int n_actions, const int* __restrict__ frontier, int n_front,
-                                     int* __restrict__ mark, int* __restrict__ next_frontier,
-                                     unsigned int* __restrict__ counters /* [0] next frontier size, [1] new node count */) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_front * n_actions) return;
-  const int f = frontier[i / n_actions], a = (int)(i % n_actions);
-  for (int c = S.an_first[f * n_actions + a]; c >= 0; c = S.node_next[c]) {
-    mark[c] = (int)atomicAdd(&counters[1], 1u);
-    next_frontier[atomicAdd(&counters[0], 1u)] = c;
+// reference to parent, effectively pruning dead branches") by copying it, renumbered breadth-first,
+// into a second arena.  Everything is sized by the KEPT subtree, not by the arena:
+//  * reroot_bfs_kernel: ONE cooperative launch walks the subtree level by level (grid barrier between
+//    levels, no host round trips); order[new id] = old id, mark[old id] = new id; the appends to the
+//    frontier are aggregated per warp (one atomic per warp and list step, not one per node);
+//  * reroot_copy_kernel: new-id major, so every write of the destination arrays is coalesced;
+//  * reroot_clear_kernel: the destination's stale slots [kept, its previous high-water mark) are
+//    re-initialised (the arenas ping-pong; a slot past the high-water mark is still clean).
+__global__ void __launch_bounds__(256)
+reroot_bfs_kernel(search::Tree S, int n_actions, int new_root, int* __restrict__ mark, int* __restrict__ order,
+                  unsigned int* __restrict__ counters /* [0] nodes kept */) {
+  cg::grid_group grid = cg::this_grid();
+  const unsigned lane = threadIdx.x & 31u;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  if (tid == 0) { order[0] = new_root; mark[new_root] = 0; counters[0] = 1u; }
+  grid.sync();
+  unsigned lo = 0, hi = 1;
+  while (lo < hi) {
+    const long long work = (long long)(hi - lo) * n_actions;
+    // whole warps iterate together (the ballots below need every lane of the warp)
+    for (long long i0 = tid - lane; i0 < work; i0 += nthr) {
+      const long long i = i0 + lane;
+      int c = -1;
+      if (i < work) c = S.an_first[(long long)order[lo + i / n_actions] * n_actions + (int)(i % n_actions)];
+      while (true) {
+        const unsigned has = __ballot_sync(0xffffffffu, c >= 0);
+        if (!has) break;
+        unsigned base = 0;
+        const int leader = __ffs(has) - 1;
+        if ((int)lane == leader) base = atomicAdd(&counters[0], (unsigned)__popc(has));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (c >= 0) {
+          const unsigned id = base + __popc(has & ((1u << lane) - 1u));
+          order[id] = c;
+          mark[c] = (int)id;
+          c = S.node_next[c];
+        }
+      }
+    }
+    grid.sync();
+    lo = hi;
+    hi = *((volatile unsigned int*)&counters[0]);
+    grid.sync();   // every thread has read the level's end before the next level appends
   }
 }
 
 __global__ void reroot_copy_kernel(search::Tree S, search::Tree D, int n_actions, int obs_words,
-                                   const int* __restrict__ mark, long long n_old) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_old;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int j = mark[i];
-    if (j < 0) continue;
+                                   const int* __restrict__ mark, const int* __restrict__ order,
+                                   const unsigned int* __restrict__ counters) {
+  const long long n_new = counters[0];
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_new;
+       j += (long long)gridDim.x * blockDim.x) {
+    const long long i = order[j];
     D.node_visits[j] = S.node_visits[i];
     D.node_flags[j] = S.node_flags[i];
     D.node_t[j] = S.node_t[i];
@@ -110,14 +172,32 @@ __global__ void reroot_copy_kernel(search::Tree S, search::Tree D, int n_actions
     const int nx = S.node_next[i], pa = S.node_parent[i];
     D.node_next[j] = (j == 0 || nx < 0) ? -1 : mark[nx];
     D.node_parent[j] = (j == 0 || pa < 0) ? -1 : mark[pa / n_actions] * n_actions + pa % n_actions;
-    for (int a = 0; a < n_actions; ++a) {
-      const long long so = i * n_actions + a, dn = (long long)j * n_actions + a;
-      const int first = S.an_first[so];
-      D.an_first[dn] = first >= 0 ? mark[first] : -1;
-      D.an_visits[dn] = S.an_visits[so];
-      D.an_done[dn] = S.an_done[so];
-      D.an_total[dn] = S.an_total[so];
-    }
+  }
+  // action-node arrays: one thread per (new node, action), new-id major
+  const long long n_an = n_new * n_actions;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_an; e += (long long)gridDim.x * blockDim.x) {
+    const long long j = e / n_actions;
+    const long long so = (long long)order[j] * n_actions + (e - j * n_actions);
+    const int first = S.an_first[so];
+    D.an_first[e] = first >= 0 ? mark[first] : -1;
+    D.an_visits[e] = S.an_visits[so];
+    D.an_done[e] = S.an_done[so];
+    D.an_total[e] = S.an_total[so];
+  }
+}
+
+// slots [kept, dirty) of the destination back to their initial state (posg_tree_reset's)
+__global__ void reroot_clear_kernel(search::Tree D, int n_actions, int obs_words, const unsigned int* __restrict__ counters,
+                                    long long dirty) {
+  const long long n_new = counters[0];
+  for (long long j = n_new + (long long)blockIdx.x * blockDim.x + threadIdx.x; j < dirty;
+       j += (long long)gridDim.x * blockDim.x) {
+    D.node_visits[j] = 0; D.node_next[j] = 0; D.node_parent[j] = 0; D.node_flags[j] = 0; D.node_t[j] = 0;
+    for (int k = 0; k < obs_words; ++k) D.node_obs[(size_t)j * obs_words + k] = 0ULL;
+  }
+  for (long long e = n_new * n_actions + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < dirty * n_actions;
+       e += (long long)gridDim.x * blockDim.x) {
+    D.an_first[e] = -1; D.an_visits[e] = 0; D.an_done[e] = 0; D.an_total[e] = 0.0;
   }
 }
 
@@ -144,12 +224,23 @@ __global__ void reroot_log_kernel(search::Tree S, search::Tree D, int state_word
 
 __global__ void reroot_finish_kernel(search::Tree S, search::Tree D, const unsigned int* __restrict__ counters,
                                      const unsigned long long* __restrict__ log_count) {
-  D.ctr->node_count = counters[1];
+  D.ctr->node_count = counters[0];
   D.ctr->log_count = *log_count;
   D.ctr->min_key = S.ctr->min_key;
   D.ctr->max_key = S.ctr->max_key;
-  D.ctr->max_depth = 0; D.ctr->overflow = 0;
+  D.ctr->max_depth = 0; D.ctr->overflow = 0; D.ctr->nodes_created = 0;
+  D.ctr->gmin_key = S.ctr->gmin_key; D.ctr->gmax_key = S.ctr->gmax_key;
   D.ctr->sims_done = S.ctr->sims_done;
+}
+
+// ActionNode.visits / total_value of a node's children as doubles, left on the device (the buffer of
+// the root-parallel allreduce)
+__global__ void root_stats_kernel(search::Tree T, int n_actions, int node, double* __restrict__ out) {
+  const int a = threadIdx.x;
+  if (a < n_actions) {
+    out[a] = (double)T.an_done[(size_t)node * n_actions + a];
+    out[n_actions + a] = T.an_total[(size_t)node * n_actions + a];
+  }
 }
 
 template <int OW>
@@ -316,39 +407,44 @@ int posg_tree_reroot(posg_model_t m, void* src_arena, void* dst_arena, int64_t c
   rc = make_tree(m, dst_arena, cap_nodes, cap_log, &D, &k); if (rc) return rc;
   POSG_REQUIRE(src_arena != dst_arena && scratch && result_host && new_root >= 0 && new_root < cap_nodes, "bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  search::Counters c;
-  POSG_CUDA(cudaMemcpyAsync(&c, S.ctr, sizeof(c), cudaMemcpyDeviceToHost, s));
+  // source sizes and the destination's high-water mark (its counter block still holds the node count of
+  // the last time it was the live arena: posg_tree_reset or an earlier re-root)
+  search::Counters c[2];
+  POSG_CUDA(cudaMemcpyAsync(&c[0], S.ctr, sizeof(search::Counters), cudaMemcpyDeviceToHost, s));
+  POSG_CUDA(cudaMemcpyAsync(&c[1], D.ctr, sizeof(search::Counters), cudaMemcpyDeviceToHost, s));
   POSG_CUDA(cudaStreamSynchronize(s));
-  const long long n_old = (long long)(c.node_count < (unsigned long long)cap_nodes ? c.node_count : (unsigned long long)cap_nodes);
-  const unsigned long long n_log = c.log_count < (unsigned long long)cap_log ? c.log_count : (unsigned long long)cap_log;
-  // clean destination (an_first = -1, everything else 0)
-  rc = posg_tree_reset(m, dst_arena, cap_nodes, cap_log, 0, 1.0, 0.0, stream); if (rc) return rc;
+  const long long n_old = (long long)(c[0].node_count < (unsigned long long)cap_nodes ? c[0].node_count : (unsigned long long)cap_nodes);
+  const unsigned long long n_log = c[0].log_count < (unsigned long long)cap_log ? c[0].log_count : (unsigned long long)cap_log;
+  // (a nearly full arena may also have used its last slot as a transient root: posg_tree_advance)
+  const long long dirty = (c[1].node_count + search::RESERVE >= (unsigned long long)cap_nodes) ? (long long)cap_nodes
+                                                                                               : (long long)c[1].node_count;
   int* mark = scratch;
-  int* front[2] = {scratch + cap_nodes, scratch + 2 * cap_nodes};
-  unsigned int* counters = nullptr;   // [0] next frontier size, [1] new node count, then the 64-bit log counter
+  int* order = scratch + cap_nodes;
+  unsigned int* counters = nullptr;   // [0] nodes kept, then the 64-bit log counter
   POSG_CUDA(cudaMallocAsync((void**)&counters, 32, s));
   unsigned long long* d_log = (unsigned long long*)(counters + 4);
   POSG_CUDA(cudaMemsetAsync(counters, 0, 32, s));
   POSG_CUDA(cudaMemsetAsync(mark, 0xFF, (size_t)n_old * 4, s));
-  const int zero = 0; const unsigned int one = 1;
-  POSG_CUDA(cudaMemcpyAsync(mark + new_root, &zero, 4, cudaMemcpyHostToDevice, s));
-  POSG_CUDA(cudaMemcpyAsync(front[0], &new_root, 4, cudaMemcpyHostToDevice, s));
-  POSG_CUDA(cudaMemcpyAsync(counters + 1, &one, 4, cudaMemcpyHostToDevice, s));
-  int n_front = 1, cur = 0;
-  while (n_front > 0) {
-    POSG_CUDA(cudaMemsetAsync(counters, 0, 4, s));
-    const long long work = (long long)n_front * k.n_actions;
-    reroot_expand_kernel<<<(int)((work + 255) / 256), 256, 0, s>>>(S, k.n_actions, front[cur], n_front, mark,
-                                                                    front[cur ^ 1], counters);
-    POSG_CUDA(cudaGetLastError());
-    unsigned int nf = 0;
-    POSG_CUDA(cudaMemcpyAsync(&nf, counters, 4, cudaMemcpyDeviceToHost, s));
-    POSG_CUDA(cudaStreamSynchronize(s));
-    n_front = (int)nf;
-    cur ^= 1;
+  {
+    static int bfs_grid[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!bfs_grid[dev]) {
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reroot_bfs_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+      bfs_grid[dev] = sm_count() * (per_sm > 4 ? 4 : per_sm);
+    }
+    int na = k.n_actions;
+    void* args[] = {(void*)&S, (void*)&na, (void*)&new_root, (void*)&mark, (void*)&order, (void*)&counters};
+    POSG_CUDA(cudaLaunchCooperativeKernel((const void*)reroot_bfs_kernel, dim3(bfs_grid[dev]), dim3(256), args, 0, s));
   }
-  reroot_copy_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.n_actions, k.obs_words, mark, n_old);
+  reroot_copy_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.n_actions, k.obs_words, mark, order, counters);
   POSG_CUDA(cudaGetLastError());
+  if (dirty > 0) {
+    reroot_clear_kernel<<<sm_count() * 8, 256, 0, s>>>(D, k.n_actions, k.obs_words, counters, dirty);
+    POSG_CUDA(cudaGetLastError());
+  }
   if (n_log > 0) {
     reroot_log_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.state_words, mark, n_log, d_log);
     POSG_CUDA(cudaGetLastError());
@@ -360,7 +456,7 @@ int posg_tree_reroot(posg_model_t m, void* src_arena, void* dst_arena, int64_t c
   POSG_CUDA(cudaMemcpyAsync(&h_log, d_log, 8, cudaMemcpyDeviceToHost, s));
   POSG_CUDA(cudaStreamSynchronize(s));
   cudaFreeAsync(counters, s);
-  result_host[0] = h_cnt[1];
+  result_host[0] = h_cnt[0];
   result_host[1] = (int64_t)h_log;
   return POSG_OK;
 }
@@ -384,17 +480,27 @@ template <class M>
 static void launch_search(const posg_model* m, const search::Tree& T, const search::Params& P,
                           const typename M::Ctx& ctx, int root, int root_t, const uint32_t* particles,
                           long long n_particles, const search::RootSelect& sel, long long n_sims,
-                          unsigned long long sim_id0, cudaStream_t s) {
+                          unsigned long long sim_id0, cudaStream_t s, int n_waves = 1) {
+  if (n_waves > 1 && n_sims <= 1024) {
+    // consecutive small waves inside one CTA
+    const int threads = (int)((n_sims + 31) / 32) * 32;
+    smem_optin(search_waves_kernel<M>, m->blob_bytes);
+    search_waves_kernel<M><<<1, threads, m->blob_bytes, s>>>(
+        (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, ctx, root, root_t, particles, n_particles,
+        sel, (int)n_sims, n_waves, sim_id0);
+    return;
+  }
   const int grid = (int)((n_sims + SEARCH_THREADS - 1) / SEARCH_THREADS);
   smem_optin(search_kernel<M>, m->blob_bytes);
-  search_kernel<M><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
-      (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, ctx, root, root_t, particles, n_particles,
-      sel, n_sims, sim_id0);
+  for (int w = 0; w < n_waves; ++w)   // stream order = wave order
+    search_kernel<M><<<grid, SEARCH_THREADS, m->blob_bytes, s>>>(
+        (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, T, P, ctx, root, root_t, particles, n_particles,
+        sel, n_sims, sim_id0 + (unsigned long long)w * (unsigned long long)n_sims);
 }
 
 static int search_common(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
                          const uint32_t* particles, int64_t n_particles, const search::RootSelect& sel, int64_t n_sims,
-                         uint64_t sim_id0, const posg_search_params* p, void* stream) {
+                         uint64_t sim_id0, const posg_search_params* p, void* stream, int n_waves = 1) {
   search::Tree T; KindInfo k;
   int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
   POSG_REQUIRE(particles && n_particles > 0 && n_sims >= 0 && root >= 0 && root < cap_nodes, "bad search arguments");
@@ -404,11 +510,15 @@ static int search_common(posg_model_t m, void* arena, int64_t cap_nodes, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   switch (m->kind) {
     case KIND_DRIVING:
-      launch_search<DrivingSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
-    case KIND_PREDATOR_PREY:
-      launch_search<PPSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
+      launch_search<DrivingSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s, n_waves); break;
+    case KIND_PREDATOR_PREY:   // the table-driven adapter where its tables are exact (pp.cuh)
+      if (((const pp::Blob*)m->h_blob)->lut_ok)
+        launch_search<PPSimLut>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s, n_waves);
+      else
+        launch_search<PPSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s, n_waves);
+      break;
     case KIND_LBF:
-      launch_search<LBFSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s); break;
+      launch_search<LBFSim>(m, T, P, NoCtx{}, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s, n_waves); break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
   }
   POSG_CUDA(cudaGetLastError());
@@ -439,6 +549,16 @@ int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log,
                        stream);
 }
 
+int posg_search_waves(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
+                      const uint32_t* particles, int64_t n_particles, int64_t wave_size, int n_waves, uint64_t sim_id0,
+                      const posg_search_params* p, void* stream) {
+  POSG_REQUIRE(n_waves >= 0 && n_waves <= (1 << 20) && wave_size >= 0, "bad wave arguments");
+  if (n_waves == 0) return POSG_OK;
+  search::RootSelect sel = {nullptr, nullptr, nullptr, 0};
+  return search_common(m, arena, cap_nodes, cap_log, root, root_t, particles, n_particles, sel, wave_size, sim_id0, p,
+                       stream, n_waves);
+}
+
 int posg_search_multi(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root_t,
                       const uint32_t* particles, int64_t n_particles, const int32_t* sel_root,
                       const int64_t* sel_off, const int32_t* sel_cnt, int64_t n_sel, int64_t n_sims,
@@ -446,7 +566,7 @@ int posg_search_multi(posg_model_t m, void* arena, int64_t cap_nodes, int64_t ca
   POSG_REQUIRE(m && sel_root && sel_off && sel_cnt && n_sel > 0, "bad selection arguments");
   search::RootSelect sel = {sel_root, (const long long*)sel_off, sel_cnt, (long long)n_sel};
   return search_common(m, arena, cap_nodes, cap_log, 0, root_t, particles, n_particles, sel, n_sims, sim_id0, p,
-                       stream);
+                       stream, (p && p->n_waves > 1) ? p->n_waves : 1);
 }
 
 int posg_search_nested(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, void* other_arena,
@@ -467,12 +587,14 @@ int posg_search_nested(posg_model_t m, void* arena, int64_t cap_nodes, int64_t c
     case KIND_DRIVING: {
       NestedSim<DrivingSim>::Ctx ctx;
       rc = nested_ctx<DrivingSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
-      launch_search<NestedSim<DrivingSim>>(m, T, P, ctx, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s);
+      launch_search<NestedSim<DrivingSim>>(m, T, P, ctx, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s,
+                                           p->n_waves > 1 ? p->n_waves : 1);
     } break;
     case KIND_PREDATOR_PREY: {
       NestedSim<PPSim>::Ctx ctx;
       rc = nested_ctx<PPSim>(m, other_arena, other_cap_nodes, other_cap_log, other_agent, &ctx); if (rc) return rc;
-      launch_search<NestedSim<PPSim>>(m, T, P, ctx, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s);
+      launch_search<NestedSim<PPSim>>(m, T, P, ctx, root, root_t, particles, n_particles, sel, n_sims, sim_id0, s,
+                                      p->n_waves > 1 ? p->n_waves : 1);
     } break;
     default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
   }
@@ -550,6 +672,17 @@ int posg_tree_node_stats(posg_model_t m, void* arena, int64_t cap_nodes, int64_t
   };
   e[0] = nv; e[1] = (double)c.node_count; e[2] = (double)c.log_count; e[3] = c.max_depth;
   e[4] = unkey(c.min_key); e[5] = unkey(c.max_key); e[6] = c.overflow; e[7] = (double)c.sims_done; e[8] = fl;
+  e[9] = (double)c.nodes_created;
+  return POSG_OK;
+}
+
+int posg_tree_root_stats_device(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int node,
+                                double* out_device, void* stream) {
+  search::Tree T; KindInfo k;
+  int rc = make_tree(m, arena, cap_nodes, cap_log, &T, &k); if (rc) return rc;
+  POSG_REQUIRE(out_device && node >= 0 && node < cap_nodes, "bad arguments");
+  root_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(T, k.n_actions, node, out_device);
+  POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
 

@@ -48,6 +48,18 @@ def merge_root_statistics(visits: np.ndarray, total_value: np.ndarray, device=No
     return out[:a], out[a:]
 
 
+def merge_root_statistics_device(buf: torch.Tensor) -> Tuple[np.ndarray, np.ndarray]:
+    """``buf``: device tensor of ``2 * |A|`` float64 (visits then value sums, filled by
+    ``posg_tree_root_stats_device``).  ONE allreduce on the device buffer, ONE read-back."""
+    import torch.distributed as dist
+
+    if world()[1] > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    out = buf.cpu().numpy()
+    a = out.shape[0] // 2
+    return out[:a].copy(), out[a:].copy()
+
+
 def select_root_action(visits: np.ndarray, total_value: np.ndarray, actions: Sequence[int], mode: str,
                        tie_seed: int) -> int:
     """Final action from (merged) root statistics: max value for ucb / uniform, max visits for

@@ -136,11 +136,15 @@ class INTMCP:
             n0 = _lib.check(int(lib.posg_tree_arena_bytes(self._b._handle, self._cap_nodes, self._cap_log)))
             self._arena1 = torch.empty(n1, dtype=torch.uint8, device=self._b.device)
             self._arena1_spare = torch.empty(n1, dtype=torch.uint8, device=self._b.device)
+            # the spare must be clean once: posg_tree_reroot only re-initialises the slots its previous life used
+            with self._dev():
+                _lib.check(lib.posg_tree_reset(self._nested, _lib.ptr(self._arena1_spare), self._cap_nodes,
+                                               self._cap_log, 0, 1.0, 0.0, self._stream()))
             self._scratch = torch.empty(3 * self._cap_nodes, dtype=torch.int32, device=self._b.device)
             self._arena0 = torch.empty(n0, dtype=torch.uint8, device=self._b.device)
 
     def _stats(self, level: int, node: int):
-        out = np.zeros(3 * self._A + 9, np.float64)
+        out = np.zeros(3 * self._A + 10, np.float64)
         handle, arena = (self._nested, self._arena1) if level == 1 else (self._b._handle, self._arena0)
         with self._dev():
             _lib.check(_lib.lib().posg_tree_node_stats(handle, _lib.ptr(arena), self._cap_nodes, self._cap_log, node,
@@ -376,38 +380,33 @@ class INTMCP:
             d_root = torch.tensor(sel_root, dtype=torch.int32, device=b.device)
             d_off = torch.tensor(sel_off, dtype=torch.int64, device=b.device)
             d_cnt = torch.tensor(sel_cnt, dtype=torch.int32, device=b.device)
-            wave, done, t_level = (self.wave_size or 32), 0, time.time()
-            with self._dev():
-                while done < budget and (not timed or time.time() - t_level < per_level):
-                    w = min(wave, budget - done)
-                    _lib.check(lib.posg_search_multi(
-                        b._handle, _lib.ptr(self._arena0), self._cap_nodes, self._cap_log, self._root_t,
-                        _lib.ptr(pcat), pcat.shape[0], _lib.ptr(d_root), _lib.ptr(d_off), _lib.ptr(d_cnt),
-                        len(sel_root), w, self._sim0, C.byref(self._params0), self._stream()))
-                    self._sim0 += w
-                    done += w
-                    torch.cuda.current_stream().synchronize()
-                    if not self.wave_size:
-                        wave = min(wave * 2, self.max_wave)
+            def launch0(w, k, sim0):
+                self._params0.n_waves = k
+                _lib.check(lib.posg_search_multi(
+                    b._handle, _lib.ptr(self._arena0), self._cap_nodes, self._cap_log, self._root_t,
+                    _lib.ptr(pcat), pcat.shape[0], _lib.ptr(d_root), _lib.ptr(d_off), _lib.ptr(d_cnt),
+                    len(sel_root), w, sim0, C.byref(self._params0), self._stream()))
+
+            # the visits of a level-0 simulation spread over the histories of the root belief: the schedule is
+            # driven by the simulations this tree has had so far
+            done = self._run_waves(launch0, budget, per_level if timed else None, self._sim0, self._sim0)
+            self._sim0 += done
             n_sims_total += done
 
         # ---- level 1: search the ego tree, the other agent acting by its tree.  This tree is
         # compacted at every re-root, so its budget is whatever room is left in the arena.
         if timed:
             budget = max(1024, self._cap_nodes - self._nodes1 - 4096)
-        wave, done, t_level = (self.wave_size or 32), 0, time.time()
-        with self._dev():
-            while done < budget and (not timed or time.time() - t_level < per_level):
-                w = min(wave, budget - done)
-                _lib.check(lib.posg_search_nested(
-                    self._nested, _lib.ptr(self._arena1), self._cap_nodes, self._cap_log, _lib.ptr(self._arena0),
-                    self._cap_nodes, self._cap_log, self._other, self._root1, self._root_t, _lib.ptr(self._P1),
-                    self._P1.shape[0], w, self._sim1, C.byref(self._params1), self._stream()))
-                self._sim1 += w
-                done += w
-                torch.cuda.current_stream().synchronize()
-                if not self.wave_size:
-                    wave = min(wave * 2, self.max_wave)
+        def launch1(w, k, sim0):
+            self._params1.n_waves = k
+            _lib.check(lib.posg_search_nested(
+                self._nested, _lib.ptr(self._arena1), self._cap_nodes, self._cap_log, _lib.ptr(self._arena0),
+                self._cap_nodes, self._cap_log, self._other, self._root1, self._root_t, _lib.ptr(self._P1),
+                self._P1.shape[0], w, sim0, C.byref(self._params1), self._stream()))
+
+        root_visits = int(self._stats(1, self._root1)["node_visits"])
+        done = self._run_waves(launch1, budget, per_level if timed else None, self._sim1, root_visits)
+        self._sim1 += done
         n_sims_total += done
 
         st = self._stats(1, self._root1)
@@ -427,6 +426,41 @@ class INTMCP:
         values = np.where(done_v > 0, total / np.maximum(done_v, 1), 0.0)
         best = values.max()
         return random.choice([a for a in actions if values[a] == best])
+
+    def _run_waves(self, launch, budget: int, time_limit, sim0: int, visits: int) -> int:
+        """Runs chained search waves (``launch(wave, n_waves, first simulation id)``) until ``budget`` simulations
+        or ``time_limit`` seconds: a fixed ``wave_size`` when one was given, else the schedule that keeps the
+        wave-parallel search equivalent to the sequential one (MCTS._scheduled_wave: one warp, two warps, then
+        1/2048 of the visits the tree already has)."""
+        from posggym_baselines_b200.planning.mcts import MCTS
+
+        done, chunk, t0 = 0, 8, time.time()
+        with self._dev():
+            while done < budget:
+                if self.wave_size:
+                    wave = self.wave_size
+                else:
+                    floor = 32 if visits < 8192 else 64
+                    wave = max(floor, min(self.max_wave, (int(visits * MCTS.WAVE_GROWTH) // 32) * 32))
+                left = budget - done
+                if left < wave:
+                    wave, waves = left, 1
+                else:
+                    waves = max(1, min(chunk, left // wave))
+                t_chunk = time.time()
+                launch(wave, waves, sim0 + done)
+                done += wave * waves
+                visits += wave * waves
+                torch.cuda.current_stream().synchronize()
+                now = time.time()
+                if time_limit is not None:
+                    if now - t0 >= time_limit:
+                        break
+                    per_wave = (now - t_chunk) / waves
+                    chunk = int(max(1, min(4096, 0.002 / max(per_wave, 1e-6), (time_limit - (now - t0)) / max(per_wave, 1e-6))))
+                else:
+                    chunk = 256
+        return done
 
     def close(self):
         for p in self.search_policies.values():

@@ -79,6 +79,10 @@ class _RootView:
 class MCTS:
     """Partially observable multi-agent Monte-Carlo planning on the GPU."""
 
+    #: largest wave as a fraction of the root's visits for which the wave-parallel search reproduces the
+    #: reference planner's root statistics at large budgets (tests/test_pomcp_gpu.py)
+    WAVE_GROWTH = 1.0 / 2048.0
+
     def __init__(
         self,
         model,
@@ -90,8 +94,9 @@ class MCTS:
         max_sims: Optional[int] = None,
         wave_size: Optional[int] = None,
         max_wave: int = 262144,
-        node_capacity: int = 1 << 25,
-        log_capacity: int = 1 << 26,
+        wave_growth: float = 0.0,
+        node_capacity: int = 1 << 27,
+        log_capacity: int = 1 << 28,
         root_parallel: bool = False,
     ):
         self.model = model
@@ -109,8 +114,10 @@ class MCTS:
                 "the B200 planner executes RandomSearchPolicy / RandomOtherAgentPolicy in-kernel; "
                 "other plugins are not supported yet"
             )
-        if not config.state_belief_only:
-            raise NotImplementedError("only state_belief_only=True (the POMCP configuration) is supported")
+        # state_belief_only=False (mcts.py:344-354) makes particles carry the joint history and the other agents'
+        # policy states.  With RandomOtherAgentPolicy the policy state is empty and nothing the search computes
+        # reads the history, so the device search is the same; the histories are not materialised
+        # (planner.root.belief.particles shows states).
         if not hasattr(model, "batched"):
             raise TypeError("model must be a posggym_baselines_b200 model facade (needs `.batched`)")
         self._b = model.batched
@@ -129,6 +136,7 @@ class MCTS:
         self.max_sims = max_sims
         self.wave_size = wave_size
         self.max_wave = max_wave
+        self.wave_growth = float(wave_growth) if wave_growth else self.WAVE_GROWTH
         self.root_parallel = root_parallel
         self.allreduce_time = 0.0
         self._seed_shared = config.seed if config.seed is not None else 0
@@ -178,10 +186,14 @@ class MCTS:
             _lib.check(int(nbytes))
             self._arena = torch.empty(int(nbytes), dtype=torch.uint8, device=self._b.device)
             self._arena_spare = torch.empty(int(nbytes), dtype=torch.uint8, device=self._b.device)
+            # the spare must be clean once: posg_tree_reroot only re-initialises the slots its previous life used
+            with torch.cuda.device(self._b.device):
+                _lib.check(lib.posg_tree_reset(self._b._handle, _lib.ptr(self._arena_spare), self._cap_nodes,
+                                               self._cap_log, 0, 1.0, 0.0, self._stream()))
             self._reroot_scratch = torch.empty(3 * self._cap_nodes, dtype=torch.int32, device=self._b.device)
 
     def _stats(self, node: Optional[int] = None) -> Dict[str, object]:
-        out = np.zeros(3 * self._A + 9, np.float64)
+        out = np.zeros(3 * self._A + 10, np.float64)
         with torch.cuda.device(self._b.device):
             _lib.check(_lib.lib().posg_tree_node_stats(
                 self._b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log,
@@ -192,6 +204,7 @@ class MCTS:
             "visits": out[:A].copy(), "done": out[A:2 * A].copy(), "total": out[2 * A:3 * A].copy(),
             "node_visits": e[0], "node_count": e[1], "log_count": e[2], "max_depth": e[3],
             "min_value": e[4], "max_value": e[5], "overflow": e[6], "sims_done": e[7], "flags": int(e[8]),
+            "nodes_created": e[9],
         }
 
     # ------------------------------------------------------------------ step / reset
@@ -232,6 +245,7 @@ class MCTS:
         self._log_bound = 0
         self._min_value, self._max_value = float("inf"), -float("inf")
         self.tree_compactions = 0
+        self.search_info = {}
         self._reset_step_statistics()
 
     def _reset_step_statistics(self):
@@ -338,36 +352,65 @@ class MCTS:
             return self.action_space[0]
         cfg, b = self.config, self._b
         start = time.time()
-        n_sims = 0
-        wave = self.wave_size if self.wave_size else 32
+        n_sims = n_waves = wave_now = 0
+        nodes_before = self._nodes_bound
+        # Simulations of one wave see each other's virtual visits but not each other's returns, so a wave may
+        # only be a small fraction of the visits the root already has: wave = wave_growth * N, at least 32 (one
+        # warp).  At equal budgets the search then matches the reference's sequential loop (tests/
+        # test_pomcp_gpu.py: 65 536 simulations against the unmodified reference planner; waves of N / 512 no
+        # longer do).  The root keeps its subtree's visits across re-roots, so later decisions of an episode
+        # start with larger waves.  Consecutive waves are chained inside one launch (posg_search_waves); the
+        # clock is read between chunks of waves sized for ~2 ms.
+        root_visits = 0 if self.wave_size else int(self._stats()["node_visits"])
         lib = _lib.lib()
+        chunk = 8          # waves per launch, adapted to ~2 ms per chunk
         with torch.cuda.device(b.device):
             stream = self._stream()
             while True:
-                if self.max_sims is not None:
-                    if n_sims >= self.max_sims:
-                        break
-                    wave_now = min(wave, self.max_sims - n_sims)
+                if self.wave_size:
+                    wave = self.wave_size
                 else:
-                    wave_now = wave
-                # every simulation adds at most one node (none once the arena is full: the
-                # kernel then evaluates unexpanded histories by rollouts without storing them)
-                self._nodes_bound = min(self._cap_nodes, self._nodes_bound + wave_now)
-                _lib.check(lib.posg_search(
+                    wave = self._scheduled_wave(root_visits)
+                waves = chunk
+                if not self.wave_size:   # stay on this wave size only while the schedule allows it
+                    grow_at = 8192 if root_visits < 8192 else (
+                        int((wave + 32) / self.wave_growth) + 1 if wave < self.max_wave else 1 << 62)
+                    waves = max(1, min(chunk, (grow_at - root_visits + wave - 1) // wave))
+                if self.max_sims is not None:
+                    left = self.max_sims - n_sims
+                    if left <= 0:
+                        break
+                    if left < wave:
+                        wave, waves = left, 1
+                    else:
+                        waves = min(waves, left // wave)
+                wave_now = wave
+                t_chunk = time.time()
+                # every simulation reserves one node id (none once the arena is full: the kernel then evaluates
+                # unexpanded histories by rollouts without storing them)
+                self._nodes_bound = min(self._cap_nodes, self._nodes_bound + wave * waves)
+                _lib.check(lib.posg_search_waves(
                     b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, self._root_t,
-                    _lib.ptr(self._root_particles), self._root_particles.shape[0], wave_now,
-                    self._sim_base + self._sim_counter,
-                    C.byref(self._params), stream))
-                self._sim_counter += wave_now
-                n_sims += wave_now
+                    _lib.ptr(self._root_particles), self._root_particles.shape[0], wave, waves,
+                    self._sim_base + self._sim_counter, C.byref(self._params), stream))
+                self._sim_counter += wave * waves
+                n_sims += wave * waves
+                n_waves += waves
+                root_visits += wave * waves
                 torch.cuda.current_stream().synchronize()
-                if self.max_sims is None and time.time() - start >= cfg.search_time_limit:
+                now = time.time()
+                if self.max_sims is None and now - start >= cfg.search_time_limit:
                     break
                 if self.max_sims is not None and cfg.search_time_limit < float("inf") and self._respect_time \
-                        and time.time() - start >= cfg.search_time_limit:
+                        and now - start >= cfg.search_time_limit:
                     break
-                if not self.wave_size:
-                    wave = min(wave * 2, self.max_wave)
+                dt = now - t_chunk
+                if waves == chunk:
+                    chunk = int(max(1, min(4096, chunk * 0.002 / max(dt, 1e-5))))
+                if self.max_sims is None:   # never start a chunk that would overshoot the budget by more than ~2 ms
+                    remaining = cfg.search_time_limit - (now - start)
+                    per_wave = dt / max(1, waves)
+                    chunk = int(max(1, min(chunk, remaining / max(per_wave, 1e-6))))
         st = self._stats()
         self._nodes_bound, self._log_bound = int(st["node_count"]), int(st["log_count"])
         self._min_value, self._max_value = st["min_value"], st["max_value"]
@@ -377,7 +420,22 @@ class MCTS:
         self.step_statistics["min_value"] = self._min_value
         self.step_statistics["max_value"] = self._max_value
         self._last_root_stats = st
+        # B200-only diagnostics (not a reference key): how much of the search could still grow the tree
+        overflow = int(st["overflow"])
+        self.search_info = {
+            "num_sims": n_sims, "expanding_sims": n_sims - overflow, "overflow_sims": overflow,
+            "overflow_share": overflow / max(1, n_sims), "nodes_created": int(st["nodes_created"]),
+            "ids_reserved": int(st["node_count"]) - nodes_before,
+            "nodes_in_tree": int(st["node_count"]), "arena_fill": int(st["node_count"]) / self._cap_nodes,
+            "log_fill": min(1.0, int(st["log_count"]) / self._cap_log), "waves": n_waves, "last_wave": wave_now}
         return self._final_action(st)
+
+    def _scheduled_wave(self, root_visits: int) -> int:
+        """Simulations per wave for a root with ``root_visits`` visits: one warp while the tree is young, two
+        warps from 8 192 visits on, then ``wave_growth`` (1/2048) of the visits -- the sizes for which the
+        search reproduces the reference planner's root statistics at 65 536 and 262 144 simulations."""
+        floor = 32 if root_visits < 8192 else 64
+        return max(floor, min(self.max_wave, (int(root_visits * self.wave_growth) // 32) * 32))
 
     _respect_time = False  # with max_sims set, the time limit only applies when asked for
 
@@ -389,7 +447,12 @@ class MCTS:
         if self.root_parallel and parallel.world()[1] > 1:
             # root-parallel merge: one allreduce of |A| x {visits, total_value} per decision
             t0 = time.time()
-            done, total = parallel.merge_root_statistics(done, total, device=self._b.device)
+            buf = torch.empty(2 * self._A, dtype=torch.float64, device=self._b.device)
+            with torch.cuda.device(self._b.device):
+                _lib.check(_lib.lib().posg_tree_root_stats_device(
+                    self._b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, _lib.ptr(buf),
+                    self._stream()))
+            done, total = parallel.merge_root_statistics_device(buf)
             self.allreduce_time = time.time() - t0
             merged = True
         self._merged_root = (done, total)
