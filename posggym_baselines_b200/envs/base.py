@@ -153,8 +153,13 @@ class ModelFacade:
         return list(self.possible_agents)
 
     def sample_initial_state(self):
+        # the picks come from model.rng one by one; the state is built by the kernel from the explicit picks
         b = self.batched
-        return b.unpack_state(b.sample_initial_state(1, seed=self._rng.getrandbits(63)))[0]
+        picks: List[int] = []
+        for _ in range(b.num_picks):
+            picks.append(self._rng.randrange(b.initial_pick_bounds(picks)))
+        st = b.sample_initial_state(1, picks=torch.tensor([picks], dtype=torch.uint8, device=b.device))
+        return b.unpack_state(st)[0]
 
     def sample_initial_obs(self, state):
         b = self.batched
@@ -165,12 +170,20 @@ class ModelFacade:
     def sample_agent_initial_state(self, agent_id: str, obs):
         raise NotImplementedError
 
+    def batched_step_noise(self, n: int):
+        """Explicit noise for ``n`` rows of ``batched.step``: what ``step`` draws from ``self.rng``, n times."""
+        if getattr(self.batched, "noise_is_dummy", False):     # deterministic transition: nothing is drawn
+            noise = np.zeros((n, self.batched.noise_words), np.uint32)
+        else:
+            noise = np.array([[self._rng.getrandbits(32) for _ in range(self.batched.noise_words)] for _ in range(n)],
+                             dtype=np.uint32).reshape(n, self.batched.noise_words)
+        return torch.from_numpy(noise.view(np.int32)).to(self.batched.device)
+
     def step(self, state, actions: Dict[str, int]) -> JointTimestep:
         b = self.batched
         packed = torch.from_numpy(b.pack_state([state])).to(b.device)
         act = torch.tensor([[int(actions[i]) for i in self.possible_agents]], dtype=torch.uint8, device=b.device)
-        noise = np.array([[self._rng.getrandbits(32) for _ in range(b.noise_words)]], dtype=np.uint32)
-        out = b.step(packed, act, torch.from_numpy(noise.view(np.int32)).to(b.device))
+        out = b.step(packed, act, self.batched_step_noise(1))
         nstate = b.unpack_state(out.state)[0]
         obs = b.unpack_obs(out.obs)[0]
         rew = out.rewards.cpu().numpy()[0]

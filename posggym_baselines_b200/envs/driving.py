@@ -100,6 +100,11 @@ class BatchedDriving:
         rows = [r for r in self.grid_str.splitlines() if r]
         self.width, self.height = len(rows[0]), len(rows)
         self.dest_coords = [(x, y) for y, r in enumerate(rows) for x, ch in enumerate(r) if ch == "-" or ch in "abcdefghij"]
+        # per-agent start / destination cells in parse order ('+' / '-': every agent; digit / letter: that agent)
+        self.agent_starts = [[(x, y) for y, r in enumerate(rows) for x, ch in enumerate(r) if ch == "+" or ch == str(i)]
+                             for i in range(self.num_agents)]
+        self.agent_dests = [[(x, y) for y, r in enumerate(rows) for x, ch in enumerate(r) if ch == "-" or ch == "abcdefghij"[i]]
+                            for i in range(self.num_agents)]
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         if device is None:
@@ -122,6 +127,24 @@ class BatchedDriving:
             except Exception:
                 pass
             self._handle = None
+
+    def initial_pick_bounds(self, picks_so_far: Sequence[int]) -> int:
+        """Number of choices of the next initial-state pick given the earlier ones (per agent: a start cell among
+        those still free, then a destination among those still free and different from the start) -- the bounds
+        of the explicit ``picks`` of ``sample_initial_state``."""
+        i, is_dest = divmod(len(picks_so_far), 2)
+        used_s, used_d = set(), set()
+        for j in range(i):
+            s = [c for c in self.agent_starts[j] if c not in used_s][picks_so_far[2 * j]]
+            used_s.add(s)
+            used_d.add([c for c in self.agent_dests[j] if c not in used_d and c != s][picks_so_far[2 * j + 1]])
+        avail = [c for c in self.agent_starts[i] if c not in used_s]
+        if not is_dest:
+            return len(avail)
+        s = avail[picks_so_far[2 * i]]
+        return len([c for c in self.agent_dests[i] if c not in used_d and c != s])
+
+    num_picks = property(lambda self: 2 * self.num_agents)
 
     # ---- batched model calls -------------------------------------------------------
     def _empty(self, shape, dtype):
@@ -319,8 +342,13 @@ class DrivingModel:
         return list(self.possible_agents)
 
     def sample_initial_state(self):
+        # the picks come from model.rng one by one (like posggym's model draws its start / destination cells);
+        # the state is built by the kernel from the explicit picks
         b = self.batched
-        st = b.sample_initial_state(1, seed=self._rng.getrandbits(63), particle_offset=0)
+        picks: List[int] = []
+        for _ in range(b.num_picks):
+            picks.append(self._rng.randrange(b.initial_pick_bounds(picks)))
+        st = b.sample_initial_state(1, picks=torch.tensor([picks], dtype=torch.uint8, device=b.device))
         return b.unpack_state(st)[0]
 
     def sample_initial_obs(self, state) -> Dict[str, tuple]:
@@ -332,14 +360,18 @@ class DrivingModel:
     def sample_agent_initial_state(self, agent_id: str, obs):
         raise NotImplementedError
 
+    def batched_step_noise(self, n: int):
+        """Explicit noise for ``n`` rows of ``batched.step``: the processing-order draw of ``step``, n times."""
+        import math
+
+        k = math.factorial(len(self.possible_agents))
+        return torch.tensor([self._rng.randrange(k) for _ in range(n)], dtype=torch.uint8, device=self.batched.device)
+
     def step(self, state, actions: Dict[str, int]) -> JointTimestep:
         b = self.batched
         packed = torch.from_numpy(b.pack_state([state])).to(b.device)
         act = torch.tensor([[int(actions[i]) for i in self.possible_agents]], dtype=torch.uint8, device=b.device)
-        import math
-        order = torch.tensor([self._rng.randrange(math.factorial(len(self.possible_agents)))],
-                             dtype=torch.uint8, device=b.device)
-        out = b.step(packed, act, order)
+        out = b.step(packed, act, self.batched_step_noise(1))
         nstate = b.unpack_state(out.state)[0]
         obs = b.unpack_obs(out.obs)[0]
         rew = out.rewards.cpu().numpy()[0]

@@ -56,6 +56,7 @@ def static_player_coords(size: int, num_agents: int) -> List[Tuple[int, int]]:
 class BatchedLBF(BatchedModel):
     env_id = "LevelBasedForaging-v3"
     num_agents, state_words, obs_words, noise_words, num_picks = 2, 2, 2, 1, 10
+    noise_is_dummy = True   # LevelBasedForaging's step takes no noise (one placeholder word in the C-ABI)
 
     def __init__(self, num_agents: int = 2, max_agent_level: int = 3, size: int = 10, max_food: int = 8,
                  sight: int = 2, force_coop: bool = False, static_layout: bool = True,
@@ -76,6 +77,12 @@ class BatchedLBF(BatchedModel):
                 self.size, num_agents, self.max_agent_level, self.max_food, self.sight, int(self.force_coop),
                 int(bool(normalize_reward)), food_xy.ctypes.data_as(C.c_void_p), player_xy.ctypes.data_as(C.c_void_p),
                 C.byref(self._handle)))
+
+    def initial_pick_bounds(self, picks_so_far) -> int:
+        """Player levels (level - 1), then food levels (level - 1, at most the players' level sum)."""
+        if len(picks_so_far) < self.num_agents:
+            return self.max_agent_level
+        return 1 if self.force_coop else sum(p + 1 for p in picks_so_far[: self.num_agents])
 
     # ---- codec ---------------------------------------------------------------------
     def pack_state(self, states) -> np.ndarray:

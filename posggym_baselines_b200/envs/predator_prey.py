@@ -41,6 +41,17 @@ class BatchedPredatorPrey(BatchedModel):
             _lib.check(_lib.lib().posg_pp_create(self.size, None, num_predators, num_prey, int(cooperative),
                                                  prey_strength, obs_dim, C.byref(self._handle)))
 
+    def initial_pick_bounds(self, picks_so_far) -> int:
+        """Predators then prey, drawn without replacement from their start-cell lists (8 border cells; whole
+        rings around the centre until there are at least ``num_prey`` cells)."""
+        k = len(picks_so_far)
+        n_pred_start = 8
+        n_prey_start, ring = 0, 0
+        while n_prey_start < self.num_prey:
+            n_prey_start += 1 if ring == 0 else 8 * ring
+            ring += 1
+        return n_pred_start - k if k < self.num_agents else n_prey_start - (k - self.num_agents)
+
     # ---- codec ---------------------------------------------------------------------
     def pack_state(self, states) -> np.ndarray:
         out = np.zeros((len(states), 2), np.uint32)

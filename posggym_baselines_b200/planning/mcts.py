@@ -7,10 +7,11 @@ obs)``, ``get_action()``, ``close()``, ``step_statistics`` (keys of mcts.py:140-
 leaf rollouts, backups, the initial-belief rejection loop and reinvigoration all run in
 libposg_b200.so; this file only sequences launches and applies the wall-clock budget.
 
-Supported configuration = the POMCP one: ``RandomSearchPolicy`` for the ego agent,
-``RandomOtherAgentPolicy`` for the others, ``state_belief_only=True``; ``truncated`` is
-irrelevant because ``RandomSearchPolicy.get_value`` raises (rollout fallback,
-mcts.py:392-399).  Other plugins raise ``NotImplementedError``.
+Device search = the POMCP configuration: ``RandomSearchPolicy`` for the ego agent and
+``RandomOtherAgentPolicy`` for the others (either value of ``state_belief_only``; ``truncated`` is
+irrelevant because ``RandomSearchPolicy.get_value`` raises: rollout fallback, mcts.py:392-399).  Any
+other ``SearchPolicy`` / ``OtherAgentPolicy`` plugin runs through its scalar methods on the host
+(planning/host_search.py) with the model arithmetic on the device.
 
 Extra, B200-only knobs are keyword arguments of the constructor, never config fields:
 ``max_sims`` (stop after that many simulations instead of / as well as the time limit),
@@ -107,13 +108,11 @@ class MCTS:
         assert agent_id not in other_agent_policies
         self.other_agent_policies = other_agent_policies
         self.search_policy = search_policy
-        if not isinstance(search_policy, RandomSearchPolicy) or not all(
-            isinstance(p, RandomOtherAgentPolicy) for p in other_agent_policies.values()
-        ):
-            raise NotImplementedError(
-                "the B200 planner executes RandomSearchPolicy / RandomOtherAgentPolicy in-kernel; "
-                "other plugins are not supported yet"
-            )
+        # RandomSearchPolicy / RandomOtherAgentPolicy are executed inside the kernels; any other plugin is a
+        # stateful Python object, so the descent that calls its scalar methods runs on the host
+        # (planning/host_search.py) with the model arithmetic still on the device
+        self._host_mode = not (type(search_policy) is RandomSearchPolicy and all(
+            type(p) is RandomOtherAgentPolicy for p in other_agent_policies.values()))
         # state_belief_only=False (mcts.py:344-354) makes particles carry the joint history and the other agents'
         # policy states.  With RandomOtherAgentPolicy the policy state is empty and nothing the search computes
         # reads the history, so the device search is the same; the histories are not materialised
@@ -169,11 +168,47 @@ class MCTS:
         else:
             self._sim_base = 0
 
-        self.root = _RootView(self)
+        self._device_root = _RootView(self)
         self._logger = logging.getLogger()
         self.step_statistics: Dict[str, float] = {}
         self.stat_tracker = PlanningStatTracker(self)
+        self._host = None
+        if self._host_mode:
+            from posggym_baselines_b200.planning.host_search import HostSearch
+
+            self._reset_step_statistics_host()
+            self._host = HostSearch(self)
         self.reset()
+
+    @property
+    def root(self):
+        """``planner.root``: ``belief.size()`` / ``belief.particles``, ``t``, ``is_absorbing``, ``visits``."""
+        return self._host.root if self._host is not None else self._device_root
+
+    def _reset_step_statistics_host(self):
+        self._min_value, self._max_value = float("inf"), -float("inf")
+        self._reset_step_statistics()
+
+    def _device_initial_belief(self, init_obs, need: int) -> torch.Tensor:
+        """MCTS._initial_update's rejection loop (mcts.py:186-194) in one launch: ``need`` packed states whose
+        first ego observation is ``init_obs``."""
+        b = self._b
+        out = torch.empty((need, self._SW), dtype=torch.int32, device=b.device)
+        res = np.zeros(3, np.int64)
+        key = np.ascontiguousarray(b.pack_obs(init_obs), dtype=np.uint64)
+        max_attempts = 1 << 26
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().posg_belief_initial(
+                b._handle, self._ego, _lib.ptr(key), need, max_attempts, self._params.seed,
+                self._next_draw(max_attempts), _lib.ptr(out), _lib.ptr(res), self._stream()))
+        if res[0] < need:
+            raise RuntimeError(f"initial belief: only {res[0]} of {need} particles matched the first observation")
+        return out
+
+    def _facade_noise(self, n: int):
+        """Explicit step noise for ``n`` batched ``model.step`` rows, drawn from ``model.rng`` like the facade's
+        scalar ``step`` does."""
+        return self.model.batched_step_noise(n)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -209,8 +244,8 @@ class MCTS:
 
     # ------------------------------------------------------------------ step / reset
     def step(self, obs):
-        assert self._root_t <= self.step_limit
-        if self._root_absorbing:
+        assert self.root.t <= self.step_limit
+        if self.root.is_absorbing:
             for k in self.step_statistics:
                 self.step_statistics[k] = np.nan
             return self._last_action
@@ -233,6 +268,8 @@ class MCTS:
 
     def reset(self):
         self.stat_tracker.reset_episode()
+        if self._host is not None:
+            self._host.reset()
         self._step_num = 0
         self._root = 0
         self._root_t = 0
@@ -257,6 +294,13 @@ class MCTS:
 
     # ------------------------------------------------------------------ update
     def update(self, action, obs):
+        if self._host is not None:
+            start = time.time()
+            if self._host.root.t == 0:
+                self._last_action = None
+            self._host.update(action, obs)
+            self.step_statistics["update_time"] = time.time() - start
+            return
         if self._root_absorbing:
             return
         start = time.time()
@@ -278,19 +322,11 @@ class MCTS:
         self._ensure_arena()
         need = cfg.num_particles + cfg.extra_particles
         kb = cfg.known_bounds
-        out = torch.empty((need, self._SW), dtype=torch.int32, device=b.device)
-        res = np.zeros(3, np.int64)
-        key = np.ascontiguousarray(b.pack_obs(init_obs), dtype=np.uint64)
-        max_attempts = 1 << 26
         with torch.cuda.device(b.device):
             _lib.check(_lib.lib().posg_tree_reset(
                 b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, 1,
                 kb.min if kb else 1.0, kb.max if kb else 0.0, self._stream()))
-            _lib.check(_lib.lib().posg_belief_initial(
-                b._handle, self._ego, _lib.ptr(key), need, max_attempts, self._params.seed,
-                self._next_draw(max_attempts), _lib.ptr(out), _lib.ptr(res), self._stream()))
-        if res[0] < need:
-            raise RuntimeError(f"initial belief: only {res[0]} of {need} particles matched the first observation")
+        out = self._device_initial_belief(init_obs, need)
         self._root, self._root_t, self._root_absorbing = 0, 1, False
         self._root_particles = out
         self._nodes_bound, self._log_bound = 1, 0
@@ -348,6 +384,8 @@ class MCTS:
 
     # ------------------------------------------------------------------ search
     def get_action(self):
+        if self._host is not None:
+            return self._host.get_action()
         if self._root_absorbing:
             return self.action_space[0]
         cfg, b = self.config, self._b

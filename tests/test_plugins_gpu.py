@@ -1,0 +1,296 @@
+"""The drop-in boundary from both sides:
+
+* the UNMODIFIED reference planner (imported through oracle.shims from /root/reference when that tree is
+  present; on the GPU box it is not, and those tests skip) driving the GPU model facade produces, call for
+  call, what it produces on the CPU oracle model under the same RNG seeds;
+* arbitrary ``SearchPolicy`` / ``OtherAgentPolicy`` plugins run through the B200 planner's host path
+  (planning/host_search.py) -- the reference's own tests/planning/test_mcts.py scenario included.
+"""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HAVE_REF = os.path.isdir("/root/reference/posggym_baselines")
+
+
+class FakeClock:
+    """``time`` stand-in for the reference planner: the search budget becomes a fixed number of clock reads."""
+
+    def __init__(self, tick):
+        self.now, self.tick = 0.0, tick
+
+    def time(self):
+        self.now += self.tick
+        return self.now
+
+
+def _run_reference_planner(model, env_cls, seed, clock_tick, max_steps=12):
+    import posggym_baselines.planning.mcts as ref_mcts
+    from posggym_baselines.planning import POMCP, MCTSConfig, RandomSearchPolicy
+
+    ref_mcts.time = FakeClock(clock_tick)
+    random.seed(seed)
+    np.random.seed(seed)
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb",
+                     state_belief_only=True, seed=seed)
+    env = env_cls(model)
+    obs, _ = env.reset(seed=seed)
+    planner = POMCP(model, "0", cfg, search_policy=RandomSearchPolicy(model, "0"))
+    planner.reset()
+    rng = random.Random(seed + 1)
+    trace = []
+    for _ in range(max_steps):
+        a = planner.step(obs["0"])
+        b = rng.randrange(5)
+        obs, rew, term, trunc, done, _ = env.step({"0": a, "1": b})
+        trace.append((a, b, planner.step_statistics["num_sims"], obs["0"], obs["1"], rew["0"], rew["1"], done))
+        if done:
+            break
+    planner.close()
+    return trace
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="needs the reference tree (build container)")
+@pytest.mark.parametrize("env_id", ["Driving-v1", "PredatorPrey-v0", "LevelBasedForaging-v3"])
+def test_unmodified_reference_planner_on_the_gpu_facade(oracle_env, env_id):
+    """Same seeds for ``random``, ``model.rng``, the action spaces and the planner; a fake clock fixes the
+    number of simulations.  Every chosen action, simulation count, observation and reward of the episode
+    prefix is identical -- i.e. the facade is the oracle model as far as the reference planner can tell
+    (states / observations hashable and comparable, rewards bit-equal, RNG draws in the same order)."""
+    import time as real_time
+
+    import posggym_baselines.planning.mcts as ref_mcts
+    from oracle.driving import DrivingModel as OracleDriving
+    from oracle.lbf import LevelBasedForagingModel as OracleLBF
+    from oracle.predator_prey import PredatorPreyModel as OraclePP
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.envs.lbf import LBFModel
+    from posggym_baselines_b200.envs.predator_prey import PredatorPreyModel
+
+    gpu_cls, cpu_cls = {"Driving-v1": (DrivingModel, OracleDriving), "PredatorPrey-v0": (PredatorPreyModel, OraclePP),
+                        "LevelBasedForaging-v3": (LBFModel, OracleLBF)}[env_id]
+    try:
+        results = []
+        for cls in (gpu_cls, cpu_cls):
+            m = cls()
+            if m.spec is None:
+                m.spec = type("S", (), {"max_episode_steps": 50, "id": env_id})()
+            results.append(_run_reference_planner(m, Env, seed=7, clock_tick=0.0004, max_steps=6))
+    finally:
+        ref_mcts.time = real_time
+    gpu, cpu = results
+    assert len(gpu) == len(cpu) and len(gpu) >= 3
+    for g, c in zip(gpu, cpu):
+        assert g[:3] == c[:3], (g[:3], c[:3])                  # ego action, other action, simulations
+        assert g[5:] == c[5:]                                    # rewards (bit-equal floats), done
+        assert _plain(g[3]) == _plain(c[3]) and _plain(g[4]) == _plain(c[4])
+    assert all(s[2] > 10 for s in gpu)
+
+
+def _plain(x):
+    return tuple(_plain(v) for v in x) if isinstance(x, (tuple, list)) else int(x)
+
+
+@pytest.mark.parametrize("env_id", ["Driving-v1", "PredatorPrey-v0", "LevelBasedForaging-v3"])
+def test_restated_reference_planner_on_the_gpu_facade(oracle_env, env_id):
+    """The same check where the reference tree is absent (the GPU box): oracle/pomcp.py -- the scalar
+    restatement of the reference planner, pinned to the unmodified planner by tests/test_oracle_planner.py --
+    runs an episode prefix on the GPU facade and on the CPU oracle model with the same seeds and a fixed
+    simulation count; every action, observation and reward is identical, so the facade consumes ``model.rng``
+    and the action spaces exactly like the oracle model and returns equal, hashable values."""
+    from oracle.driving import DrivingModel as OracleDriving
+    from oracle.lbf import LevelBasedForagingModel as OracleLBF
+    from oracle.pomcp import OraclePOMCP
+    from oracle.predator_prey import PredatorPreyModel as OraclePP
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.envs.lbf import LBFModel
+    from posggym_baselines_b200.envs.predator_prey import PredatorPreyModel
+
+    gpu_cls, cpu_cls = {"Driving-v1": (DrivingModel, OracleDriving), "PredatorPrey-v0": (PredatorPreyModel, OraclePP),
+                        "LevelBasedForaging-v3": (LBFModel, OracleLBF)}[env_id]
+    traces = []
+    for cls in (gpu_cls, cpu_cls):
+        m = cls()
+        if m.spec is None:
+            m.spec = type("S", (), {"max_episode_steps": 50, "id": env_id})()
+        random.seed(11)
+        env = Env(m)
+        obs, _ = env.reset(seed=11)
+        n_act = m.action_spaces["0"].n
+        planner = OraclePOMCP(m, "0", 0.95, 0.1, 1.414, seed=11)
+        planner.reset()
+        rng, trace, last = random.Random(12), [], None
+        for _ in range(6):
+            planner.update(last, obs["0"])
+            last = planner.get_action(max_sims=40)
+            b = rng.randrange(n_act)
+            obs, rew, term, trunc, done, _ = env.step({"0": last, "1": b})
+            trace.append((last, b, _plain(obs["0"]), _plain(obs["1"]), rew["0"], rew["1"], done))
+            if done or planner.root.is_absorbing:
+                break
+        traces.append(trace)
+    assert traces[0] == traces[1] and len(traces[0]) >= 3
+
+
+# ---------------------------------------------------------------- plugins through the B200 planner
+def _plugin_classes():
+    from posggym_baselines_b200.planning import OtherAgentPolicy, SearchPolicy
+
+    class CountingSearchPolicy(SearchPolicy):
+        """A stateful plugin: remembers how many steps it has seen, prefers ACCELERATE early on, and
+        offers a value estimate."""
+
+        def __init__(self, model, agent_id):
+            super().__init__(model, agent_id, "counting")
+            self.n = model.action_spaces[agent_id].n
+            self.calls = 0
+
+        def get_initial_state(self):
+            return {"k": 0, "last_obs": None}
+
+        def get_next_state(self, action, obs, state):
+            self.calls += 1
+            return {"k": state["k"] + 1, "last_obs": obs}
+
+        def sample_action(self, state):
+            return random.choices(range(self.n), weights=list(self.get_pi(state).values()))[0]
+
+        def get_pi(self, state):
+            w = [1.0] * self.n
+            w[1] += 3.0 / (1 + state["k"])
+            z = sum(w)
+            return {a: w[a] / z for a in range(self.n)}
+
+        def get_value(self, state):
+            return 0.01 * state["k"]
+
+    class StickyOther(OtherAgentPolicy):
+        """Repeats its previous action with probability 0.8 (needs its own state per particle)."""
+
+        def __init__(self, model, agent_id):
+            super().__init__(model, agent_id)
+            self.n = model.action_spaces[agent_id].n
+
+        def sample_initial_state(self):
+            return {"last": None}
+
+        def get_next_state(self, action, obs, state):
+            return {"last": action}
+
+        def sample_action(self, state):
+            if state["last"] is not None and random.random() < 0.8:
+                return state["last"]
+            return random.randrange(self.n)
+
+        def get_pi(self, state):
+            return {a: 1.0 / self.n for a in range(self.n)}
+
+    return CountingSearchPolicy, StickyOther
+
+
+@pytest.mark.parametrize("truncated", [True, False])
+def test_stateful_plugins_run_through_the_host_path(truncated):
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.planning import MCTS, MCTSConfig, PlanningStatTracker
+
+    Search, Other = _plugin_classes()
+    model = DrivingModel()
+    env = Env(model)
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.05, c=1.414, truncated=truncated, action_selection="pucb",
+                     state_belief_only=False, seed=3)
+    sp = Search(model, "0")
+    planner = MCTS(model, "0", cfg, {"1": Other(model, "1")}, sp, max_sims=24 if truncated else 6)
+    assert planner._host is not None
+    obs, _ = env.reset(seed=3)
+    planner.reset()
+    random.seed(0)
+    for step in range(4):
+        a = planner.step(obs["0"])
+        assert a in range(5)
+        st = planner.step_statistics
+        assert set(st) == set(PlanningStatTracker.STAT_KEYS)
+        assert st["num_sims"] == (24 if truncated else 6) and st["policy_calls"] > 0
+        root = planner.root
+        assert root.t == step + 1 and root.belief.size() >= cfg.num_particles + cfg.extra_particles
+        p0 = root.belief.particles[0]
+        assert len(p0.history) == step + 1 and set(p0.policy_state) == {"1"} and p0.t == step + 1
+        assert set(p0.policy_state["1"]) == {"last"}
+        obs, _, _, _, done, _ = env.step({"0": a, "1": random.randrange(5)})
+        if done:
+            break
+    assert sp.calls > 0
+    planner.close()
+
+
+def test_reference_mcts_test_scenario():
+    """tests/planning/test_mcts.py:13-27 of the reference: MCTS with the Random pair, epsilon 0.92
+    (depth_limit 2), state_belief_only=False -- runs on the device search."""
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.planning import MCTS, MCTSConfig, RandomOtherAgentPolicy, RandomSearchPolicy
+
+    model = DrivingModel()
+    env = Env(model)
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=math.sqrt(2), truncated=False, action_selection="ucb",
+                     pucb_exploration_fraction=0.25, known_bounds=None, step_limit=None, epsilon=0.92, seed=0,
+                     state_belief_only=False)
+    assert cfg.depth_limit == 2
+    planner = MCTS(model, "0", cfg, other_agent_policies={"1": RandomOtherAgentPolicy(model, "1")},
+                   search_policy=RandomSearchPolicy(model, "0"), node_capacity=1 << 22, log_capacity=1 << 24)
+    assert planner._host is None
+    obs, _ = env.reset(seed=0)
+    planner.reset()
+    rng, done, steps = random.Random(0), False, 0
+    while not done:
+        a = planner.step(obs["0"])
+        obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+        steps += 1
+    assert steps <= 50
+    planner.close()
+
+
+def test_random_pair_subclasses_match_the_device_search_statistically():
+    """The host path is the same algorithm as the device path: a SUBCLASS of the Random pair (not recognised by
+    type, so it goes through host_search.py) gives root action values within 4 standard errors + 0.03 of the
+    device search after 192 simulations from the same first observation."""
+    import json
+
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.planning import MCTS, MCTSConfig, RandomOtherAgentPolicy, RandomSearchPolicy
+    from tests.conftest import GOLDEN
+
+    class MySearch(RandomSearchPolicy):
+        pass
+
+    class MyOther(RandomOtherAgentPolicy):
+        pass
+
+    scen = json.load(open(os.path.join(GOLDEN, "planner_driving.json")))["root_stats"][0]
+    f = scen["ego_obs"]
+    obs = (tuple(f[:15]), f[15], (f[16], f[17]), (f[18], f[19]), f[20], f[21])
+    model = DrivingModel()
+    vals = []
+    for rep in range(6):
+        cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb",
+                         state_belief_only=True, seed=rep)
+        random.seed(rep)
+        model.seed(100 + rep)
+        p = MCTS(model, "0", cfg, {"1": MyOther(model, "1")}, MySearch(model, "0"), max_sims=192)
+        assert p._host is not None
+        p.reset()
+        p.update(None, obs)
+        p.get_action()
+        vals.append([p.root.children[a].value for a in range(5)])
+        p.close()
+    vals = np.array(vals)
+    ref_mean, ref_std = np.array(scen["value_mean"]), np.array(scen["value_std"])
+    se = np.sqrt(ref_std**2 / scen["reps"] + vals.std(0) ** 2 / len(vals))
+    assert (np.abs(vals.mean(0) - ref_mean) < 4 * se + 0.03).all(), (vals.mean(0), ref_mean, se)
