@@ -53,6 +53,7 @@ extern "C" {
 #define POSG_FLAG_ALL_DONE 0x80u
 
 typedef struct posg_model* posg_model_t;
+typedef struct posg_policy* posg_policy_t;
 
 const char* posg_last_error(void);
 int posg_version(void);
@@ -347,6 +348,30 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
  * the one-hot rows altogether. */
 int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const float* wT, const float* bias,
                    int hidden, int apply_tanh, float* out, void* stream);
+
+/* The rest of the collector's policy step: PPOLSTMModel.get_action_and_value
+ * (ppo/network.py:212-268,305-330) after trunk[0:2] for trunk_sizes [64, 64], lstm_size 64, one LSTM layer,
+ * head_sizes [64] (baseline_exps/exp_utils.py:101-104), fused into one tcgen05 tensor-core kernel
+ * (csrc/policy_kernels.cu).  posg_policy_create takes HOST pointers to the fp32 parameters in PyTorch's
+ * layouts -- trunk.2.weight [64, 64] / bias, lstm.weight_ih_l0 [256, 64], lstm.weight_hh_l0 [256, 64],
+ * lstm.bias_ih_l0 / bias_hh_l0 [256], actor.0.weight [64, 64] / bias, actor.2.weight [A, 64] / bias,
+ * critic.0.weight [64, 64] / bias, critic.2.weight [1, 64] / bias -- and packs them (fp16, tensor-core operand
+ * layout) on the current device.
+ * posg_policy_step, all DEVICE pointers: x0 [n, 64] f32 = tanh(trunk.0(obs)) (posg_vec_embed's output),
+ * h_in / c_in [n, 64] f32 (the LSTM state), done [n] f32 (1 = reset the state first: get_states' (1 - d) mask),
+ * action_in [n] i64 or NULL (NULL: sample from Categorical(logits) with Philox counter (row_offset + row, step));
+ * outputs h_out / c_out [n, 64] f32 (may alias the inputs), action_out [n] i64, logprob_out / entropy_out /
+ * value_out [n] f32, logits_out [n, A] f32 or NULL.  fp16 operands, fp32 accumulation and epilogues: results
+ * agree with the fp32 PyTorch module within 5e-3 (tests/test_policy_gpu.py). */
+int posg_policy_create(int hidden, int n_actions, const float* trunk1_w, const float* trunk1_b, const float* w_ih,
+                       const float* w_hh, const float* b_ih, const float* b_hh, const float* actor0_w,
+                       const float* actor0_b, const float* actor2_w, const float* actor2_b, const float* critic0_w,
+                       const float* critic0_b, const float* critic2_w, const float* critic2_b, posg_policy_t* out);
+int posg_policy_destroy(posg_policy_t p);
+int posg_policy_step(posg_policy_t p, int64_t n_rows, const float* x0, const float* h_in, const float* c_in,
+                     const float* done, uint64_t seed, uint32_t step, uint64_t row_offset, const int64_t* action_in,
+                     float* h_out, float* c_out, int64_t* action_out, float* logprob_out, float* entropy_out,
+                     float* value_out, float* logits_out, void* stream);
 
 /* Generalised advantage estimation of the PPO learner (ppo/core.py:226-244): the
  * backward loop over seq_len steps of PPOTrainer.update in one launch.  rewards [T, n_cols] f32,

@@ -1,0 +1,92 @@
+"""The fused tensor-core policy step (posg_policy_step, csrc/policy_kernels.cu) against a plain fp32
+PyTorch restatement of the same op -- PPOLSTMModel.get_action_and_value of the reference
+(ppo/network.py:212-268,305-330) with trunk_sizes [64, 64], lstm_size 64, head_sizes [64]
+(baseline_exps/exp_utils.py:101-104).  Operands are fp16 on the tensor cores (fp32 accumulation and
+epilogues): tolerance 5e-3 absolute on logits / value / log-prob / entropy / h / c, stated per assert."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class RefNet(torch.nn.Module):
+    """The reference module's layers under the reference's parameter names."""
+
+    def __init__(self, obs_dim, n_actions):
+        super().__init__()
+        nn = torch.nn
+        self.trunk = nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+        self.lstm = nn.LSTM(64, 64, num_layers=1, batch_first=False)
+        self.actor = nn.Sequential(nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, n_actions))
+        self.critic = nn.Sequential(nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, 1))
+
+    def get_action_and_value(self, x, lstm_state, done, action):
+        hidden = self.trunk(x)
+        keep = (1.0 - done).view(1, -1, 1)
+        out, state = self.lstm(hidden.unsqueeze(0), (keep * lstm_state[0], keep * lstm_state[1]))
+        out = out.squeeze(0)
+        logits = self.actor(out)
+        probs = torch.distributions.Categorical(logits=logits)
+        return logits, probs.log_prob(action), probs.entropy(), self.critic(out).squeeze(-1), state
+
+
+@pytest.mark.parametrize("n,n_actions", [(128, 6), (1000, 5), (16384, 6)])
+def test_policy_step_matches_fp32_torch(n, n_actions):
+    from posggym_baselines_b200.ppo import FusedPolicy
+
+    torch.manual_seed(n)
+    dev = torch.device("cuda")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = RefNet(300, n_actions).to(dev)
+        with torch.no_grad():                       # trained-looking magnitudes, biases included
+            for p in net.parameters():
+                p.mul_(1.5).add_(0.05 * torch.randn_like(p))
+        pol = FusedPolicy(net.state_dict(), device=dev)
+        x = (torch.rand(n, 300, device=dev) < 0.1).float()
+        h = torch.randn(1, n, 64, device=dev) * 0.5
+        c = torch.randn(1, n, 64, device=dev)
+        done = (torch.rand(n, device=dev) < 0.2).float()
+        action = torch.randint(0, n_actions, (n,), device=dev)
+        with torch.no_grad():
+            logits, logp, ent, val, (h1, c1) = net.get_action_and_value(x, (h, c), done, action)
+            x0 = net.trunk[1](net.trunk[0](x)).contiguous()
+        hh, cc = h[0].clone(), c[0].clone()
+        out = pol.step(x0, (hh, cc), done, action=action, want_logits=True)
+        torch.cuda.synchronize()
+        tol = 5e-3
+        assert (out["logits"] - logits).abs().max().item() < tol
+        assert (out["value"] - val).abs().max().item() < tol
+        assert (out["logprob"] - logp).abs().max().item() < tol
+        assert (out["entropy"] - ent).abs().max().item() < tol
+        assert (hh - h1[0]).abs().max().item() < tol and (cc - c1[0]).abs().max().item() < tol
+        assert torch.equal(out["action"], action)
+        # sampling: Philox-driven inverse CDF -- reproducible, and distributed like Categorical(logits)
+        hh2, cc2 = h[0].clone(), c[0].clone()
+        s1 = pol.step(x0, (hh2, cc2), done, seed=5, step_idx=3)["action"]
+        hh3, cc3 = h[0].clone(), c[0].clone()
+        s2 = pol.step(x0, (hh3, cc3), done, seed=5, step_idx=3)["action"]
+        assert torch.equal(s1, s2) and int(s1.min()) >= 0 and int(s1.max()) < n_actions
+        if n >= 16384:
+            counts = torch.zeros(n_actions, device=dev)
+            expect = torch.softmax(logits, -1).sum(0)
+            for k in range(8):
+                a = pol.step(x0, (h[0].clone(), c[0].clone()), done, seed=9, step_idx=k)["action"]
+                counts += torch.bincount(a, minlength=n_actions).float()
+            freq, p = (counts / (8 * n)).cpu().numpy(), (expect / n).cpu().numpy()
+            assert np.abs(freq - p).max() < 4 * np.sqrt(p.max() / (8 * n)) + 2e-3, (freq, p)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_sass_uses_the_tensor_core_path():
+    """UTCHMMA (tcgen05.mma kind::f16) and LDTM (tcgen05.ld) are in the shipped library."""
+    import subprocess
+
+    from posggym_baselines_b200 import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.library_path()], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UTCBAR" in sass
