@@ -391,6 +391,50 @@ def bench_particle_sweep(env, dev, rank, seed, barrier):
     return out
 
 
+def bench_collector(dev, rank, world, seed, barrier):
+    """BASELINE.json configs[4] with the policy in the loop: the rollout worker's step --
+    policy.get_action_and_value on the current observations, envs.step with the sampled actions, store
+    reward / done / value / log-prob (ppo/worker.py:135-224) -- for LevelBasedForaging-v3, 8 192 envs per GPU, 64
+    steps: three launches per step (posg_vec_embed, posg_policy_step on the tensor cores, posg_vec_step) and the
+    whole 64-step rollout captured in ONE CUDA graph.  Random-init network of the experiments' shape
+    (trunk [64, 64], LSTM 64, heads [64]; exp_utils.py:101-104)."""
+    import torch
+    import torch.distributed as dist
+
+    from posggym_baselines_b200.envs.lbf import LBFModel
+    from posggym_baselines_b200.ppo.collector import DeviceCollector
+
+    nn = torch.nn
+    torch.manual_seed(0)
+    sd = {}
+    for name, mod in (("trunk.0", nn.Linear(300, 64)), ("trunk.2", nn.Linear(64, 64)), ("actor.0", nn.Linear(64, 64)),
+                      ("actor.2", nn.Linear(64, 6)), ("critic.0", nn.Linear(64, 64)), ("critic.2", nn.Linear(64, 1))):
+        sd[name + ".weight"], sd[name + ".bias"] = mod.weight.detach(), mod.bias.detach()
+    lstm = nn.LSTM(64, 64)
+    for k, v in lstm.state_dict().items():
+        sd["lstm." + k] = v
+    out = {"rollout_steps": 64, "launches_per_step": 3,
+           "network": "PPOLSTMModel trunk [64, 64], LSTM 64, heads [64], random init; fp16 tensor-core operands, fp32 accumulate"}
+    for label, nv in (("envs_8192_per_gpu", 8192), ("envs_131072_per_gpu", 131072)):
+        col = DeviceCollector(LBFModel(device=dev), sd, nv, rollout_length=64, seed=seed, env_offset=rank * nv)
+        col.capture()
+        col.rollout()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            col.rollout()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[label] = {"us_per_step": 1e3 * ms.item() / 64, "env_steps_per_s": world * nv * 64 / (ms.item() / 1e3),
+                      "agent_steps_per_s": 2 * world * nv * 64 / (ms.item() / 1e3)}
+        del col
+    return out
+
+
 def bench_vec_env(dev, rank, world, seed, barrier, cpu: bool):
     """``envs.step`` of the PPO rollout worker (ppo/worker.py:176-216) for 64 rollout steps
     (exp_utils.py:81): one launch per step does model.step, TimeLimit, episode statistics,
@@ -740,6 +784,14 @@ def main():
     except Exception as ex:
         vec = {"error": repr(ex)}
 
+    collector = None
+    try:
+        if args.only_sweep:
+            raise RuntimeError("skipped (--only-sweep)")
+        collector = bench_collector(dev, rank, world, seed, barrier)
+    except Exception as ex:
+        collector = {"error": repr(ex)}
+
     # ---- the other two models' step kernels and the particle sweep of configs[1] ----
     models, psweep = None, None
     try:
@@ -771,7 +823,7 @@ def main():
                          "traffic": traffic, "kernel": "posg::driving::step_fast_kernel<true, true>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
                          "launch_ms": launch_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "clocks": clocks, "rollout_fused": rl, "models": models, "particle_sweep": psweep,
-            "pomcp": pomcp, "vec_env": vec,
+            "pomcp": pomcp, "vec_env": vec, "collector": collector,
         }
         emit(line)
     if world > 1:

@@ -358,8 +358,11 @@ int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const 
  * critic.0.weight [64, 64] / bias, critic.2.weight [1, 64] / bias -- and packs them (fp16, tensor-core operand
  * layout) on the current device.
  * posg_policy_step, all DEVICE pointers: x0 [n, 64] f32 = tanh(trunk.0(obs)) (posg_vec_embed's output),
- * h_in / c_in [n, 64] f32 (the LSTM state), done [n] f32 (1 = reset the state first: get_states' (1 - d) mask),
- * action_in [n] i64 or NULL (NULL: sample from Categorical(logits) with Philox counter (row_offset + row, step));
+ * h_in / c_in [n, 64] f32 (the LSTM state), done [n] f32 (1 = reset the state first: get_states' (1 - d) mask) or,
+ * with done == NULL, terminated / truncated [n] u8 as posg_vec_step writes them (done = their OR, worker.py:191-195),
+ * action_in [n] i64 or NULL (NULL: sample from Categorical(logits) with Philox counter (row_offset + row, step);
+ * step_device != NULL: the step index is read from that device word -- posg_vec_step's step_counter -- so that a
+ * collector loop captured in a CUDA graph draws fresh numbers at every replay);
  * outputs h_out / c_out [n, 64] f32 (may alias the inputs), action_out [n] i64, logprob_out / entropy_out /
  * value_out [n] f32, logits_out [n, A] f32 or NULL.  fp16 operands, fp32 accumulation and epilogues: results
  * agree with the fp32 PyTorch module within 5e-3 (tests/test_policy_gpu.py). */
@@ -369,7 +372,8 @@ int posg_policy_create(int hidden, int n_actions, const float* trunk1_w, const f
                        const float* critic0_b, const float* critic2_w, const float* critic2_b, posg_policy_t* out);
 int posg_policy_destroy(posg_policy_t p);
 int posg_policy_step(posg_policy_t p, int64_t n_rows, const float* x0, const float* h_in, const float* c_in,
-                     const float* done, uint64_t seed, uint32_t step, uint64_t row_offset, const int64_t* action_in,
+                     const float* done, const uint8_t* terminated, const uint8_t* truncated, uint64_t seed,
+                     uint32_t step, const uint32_t* step_device, uint64_t row_offset, const int64_t* action_in,
                      float* h_out, float* c_out, int64_t* action_out, float* logprob_out, float* entropy_out,
                      float* value_out, float* logits_out, void* stream);
 

@@ -4,7 +4,8 @@
 // actor / critic heads Linear(64, 64) + Tanh + Linear(64, A | 1), Categorical sample, log-prob, entropy --
 // as ONE kernel on the 5th-generation tensor cores:
 //
-//   * a CTA owns 128 rows (= the 128 TMEM lanes); its 128 threads own one row each in the epilogues;
+//   * a CTA owns 128 rows (= the 128 TMEM lanes); two of its 256 threads share a row in the epilogues (half the
+//     columns each);
 //   * all weights (fp16, 94 KB) are staged once per CTA by one TMA bulk copy and stay in shared memory
 //     in the UMMA K-major no-swizzle "core matrix" layout; activations are written back to shared
 //     memory in that layout by the epilogues, so no activation ever leaves the SM between the layers;
@@ -29,7 +30,8 @@
 namespace posg {
 namespace policy {
 
-constexpr int TILE = 128;   // rows per CTA = TMEM lanes = threads per CTA
+constexpr int TILE = 128;   // rows per CTA = TMEM lanes
+constexpr int THREADS = 256; // two threads per row: warp w and warp w + 4 read the same 32 TMEM lanes and split the columns
 constexpr int H = 64;       // trunk / LSTM / head width (baseline_exps/exp_utils.py:101-104)
 constexpr int NF = 16;      // final layer: logits in columns 0..A-1 (A <= 8), value in column VCOL
 constexpr int VCOL = 8;
@@ -107,7 +109,13 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
                     *reinterpret_cast<uint32_t*>(&d));
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// one MUFU.TANH each (max relative error 2^-11, the precision of the fp16 operands)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 0.5f * tanh_fast(0.5f * x) + 0.5f; }
 
 // generic-proxy writes to shared memory -> visible to the tensor core (async proxy), then CTA barrier
 __device__ __forceinline__ void publish_smem() {
@@ -117,10 +125,11 @@ __device__ __forceinline__ void publish_smem() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(TILE, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float* __restrict__ x0,
                    const float* h_in, const float* c_in, const float* __restrict__ done,
-                   int n_actions, uint64_t seed, uint32_t step, uint64_t row_offset,
+                   const uint8_t* __restrict__ term, const uint8_t* __restrict__ trunc, int n_actions, uint64_t seed,
+                   uint32_t step, const uint32_t* __restrict__ step_device, uint64_t row_offset,
                    const long long* __restrict__ action_in, float* h_out, float* c_out,
                    long long* __restrict__ action_out, float* __restrict__ logprob_out, float* __restrict__ entropy_out,
                    float* __restrict__ value_out, float* __restrict__ logits_out) {
@@ -129,6 +138,8 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_keep[TILE];   // 1 - done per row
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int r_ = ((warp & 3) << 5) | (tid & 31);   // this thread's row of the tile (= TMEM lane)
+  const int half = warp >> 2;                       // which half of the columns it owns
   const Weights& W = *reinterpret_cast<const Weights*>(smem);
   const uint32_t sbase = smem_u32(smem), bar = smem_u32(&mma_bar);
 
@@ -146,19 +157,25 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes
   uint32_t parity = 0;
 
   const long long n_tiles = (n_rows + TILE - 1) / TILE;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long row0 = tile * TILE, row = row0 + tid;
+    const long long row0 = tile * TILE, row = row0 + r_;
     const bool live = row < n_rows;
-    s_keep[tid] = live ? 1.0f - done[row] : 0.0f;
+    if (half == 0)
+      s_keep[r_] = !live ? 0.0f : (done != nullptr ? 1.0f - done[row] : ((term[row] | trunc[row]) ? 0.0f : 1.0f));
+    // this thread's 32 cell-state values: requested now, needed after the second MMA group
+    float4 cprev[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      cprev[q] = live ? *reinterpret_cast<const float4*>(c_in + row * H + half * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     // ---- x0 -> A0, (1 - done) * h -> AL[:, 64:128): coalesced float4 loads, fp16 core-matrix stores
 #pragma unroll 4
-    for (int it = 0; it < (TILE * H) / (4 * TILE); ++it) {
-      const int e = 4 * (it * TILE + tid), r = e / H, k = e % H;
+    for (int it = 0; it < (TILE * H) / (4 * THREADS); ++it) {
+      const int e = 4 * (it * THREADS + tid), r = e / H, k = e % H;
       float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), hv = xv;
       if (row0 + r < n_rows) {
         xv = __ldg(reinterpret_cast<const float4*>(x0 + (row0 + r) * H + k));
@@ -179,13 +196,14 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int jc = 0; jc < H / 16; ++jc) {
+    for (int jj = 0; jj < H / 32; ++jj) {
+      const int jc = half * (H / 32) + jj;
       float v[16];
       tmem_ld16(trow + TM_D1 + jc * 16, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j] + W.b1[jc * 16 + j]);
-      *reinterpret_cast<uint4*>(smem + SM_AL + core_off(tid, jc * 16, 2 * H)) = pack8(v);
-      *reinterpret_cast<uint4*>(smem + SM_AL + core_off(tid, jc * 16 + 8, 2 * H)) = pack8(v + 8);
+      for (int j = 0; j < 16; ++j) v[j] = tanh_fast(v[j] + W.b1[jc * 16 + j]);
+      *reinterpret_cast<uint4*>(smem + SM_AL + core_off(r_, jc * 16, 2 * H)) = pack8(v);
+      *reinterpret_cast<uint4*>(smem + SM_AL + core_off(r_, jc * 16 + 8, 2 * H)) = pack8(v + 8);
     }
     publish_smem();
 
@@ -194,9 +212,10 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
-      const float keep = s_keep[tid];
-#pragma unroll 1
-      for (int jc = 0; jc < H / 16; ++jc) {
+      const float keep = s_keep[r_];
+#pragma unroll
+      for (int jj = 0; jj < H / 32; ++jj) {
+        const int jc = half * (H / 32) + jj;
         float gi[16], gf[16], gg[16], go[16], hn[16], cn[16];
         tmem_ld16(trow + TM_G + 0 * H + jc * 16, gi);
         tmem_ld16(trow + TM_G + 1 * H + jc * 16, gf);
@@ -204,24 +223,23 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
         tmem_ld16(trow + TM_G + 3 * H + jc * 16, go);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live) cv = *reinterpret_cast<const float4*>(c_in + row * H + jc * 16 + 4 * q);
+          const float4 cv = cprev[jj * 4 + q];
           const float cp[4] = {cv.x * keep, cv.y * keep, cv.z * keep, cv.w * keep};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int j = 4 * q + u, col = jc * 16 + j;
             const float i_ = sigmoidf_(gi[j] + W.bl[col]), f_ = sigmoidf_(gf[j] + W.bl[H + col]);
-            const float g_ = tanhf(gg[j] + W.bl[2 * H + col]), o_ = sigmoidf_(go[j] + W.bl[3 * H + col]);
+            const float g_ = tanh_fast(gg[j] + W.bl[2 * H + col]), o_ = sigmoidf_(go[j] + W.bl[3 * H + col]);
             cn[j] = f_ * cp[u] + i_ * g_;
-            hn[j] = o_ * tanhf(cn[j]);
+            hn[j] = o_ * tanh_fast(cn[j]);
           }
           if (live) {
             *reinterpret_cast<float4*>(c_out + row * H + jc * 16 + 4 * q) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
             *reinterpret_cast<float4*>(h_out + row * H + jc * 16 + 4 * q) = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
           }
         }
-        *reinterpret_cast<uint4*>(smem + SM_AH + core_off(tid, jc * 16, H)) = pack8(hn);
-        *reinterpret_cast<uint4*>(smem + SM_AH + core_off(tid, jc * 16 + 8, H)) = pack8(hn + 8);
+        *reinterpret_cast<uint4*>(smem + SM_AH + core_off(r_, jc * 16, H)) = pack8(hn);
+        *reinterpret_cast<uint4*>(smem + SM_AH + core_off(r_, jc * 16 + 8, H)) = pack8(hn + 8);
       }
     }
     publish_smem();
@@ -231,13 +249,14 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int jc = 0; jc < 2 * H / 16; ++jc) {
+    for (int jj = 0; jj < 2 * H / 32; ++jj) {
+      const int jc = half * (2 * H / 32) + jj;
       float v[16];
       tmem_ld16(trow + TM_HD + jc * 16, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j] + W.bh[jc * 16 + j]);
-      *reinterpret_cast<uint4*>(smem + SM_AF + core_off(tid, jc * 16, 2 * H)) = pack8(v);
-      *reinterpret_cast<uint4*>(smem + SM_AF + core_off(tid, jc * 16 + 8, 2 * H)) = pack8(v + 8);
+      for (int j = 0; j < 16; ++j) v[j] = tanh_fast(v[j] + W.bh[jc * 16 + j]);
+      *reinterpret_cast<uint4*>(smem + SM_AF + core_off(r_, jc * 16, 2 * H)) = pack8(v);
+      *reinterpret_cast<uint4*>(smem + SM_AF + core_off(r_, jc * 16 + 8, 2 * H)) = pack8(v + 8);
     }
     publish_smem();
 
@@ -245,7 +264,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     if (tid == 0) gemm(tmem + TM_F, sbase + SM_AF, sbase + (uint32_t)offsetof(Weights, wf), 2 * H, NF, bar);
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
+    if (half == 0) {
       float v[16];
       tmem_ld16(trow + TM_F, v);
       float mx = -3.0e38f;
@@ -267,7 +286,8 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
           act = action_in[row];
         } else {
           // inverse CDF on one Philox word per (row, step)
-          const uint4 w = philox_block(seed, row_offset + (uint64_t)row, step, STREAM_POLICY);
+          const uint4 w = philox_block(seed, row_offset + (uint64_t)row, step_device != nullptr ? __ldg(step_device) : step,
+                                       STREAM_POLICY);
           const float u = (float)(w.x >> 8) * (1.0f / 16777216.0f) * z;
           float acc = 0.f;
           int pick = n_actions - 1;
@@ -361,19 +381,21 @@ int posg_policy_destroy(posg_policy_t p) {
 }
 
 int posg_policy_step(posg_policy_t p, int64_t n_rows, const float* x0, const float* h_in, const float* c_in,
-                     const float* done, uint64_t seed, uint32_t step, uint64_t row_offset, const int64_t* action_in,
+                     const float* done, const uint8_t* terminated, const uint8_t* truncated, uint64_t seed,
+                     uint32_t step, const uint32_t* step_device, uint64_t row_offset, const int64_t* action_in,
                      float* h_out, float* c_out, int64_t* action_out, float* logprob_out, float* entropy_out,
                      float* value_out, float* logits_out, void* stream) {
   POSG_REQUIRE(p, "null policy");
   if (n_rows == 0) return POSG_OK;
-  POSG_REQUIRE(n_rows > 0 && x0 && h_in && c_in && done && h_out && c_out && action_out && logprob_out && entropy_out &&
-               value_out, "bad arguments");
+  POSG_REQUIRE(n_rows > 0 && x0 && h_in && c_in && (done || (terminated && truncated)) && h_out && c_out && action_out &&
+               logprob_out && entropy_out && value_out, "bad arguments");
   POSG_REQUIRE((((uintptr_t)x0 | (uintptr_t)h_in | (uintptr_t)c_in | (uintptr_t)h_out | (uintptr_t)c_out) & 15u) == 0,
                "activation buffers must be 16-byte aligned");
   const long long tiles = (n_rows + policy::TILE - 1) / policy::TILE;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  policy::policy_step_kernel<<<grid, policy::TILE, policy::SM_TOTAL, (cudaStream_t)stream>>>(
-      p->d_w, (long long)n_rows, x0, h_in, c_in, done, p->n_actions, seed, step, row_offset,
+  policy::policy_step_kernel<<<grid, policy::THREADS, policy::SM_TOTAL, (cudaStream_t)stream>>>(
+      p->d_w, (long long)n_rows, x0, h_in, c_in, done, terminated, truncated, p->n_actions, seed, step, step_device,
+      row_offset,
       (const long long*)action_in, h_out, c_out, (long long*)action_out, logprob_out, entropy_out, value_out, logits_out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;

@@ -190,7 +190,9 @@ constexpr int EMB_THREADS = 256, EMB_EPC = 128, EMB_MAX_H = 128;
 
 // LPR = lanes per row (each lane owns four consecutive hidden units: one 16-byte weight load per
 // field); H = 4 * LPR in {32, 64, 128}.  LPR == 0: any H <= 128, one warp per row, scalar loads.
-template <class M, int LPR>
+// EPC = envs per CTA (128 for large batches; 32 at the few-thousand-env batches of the reference-scale collector,
+// where 128 would leave most SMs without a CTA)
+template <class M, int LPR, int EPC>
 __global__ void __launch_bounds__(EMB_THREADS)
 vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
                  const uint32_t* __restrict__ state, const uint16_t* __restrict__ field_offset,
@@ -201,15 +203,15 @@ vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
   constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NF = M::NFIELD;
   // per row: the weight-row index offset_f + value_f of every field.  Row stride 17 words: the env
   // threads of phase 1 store to consecutive rows, which then fall into consecutive banks
-  __shared__ uint16_t s_idx[EMB_EPC * NAG][MAX_FIELDS + 2];
+  __shared__ uint16_t s_idx[EPC * NAG][MAX_FIELDS + 2];
   __shared__ uint16_t s_off[MAX_FIELDS];
   if (threadIdx.x < MAX_FIELDS) s_off[threadIdx.x] = threadIdx.x < NF ? field_offset[threadIdx.x] : 0;
   stage_blob(smem_raw, gblob, blob_size, &mbar);
   const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int64_t base = (int64_t)blockIdx.x * EMB_EPC; base < n; base += (int64_t)gridDim.x * EMB_EPC) {
+  for (int64_t base = (int64_t)blockIdx.x * EPC; base < n; base += (int64_t)gridDim.x * EPC) {
     const int64_t i = base + tid;
-    if (tid < EMB_EPC && i < n) {
+    if (tid < EPC && i < n) {
       typename M::State s;
 #pragma unroll
       for (int k = 0; k < SW; ++k) s.w[k] = __ldg(state + i * SW + k);
@@ -230,7 +232,7 @@ vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
     }
     __syncthreads();
     const int64_t left = n - base;
-    const int rows = (int)(left < EMB_EPC ? left : EMB_EPC) * NAG;
+    const int rows = (int)(left < EPC ? left : EPC) * NAG;
     if constexpr (LPR > 0) {
       constexpr int RPW = 32 / LPR;                 // rows per warp iteration
       const int sub = lane / LPR, col = (lane % LPR) * 4;

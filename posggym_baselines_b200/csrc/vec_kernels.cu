@@ -71,10 +71,18 @@ static int ensure_desc(posg_model* m) {
 template <class M, int LPR>
 static int launch_embed_lpr(posg_model* m, int64_t n, const uint32_t* state, const float* wT, const float* bias, int H,
                             int apply_tanh, float* out, cudaStream_t s) {
-  smem_optin(vec::vec_embed_kernel<M, LPR>, m->blob_bytes);
-  const int64_t need = (n + vec::EMB_EPC - 1) / vec::EMB_EPC;
   const uint16_t* off = (const uint16_t*)((const char*)m->d_flat_desc + (size_t)(m->flat_dim / 4) * sizeof(vec::Quad));
-  vec::vec_embed_kernel<M, LPR><<<(int)(need < (1 << 30) ? need : (1 << 30)), vec::EMB_THREADS, m->blob_bytes, s>>>(
+  if (n < (int64_t)sm_count() * 2 * vec::EMB_EPC) {   // small batch: more, smaller CTAs
+    constexpr int EPC = 32;
+    smem_optin(vec::vec_embed_kernel<M, LPR, EPC>, m->blob_bytes);
+    vec::vec_embed_kernel<M, LPR, EPC><<<(int)((n + EPC - 1) / EPC), vec::EMB_THREADS, m->blob_bytes, s>>>(
+        (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, off, wT, bias, H, apply_tanh, out);
+    POSG_CUDA(cudaGetLastError());
+    return POSG_OK;
+  }
+  smem_optin(vec::vec_embed_kernel<M, LPR, vec::EMB_EPC>, m->blob_bytes);
+  const int64_t need = (n + vec::EMB_EPC - 1) / vec::EMB_EPC;
+  vec::vec_embed_kernel<M, LPR, vec::EMB_EPC><<<(int)(need < (1 << 30) ? need : (1 << 30)), vec::EMB_THREADS, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, off, wT, bias, H, apply_tanh, out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;

@@ -47,11 +47,14 @@ class FusedPolicy:
                 pass
             self._handle = None
 
-    def step(self, x0: torch.Tensor, lstm_state: Tuple[torch.Tensor, torch.Tensor], done: torch.Tensor,
+    def step(self, x0: torch.Tensor, lstm_state: Tuple[torch.Tensor, torch.Tensor], done: Optional[torch.Tensor],
              action: Optional[torch.Tensor] = None, seed: int = 0, step_idx: int = 0, row_offset: int = 0,
-             want_logits: bool = False, out: Optional[dict] = None):
+             want_logits: bool = False, out: Optional[dict] = None, terminated: Optional[torch.Tensor] = None,
+             truncated: Optional[torch.Tensor] = None, step_device: Optional[torch.Tensor] = None):
         """``x0``: [n, 64] = tanh(trunk.0(obs)); ``lstm_state``: (h, c), each [n, 64] (updated IN PLACE);
-        ``done``: [n] float.  Returns dict(action, logprob, entropy, value[, logits])."""
+        ``done``: [n] float, or None with ``terminated`` / ``truncated`` [n] uint8 (the vec env's buffers);
+        ``step_device``: int32 device tensor whose first word is the Philox step index (captured graphs).
+        Returns dict(action, logprob, entropy, value[, logits])."""
         n = x0.shape[0]
         h, c = lstm_state
         if out is None:
@@ -63,7 +66,8 @@ class FusedPolicy:
                 out["logits"] = torch.empty((n, self.num_actions), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().posg_policy_step(
-                self._handle, n, _lib.ptr(x0), _lib.ptr(h), _lib.ptr(c), _lib.ptr(done), seed, step_idx, row_offset,
+                self._handle, n, _lib.ptr(x0), _lib.ptr(h), _lib.ptr(c), _lib.ptr(done), _lib.ptr(terminated),
+                _lib.ptr(truncated), seed, step_idx, _lib.ptr(step_device), row_offset,
                 _lib.ptr(action), _lib.ptr(h), _lib.ptr(c), _lib.ptr(out["action"]), _lib.ptr(out["logprob"]),
                 _lib.ptr(out["entropy"]), _lib.ptr(out["value"]), _lib.ptr(out.get("logits")), _lib.stream_ptr()))
         return out
