@@ -601,6 +601,7 @@ def main():
     ap.add_argument("--particles", type=int, default=1 << 24, help="particles per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="multi-GPU: do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only-sweep", action="store_true", help="skip the rollout / vec-env / POMCP side sections")
     args = ap.parse_args()
@@ -620,6 +621,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # multi-GPU: every rank on the cores / memory of its GPU's NUMA node before any pinned buffer exists (at N = 1
+    # the process stays unbound: the CPU baseline wants every core)
+    host_binding = None
+    if world > 1 and not args.no_bind:
+        from posggym_baselines_b200.hostbind import bind_to_gpu_node
+
+        host_binding = bind_to_gpu_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -753,8 +761,32 @@ def main():
             dist.all_reduce(lv_t, op=dist.ReduceOp.SUM)
         e2e = {"value": int(lv_t.item()) / w.item(), "unit": UNIT,
                "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * (8 + 16 + 16 + 1) + 8,
-               "ms_per_step": 1e3 * w.item() / e_steps, "steps": e_steps,
+               "ms_per_step": 1e3 * w.item() / e_steps, "steps": e_steps, "host_binding": host_binding,
                "api": "posg_driving_sweep_host (pinned host state in; last step's state/obs/rewards/flags out)"}
+        # compact result mode: rewards as one code byte per env (decoded exactly on the host from the reward table
+        # and the returned state: posg_driving_decode_rewards_host): 26 instead of 41 B/env device -> host
+        try:
+            c_outs = (outs[0], outs[1], torch.empty((n,), dtype=torch.uint8).pin_memory().numpy(), outs[3])
+            for _ in range(2):
+                env.sweep_host_compact(h_np, DEPTH, seed=seed, particle_offset=offset, outs=c_outs)
+            barrier()
+            w0 = time.perf_counter()
+            c_live = 0
+            for _ in range(e_steps):
+                _, lv = env.sweep_host_compact(h_np, DEPTH, seed=seed, particle_offset=offset, outs=c_outs)
+                c_live += lv
+            torch.cuda.synchronize()
+            wc = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+            lc_t = torch.tensor([c_live], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.barrier()
+                dist.all_reduce(wc, op=dist.ReduceOp.MAX)
+                dist.all_reduce(lc_t, op=dist.ReduceOp.SUM)
+            e2e["compact_results"] = {"value": int(lc_t.item()) / wc.item(), "unit": UNIT, "h2d_bytes_per_step": n * 8,
+                                      "d2h_bytes_per_step": n * (8 + 16 + 1 + 1) + 8, "ms_per_step": 1e3 * wc.item() / e_steps,
+                                      "api": "posg_driving_sweep_host_compact (rewards as reward-table codes)"}
+        except Exception as ex:
+            e2e["compact_results"] = {"error": repr(ex)}
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores ----
     cpu = None

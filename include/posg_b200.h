@@ -132,6 +132,19 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
                             unsigned long long* live_count_host);
 
 
+/* The same sweep with the rewards delivered as ONE byte per env instead of two float64 (every step of the sweep
+ * writes the code, the last step's is copied back): per vehicle, progress made in the step (2 bits) | reward kind
+ * (2 bits: plain, destination reached, crashed, already done), vehicle 1 in the high nibble.  Together with
+ * init_dest_dist in the returned state word that is the index of the model's reward table;
+ * posg_driving_decode_rewards_host expands it on the host to exactly the doubles posg_driving_sweep_host returns
+ * (26 instead of 41 bytes per env cross PCIe).  n must be a multiple of 128 and particle_offset a multiple of 4. */
+int posg_driving_sweep_host_compact(posg_model_t m, int64_t n, const uint32_t* state_in_host, int num_steps,
+                                    uint64_t seed, uint64_t particle_offset, uint32_t* state_out_host,
+                                    uint64_t* obs_out_host, uint8_t* reward_code_out_host, uint8_t* flags_out_host,
+                                    unsigned long long* live_count_host);
+int posg_driving_decode_rewards_host(posg_model_t m, int64_t n, const uint32_t* state_host,
+                                     const uint8_t* reward_code_host, double* rewards_out_host);
+
 /* ------------------------------------------------------------------ PredatorPrey-v0 and
  * the model-generic batch entry points (every model kind except Driving-v1, which has
  * the hand-tuned posg_driving_* kernels above).

@@ -45,6 +45,8 @@ SIGNATURES = {
         [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp],
     ),
     "posg_driving_sweep_host": (_int, [_vp, _i64, _vp, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "posg_driving_sweep_host_compact": (_int, [_vp, _i64, _vp, _int, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
+    "posg_driving_decode_rewards_host": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "posg_pp_create": (_int, [_int, C.c_char_p, _int, _int, _int, _int, _int, C.POINTER(_vp)]),
     "posg_lbf_create": (_int, [_int, _int, _int, _int, _int, _int, _int, _vp, _vp, C.POINTER(_vp)]),
     "posg_model_sample_initial_state": (_int, [_vp, _i64, _vp, _u64, _u64, _vp, _vp]),

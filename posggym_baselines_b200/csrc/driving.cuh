@@ -142,6 +142,13 @@ __device__ __forceinline__ double reward_raw(const Blob& B, uint32_t before, uin
   return B.reward_tab[((after_raw >> 24) << 2) | kind];
 }
 
+// the part of reward_raw's table index that is not in the stored state word: progress | kind << 2
+__device__ __forceinline__ uint32_t reward_code(uint32_t before, uint32_t after_raw) {
+  const uint32_t fl = min((after_raw >> 15) & 3u, 2u);
+  const uint32_t kind = (before & 0x18000u) ? 3u : fl;
+  return (after_raw >> 30) | (kind << 2);
+}
+
 // ---- observation --------------------------------------------------------------------
 // `cidx` = window cell (0..14) the other vehicle occupies, 15 = outside the window
 __device__ __forceinline__ uint64_t observe_with(const Blob& B, uint32_t me, int cidx) {

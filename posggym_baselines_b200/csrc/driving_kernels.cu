@@ -174,13 +174,18 @@ constexpr int WARP_ENVS = 128;
 #define STEP_FAST_MIN_CTAS 3
 #endif
 
-template <bool WRITE_ACTIONS, bool COUNT_LIVE>
+// REWARD_CODE: instead of the two float64 rewards (16 B) the kernel writes ONE byte per env to
+// `reward_code_out` -- per vehicle the progress made (2 bits) and the reward kind (2 bits), vehicle 1 in the
+// high nibble: the index of reward_tab is that code plus init_dest_dist, which the state word carries, so the
+// host decodes the exact double (posg_driving_decode_rewards_host).  The compact result of the host-buffer
+// sweep: 26 instead of 41 bytes per env cross PCIe.
+template <bool WRITE_ACTIONS, bool COUNT_LIVE, bool REWARD_CODE = false>
 __global__ void __launch_bounds__(THREADS, STEP_FAST_MIN_CTAS)
 step_fast_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nblocks,
                  const uint2* __restrict__ state_in, uint64_t seed, uint32_t step_idx, uint64_t group_offset,
                  uint2* __restrict__ state_out, ulonglong2* __restrict__ obs_out, double2* __restrict__ rewards_out,
                  uint8_t* __restrict__ flags_out, uchar2* __restrict__ actions_out,
-                 unsigned long long* __restrict__ live_count) {
+                 unsigned long long* __restrict__ live_count, uint8_t* __restrict__ reward_code_out = nullptr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ alignas(8) uint64_t mbar;
   __shared__ alignas(16) uint32_t s_words[THREADS / 32][WARP_ENVS];
@@ -240,7 +245,10 @@ step_fast_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nb
       if (COUNT_LIVE) live += ((b0 & 0x18000u) && (b1 & 0x18000u)) ? 0u : 1u;
       transition16(B, v0, v1, (nz << 4) & 0x70u, (nz << 1) & 0x70u, (nz & 0x40u) != 0u);
       const uint32_t e = e0 + 32 * j;
-      rewards_out[e] = make_double2(reward_raw(B, b0, v0), reward_raw(B, b1, v1));
+      if constexpr (REWARD_CODE)
+        reward_code_out[e] = (uint8_t)(reward_code(b0, v0) | (reward_code(b1, v1) << 4));
+      else
+        rewards_out[e] = make_double2(reward_raw(B, b0, v0), reward_raw(B, b1, v1));
       v0 &= STATE_MASK; v1 &= STATE_MASK;
       state_out[e] = make_uint2(v0, v1);
       const uint32_t t0 = (v0 & 0x18000u) ? 1u : 0u, t1 = (v1 & 0x18000u) ? 1u : 0u;
@@ -576,6 +584,19 @@ static int grid_for(K kernel, size_t smem, int64_t work_items) {
 using namespace posg;
 using namespace posg::driving;
 
+// posg_driving_step restricted to whole fast-kernel blocks with the reward CODE as output (compact sweep)
+static int step_fast_coded(posg_model_t m, int64_t n, const uint32_t* state_in, uint64_t seed, uint32_t step_idx,
+                           uint64_t particle_offset, uint32_t* state_out, uint64_t* obs_out, uint8_t* code_out,
+                           uint8_t* flags_out, uint8_t* actions_out, unsigned long long* live_count, cudaStream_t s) {
+  const uint32_t nb = (uint32_t)(n / WARP_ENVS);
+  step_fast_kernel<true, true, true><<<grid_for(step_fast_kernel<true, true, true>, m->blob_bytes, (int64_t)nb * 32), THREADS,
+                                        m->blob_bytes, s>>>(
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, seed, step_idx, particle_offset >> 2,
+      (uint2*)state_out, (ulonglong2*)obs_out, nullptr, flags_out, (uchar2*)actions_out, live_count, code_out);
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
 // staging context of posg_driving_sweep_host (see posg_model::host_stage)
 struct HostStage {
   static constexpr int NSLOT = 3;
@@ -767,13 +788,18 @@ int posg_driving_rollout_host(posg_model_t m, int64_t n, const uint32_t* state_i
 // Pipelined over CHUNKS slices of the batch on two streams so that, after the first
 // slice, the H2D copy of slice k+1, the 50 step launches of slice k and the D2H copy of
 // slice k-1 overlap (PCIe is full duplex; the copy engines run beside the SMs).
-int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_host, int num_steps,
-                            uint64_t seed, uint64_t particle_offset, uint32_t* state_out_host,
-                            uint64_t* obs_out_host, double* rewards_out_host, uint8_t* flags_out_host,
-                            unsigned long long* live_count_host) {
+}  // extern "C"
+
+static int sweep_host_impl(posg_model_t m, int64_t n, const uint32_t* state_in_host, int num_steps,
+                           uint64_t seed, uint64_t particle_offset, uint32_t* state_out_host,
+                           uint64_t* obs_out_host, double* rewards_out_host, uint8_t* code_out_host,
+                           uint8_t* flags_out_host, unsigned long long* live_count_host) {
   int rc = check_driving(m); if (rc) return rc;
   if (n == 0) return POSG_OK;
   POSG_REQUIRE(n > 0 && state_in_host && num_steps >= 1, "bad arguments");
+  const bool coded = code_out_host != nullptr;
+  POSG_REQUIRE(!coded || ((n % WARP_ENVS) == 0 && (particle_offset & 3ULL) == 0),
+               "the compact sweep needs a multiple of 128 envs and a particle offset that is a multiple of 4");
   // Slices are multiples of 128 envs (whole fast-kernel blocks; also keeps the Philox word
   // grouping of the monolithic call).  Three slots: while one slice computes, the previous one
   // drains to the host and the next one is uploaded (PCIe is full duplex).
@@ -807,9 +833,12 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
     uint8_t* d_act = base + (((size_t)chunk * 41 + 255) & ~(size_t)255);
     SWEEP_CUDA(cudaMemcpyAsync(d_state, state_in_host + 2 * off, (size_t)c * 8, cudaMemcpyHostToDevice, s));
     for (int k = 0; k < num_steps && rc == POSG_OK; ++k)
-      rc = posg_driving_step(m, c, d_state, nullptr, nullptr, seed, (uint32_t)k, particle_offset + (uint64_t)off,
-                             d_state, d_obs, d_rew, d_flags, d_act, hs->d_live, s);
+      rc = coded ? step_fast_coded(m, c, d_state, seed, (uint32_t)k, particle_offset + (uint64_t)off, d_state, d_obs,
+                                   (uint8_t*)d_rew, d_flags, d_act, hs->d_live, s)
+                 : posg_driving_step(m, c, d_state, nullptr, nullptr, seed, (uint32_t)k, particle_offset + (uint64_t)off,
+                                     d_state, d_obs, d_rew, d_flags, d_act, hs->d_live, s);
     if (rc != POSG_OK) break;
+    if (coded) SWEEP_CUDA(cudaMemcpyAsync(code_out_host + off, d_rew, (size_t)c, cudaMemcpyDeviceToHost, s));
     if (state_out_host) SWEEP_CUDA(cudaMemcpyAsync(state_out_host + 2 * off, d_state, (size_t)c * 8, cudaMemcpyDeviceToHost, s));
     if (obs_out_host) SWEEP_CUDA(cudaMemcpyAsync(obs_out_host + 2 * off, d_obs, (size_t)c * 16, cudaMemcpyDeviceToHost, s));
     if (rewards_out_host) SWEEP_CUDA(cudaMemcpyAsync(rewards_out_host + 2 * off, d_rew, (size_t)c * 16, cudaMemcpyDeviceToHost, s));
@@ -822,6 +851,41 @@ int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_
   if (rc == POSG_OK && live_count_host) SWEEP_CUDA(cudaMemcpy(live_count_host, hs->d_live, 8, cudaMemcpyDeviceToHost));
 #undef SWEEP_CUDA
   return rc;
+}
+
+extern "C" {
+
+int posg_driving_sweep_host(posg_model_t m, int64_t n, const uint32_t* state_in_host, int num_steps,
+                            uint64_t seed, uint64_t particle_offset, uint32_t* state_out_host,
+                            uint64_t* obs_out_host, double* rewards_out_host, uint8_t* flags_out_host,
+                            unsigned long long* live_count_host) {
+  return sweep_host_impl(m, n, state_in_host, num_steps, seed, particle_offset, state_out_host, obs_out_host,
+                         rewards_out_host, nullptr, flags_out_host, live_count_host);
+}
+
+int posg_driving_sweep_host_compact(posg_model_t m, int64_t n, const uint32_t* state_in_host, int num_steps,
+                                    uint64_t seed, uint64_t particle_offset, uint32_t* state_out_host,
+                                    uint64_t* obs_out_host, uint8_t* reward_code_out_host, uint8_t* flags_out_host,
+                                    unsigned long long* live_count_host) {
+  POSG_REQUIRE(reward_code_out_host, "null reward code buffer");
+  return sweep_host_impl(m, n, state_in_host, num_steps, seed, particle_offset, state_out_host, obs_out_host, nullptr,
+                         reward_code_out_host, flags_out_host, live_count_host);
+}
+
+int posg_driving_decode_rewards_host(posg_model_t m, int64_t n, const uint32_t* state_host,
+                                     const uint8_t* reward_code_host, double* rewards_out_host) {
+  int rc = check_driving(m); if (rc) return rc;
+  POSG_REQUIRE(n >= 0 && (n == 0 || (state_host && reward_code_host && rewards_out_host)), "bad arguments");
+  const Blob* B = (const Blob*)m->h_blob;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t code = reward_code_host[i];
+#pragma GCC unroll 2
+    for (int a = 0; a < 2; ++a) {
+      const uint32_t c4 = (code >> (4 * a)) & 15u, d0 = (state_host[2 * i + a] >> 24) & 63u;
+      rewards_out_host[2 * i + a] = B->reward_tab[((d0 | ((c4 & 3u) << 6)) << 2) | (c4 >> 2)];
+    }
+  }
+  return POSG_OK;
 }
 
 }  // extern "C"

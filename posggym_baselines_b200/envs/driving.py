@@ -224,6 +224,27 @@ class BatchedDriving:
                 _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]), _lib.ptr(live)))
         return outs, int(live[0])
 
+    def sweep_host_compact(self, state_host: np.ndarray, num_steps: int, seed: int = 0, particle_offset: int = 0,
+                           outs: Optional[tuple] = None):
+        """``sweep_host`` with the rewards as one code byte per env (``decode_rewards`` expands them to the same
+        float64 values): ``outs`` = (state [n, A] i32, obs [n, A] i64, reward code [n] u8, flags [n] u8)."""
+        n, a = state_host.shape[0], self.num_agents
+        if outs is None:
+            outs = (np.empty((n, a), np.int32), np.empty((n, a), np.int64), np.empty(n, np.uint8), np.empty(n, np.uint8))
+        live = np.zeros(1, np.uint64)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().posg_driving_sweep_host_compact(
+                self._handle, n, _lib.ptr(state_host), num_steps, seed, particle_offset,
+                _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]), _lib.ptr(live)))
+        return outs, int(live[0])
+
+    def decode_rewards(self, state_host: np.ndarray, code_host: np.ndarray, out: Optional[np.ndarray] = None):
+        n = state_host.shape[0]
+        out = out if out is not None else np.empty((n, self.num_agents), np.float64)
+        _lib.check(_lib.lib().posg_driving_decode_rewards_host(self._handle, n, _lib.ptr(state_host), _lib.ptr(code_host),
+                                                               _lib.ptr(out)))
+        return out
+
     # ---- codec: packed words <-> posggym-style tuples -----------------------------------
     def pack_state(self, states: Sequence[Sequence[VehicleState]]) -> np.ndarray:
         out = np.zeros((len(states), self.num_agents), np.uint32)

@@ -256,3 +256,18 @@ def test_million_rollouts_bit_exact_vs_c_oracle(env, oracle_env):
     got = np.array([[vs_fields(v) for v in row] for row in env.unpack_state(g_final)], np.int32)
     assert (got == final).all()
     assert int(live.item()) == executed
+
+
+def test_compact_host_sweep_decodes_to_the_same_rewards(env):
+    """posg_driving_sweep_host_compact: rewards cross PCIe as one code byte per env; decoded on the host with the
+    model's reward table and init_dest_dist of the returned state they are the float64 values of the full sweep,
+    bit for bit; state / observations / flags / executed count are identical."""
+    n, seed, depth, off = 128 * 5000, 91, 50, 8192
+    st = env.sample_initial_state(n, seed=seed, particle_offset=off).cpu().numpy()
+    for d in (1, 7, depth):
+        (f_state, f_obs, f_rew, f_flags), f_live = env.sweep_host(st, d, seed=seed, particle_offset=off)
+        (c_state, c_obs, c_code, c_flags), c_live = env.sweep_host_compact(st, d, seed=seed, particle_offset=off)
+        assert (c_state == f_state).all() and (c_obs == f_obs).all() and (c_flags == f_flags).all() and c_live == f_live
+        dec = env.decode_rewards(c_state, c_code)
+        assert (dec.view(np.uint64) == f_rew.view(np.uint64)).all()
+        assert (f_rew != 0).any()
