@@ -398,6 +398,21 @@ int posg_policy_step(posg_policy_t p, int64_t n_rows, const float* x0, const flo
 int posg_gae(int T, int64_t n_cols, const float* rewards, const float* dones, const float* values, double gamma,
              double gae_lambda, float* advantages, float* returns, void* stream);
 
+/* Sequence chunks of a rollout batch for BPTT (ppo/utils.py:240-292 get_seq_idxs): dones [T, B] f32
+ * (device; non-zero where the step starts a new episode).  A piece starts at step 0 and at every done step and is
+ * cut every max_seq_len steps; chunk i = (chunk_env[i], chunk_start[i], chunk_len[i]) (device, capacity entries
+ * each), env-major then by start.  result_host = {number of chunks, longest chunk}.  One launch. */
+int posg_seq_chunks(int T, int64_t B, const float* dones, int max_seq_len, int32_t* chunk_env, int32_t* chunk_start,
+                    int32_t* chunk_len, int64_t capacity, int64_t* result_host, void* stream);
+/* split_and_pad_batch (ppo/utils.py:295-344) for up to 16 batch entries in one launch: entry k is src[k]
+ * [T (+ 1 if overlapping[k]), B, row_bytes[k]] -> dst[k] [max_seq_len (+ 1), n_chunks, row_bytes[k]] (device
+ * pointers in HOST arrays); rows past a chunk's end get pad_bits[k] (an elem_bytes[k]-wide pattern) up to the
+ * longest chunk and zeros after it, as pad_sequence + F.pad leave them. */
+int posg_seq_gather(int n_entries, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                    const int32_t* overlapping, const int32_t* elem_bytes, const uint64_t* pad_bits,
+                    const int32_t* chunk_env, const int32_t* chunk_start, const int32_t* chunk_len, int64_t n_chunks,
+                    int64_t B, int max_seq_len, int longest, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ SIGNATURES = {
     "posg_policy_destroy": (_int, [_vp]),
     "posg_policy_step": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp]),
+    "posg_seq_chunks": (_int, [_int, _i64, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "posg_seq_gather": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
     "posg_gae": (_int, [_int, _i64, _vp, _vp, _vp, _dbl, _dbl, _vp, _vp, _vp]),
     "posg_model_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "posg_tree_arena_bytes": (_i64, [_vp, _i64, _i64]),

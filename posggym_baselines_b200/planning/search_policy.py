@@ -71,3 +71,97 @@ class RandomSearchPolicy(SearchPolicy):
 
     def get_value(self, state: PolicyState) -> float:
         raise NotImplementedError("RandomSearchPolicy does not support value estimates.")
+
+
+def _flat_index_layout(space):
+    """(offset, start) of every Discrete leaf of a (nested) Tuple space in gymnasium's ``flatten`` order, and the
+    flattened width -- the one-hot layout ``processors.FlattenProcessor`` produces for the reference's policies."""
+    leaves, width = [], 0
+
+    def walk(sp):
+        nonlocal width
+        if hasattr(sp, "spaces"):
+            for s in sp.spaces:
+                walk(s)
+        else:
+            leaves.append((width, int(getattr(sp, "start", 0))))
+            width += int(sp.n)
+
+    walk(space)
+    return leaves, width
+
+
+def _flat_values(obs):
+    if isinstance(obs, (tuple, list)):
+        for o in obs:
+            yield from _flat_values(o)
+    else:
+        yield int(obs)
+
+
+class PPOLSTMSearchPolicy(SearchPolicy):
+    """The reference's ``PPOLSTMSearchPolicy`` (planning/search_policy.py:235-288; built by
+    baseline_exps/run_combined_exps.py:48-91 from a BR checkpoint): a trained ``PPOLSTMModel`` as search policy
+    -- action prior for PUCB, value estimate for truncated search, LSTM state carried along the tree.
+
+    Here the network runs on the GPU: trunk layer 0 as a sum of the weight columns of the observation's one-hot
+    inputs, everything else in the tensor-core policy kernel (``posg_policy_step``, ppo/policy.py) -- also for
+    the one-row calls of the planner's host path (``get_next_state``), and for whole batches of tree nodes
+    through ``get_next_state_batch``.  ``state_dict`` uses the reference's parameter names
+    (``checkpoint["model"]``); the LSTM state stays on the device."""
+
+    def __init__(self, model, agent_id: str, policy_id: str, state_dict, device=None):
+        import torch
+
+        from posggym_baselines_b200.ppo.policy import FusedPolicy
+
+        super().__init__(model, agent_id, policy_id)
+        self.action_space = list(range(model.action_spaces[agent_id].n))
+        self._torch = torch
+        dev = device if device is not None else getattr(getattr(model, "batched", None), "device", None)
+        self.policy = FusedPolicy(state_dict, device=dev)
+        self.device = self.policy.device
+        self._leaves, width = _flat_index_layout(model.observation_spaces[agent_id])
+        if width != self.policy.w0_t.shape[0]:
+            raise ValueError(f"the policy expects {self.policy.w0_t.shape[0]} inputs, the observation space flattens to {width}")
+        self._zero_done = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    def get_initial_state(self) -> PolicyState:
+        t = self._torch
+        z = lambda: t.zeros((1, self.policy.hidden), dtype=t.float32, device=self.device)  # noqa: E731
+        return {"lstm_state": (z(), z()), "pi": None, "value": 0.0}
+
+    def _x0(self, obs_list):
+        t = self._torch
+        idx = t.tensor([[off + v - start for (off, start), v in zip(self._leaves, _flat_values(o))] for o in obs_list],
+                       dtype=t.int64, device=self.device)
+        return t.tanh(self.policy.w0_t[idx].sum(1) + self.policy.b0).contiguous()
+
+    def get_next_state_batch(self, obs_list, states):
+        """``get_next_state`` for many (observation, policy state) pairs in one launch of the policy kernel."""
+        t = self._torch
+        n = len(obs_list)
+        h = t.cat([s["lstm_state"][0] for s in states], 0).contiguous()
+        c = t.cat([s["lstm_state"][1] for s in states], 0).contiguous()
+        done = self._zero_done.expand(n).contiguous()
+        out = self.policy.step(self._x0(obs_list), (h, c), done, action=t.zeros(n, dtype=t.int64, device=self.device),
+                               want_logits=True)
+        probs = t.softmax(out["logits"], -1).cpu().numpy()
+        values = out["value"].cpu().numpy()
+        return [{"lstm_state": (h[k:k + 1], c[k:k + 1]),
+                 "pi": {a: float(probs[k, a]) for a in self.action_space}, "value": float(values[k])} for k in range(n)]
+
+    def get_next_state(self, action, obs, state: PolicyState) -> PolicyState:
+        return self.get_next_state_batch([obs], [state])[0]
+
+    def sample_action(self, state: PolicyState):
+        import random
+
+        pi = state["pi"]
+        return random.choices(list(pi.keys()), weights=list(pi.values()), k=1)[0]
+
+    def get_pi(self, state: PolicyState) -> Dict[Any, float]:
+        return state["pi"]
+
+    def get_value(self, state: PolicyState) -> float:
+        return state["value"]

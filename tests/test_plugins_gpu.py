@@ -294,3 +294,55 @@ def test_random_pair_subclasses_match_the_device_search_statistically():
     ref_mean, ref_std = np.array(scen["value_mean"]), np.array(scen["value_std"])
     se = np.sqrt(ref_std**2 / scen["reps"] + vals.std(0) ** 2 / len(vals))
     assert (np.abs(vals.mean(0) - ref_mean) < 4 * se + 0.03).all(), (vals.mean(0), ref_mean, se)
+
+
+def test_ppo_lstm_search_policy_combined_planner():
+    """SURVEY 8(f) N3, first slice -- the COMBINED planner of baseline_exps/run_combined_exps.py:48-91: MCTS with
+    a trained PPOLSTMModel as search policy (PUCB prior, value-function leaf evaluation, truncated=True).  The
+    network is evaluated on the GPU (tensor-core policy kernel); its prior / value / LSTM state agree with the
+    fp32 PyTorch module within 5e-3, and the planner runs an episode prefix through the host path."""
+    import torch
+
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.planning import MCTS, MCTSConfig, PPOLSTMSearchPolicy, RandomOtherAgentPolicy
+    from tests.test_policy_gpu import RefNet
+
+    torch.manual_seed(0)
+    model = DrivingModel()
+    dev = model.batched.device
+    net = RefNet(124, 5).to(dev)
+    sp = PPOLSTMSearchPolicy(model, "0", "BR_test_seed0", net.state_dict())
+    env = Env(model)
+    obs, _ = env.reset(seed=2)
+    # one-hot flattening of the observation tuple = the layout the reference's FlattenProcessor produces
+    leaves = [(0, 4)] * 15 + [(0, 4), (0, 14), (0, 14), (0, 14), (0, 14), (0, 2), (0, 2)]
+    flat, off = torch.zeros(124, device=dev), 0
+    vals = list(obs["0"][0]) + [obs["0"][1], *obs["0"][2], *obs["0"][3], obs["0"][4], obs["0"][5]]
+    for (_, n), v in zip(leaves, vals):
+        flat[off + v] = 1.0
+        off += n
+    assert off == 124
+    st = sp.get_next_state(None, obs["0"], sp.get_initial_state())
+    with torch.no_grad():
+        logits, _, _, val, (h1, c1) = net.get_action_and_value(flat.unsqueeze(0), (torch.zeros(1, 1, 64, device=dev),) * 2,
+                                                               torch.zeros(1, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
+    ref_pi = torch.softmax(logits[0], -1).cpu().numpy()
+    assert np.abs(np.array([st["pi"][a] for a in range(5)]) - ref_pi).max() < 5e-3
+    assert abs(st["value"] - val.item()) < 5e-3 and (st["lstm_state"][0] - h1[0]).abs().max().item() < 5e-3
+    cfg = MCTSConfig(discount=0.99, search_time_limit=0.1, c=1.25, truncated=True, action_selection="pucb",
+                     state_belief_only=False, seed=1)
+    planner = MCTS(model, "0", cfg, {"1": RandomOtherAgentPolicy(model, "1")}, sp)
+    assert planner._host is not None
+    planner.reset()
+    rng, sims = random.Random(0), []
+    for _ in range(3):
+        a = planner.step(obs["0"])
+        assert a in range(5)
+        sims.append(planner.step_statistics["num_sims"])
+        obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+        if done:
+            break
+    assert min(sims) >= 5, sims        # the reference's COMBINED planner does ~37 simulations per 0.1 s on Driving
+    print("COMBINED planner simulations per 0.1 s decision:", sims)
+    planner.close()
