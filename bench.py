@@ -138,6 +138,9 @@ def run_reference(args):
     emit(line)
 
 
+FOREST_TREES = 32
+
+
 def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
     """README configuration (README.md:52-88): POMCP on Driving-v1 vs a uniform-random other
     agent, discount 0.95, c 1.414, search_time_limit 0.1 s, UCB.  Simulations per decision on
@@ -155,23 +158,28 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
     model = DrivingModel(device=dev)
     env = Env(model)
     cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb", seed=rank)
-    planner = POMCP(model, "0", cfg, RandomSearchPolicy(model, "0"))
-    rng = random.Random(rank)
-    obs, _ = env.reset(seed=100 + rank)
-    planner.reset()
-    sims, times, upd, infos = [], [], [], []
-    for d in range(decisions + 1):
-        a = planner.step(obs["0"])
-        if d > 0 and planner.step_statistics["num_sims"] == planner.step_statistics["num_sims"]:  # skip warm-up / NaN
-            sims.append(planner.step_statistics["num_sims"])
-            times.append(planner.step_statistics["search_time"])
-            upd.append(planner.step_statistics["update_time"])
-            infos.append(dict(planner.search_info))
-        obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
-        if done:
-            obs, _ = env.reset()
-            planner.reset()
-    planner.close()
+    def episode(trees_per_gpu):
+        planner = POMCP(model, "0", cfg, RandomSearchPolicy(model, "0"), trees_per_gpu=trees_per_gpu)
+        rng = random.Random(rank)
+        obs, _ = env.reset(seed=100 + rank)
+        planner.reset()
+        sims, times, upd, infos = [], [], [], []
+        for d in range(decisions + 1):
+            a = planner.step(obs["0"])
+            if d > 0 and planner.step_statistics["num_sims"] == planner.step_statistics["num_sims"]:  # skip warm-up / NaN
+                sims.append(planner.step_statistics["num_sims"])
+                times.append(planner.step_statistics["search_time"])
+                upd.append(planner.step_statistics["update_time"])
+                infos.append(dict(planner.search_info))
+            obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+            if done:
+                obs, _ = env.reset()
+                planner.reset()
+        cap = planner._cap_nodes
+        planner.close()
+        return sims, times, upd, infos, cap
+
+    sims, times, upd, infos, cap_nodes = episode(1)
     tot = torch.tensor([sum(sims), len(sims)], dtype=torch.float64, device=dev)
     tmax = torch.tensor([sum(times) / max(1, len(times))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -189,7 +197,26 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
            "nodes_created_per_decision": sum(i["nodes_created"] for i in infos) / max(1, len(infos)),
            "arena_fill_max": max([i["arena_fill"] for i in infos] or [0.0]),
            "waves_per_decision": sum(i["waves"] for i in infos) / max(1, len(infos)),
-           "node_capacity": planner._cap_nodes}
+           "node_capacity": cap_nodes}
+    # Root parallelisation INSIDE the GPU (trees_per_gpu): FOREST_TREES independent trees, one CTA / SM each, searched
+    # by one launch per chunk and merged at the root -- the same merge as the cross-GPU allreduce.  Every tree is
+    # the validated single-tree search (tests/test_pomcp_gpu.py::test_forest_*), so a decision sees that many
+    # times the simulations of one tree; the update (re-root + belief per tree) is still sequential over the trees.
+    try:
+        fs, ft, fu, fi, fcap = episode(FOREST_TREES)
+        ftot = torch.tensor([sum(fs), len(fs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ftot)
+        out["root_parallel_per_gpu"] = {
+            "trees_per_gpu": FOREST_TREES,
+            "sims_per_decision_per_gpu": ftot[0].item() / max(1.0, ftot[1].item()),
+            "sims_per_decision_all_gpus": world * ftot[0].item() / max(1.0, ftot[1].item()),
+            "sims_per_tree_per_decision": sum(i["sims_per_tree"] for i in fi) / max(1, len(fi)),
+            "search_time_s": sum(ft) / max(1, len(ft)), "update_time_s": sum(fu) / max(1, len(fu)),
+            "overflow_share": sum(i["overflow_share"] for i in fi) / max(1, len(fi)),
+            "arena_fill_max": max([i["arena_fill"] for i in fi] or [0.0]), "node_capacity_per_tree": fcap}
+    except Exception as ex:
+        out["root_parallel_per_gpu"] = {"error": repr(ex)}
     # BASELINE.json configs[2]: root-parallel POMCP on PredatorPrey-v0 -- every rank grows its own
     # tree from the same root belief; root visit counts and value sums merged by ONE allreduce
     # per decision (NCCL); every rank then takes the same action.

@@ -246,6 +246,24 @@ int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log,
 int posg_search_waves(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
                       const uint32_t* particles, int64_t n_particles, int64_t wave_size, int n_waves, uint64_t sim_id0,
                       const posg_search_params* p, void* stream);
+/* Root parallelisation inside one GPU: n_trees independent searches in ONE launch, CTA k on the tree
+ * entries_dev[k] (a DEVICE array; all trees share cap_nodes / cap_log / root_t and the Philox key, tree k uses the
+ * counters sim_id0 + (k << 32) + ...).  Each tree runs posg_search_waves' loop -- the reference's MCTS.get_action
+ * loop body (mcts.py:285-290) on its own tree; the caller sums the roots' visits / total values afterwards, the
+ * same merge as root-parallel POMCP across GPUs. */
+typedef struct posg_forest_entry {
+  void* arena;               /* the tree's arena (posg_tree_arena_bytes(cap_nodes, cap_log)) */
+  const uint32_t* particles; /* its root belief: n_particles packed states */
+  int64_t n_particles;
+  int32_t root;              /* its root node */
+  int32_t pad_;
+} posg_forest_entry;
+int posg_search_forest(posg_model_t m, const posg_forest_entry* entries_dev, int n_trees, int64_t cap_nodes,
+                       int64_t cap_log, int root_t, int wave_size, int n_waves, uint64_t sim_id0,
+                       const posg_search_params* p, void* stream);
+/* posg_tree_node_stats of every tree's root in one launch and one copy: out_host[n_trees][3 * A + 10]. */
+int posg_forest_stats(posg_model_t m, const posg_forest_entry* entries_dev, int n_trees, int64_t cap_nodes,
+                      int64_t cap_log, double* out_host, void* stream);
 /* Copies to HOST: visits[A], completed[A], total_value[A] of the node's action children
  * (ActionNode.visits / total_value, node.py:138-140) then node visits, node count, log
  * count, max search depth, min value, max value, overflow count, sims done, node flags, obs nodes created

@@ -249,11 +249,15 @@ static void initial_state(uint64_t seed, uint64_t particle, PP* s) {
     s->caught[i] = 0;
   }
 }
+/* half a Philox block per (particle, step): particles g and g + 32 (bit 5 of g clear) share the block with counter
+ * ((g >> 6) << 5 | (g & 31)); see oracle/rollout.py:pp_step_noise */
 static void step_noise(uint64_t seed, uint64_t particle, uint32_t step, int* act, uint32_t* words) {
   uint32_t w[4];
-  philox_block(seed, particle, step, STREAM_STEP, w);
-  words[0] = w[0]; words[1] = w[1]; words[2] = w[2];
-  const uint32_t idx = below(w[3], 25u);
+  philox_block(seed, ((particle >> 6) << 5) | (particle & 31u), step, STREAM_STEP, w);
+  const int hi = (int)((particle >> 5) & 1u);
+  const uint32_t a = hi ? w[2] : w[0], b = hi ? w[3] : w[1];
+  words[0] = a; words[1] = a * 0x10001u; words[2] = b;
+  const uint32_t idx = below(b * 0x10001u, 25u);
   act[1] = (int)(idx / 5u);
   act[0] = (int)(idx - 5u * (uint32_t)act[1]);
 }

@@ -74,15 +74,23 @@ def rollout(model, state, ego: str, max_steps: int, discount: float, seed: int, 
 
 # ---- PredatorPrey-v0 conventions (PPSim in posggym_baselines_b200/csrc/pp.cuh) ----------
 def pp_step_noise(seed: int, particles, step: int):
-    """(actions [n, 2], prey words [n, 3]): one Philox block per (particle, step): words
-    x, y, z -> prey 0..2; w -> joint action, idx = floor(w * 25 / 2**32), a0 = idx % 5,
-    a1 = idx // 5."""
+    """(actions [n, 2], prey words [n, 3]): HALF a Philox block per (particle, step).  Particles g and g + 32 (bit 5
+    of g clear) share the block with counter ((g >> 6) << 5 | (g & 31), step): the first takes the words (a, b) =
+    (x, y), the second (z, w).  Prey 0 uses a, prey 1 a * 0x10001 mod 2**32, prey 2 b; the joint action comes from
+    b * 0x10001 mod 2**32: idx = floor(word * 25 / 2**32), a0 = idx % 5, a1 = idx // 5."""
     particles = np.asarray(particles, dtype=np.uint64)
-    w = P.philox_block(seed, particles, step, P.STREAM_STEP)
-    idx = P.uniform_below(w[3], 25)
+    counter = ((particles >> np.uint64(6)) << np.uint64(5)) | (particles & np.uint64(31))
+    w = P.philox_block(seed, counter, step, P.STREAM_STEP)
+    hi = ((particles >> np.uint64(5)) & np.uint64(1)).astype(bool)
+    a = np.where(hi, w[2], w[0]).astype(np.uint64)
+    b = np.where(hi, w[3], w[1]).astype(np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    a2 = (a * np.uint64(0x10001)) & m32
+    b2 = (b * np.uint64(0x10001)) & m32
+    idx = P.uniform_below(b2.astype(np.uint32), 25)
     a1 = idx // 5
     a0 = idx - 5 * a1
-    return np.stack([a0, a1], axis=-1), np.stack([w[0], w[1], w[2]], axis=-1).astype(np.uint32)
+    return np.stack([a0, a1], axis=-1), np.stack([a, a2, b], axis=-1).astype(np.uint32)
 
 
 def pp_initial_picks(model, seed: int, particles):

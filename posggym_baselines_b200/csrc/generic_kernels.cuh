@@ -138,6 +138,7 @@ step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
       for (int j = 0; j < FAST_EPT; ++j) word[j] = s_words[warp][32 * j + lane];
       blk_next = philox_block(seed, group_offset + (uint64_t)(wb + wstride) * 32u + lane, step_idx, STREAM_STEP);
     }
+    uint4 pair_blk = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
     for (int j = 0; j < FAST_EPT; ++j) {
       typename M::State s;
@@ -148,6 +149,12 @@ step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
         M::actions_from_word(word[j], act);
 #pragma unroll
         for (int k = 0; k < NW; ++k) noise[k] = 0u;
+      } else if constexpr (M::NOISE_PAIR) {
+        // half a block per env: envs e and e + 32 of this thread share one (M::noise_counter; the launch
+        // guarantees that the global index of e0 has bit 5 clear)
+        if ((j & 1) == 0)
+          pair_blk = philox_block(seed, M::noise_counter(group_offset * 4u + (uint64_t)(e0 + 32 * j)), step_idx, STREAM_STEP);
+        M::noise_from_pair((j & 1) ? pair_blk.z : pair_blk.x, (j & 1) ? pair_blk.w : pair_blk.y, act, noise);
       } else {
         // one Philox block per env: counter = global particle index (the general kernel's convention)
         M::noise_from_philox(seed, group_offset * 4u + (uint64_t)(e0 + 32 * j), step_idx, act, noise);

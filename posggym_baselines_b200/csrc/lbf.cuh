@@ -224,6 +224,7 @@ struct LBFSim {
     term = all_done ? 3u : 0u;
   }
   static constexpr bool ONE_WORD_NOISE = true;   // the whole step noise is one Philox word (step_fast_kernel)
+  static constexpr bool NOISE_PAIR = false;
   // uniform joint action from one Philox word: idx = floor(w * 36 / 2^32), a0 = idx % 6, a1 = idx / 6
   __device__ static __forceinline__ void actions_from_word(uint32_t word, int (&act)[NAG]) {
     const uint32_t idx = uniform_below(word, 36u);

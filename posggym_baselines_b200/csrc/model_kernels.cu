@@ -195,7 +195,8 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
   int64_t done = 0;
   static const bool nofast = getenv("POSG_STEP_NOFAST") != nullptr;   // dev A/B switch
   const bool fast_kind = m->kind == KIND_LBF || (m->kind == KIND_PREDATOR_PREY && pp_lut(m));
-  if (!nofast && fast_kind && !actions_in && !noise_in && (particle_offset & 3ULL) == 0 &&
+  // (PredatorPrey: particles g and g + 32 share a Philox block, so its blocks of 128 must start at a multiple of 64)
+  if (!nofast && fast_kind && !actions_in && !noise_in && (particle_offset & (m->kind == KIND_LBF ? 3ULL : 63ULL)) == 0 &&
       n >= generic::FAST_WARP_ENVS && n < ((int64_t)1 << 31)) {
     // whole blocks of 128 envs through the fast kernel; a ragged tail through the general one
     const uint32_t nb = (uint32_t)(n / generic::FAST_WARP_ENVS);

@@ -47,7 +47,8 @@ struct alignas(16) Blob {
   // observation pieces: window cells that are outside the grid by column (+ the centre PREDATOR) / by row,
   // and the PREY code at the window cell of an entity at offset u = (dx + od) + 16 (dy + od), u < 80
   unsigned long long win_col[16], win_row[16];
-  unsigned long long win_obs[80];
+  unsigned long long win_pos[256];   // win_col[p & 15] | win_row[p >> 4] per packed cell p: one lookup per observation
+  unsigned long long win_obs[128];   // index (dx + 2) + 16 (dy + 2) < 128 without bit 3; zero outside the 5 x 5 window
 };
 constexpr int REL0 = 256, SENT = 0xCC, THR_FAR = 66, THR_PREY = 32, THR_RND = 64;
 // move_delta rows are addressed in the biased offset space REL0 + d of the candidate keys: flee rows sit at
@@ -78,7 +79,7 @@ inline void build_tables(Blob* b) {
     for (int x = 0; x < b->size; ++x) blocks |= ((b->rows[y + PAD] >> (x + PAD)) & 1u) != 0;
   b->lut_ok = (b->size <= 10 && od == 2 && !blocks) ? 1 : 0;
   for (int i = 0; i < 512; ++i) { b->rel_nb[i] = 0; b->rel_thr[i] = (uint8_t)THR_FAR; }
-  for (int i = 0; i < 80; ++i) b->win_obs[i] = 0;
+  for (int i = 0; i < 128; ++i) b->win_obs[i] = 0;
   for (int dy = -od; dy <= od; ++dy)
     for (int dx = -od; dx <= od; ++dx) {
       const int i = REL0 + dx + 16 * dy, man = abs(dx) + abs(dy);
@@ -98,6 +99,7 @@ inline void build_tables(Blob* b) {
     }
     b->win_col[v] = col; b->win_row[v] = row;
   }
+  for (int p = 0; p < 256; ++p) b->win_pos[p] = b->win_col[p & 15] | b->win_row[p >> 4];
   for (int c = 0; c < 8; ++c)
     b->caught_mask[c] = ((c & 1) ? 0xFFu : 0u) | ((c & 2) ? 0xFF00u : 0u) | ((c & 4) ? 0xFF0000u : 0u);
   // prey moves.  Flee: keep the free option (staying included) with the largest (distance to the threat, x, y)
@@ -442,24 +444,29 @@ __device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint
   return all == 7u;
 }
 
-// observation of predator i: out-of-grid columns / rows (and the own cell) from two 16-entry tables; another
-// entity contributes the table entry of its offset, looked up only by the lanes that have it in the window
-// (a predicated-off lane makes no shared-memory access, so the lookup costs a wavefront or two, not six)
+// observation of predator i: out-of-grid columns / rows (and the own cell) from one table indexed by the packed
+// cell; another entity contributes the table entry of its offset, looked up only by the lanes that have it in
+// (an 8 x 8 superset of) the window: a predicated-off lane makes no shared-memory access, so the lookup costs a
+// wavefront or two, not six
 __device__ __forceinline__ unsigned long long observe_lut(const Blob& B, uint32_t w0, const int (&occ)[NQ], int i) {
   const uint32_t p = (w0 >> (8 * i)) & 255u, o = (w0 >> (8 * (1 - i))) & 255u;
-  unsigned long long cells = B.win_col[p & 15u] | B.win_row[p >> 4];
   const uint32_t bias = 2u * 17u - p;     // obs_dim = 2: u = (dx + 2) + 16 (dy + 2)
+  // every entity's contribution is a value (zero when it is outside the window: the lookup is predicated off), so
+  // the six words OR together in three-input LOP3s
+  unsigned long long e[NQ + 1];
 #pragma unroll
   for (int j = 0; j < NQ; ++j) {
     const uint32_t u = (uint32_t)occ[j] + bias;
-    if ((u & 15u) <= 4u && u < 80u) cells |= B.win_obs[u];
+    e[j] = 0ULL;
+    if ((u & 0xFFFFFF88u) == 0u) e[j] = B.win_obs[u];   // one LOP3: column < 8 and row < 8; the table is zero outside 5 x 5
   }
   {
     const uint32_t u = o + bias;
-    // PREDATOR (2) = PREY (3) with the low bit of the cell cleared
-    if ((u & 15u) <= 4u && u < 80u) cells |= B.win_obs[u] & 0xAAAAAAAAAAAAAAAAULL;
+    e[NQ] = 0ULL;
+    if ((u & 0xFFFFFF88u) == 0u) e[NQ] = B.win_obs[u];
   }
-  return cells;
+  // PREDATOR (2) = PREY (3) with the low bit of the cell cleared
+  return B.win_pos[p] | e[0] | e[1] | e[2] | (e[NQ] & 0xAAAAAAAAAAAAAAAAULL);
 }
 __device__ __forceinline__ void occ_of(uint32_t w0, uint32_t w1, int (&occ)[NQ]) {
 #pragma unroll
@@ -501,7 +508,7 @@ struct PPSimT {
   using Blob = pp::Blob;
   using Ctx = NoCtx;
   static constexpr int A = 5, OW = 1, SW = 2, NAG = 2, NW = 3, NPICK = 5;
-  static constexpr bool ONE_WORD_NOISE = false;   // four Philox words per env-step
+  static constexpr bool ONE_WORD_NOISE = false;   // two Philox words per env-step (NOISE_PAIR below)
   struct State { uint32_t w[SW]; };
   __device__ static __forceinline__ void actions_from_word(uint32_t, int (&)[NAG]) {}
 
@@ -549,14 +556,26 @@ struct PPSimT {
     }
     term = all_done ? 3u : 0u;
   }
-  // uniform joint action + prey words from one Philox block (particle, step, STREAM_STEP)
-  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
-                                                           int (&act)[NAG], uint32_t (&noise)[NW]) {
-    const uint4 w = philox_block(seed, particle, step, STREAM_STEP);
-    noise[0] = w.x; noise[1] = w.y; noise[2] = w.z;
-    const uint32_t idx = uniform_below(w.w, 25u);
+  // Step noise of a particle: HALF a Philox block.  Particles g and g + 32 (g with bit 5 clear) share the block with
+  // counter ((g >> 6) << 5 | (g & 31), step, STREAM_STEP): the first takes words (x, y), the second (z, w).  Of a
+  // pair (a, b): prey 0 uses a, prey 1 a * 0x10001 (high half = low + high half of a), prey 2 b, the uniform
+  // joint action b * 0x10001.  (A prey needs a tie bit and one pick of at most five options from its word.)  The
+  // fast kernel steps particles 32 j + lane in one thread, so it computes ONE block for two of its envs.
+  static constexpr bool NOISE_PAIR = true;
+  __device__ static __forceinline__ uint64_t noise_counter(uint64_t particle) {
+    return ((particle >> 6) << 5) | (particle & 31u);
+  }
+  __device__ static __forceinline__ void noise_from_pair(uint32_t a, uint32_t b, int (&act)[NAG], uint32_t (&noise)[NW]) {
+    noise[0] = a; noise[1] = a * 0x10001u; noise[2] = b;
+    const uint32_t idx = uniform_below(b * 0x10001u, 25u);
     act[1] = (int)(idx / 5u);
     act[0] = (int)(idx - 5u * (uint32_t)act[1]);
+  }
+  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
+                                                           int (&act)[NAG], uint32_t (&noise)[NW]) {
+    const uint4 w = philox_block(seed, noise_counter(particle), step, STREAM_STEP);
+    const bool hi = (particle >> 5) & 1u;
+    noise_from_pair(hi ? w.z : w.x, hi ? w.w : w.y, act, noise);
   }
   __device__ static __forceinline__ void noise_from_word(uint32_t word, uint32_t (&noise)[NW]) {
     const uint4 w = philox4x32_10(word, 0x9E3779B9u, 0x7F4A7C15u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu);

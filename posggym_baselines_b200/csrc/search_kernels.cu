@@ -65,6 +65,66 @@ search_waves_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_si
   }
 }
 
+// Root parallelisation INSIDE one GPU: CTA k runs search_waves_kernel's loop on its own tree (entries[k]: arena,
+// root belief, root node), with its own Philox sub-sequence.  Every tree is the reference's search on its own
+// (one tree per SM instead of one tree per GPU); the root statistics are summed afterwards
+// (posg_forest_stats + the host's final selection), exactly like the cross-GPU allreduce of root-parallel POMCP.
+struct ForestEntry {
+  unsigned char* arena;
+  const uint32_t* particles;
+  long long n_particles;
+  int root;
+  int pad;
+};
+static_assert(sizeof(ForestEntry) == sizeof(posg_forest_entry), "posg_forest_entry layout");
+
+template <class M>
+__global__ void __launch_bounds__(1024, 1)
+search_forest_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
+                     const ForestEntry* __restrict__ entries, long long cap_nodes, long long cap_log,
+                     const __grid_constant__ search::Params P, const __grid_constant__ typename M::Ctx ctx, int root_t,
+                     int wave_size, int n_waves, unsigned long long sim_id0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  const ForestEntry en = entries[blockIdx.x];
+  search::Tree T;
+  search::layout(&T, en.arena, cap_nodes, cap_log, M::A, M::OW, M::SW);
+  const search::RootSelect sel = {nullptr, nullptr, nullptr, 0};
+  const unsigned long long base = sim_id0 + ((unsigned long long)blockIdx.x << 32);
+  for (int w = 0; w < n_waves; ++w) {
+    search::simulate<M>(B, ctx, T, P, en.root, root_t, en.particles, en.n_particles, sel,
+                        base + (unsigned long long)w * (unsigned long long)wave_size + threadIdx.x,
+                        (int)threadIdx.x < wave_size);
+    __threadfence();
+    __syncthreads();
+  }
+}
+
+// per tree: what posg_tree_node_stats returns for the tree's root (3 * A + 10 doubles)
+__global__ void forest_stats_kernel(const ForestEntry* __restrict__ entries, long long cap_nodes, long long cap_log,
+                                    int A, int OW, int SW, double* __restrict__ out) {
+  const ForestEntry en = entries[blockIdx.x];
+  search::Tree T;
+  search::layout(&T, en.arena, cap_nodes, cap_log, A, OW, SW);
+  double* o = out + (size_t)blockIdx.x * (3 * A + 10);
+  const int a = threadIdx.x;
+  if (a < A) {
+    o[a] = (double)T.an_visits[(size_t)en.root * A + a];
+    o[A + a] = (double)T.an_done[(size_t)en.root * A + a];
+    o[2 * A + a] = T.an_total[(size_t)en.root * A + a];
+  }
+  if (a == 0) {
+    double* e = o + 3 * A;
+    const search::Counters c = *T.ctr;
+    e[0] = (double)T.node_visits[en.root]; e[1] = (double)c.node_count; e[2] = (double)c.log_count;
+    e[3] = (double)c.max_depth; e[4] = search::dunkey(c.min_key); e[5] = search::dunkey(c.max_key);
+    e[6] = (double)c.overflow; e[7] = (double)c.sims_done; e[8] = (double)T.node_flags[en.root];
+    e[9] = (double)c.nodes_created;
+  }
+}
+
 template <class M>
 __global__ void __launch_bounds__(belief::CTA)
 reinvigorate_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
@@ -498,6 +558,17 @@ static void launch_search(const posg_model* m, const search::Tree& T, const sear
         sel, n_sims, sim_id0 + (unsigned long long)w * (unsigned long long)n_sims);
 }
 
+template <class M>
+static void launch_forest(const posg_model* m, const ForestEntry* entries, int n_trees, long long cap_nodes,
+                          long long cap_log, const search::Params& P, int root_t, int wave_size, int n_waves,
+                          unsigned long long sim_id0, cudaStream_t s) {
+  const int threads = ((wave_size + 31) / 32) * 32;
+  smem_optin(search_forest_kernel<M>, m->blob_bytes);
+  search_forest_kernel<M><<<n_trees, threads, m->blob_bytes, s>>>(
+      (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, entries, cap_nodes, cap_log, P, NoCtx{}, root_t,
+      wave_size, n_waves, sim_id0);
+}
+
 static int search_common(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
                          const uint32_t* particles, int64_t n_particles, const search::RootSelect& sel, int64_t n_sims,
                          uint64_t sim_id0, const posg_search_params* p, void* stream, int n_waves = 1) {
@@ -557,6 +628,53 @@ int posg_search_waves(posg_model_t m, void* arena, int64_t cap_nodes, int64_t ca
   search::RootSelect sel = {nullptr, nullptr, nullptr, 0};
   return search_common(m, arena, cap_nodes, cap_log, root, root_t, particles, n_particles, sel, wave_size, sim_id0, p,
                        stream, n_waves);
+}
+
+int posg_search_forest(posg_model_t m, const posg_forest_entry* entries_dev, int n_trees, int64_t cap_nodes,
+                       int64_t cap_log, int root_t, int wave_size, int n_waves, uint64_t sim_id0,
+                       const posg_search_params* p, void* stream) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  POSG_REQUIRE(entries_dev && n_trees >= 1 && n_trees <= 4096 && cap_nodes >= 2 && cap_log >= 1 &&
+               cap_nodes <= 0x7fffffffLL / (k.n_actions + 1), "bad forest arguments");
+  POSG_REQUIRE(wave_size >= 1 && wave_size <= 1024 && n_waves >= 0 && n_waves <= (1 << 20), "bad wave arguments");
+  if (n_waves == 0) return POSG_OK;
+  search::Params P;
+  int rc = fill_params(m, p, &P); if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const ForestEntry* en = (const ForestEntry*)entries_dev;
+  switch (m->kind) {
+    case KIND_DRIVING: launch_forest<DrivingSim>(m, en, n_trees, cap_nodes, cap_log, P, root_t, wave_size, n_waves, sim_id0, s); break;
+    case KIND_PREDATOR_PREY:
+      if (((const pp::Blob*)m->h_blob)->lut_ok)
+        launch_forest<PPSimLut>(m, en, n_trees, cap_nodes, cap_log, P, root_t, wave_size, n_waves, sim_id0, s);
+      else
+        launch_forest<PPSim>(m, en, n_trees, cap_nodes, cap_log, P, root_t, wave_size, n_waves, sim_id0, s);
+      break;
+    case KIND_LBF: launch_forest<LBFSim>(m, en, n_trees, cap_nodes, cap_log, P, root_t, wave_size, n_waves, sim_id0, s); break;
+    default: set_error("unsupported model kind"); return POSG_E_UNSUPPORTED;
+  }
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
+int posg_forest_stats(posg_model_t m, const posg_forest_entry* entries_dev, int n_trees, int64_t cap_nodes,
+                      int64_t cap_log, double* out_host, void* stream) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  POSG_REQUIRE(entries_dev && out_host && n_trees >= 1 && n_trees <= 4096 && cap_nodes >= 2 && cap_log >= 1, "bad forest arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)n_trees * (3 * k.n_actions + 10) * sizeof(double);
+  double* d_out = nullptr;
+  POSG_CUDA(cudaMallocAsync((void**)&d_out, bytes, s));
+  forest_stats_kernel<<<n_trees, 32, 0, s>>>((const ForestEntry*)entries_dev, cap_nodes, cap_log, k.n_actions, k.obs_words,
+                                             k.state_words, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(d_out, s);
+  POSG_CUDA(e);
+  return POSG_OK;
 }
 
 int posg_search_multi(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root_t,

@@ -17,7 +17,9 @@ Extra, B200-only knobs are keyword arguments of the constructor, never config fi
 ``max_sims`` (stop after that many simulations instead of / as well as the time limit),
 ``wave_size`` (simulations per launch; 1 = the reference's strictly sequential search),
 ``root_parallel`` (merge root statistics over torch.distributed ranks: one allreduce per
-decision), ``node_capacity`` / ``log_capacity`` (size of the device arenas).  Like the
+decision), ``trees_per_gpu`` (root parallelisation inside the GPU: that many independent trees, one CTA / SM
+each, searched by ONE launch per chunk and merged at the root like the cross-GPU allreduce; every tree is the
+single-tree search), ``node_capacity`` / ``log_capacity`` (size of the device arenas, shared by the trees).  Like the
 reference (mcts.py:261-263) the planner keeps the whole subtree under the new root -- its
 statistics, child lists and the particles logged at its nodes -- and drops the rest: at
 every re-root the subtree is copied, renumbered, into a second arena (posg_tree_reroot).
@@ -99,6 +101,8 @@ class MCTS:
         node_capacity: int = 1 << 27,
         log_capacity: int = 1 << 28,
         root_parallel: bool = False,
+        trees_per_gpu: int = 1,
+        _forest_index: int = 0,
     ):
         self.model = model
         self.agent_id = agent_id
@@ -140,6 +144,14 @@ class MCTS:
         self.allreduce_time = 0.0
         self._seed_shared = config.seed if config.seed is not None else 0
         self._cap_nodes, self._cap_log = int(node_capacity), int(log_capacity)
+        self._forest_index = int(_forest_index)
+        # tree k of a forest draws its belief particles from its own Philox sub-sequence
+        self._draw_base = self._forest_index << 48
+        trees_per_gpu = int(trees_per_gpu)
+        if trees_per_gpu > 1:
+            # the trees share the arena budget
+            self._cap_nodes = max(1 << 20, self._cap_nodes // trees_per_gpu)
+            self._cap_log = max(1 << 22, self._cap_log // trees_per_gpu)
 
         lib = _lib.lib()
         na, ow, sw = C.c_int(), C.c_int(), C.c_int()
@@ -172,6 +184,17 @@ class MCTS:
         self._logger = logging.getLogger()
         self.step_statistics: Dict[str, float] = {}
         self.stat_tracker = PlanningStatTracker(self)
+        self._siblings = []
+        if trees_per_gpu > 1:
+            if self._host_mode:
+                raise NotImplementedError("trees_per_gpu > 1 needs the device search (random search / other-agent policies)")
+            self._siblings = [
+                MCTS(model, agent_id, config, other_agent_policies, search_policy, max_sims=max_sims,
+                     wave_size=wave_size, max_wave=max_wave, wave_growth=wave_growth, node_capacity=self._cap_nodes,
+                     log_capacity=self._cap_log, root_parallel=False, _forest_index=k)
+                for k in range(1, trees_per_gpu)]
+            for sib in self._siblings:
+                sib._seed, sib._params.seed = self._seed, self._params.seed   # one Philox key, disjoint counters
         self._host = None
         if self._host_mode:
             from posggym_baselines_b200.planning.host_search import HostSearch
@@ -233,14 +256,7 @@ class MCTS:
             _lib.check(_lib.lib().posg_tree_node_stats(
                 self._b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log,
                 self._root if node is None else node, _lib.ptr(out), self._stream()))
-        A = self._A
-        e = out[3 * A:]
-        return {
-            "visits": out[:A].copy(), "done": out[A:2 * A].copy(), "total": out[2 * A:3 * A].copy(),
-            "node_visits": e[0], "node_count": e[1], "log_count": e[2], "max_depth": e[3],
-            "min_value": e[4], "max_value": e[5], "overflow": e[6], "sims_done": e[7], "flags": int(e[8]),
-            "nodes_created": e[9],
-        }
+        return self._unpack_stats(out)
 
     # ------------------------------------------------------------------ step / reset
     def step(self, obs):
@@ -270,6 +286,8 @@ class MCTS:
         self.stat_tracker.reset_episode()
         if self._host is not None:
             self._host.reset()
+        for sib in self._siblings:
+            sib.reset()
         self._step_num = 0
         self._root = 0
         self._root_t = 0
@@ -304,18 +322,24 @@ class MCTS:
         if self._root_absorbing:
             return
         start = time.time()
-        if self._root_t == 0:
-            self._last_action = None
-            self._initial_update(obs)
-        else:
-            self._update(action, obs)
+        for tree in [self] + self._siblings:
+            if tree._root_absorbing:
+                continue
+            if tree._root_t == 0:
+                tree._last_action = None
+                tree._initial_update(obs)
+            else:
+                tree._update(action, obs)
         torch.cuda.synchronize(self._b.device)
+        for sib in self._siblings:
+            self.step_statistics["reinvigoration_time"] += sib.step_statistics["reinvigoration_time"]
+            sib.step_statistics["reinvigoration_time"] = 0.0
         self.step_statistics["update_time"] = time.time() - start
 
     def _next_draw(self, n: int) -> int:
         d = self._draw_counter
         self._draw_counter += int(n)
-        return d
+        return self._draw_base + d
 
     def _initial_update(self, init_obs):
         cfg, b = self.config, self._b
@@ -347,8 +371,8 @@ class MCTS:
             t0 = time.time()
             target = cfg.num_particles + cfg.extra_particles
             # particles the searches left at the child (belief.add_particle, mcts.py:371)
-            log_count = int(self._stats()["log_count"])
-            buf = torch.empty((min(log_count, self._cap_log) + target, self._SW), dtype=torch.int32, device=b.device)
+            # (the log's length is known on the host: get_action / the last re-root recorded it)
+            buf = torch.empty((min(self._log_bound, self._cap_log) + target, self._SW), dtype=torch.int32, device=b.device)
             cnt = np.zeros(1, np.int64)
             with torch.cuda.device(b.device):
                 _lib.check(_lib.lib().posg_tree_gather_belief(
@@ -391,16 +415,31 @@ class MCTS:
         cfg, b = self.config, self._b
         start = time.time()
         n_sims = n_waves = wave_now = 0
-        nodes_before = self._nodes_bound
+        trees = [self] + [t for t in self._siblings if not t._root_absorbing]
+        forest = len(trees) > 1
+        A = self._A
+        lib = _lib.lib()
+        entries = None
+        if forest:
+            tab = np.zeros((len(trees), 4), np.int64)
+            for k, t in enumerate(trees):
+                tab[k] = (t._arena.data_ptr(), t._root_particles.data_ptr(), t._root_particles.shape[0], t._root)
+            entries = torch.from_numpy(tab).to(b.device)
+        nodes_before = sum(t._nodes_bound for t in trees)
         # Simulations of one wave see each other's virtual visits but not each other's returns, so a wave may
         # only be a small fraction of the visits the root already has: wave = wave_growth * N, at least 32 (one
         # warp).  At equal budgets the search then matches the reference's sequential loop (tests/
         # test_pomcp_gpu.py: 65 536 simulations against the unmodified reference planner; waves of N / 512 no
         # longer do).  The root keeps its subtree's visits across re-roots, so later decisions of an episode
-        # start with larger waves.  Consecutive waves are chained inside one launch (posg_search_waves); the
-        # clock is read between chunks of waves sized for ~2 ms.
-        root_visits = 0 if self.wave_size else int(self._stats()["node_visits"])
-        lib = _lib.lib()
+        # start with larger waves.  Consecutive waves are chained inside one launch (posg_search_waves; with
+        # trees_per_gpu > 1 posg_search_forest runs the same chain on every tree at once); the clock is read
+        # between chunks of waves sized for ~2 ms.
+        if self.wave_size:
+            root_visits = 0
+        elif forest:
+            root_visits = int(self._forest_stats(entries, len(trees))[:, 3 * A].min())
+        else:
+            root_visits = int(self._stats()["node_visits"])
         chunk = 8          # waves per launch, adapted to ~2 ms per chunk
         with torch.cuda.device(b.device):
             stream = self._stream()
@@ -409,6 +448,8 @@ class MCTS:
                     wave = self.wave_size
                 else:
                     wave = self._scheduled_wave(root_visits)
+                    if forest:
+                        wave = min(wave, 1024)   # one CTA per tree
                 waves = chunk
                 if not self.wave_size:   # stay on this wave size only while the schedule allows it
                     grow_at = 8192 if root_visits < 8192 else (
@@ -426,11 +467,16 @@ class MCTS:
                 t_chunk = time.time()
                 # every simulation reserves one node id (none once the arena is full: the kernel then evaluates
                 # unexpanded histories by rollouts without storing them)
-                self._nodes_bound = min(self._cap_nodes, self._nodes_bound + wave * waves)
-                _lib.check(lib.posg_search_waves(
-                    b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, self._root_t,
-                    _lib.ptr(self._root_particles), self._root_particles.shape[0], wave, waves,
-                    self._sim_base + self._sim_counter, C.byref(self._params), stream))
+                if forest:
+                    _lib.check(lib.posg_search_forest(
+                        b._handle, _lib.ptr(entries), len(trees), self._cap_nodes, self._cap_log, self._root_t, wave,
+                        waves, self._sim_base + self._sim_counter, C.byref(self._params), stream))
+                else:
+                    self._nodes_bound = min(self._cap_nodes, self._nodes_bound + wave * waves)
+                    _lib.check(lib.posg_search_waves(
+                        b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, self._root_t,
+                        _lib.ptr(self._root_particles), self._root_particles.shape[0], wave, waves,
+                        self._sim_base + self._sim_counter, C.byref(self._params), stream))
                 self._sim_counter += wave * waves
                 n_sims += wave * waves
                 n_waves += waves
@@ -449,24 +495,55 @@ class MCTS:
                     remaining = cfg.search_time_limit - (now - start)
                     per_wave = dt / max(1, waves)
                     chunk = int(max(1, min(chunk, remaining / max(per_wave, 1e-6))))
-        st = self._stats()
-        self._nodes_bound, self._log_bound = int(st["node_count"]), int(st["log_count"])
-        self._min_value, self._max_value = st["min_value"], st["max_value"]
+        if forest:
+            rows = self._forest_stats(entries, len(trees))
+            sts = [self._unpack_stats(r) for r in rows]
+        else:
+            sts = [self._stats()]
+        for t, st_k in zip(trees, sts):
+            t._nodes_bound, t._log_bound = int(st_k["node_count"]), int(st_k["log_count"])
+            t._min_value, t._max_value = st_k["min_value"], st_k["max_value"]
+            t._last_root_stats = st_k
+        st = sts[0]
+        n_total = n_sims * len(trees)
+        self._min_value = min(s_["min_value"] for s_ in sts)
+        self._max_value = max(s_["max_value"] for s_ in sts)
         self.step_statistics["search_time"] = time.time() - start
-        self.step_statistics["search_depth"] = int(st["max_depth"])
-        self.step_statistics["num_sims"] = n_sims
+        self.step_statistics["search_depth"] = int(max(s_["max_depth"] for s_ in sts))
+        self.step_statistics["num_sims"] = n_total
         self.step_statistics["min_value"] = self._min_value
         self.step_statistics["max_value"] = self._max_value
-        self._last_root_stats = st
         # B200-only diagnostics (not a reference key): how much of the search could still grow the tree
-        overflow = int(st["overflow"])
+        overflow = int(sum(s_["overflow"] for s_ in sts))
+        node_count = int(sum(s_["node_count"] for s_ in sts))
         self.search_info = {
-            "num_sims": n_sims, "expanding_sims": n_sims - overflow, "overflow_sims": overflow,
-            "overflow_share": overflow / max(1, n_sims), "nodes_created": int(st["nodes_created"]),
-            "ids_reserved": int(st["node_count"]) - nodes_before,
-            "nodes_in_tree": int(st["node_count"]), "arena_fill": int(st["node_count"]) / self._cap_nodes,
-            "log_fill": min(1.0, int(st["log_count"]) / self._cap_log), "waves": n_waves, "last_wave": wave_now}
-        return self._final_action(st)
+            "num_sims": n_total, "expanding_sims": n_total - overflow, "overflow_sims": overflow,
+            "overflow_share": overflow / max(1, n_total), "nodes_created": int(sum(s_["nodes_created"] for s_ in sts)),
+            "ids_reserved": node_count - nodes_before,
+            "nodes_in_tree": node_count,
+            "arena_fill": max(int(s_["node_count"]) for s_ in sts) / self._cap_nodes,
+            "log_fill": min(1.0, max(int(s_["log_count"]) for s_ in sts) / self._cap_log), "waves": n_waves,
+            "last_wave": wave_now, "trees": len(trees), "sims_per_tree": n_sims}
+        done = sum(s_["done"] for s_ in sts)
+        total = sum(s_["total"] for s_ in sts)
+        return self._final_action(done, total, local_trees=len(trees))
+
+    def _unpack_stats(self, out: np.ndarray) -> Dict[str, object]:
+        A = self._A
+        e = out[3 * A:]
+        return {
+            "visits": out[:A].copy(), "done": out[A:2 * A].copy(), "total": out[2 * A:3 * A].copy(),
+            "node_visits": e[0], "node_count": e[1], "log_count": e[2], "max_depth": e[3],
+            "min_value": e[4], "max_value": e[5], "overflow": e[6], "sims_done": e[7], "flags": int(e[8]),
+            "nodes_created": e[9],
+        }
+
+    def _forest_stats(self, entries: torch.Tensor, n_trees: int) -> np.ndarray:
+        out = np.zeros((n_trees, 3 * self._A + 10), np.float64)
+        with torch.cuda.device(self._b.device):
+            _lib.check(_lib.lib().posg_forest_stats(self._b._handle, _lib.ptr(entries), n_trees, self._cap_nodes,
+                                                    self._cap_log, _lib.ptr(out), self._stream()))
+        return out
 
     def _scheduled_wave(self, root_visits: int) -> int:
         """Simulations per wave for a root with ``root_visits`` visits: one warp while the tree is young, two
@@ -477,19 +554,22 @@ class MCTS:
 
     _respect_time = False  # with max_sims set, the time limit only applies when asked for
 
-    def _final_action(self, st):
+    def _final_action(self, done, total, local_trees: int = 1):
         from posggym_baselines_b200 import parallel
 
-        done, total = st["done"].copy(), st["total"].copy()
+        done, total = np.array(done, np.float64), np.array(total, np.float64)
         merged = False
         if self.root_parallel and parallel.world()[1] > 1:
             # root-parallel merge: one allreduce of |A| x {visits, total_value} per decision
             t0 = time.time()
-            buf = torch.empty(2 * self._A, dtype=torch.float64, device=self._b.device)
-            with torch.cuda.device(self._b.device):
-                _lib.check(_lib.lib().posg_tree_root_stats_device(
-                    self._b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, _lib.ptr(buf),
-                    self._stream()))
+            if local_trees > 1:
+                buf = torch.from_numpy(np.concatenate([done, total])).to(self._b.device)
+            else:
+                buf = torch.empty(2 * self._A, dtype=torch.float64, device=self._b.device)
+                with torch.cuda.device(self._b.device):
+                    _lib.check(_lib.lib().posg_tree_root_stats_device(
+                        self._b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root,
+                        _lib.ptr(buf), self._stream()))
             done, total = parallel.merge_root_statistics_device(buf)
             self.allreduce_time = time.time() - t0
             merged = True
@@ -520,6 +600,10 @@ class MCTS:
             policy.close()
         self._arena = self._arena_spare = self._reroot_scratch = None
         self._root_particles = None
+        for sib in self._siblings:
+            sib._arena = sib._arena_spare = sib._reroot_scratch = None
+            sib._root_particles = None
+        self._siblings = []
 
     def __str__(self):
         return f"{self.__class__.__name__}"

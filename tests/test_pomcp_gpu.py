@@ -31,7 +31,8 @@ def model():
 def make_planner(model, seed=0, **kw):
     from posggym_baselines_b200.planning import POMCP, MCTSConfig, RandomSearchPolicy
 
-    opts = {k: kw.pop(k) for k in list(kw) if k in ("max_sims", "wave_size", "max_wave", "node_capacity", "log_capacity")}
+    opts = {k: kw.pop(k) for k in list(kw) if k in ("max_sims", "wave_size", "max_wave", "node_capacity", "log_capacity",
+                                                    "trees_per_gpu", "_forest_index")}
     if opts.get("max_sims") is not None:   # fixed small budgets: a small arena is plenty
         opts.setdefault("node_capacity", 1 << 18)
         opts.setdefault("log_capacity", 1 << 21)
@@ -100,6 +101,82 @@ def test_root_statistics_match_reference(model, gold, wave):
         order = np.argsort(ref_mean)
         if ref_mean[order[-1]] - ref_mean[order[-2]] > 4 * se.max() + 0.02:   # only when the reference's best is clear
             assert int(np.argmax(vals.mean(0))) == int(order[-1])
+
+
+def test_forest_tree_equals_solo_tree(model, gold):
+    """trees_per_gpu = K (root parallelisation inside the GPU, posg_search_forest): tree k of the forest IS the
+    single-tree search with tree k's Philox sub-sequences -- with wave size 1 (deterministic) its root statistics
+    are exactly those of a solo planner given the same counters; the forest's decision statistics are their sum."""
+    scen = gold["root_stats"][0]
+    obs = fields_to_obs(scen["ego_obs"])
+    K, n = 3, 512
+    f = make_planner(model, seed=7, max_sims=n, wave_size=1, trees_per_gpu=K)
+    f.reset(); f.update(None, obs); f.get_action()
+    assert f.step_statistics["num_sims"] == K * n and f.search_info["trees"] == K
+    trees = [f] + f._siblings
+    total_done = np.zeros(5)
+    for k in range(K):
+        solo = make_planner(model, seed=7, max_sims=n, wave_size=1, _forest_index=k)
+        solo._sim_base = k << 32
+        solo.reset(); solo.update(None, obs); solo.get_action()
+        a, b_ = trees[k]._last_root_stats, solo._last_root_stats
+        assert (a["done"] == b_["done"]).all() and (a["total"] == b_["total"]).all(), (k, a["done"], b_["done"])
+        assert a["node_count"] == b_["node_count"]
+        total_done += a["done"]
+        solo.close()
+    assert (f._merged_root[0] == total_done).all()
+    assert not (trees[0]._last_root_stats["total"] == trees[1]._last_root_stats["total"]).all()   # different streams
+    f.close()
+
+
+def test_forest_root_statistics_match_reference(model, gold):
+    """Merged root statistics of a 4-tree forest, every tree at the reference's simulation count: the action
+    values are within 4 standard errors (+0.02) of the reference planner's means (each tree is an independent
+    sample of the reference's search, so the visit-weighted mean has the same expectation)."""
+    for scen in gold["root_stats"]:
+        reps = 20
+        vals = []
+        for rep in range(reps):
+            p = make_planner(model, seed=100 + rep, max_sims=scen["n_sims"], wave_size=1, trees_per_gpu=4)
+            p.reset(); p.update(None, fields_to_obs(scen["ego_obs"])); p.get_action()
+            vals.append(p.root_action_values())
+            p.close()
+        vals = np.array(vals)
+        ref_mean, ref_std = np.array(scen["value_mean"]), np.array(scen["value_std"])
+        se = np.sqrt(ref_std**2 / scen["reps"] + vals.std(0) ** 2 / reps)
+        assert (np.abs(vals.mean(0) - ref_mean) < 4 * se + 0.02).all(), (vals.mean(0), ref_mean, se)
+
+
+def test_forest_episode_and_throughput(model, gold):
+    """An episode with 16 trees on one GPU under the time budget: the re-root / belief update runs on every tree,
+    nothing overflows, and the decision sees (about) 16 x the single tree's simulations."""
+    import random as _random
+    from posggym_baselines_b200.envs.env import Env
+
+    planner = make_planner(model, seed=9, trees_per_gpu=16)
+    env = Env(model)
+    rng = _random.Random(9)
+    obs, _ = env.reset(seed=9)
+    planner.reset()
+    sims, per_tree = [], []
+    for d in range(6):
+        a = planner.step(obs["0"])
+        assert a in range(5)
+        if planner.root.is_absorbing:
+            break
+        info = planner.search_info
+        assert info["overflow_share"] == 0.0 and info["trees"] == 16
+        if d > 0:
+            sims.append(info["num_sims"]); per_tree.append(info["sims_per_tree"])
+        for t in planner._siblings:
+            assert t._root_t == planner._root_t and t.root.belief.size() >= planner.config.num_particles
+        obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+        if done:
+            break
+    assert len(sims) >= 3
+    assert min(per_tree) >= 300 * gold["episodes"]["mean_sims_per_decision"], per_tree
+    assert sum(sims) / len(sims) >= 8000 * gold["episodes"]["mean_sims_per_decision"], sims
+    planner.close()
 
 
 def ks_2samp(a, b):
