@@ -22,7 +22,9 @@ enum : int { NONE = 0, NORTH = 1, SOUTH = 2, WEST = 3, EAST = 4, LOAD = 5 };
 struct alignas(16) Blob {
   uint8_t food_xy[NF];        // x | y << 4 (static layout)
   uint8_t player_xy[4];       // start cells
-  uint8_t size, sight, max_agent_level, force_coop, normalize_reward, pad_[3];
+  uint8_t size, sight, max_agent_level, force_coop, normalize_reward;
+  uint8_t vis_max;            // most foods any cell can see (build_tables); <= 7: the observation stream fits 64 bits
+  uint8_t pad_[2];
   int8_t move_delta[8];       // cell-index delta (x | y << 4 arithmetic) of NONE, N, S, W, E, LOAD
   // 3 * k of the food whose cell is x | y << 4, 24 if there is none: level = (w1 >> shift) & 7
   // (w1 holds 24 level bits, so shift 24 reads 0)
@@ -32,6 +34,7 @@ struct alignas(16) Blob {
   // what a player standing on cell x | y << 4 can see: bits 0..7 food k within sight;
   // bits 8 + 6 k .. 13 + 6 k: (dx + sight + 1) | (dy + sight + 1) << 3 of food k
   unsigned long long vis[256];
+  uint32_t vis3[256];         // bit 3 k: food k within sight of cell x | y << 4 (the level bits' positions in w1)
 };
 static_assert(sizeof(Blob) % 16 == 0, "blob must be a multiple of 16 B");
 
@@ -42,6 +45,7 @@ inline void build_tables(Blob* b) {
   for (int c = 0; c < 256; ++c) b->food_sh[c] = 24;
   for (int k = 0; k < NF; ++k) b->food_sh[b->food_xy[k]] = (uint8_t)(3 * k);
   const int size = b->size, s = b->sight;
+  int vis_max = 0;
   for (int y = 0; y < 16; ++y)
     for (int x = 0; x < 16; ++x) {
       auto sh = [&](int cx, int cy) -> uint32_t {
@@ -57,7 +61,14 @@ inline void build_tables(Blob* b) {
         }
       }
       b->vis[x | (y << 4)] = v;
+      uint32_t v3 = 0;
+      for (int k = 0; k < NF; ++k) v3 |= (uint32_t)((v >> k) & 1ULL) << (3 * k);
+      b->vis3[x | (y << 4)] = v3;
+      int seen = 0;
+      for (int k = 0; k < NF; ++k) seen += (int)((v >> k) & 1ULL);
+      if (x < size && y < size && seen > vis_max) vis_max = seen;
     }
+  b->vis_max = (uint8_t)vis_max;
 }
 
 // shift (3 * food index) of the first uncollected food next to `cell` in the order N, S, W, E; 24 if none
@@ -146,16 +157,31 @@ __device__ __forceinline__ void observe(const Blob& B, uint32_t w0, uint32_t w1,
   // visible foods, packed into consecutive 9-bit slots of a 72-bit stream (slot 7 straddles)
   const unsigned long long V = B.vis[me & 255u];
   unsigned long long lo = 0;
-  uint32_t hi = 0, slot9 = 0;   // slot9 = 9 * slot
+  uint32_t hi = 0;
+  if (B.vis_max <= 7) {
+    // (uniform branch) at most seven visible foods = 63 bits: build the stream from the LAST food down, every
+    // visible food shifting the ones after it up by one slot -- constant shifts, no running slot index
+    // seen = visible from here and not loaded yet (level != 0): bit 3 k of both masks
+    const uint32_t seen3 = B.vis3[me & 255u] & (w1 | (w1 >> 1) | (w1 >> 2));
 #pragma unroll
-  for (int k = 0; k < NF; ++k) {
-    const uint32_t lv = (w1 >> (3 * k)) & 7u;
-    const bool seen = ((V >> k) & 1ULL) && lv;
-    const unsigned long long code = (unsigned long long)(((uint32_t)(V >> (8 + 6 * k)) & 63u) | (lv << 6));
-    const unsigned long long put = seen ? code : 0ULL;
-    lo |= put << slot9;
-    if (k == NF - 1) hi = (slot9 == 63u) ? (uint32_t)(put >> 1) : 0u;
-    slot9 += seen ? 9u : 0u;
+    for (int k = NF - 1; k >= 0; --k) {
+      // level << 6 of food k, straight from the state word (3 k - 6 may be negative: shift the other way)
+      const uint32_t lv6 = (3 * k >= 6 ? (w1 >> (3 * k - 6)) : (w1 << (6 - 3 * k))) & 0x1C0u;
+      const uint32_t code = ((uint32_t)(V >> (8 + 6 * k)) & 63u) | lv6;
+      if (seen3 & (1u << (3 * k))) lo = (lo << 9) | code;
+    }
+  } else {
+    uint32_t slot9 = 0;   // slot9 = 9 * slot
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+      const uint32_t lv = (w1 >> (3 * k)) & 7u;
+      const bool seen = ((V >> k) & 1ULL) && lv;
+      const unsigned long long code = (unsigned long long)(((uint32_t)(V >> (8 + 6 * k)) & 63u) | (lv << 6));
+      const unsigned long long put = seen ? code : 0ULL;
+      lo |= put << slot9;
+      if (k == NF - 1) hi = (slot9 == 63u) ? (uint32_t)(put >> 1) : 0u;
+      slot9 += seen ? 9u : 0u;
+    }
   }
   // stream -> layout: slot 0 at w0 lo bit 16; slots 1..3 in w0 hi; 4..6 in w1 lo; 7 in w1 hi
   h0 |= ((uint32_t)lo & 511u) << 16;
