@@ -138,7 +138,7 @@ def run_reference(args):
     emit(line)
 
 
-FOREST_TREES = 32
+FOREST_TREES = 128
 
 
 def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):

@@ -152,7 +152,10 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  stage_blob(smem, gw, (uint32_t)sizeof(Weights), &stage_bar);   // contains a __syncthreads()
+  // the 94 KB of weights travel while the first tile's activations are loaded and converted: waited for just
+  // before the first MMA
+  stage_blob_issue(smem, gw, (uint32_t)sizeof(Weights), &stage_bar);
+  bool weights_ready = false;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -173,7 +176,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
       cprev[q] = live ? *reinterpret_cast<const float4*>(c_in + row * H + half * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     // ---- x0 -> A0, (1 - done) * h -> AL[:, 64:128): coalesced float4 loads, fp16 core-matrix stores
-#pragma unroll 4
+#pragma unroll
     for (int it = 0; it < (TILE * H) / (4 * THREADS); ++it) {
       const int e = 4 * (it * THREADS + tid), r = e / H, k = e % H;
       float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), hv = xv;
@@ -190,6 +193,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
           make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     }
     publish_smem();
+    if (!weights_ready) { stage_blob_wait(&stage_bar); weights_ready = true; }
 
     // ---- trunk[2:4]: x1 = tanh(x0 W1^T + b1) -> AL[:, 0:64)
     if (tid == 0) gemm(tmem + TM_D1, sbase + SM_A0, sbase + (uint32_t)offsetof(Weights, w1), H, H, bar);

@@ -85,6 +85,8 @@ class MCTS:
     #: largest wave as a fraction of the root's visits for which the wave-parallel search reproduces the
     #: reference planner's root statistics at large budgets (tests/test_pomcp_gpu.py)
     WAVE_GROWTH = 1.0 / 2048.0
+    #: host threads that run the per-tree updates of a forest (trees_per_gpu >= 4)
+    UPDATE_THREADS = 8
 
     def __init__(
         self,
@@ -185,6 +187,7 @@ class MCTS:
         self.step_statistics: Dict[str, float] = {}
         self.stat_tracker = PlanningStatTracker(self)
         self._siblings = []
+        self._update_pool = None
         if trees_per_gpu > 1:
             if self._host_mode:
                 raise NotImplementedError("trees_per_gpu > 1 needs the device search (random search / other-agent policies)")
@@ -322,14 +325,40 @@ class MCTS:
         if self._root_absorbing:
             return
         start = time.time()
-        for tree in [self] + self._siblings:
+
+        def update_tree(tree):
             if tree._root_absorbing:
-                continue
+                return
             if tree._root_t == 0:
                 tree._last_action = None
                 tree._initial_update(obs)
             else:
                 tree._update(action, obs)
+
+        trees = [self] + self._siblings
+        if len(trees) < 4:
+            for tree in trees:
+                update_tree(tree)
+        else:
+            # the per-tree update is a handful of tiny launches with a host synchronisation after each: run the
+            # trees on a few host threads, each with its own stream (the C-ABI calls release the GIL while they wait)
+            if self._update_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                n = min(self.UPDATE_THREADS, len(trees))
+                self._update_pool = ThreadPoolExecutor(max_workers=n)
+                self._update_streams = [torch.cuda.Stream(device=self._b.device) for _ in range(n)]
+            torch.cuda.current_stream(self._b.device).synchronize()
+            n = len(self._update_streams)
+
+            def work(w):
+                with torch.cuda.device(self._b.device), torch.cuda.stream(self._update_streams[w]):
+                    for tree in trees[w::n]:
+                        update_tree(tree)
+                    torch.cuda.current_stream().synchronize()
+
+            for f in [self._update_pool.submit(work, w) for w in range(n)]:
+                f.result()
         torch.cuda.synchronize(self._b.device)
         for sib in self._siblings:
             self.step_statistics["reinvigoration_time"] += sib.step_statistics["reinvigoration_time"]
@@ -604,6 +633,9 @@ class MCTS:
             sib._arena = sib._arena_spare = sib._reroot_scratch = None
             sib._root_particles = None
         self._siblings = []
+        if self._update_pool is not None:
+            self._update_pool.shutdown(wait=True)
+            self._update_pool = None
 
     def __str__(self):
         return f"{self.__class__.__name__}"

@@ -1,6 +1,6 @@
 """The rollout collector's inner loop on the device (ppo/worker.py:135-224 of the reference): per step
 ``policy.get_action_and_value`` on the current observations, ``envs.step`` with the sampled actions, store
-reward / done / value / log-prob.  Three launches per step -- ``posg_vec_embed`` (trunk layer 0 on the packed
+reward / done / value / log-prob.  Three kernels of the library per step -- ``posg_vec_embed`` (trunk layer 0 on the packed
 observation), ``posg_policy_step`` (the rest of the network on the tensor cores, samples the actions),
 ``posg_vec_step`` (env step, TimeLimit, statistics, auto-reset; no one-hot rows) -- and the whole
 ``rollout_length``-step loop is captured in ONE CUDA graph: the step index of every Philox counter lives in
@@ -32,6 +32,10 @@ class DeviceCollector:
         self.actions = torch.zeros((T, R), dtype=torch.int64, device=dev)
         self.logprobs, self.values, self.entropies = (torch.zeros((T, R), **f32) for _ in range(3))
         self.rewards = torch.zeros((T, R), **f32)
+        # terminated / truncated as envs.step returned them: row t + 1 is written by step t, row 0 carries over from
+        # the previous rollout; dones = their OR, computed once per rollout
+        self.terms = torch.zeros((T + 1, R), dtype=torch.uint8, device=dev)
+        self.truncs = torch.zeros((T + 1, R), dtype=torch.uint8, device=dev)
         self.dones = torch.zeros((T + 1, R), dtype=torch.uint8, device=dev)
         self.states = torch.zeros((T, num_envs, self.envs._state.shape[1]), dtype=torch.int32, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
@@ -43,11 +47,9 @@ class DeviceCollector:
         self.states[t].copy_(e._state)                       # packed observations' source (the learner re-embeds it)
         self._embed()
         out = {"action": self.actions[t], "logprob": self.logprobs[t], "entropy": self.entropies[t], "value": self.values[t]}
-        p.step(self.x0, (self.h, self.c), None, terminated=e._term, truncated=e._trunc, seed=self.seed,
+        p.step(self.x0, (self.h, self.c), None, terminated=self.terms[t], truncated=self.truncs[t], seed=self.seed,
                row_offset=self.env_offset * e.num_agents, step_device=e._step_ctr, out=out)
-        torch.bitwise_or(e._term, e._trunc, out=self.dones[t])   # next_done of the previous step = done at t
-        e.step_device(self.actions[t])
-        self.rewards[t].copy_(e._rew)
+        e.step_device(self.actions[t], outs=(self.rewards[t], self.terms[t + 1], self.truncs[t + 1]))
 
     def _embed(self):
         from posggym_baselines_b200 import _lib
@@ -58,9 +60,11 @@ class DeviceCollector:
                                                  64, 1, _lib.ptr(self.x0), _lib.stream_ptr()))
 
     def rollout_eager(self):
+        self.terms[0].copy_(self.terms[self.T])      # next_done of the previous rollout (zeros after reset)
+        self.truncs[0].copy_(self.truncs[self.T])
         for t in range(self.T):
             self._step(t)
-        torch.bitwise_or(self.envs._term, self.envs._trunc, out=self.dones[self.T])
+        torch.bitwise_or(self.terms, self.truncs, out=self.dones)
 
     def capture(self):
         """Captures one whole rollout; afterwards ``rollout()`` is a single graph launch."""

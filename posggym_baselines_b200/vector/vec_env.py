@@ -78,7 +78,7 @@ class BatchedVecEnv:
     def single_observation_shape(self):
         return (self.flat_dim,)
 
-    def _launch(self, actions, reset_only: int, graphed: bool = False):
+    def _launch(self, actions, reset_only: int, graphed: bool = False, outs=None):
         # hot loop of the collector: buffer pointers are cached (the buffers live as long as the
         # env), the device guard is only entered when another device is current
         if self._args is None:
@@ -91,6 +91,11 @@ class BatchedVecEnv:
                  _lib.ptr(self._done), _lib.ptr(self._stat_r), _lib.ptr(self._stat_l)),
                 (_lib.ptr(self._t0), _lib.ptr(self._stat_t)))
         head, tail, clock = self._args
+        if outs is not None:
+            # the collector's rollout storage: rewards / terminated / truncated of this step go straight into its
+            # [T, rows] buffers (no copy kernels between the launches of a captured rollout)
+            rew, term, trunc = outs
+            tail = (tail[0], _lib.ptr(rew), _lib.ptr(term), _lib.ptr(trunc)) + tail[4:]
         a = None if actions is None else actions.data_ptr()
         now = time.perf_counter()
         # device-counter mode (capture_step / enable_device_counter): the step index lives on the
@@ -164,7 +169,7 @@ class BatchedVecEnv:
             self._step_ctr[0] = self._global_step
             self._device_counter = True
 
-    def step_device(self, actions: torch.Tensor):
+    def step_device(self, actions: torch.Tensor, outs=None):
         """Graph-capturable ``envs.step``: ``actions`` must be an int64 CUDA tensor of
         ``num_envs * num_agents`` entries; no host-side conversion, clock or synchronisation.  Call
         it inside ``torch.cuda.graph(...)`` (after ``enable_device_counter()``) together with the
@@ -175,7 +180,7 @@ class BatchedVecEnv:
             self.enable_device_counter()
         assert self._device_counter, "call enable_device_counter() before capturing"
         self._global_step += 1    # informational in this mode: the device counter is authoritative
-        self._launch(actions, 0, graphed=capturing)
+        self._launch(actions, 0, graphed=capturing, outs=outs)
         return self.step(None, _replay_only=True)
 
     def capture_step(self):
