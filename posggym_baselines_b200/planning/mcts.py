@@ -161,6 +161,7 @@ class MCTS:
         self._A, self._OW, self._SW = na.value, ow.value, sw.value
         assert self._A == len(self.action_space)
         self._arena: Optional[torch.Tensor] = None
+        self._bbuf, self._bflip, self._rej = [None, None], 0, None
         self._params = _lib.SearchParams()
         kb = config.known_bounds
         self._params.discount = config.discount
@@ -400,18 +401,27 @@ class MCTS:
             t0 = time.time()
             target = cfg.num_particles + cfg.extra_particles
             # particles the searches left at the child (belief.add_particle, mcts.py:371)
-            # (the log's length is known on the host: get_action / the last re-root recorded it)
-            buf = torch.empty((min(self._log_bound, self._cap_log) + target, self._SW), dtype=torch.int32, device=b.device)
+            # (the log's length is known on the host: get_action / the last re-root recorded it).  Two persistent
+            # buffers, grown geometrically and used in turn (the old belief is the parent of the reinvigoration):
+            # no allocator traffic in the update
+            rows = min(self._log_bound, self._cap_log) + target
+            self._bflip ^= 1
+            buf = self._bbuf[self._bflip]
+            if buf is None or buf.shape[0] < rows:
+                cap = 1 << max(12, int(rows - 1).bit_length())
+                buf = self._bbuf[self._bflip] = torch.empty((cap, self._SW), dtype=torch.int32, device=b.device)
             cnt = np.zeros(1, np.int64)
             with torch.cuda.device(b.device):
                 _lib.check(_lib.lib().posg_tree_gather_belief(
                     b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, child, _lib.ptr(buf),
-                    buf.shape[0] - target, _lib.ptr(cnt), self._stream()))
+                    rows - target, _lib.ptr(cnt), self._stream()))
             have = int(cnt[0])
             need = target - have
             if need > 0:
                 limit = int(cfg.reinvigoration_sample_limit_factor * need)
-                rej = torch.empty((need, self._SW), dtype=torch.int32, device=b.device)
+                if self._rej is None or self._rej.shape[0] < need:
+                    self._rej = torch.empty((max(need, target), self._SW), dtype=torch.int32, device=b.device)
+                rej = self._rej
                 res = np.zeros(3, np.int64)
                 with torch.cuda.device(b.device):
                     _lib.check(_lib.lib().posg_belief_reinvigorate(
