@@ -310,6 +310,7 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
         o = m.sample_initial_obs(s)
         p.reset()
         c_sims = []
+        rng = random.Random(rank)
         for d in range(12):
             a = p.step(o["0"])
             if p.step_statistics["num_sims"] == p.step_statistics["num_sims"]:

@@ -497,7 +497,12 @@ int posg_tree_reroot(posg_model_t m, void* src_arena, void* dst_arena, int64_t c
     }
     int na = k.n_actions;
     void* args[] = {(void*)&S, (void*)&na, (void*)&new_root, (void*)&mark, (void*)&order, (void*)&counters};
-    POSG_CUDA(cudaLaunchCooperativeKernel((const void*)reroot_bfs_kernel, dim3(bfs_grid[dev]), dim3(256), args, 0, s));
+    // a small tree gets a small grid: the level barriers are cheaper, and the re-roots of a forest's trees (issued
+    // from several streams) fit on the GPU side by side instead of each waiting for all of it
+    long long want = (n_old + 2047) / 2048;
+    if (want < 8) want = 8;
+    const int grid = (int)(want < (long long)bfs_grid[dev] ? want : (long long)bfs_grid[dev]);
+    POSG_CUDA(cudaLaunchCooperativeKernel((const void*)reroot_bfs_kernel, dim3(grid), dim3(256), args, 0, s));
   }
   reroot_copy_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.n_actions, k.obs_words, mark, order, counters);
   POSG_CUDA(cudaGetLastError());
@@ -952,6 +957,49 @@ int posg_belief_initial(posg_model_t m, int ego_agent, const uint64_t* target_ob
   POSG_CUDA(cudaMemcpyAsync(result_host, d_res, 24, cudaMemcpyDeviceToHost, s));
   POSG_CUDA(cudaStreamSynchronize(s));
   cudaFreeAsync(d_obs, s);
+  return POSG_OK;
+}
+
+// MCTS._update (mcts.py:229-263) for one tree in ONE call: advance to the (action, observation) child, collect the
+// particles the searches left there, top the belief up by rejection sampling from the old root belief, re-root.
+// The steps are the entry points above (each ends with the read-back its successor's arguments need); doing them
+// behind one call lets a host thread per stream update the trees of a forest without taking the interpreter lock
+// between the steps.
+int posg_tree_update(posg_model_t m, void* arena, void* spare_arena, int64_t cap_nodes, int64_t cap_log, int root,
+                     int action, const uint64_t* obs_host, int ego_agent, const uint32_t* parent_particles,
+                     int64_t n_parent, uint32_t* belief_out, int64_t belief_capacity, int64_t log_bound, int64_t target,
+                     double sample_limit_factor, uint64_t seed, uint64_t draw_id, uint32_t* reject_scratch,
+                     int32_t* reroot_scratch, int64_t* result_host, void* stream) {
+  POSG_REQUIRE(result_host && belief_out && target >= 0 && log_bound >= 0 && belief_capacity >= log_bound + target,
+               "bad arguments");
+  for (int i = 0; i < 8; ++i) result_host[i] = 0;
+  int out4[4] = {0, 0, 0, 0};
+  int rc = posg_tree_advance(m, arena, cap_nodes, cap_log, root, action, obs_host, 1, out4, stream); if (rc) return rc;
+  const int child = out4[0], flags = out4[2];
+  result_host[0] = child; result_host[1] = flags;
+  if (child < 0) return POSG_OK;   // arena full: the caller reports it
+  int64_t have = 0;
+  if (!(flags & 2)) {
+    rc = posg_tree_gather_belief(m, arena, cap_nodes, cap_log, child, belief_out, log_bound, &have, stream); if (rc) return rc;
+    if (have > log_bound) have = log_bound;
+    const int64_t need = target - have;
+    if (need > 0) {
+      const int64_t limit = (int64_t)(sample_limit_factor * (double)need);
+      int64_t res[3] = {0, 0, 0};
+      KindInfo k;
+      if (!kind_info(m, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+      rc = posg_belief_reinvigorate(m, parent_particles, n_parent, ego_agent, action, obs_host, need, limit, seed, draw_id,
+                                    belief_out + have * k.state_words, reject_scratch, res, stream);
+      if (rc) return rc;
+      have += res[2];
+      result_host[5] = limit;     // draw counters consumed
+      result_host[6] = 1;         // reinvigoration ran
+    }
+  }
+  result_host[2] = have;
+  int64_t rr[2] = {0, 0};
+  rc = posg_tree_reroot(m, arena, spare_arena, cap_nodes, cap_log, child, reroot_scratch, rr, stream); if (rc) return rc;
+  result_host[3] = rr[0]; result_host[4] = rr[1];
   return POSG_OK;
 }
 

@@ -253,6 +253,13 @@ class MCTS:
                 _lib.check(lib.posg_tree_reset(self._b._handle, _lib.ptr(self._arena_spare), self._cap_nodes,
                                                self._cap_log, 0, 1.0, 0.0, self._stream()))
             self._reroot_scratch = torch.empty(3 * self._cap_nodes, dtype=torch.int32, device=self._b.device)
+            # belief buffers of the update, sized for a typical decision's particle log up front: an allocation
+            # during the update (cudaMalloc behind the caching allocator) stalls every stream of a forest's update
+            rows = min(self._cap_log, 1 << 19) + self.config.num_particles + self.config.extra_particles
+            cap = 1 << max(12, int(rows - 1).bit_length())
+            self._bbuf = [torch.empty((cap, self._SW), dtype=torch.int32, device=self._b.device) for _ in range(2)]
+            self._rej = torch.empty((max(1, self.config.num_particles + self.config.extra_particles), self._SW),
+                                    dtype=torch.int32, device=self._b.device)
 
     def _stats(self, node: Optional[int] = None) -> Dict[str, object]:
         out = np.zeros(3 * self._A + 10, np.float64)
@@ -350,12 +357,15 @@ class MCTS:
                 self._update_pool = ThreadPoolExecutor(max_workers=n)
                 self._update_streams = [torch.cuda.Stream(device=self._b.device) for _ in range(n)]
             torch.cuda.current_stream(self._b.device).synchronize()
+            self._update_trace = []
             n = len(self._update_streams)
 
             def work(w):
                 with torch.cuda.device(self._b.device), torch.cuda.stream(self._update_streams[w]):
                     for tree in trees[w::n]:
+                        t_tree = time.time()
                         update_tree(tree)
+                        self._update_trace.append((tree._forest_index, w, t_tree - start, time.time() - t_tree))
                     torch.cuda.current_stream().synchronize()
 
             for f in [self._update_pool.submit(work, w) for w in range(n)]:
@@ -386,63 +396,49 @@ class MCTS:
         self._nodes_bound, self._log_bound = 1, 0
 
     def _update(self, action, obs):
+        """``MCTS._update`` (mcts.py:229-263) in one library call (posg_tree_update): advance to the child, gather
+        the particles the searches left there (belief.add_particle, mcts.py:371), reinvigorate, re-root keeping the
+        subtree.  One call = one interpreter-lock hand-over per tree when a forest updates on several threads."""
         cfg, b = self.config, self._b
         key = np.ascontiguousarray(b.pack_obs(obs), dtype=np.uint64)
-        out4 = np.zeros(4, np.int32)
+        target = cfg.num_particles + cfg.extra_particles
+        # (the log's length is known on the host: get_action / the last re-root recorded it).  Two persistent belief
+        # buffers, grown geometrically and used in turn (the old belief is the parent of the reinvigoration): no
+        # allocator traffic in the update
+        log_bound = min(self._log_bound, self._cap_log)
+        rows = log_bound + target
+        self._bflip ^= 1
+        buf = self._bbuf[self._bflip]
+        if buf is None or buf.shape[0] < rows:
+            cap = 1 << max(12, int(rows - 1).bit_length())
+            buf = self._bbuf[self._bflip] = torch.empty((cap, self._SW), dtype=torch.int32, device=b.device)
+        if self._rej is None:
+            self._rej = torch.empty((max(target, 1), self._SW), dtype=torch.int32, device=b.device)
+        res = np.zeros(8, np.int64)
+        t0 = time.time()
         with torch.cuda.device(b.device):
-            _lib.check(_lib.lib().posg_tree_advance(
-                b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, self._root, int(action),
-                _lib.ptr(key), 1, _lib.ptr(out4), self._stream()))
-        child, flags = int(out4[0]), int(out4[2])
+            _lib.check(_lib.lib().posg_tree_update(
+                b._handle, _lib.ptr(self._arena), _lib.ptr(self._arena_spare), self._cap_nodes, self._cap_log,
+                self._root, int(action), _lib.ptr(key), self._ego, _lib.ptr(self._root_particles),
+                self._root_particles.shape[0], _lib.ptr(buf), buf.shape[0], log_bound, target,
+                float(cfg.reinvigoration_sample_limit_factor), self._params.seed ^ 0x5DEECE66D,
+                self._draw_base + self._draw_counter, _lib.ptr(self._rej), _lib.ptr(self._reroot_scratch),
+                _lib.ptr(res), self._stream()))
+        child, flags = int(res[0]), int(res[1])
         if child < 0:
             raise RuntimeError("search tree arena is full; raise node_capacity")
+        self._draw_counter += int(res[5])
         absorbing = bool(flags & 2)
         if not absorbing:
-            t0 = time.time()
-            target = cfg.num_particles + cfg.extra_particles
-            # particles the searches left at the child (belief.add_particle, mcts.py:371)
-            # (the log's length is known on the host: get_action / the last re-root recorded it).  Two persistent
-            # buffers, grown geometrically and used in turn (the old belief is the parent of the reinvigoration):
-            # no allocator traffic in the update
-            rows = min(self._log_bound, self._cap_log) + target
-            self._bflip ^= 1
-            buf = self._bbuf[self._bflip]
-            if buf is None or buf.shape[0] < rows:
-                cap = 1 << max(12, int(rows - 1).bit_length())
-                buf = self._bbuf[self._bflip] = torch.empty((cap, self._SW), dtype=torch.int32, device=b.device)
-            cnt = np.zeros(1, np.int64)
-            with torch.cuda.device(b.device):
-                _lib.check(_lib.lib().posg_tree_gather_belief(
-                    b._handle, _lib.ptr(self._arena), self._cap_nodes, self._cap_log, child, _lib.ptr(buf),
-                    rows - target, _lib.ptr(cnt), self._stream()))
-            have = int(cnt[0])
-            need = target - have
-            if need > 0:
-                limit = int(cfg.reinvigoration_sample_limit_factor * need)
-                if self._rej is None or self._rej.shape[0] < need:
-                    self._rej = torch.empty((max(need, target), self._SW), dtype=torch.int32, device=b.device)
-                rej = self._rej
-                res = np.zeros(3, np.int64)
-                with torch.cuda.device(b.device):
-                    _lib.check(_lib.lib().posg_belief_reinvigorate(
-                        b._handle, _lib.ptr(self._root_particles), self._root_particles.shape[0], self._ego,
-                        int(action), _lib.ptr(key), need, limit, self._params.seed ^ 0x5DEECE66D,
-                        self._next_draw(limit), _lib.ptr(buf[have:]), _lib.ptr(rej), _lib.ptr(res), self._stream()))
-                have += int(res[2])
-            self._root_particles = buf[:have]
-            self.step_statistics["reinvigoration_time"] += time.time() - t0
-        self._root = child
+            self._root_particles = buf[:int(res[2])]
+            if res[6]:
+                self.step_statistics["reinvigoration_time"] += time.time() - t0   # (the whole call: it ran inside)
         self._root_t += 1
         self._root_absorbing = absorbing
-        # keep the subtree under the new root, drop everything else (mcts.py:261-263)
-        res = np.zeros(2, np.int64)
-        with torch.cuda.device(b.device):
-            _lib.check(_lib.lib().posg_tree_reroot(
-                b._handle, _lib.ptr(self._arena), _lib.ptr(self._arena_spare), self._cap_nodes, self._cap_log,
-                child, _lib.ptr(self._reroot_scratch), _lib.ptr(res), self._stream()))
+        # the subtree under the new root was kept, renumbered into the other arena (mcts.py:261-263)
         self._arena, self._arena_spare = self._arena_spare, self._arena
         self._root = 0
-        self._nodes_bound, self._log_bound = int(res[0]), int(res[1])
+        self._nodes_bound, self._log_bound = int(res[3]), int(res[4])
         self.tree_compactions += 1
 
     # ------------------------------------------------------------------ search

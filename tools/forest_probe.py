@@ -21,6 +21,10 @@ for K in [int(a) for a in sys.argv[1:]] or [1, 8, 32]:
         if p.root.is_absorbing:
             break
         st, info = p.step_statistics, p.search_info
+        tr = sorted(getattr(p, "_update_trace", []), key=lambda r: -r[3])[:3]
+        if tr and st["update_time"] > 0.08:
+            print("   slow update: total %.3f; slowest trees (idx, thread, start, dur):" % st["update_time"], [(a, b, round(c, 4), round(d, 4)) for a, b, c, d in tr],
+                  "sum of durations %.3f" % sum(r[3] for r in p._update_trace))
         rows.append((info["num_sims"], info["sims_per_tree"], round(st["search_time"], 4), round(st["update_time"], 4),
                      info["waves"], info["last_wave"], round(info["arena_fill"], 4)))
         obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
