@@ -366,7 +366,7 @@ __device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint
     const int f1 = i == 2 ? t02 : t01, f2 = i == 0 ? t02 : t12;
     // candidate keys score << 10 | biased offset: the second of a pair wins a tie iff the pick says so
     // (score - 1 instead of + 1)
-    const int second = 2048 * sgn + 1024;
+    const int second = (sgn & (int)0xFFFFF800u) | 0x400;   // 2048 * sgn + 1024 = +-1024 in one LOP3
     const int d0 = p0 + rc, d1 = p1 + rc, e1 = occ[j1] + rc, e2 = occ[j2] + rc;
     const int k0 = THR[d0 - REL0] * 1024 + d0;
     const int k1 = THR[d1 - REL0] * 1024 + (second + d1);
@@ -397,10 +397,13 @@ __device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint
   // predators: simultaneous moves; prey cells and shared targets block
   int pot[NP];
   const int pc[NP] = {p0, p1};
+  // (the prey cells as three bytes: "c equals one of them" is the zero-byte test on the XOR with c in every byte)
+  const uint32_t occ3 = (uint32_t)occ[0] + ((uint32_t)occ[1] * 256u + (uint32_t)occ[2] * 65536u);
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
     const int c = (int)B.pred_move[act[i] * 256 + pc[i]];
-    const bool on_prey = (c == occ[0]) || (c == occ[1]) || (c == occ[2]);
+    const uint32_t x = occ3 ^ ((uint32_t)c * 0x010101u);
+    const bool on_prey = ((x - 0x010101u) & ~x & 0x808080u) != 0u;
     pot[i] = on_prey ? pc[i] : c;
   }
   const bool clash = pot[0] == pot[1];
@@ -435,7 +438,7 @@ __device__ __forceinline__ bool transition_lut(const Blob& B, uint32_t& w0, uint
     }
   }
   // caught prey keep the cell they had; newly caught ones the cell they were caught on
-  const uint32_t moved = (uint32_t)occ[0] + ((uint32_t)occ[1] * 256u + (uint32_t)occ[2] * 65536u);
+  const uint32_t moved = occ3;
   const uint32_t all = caught | newly;
   w0 = (uint32_t)n0 + ((uint32_t)n1 * 256u + all * 65536u);
   w1 = (w1 & cmask) | (moved & ~cmask);
