@@ -35,7 +35,14 @@ struct alignas(16) Blob {
   // bits 8 + 6 k .. 13 + 6 k: (dx + sight + 1) | (dy + sight + 1) << 3 of food k
   unsigned long long vis[256];
   uint32_t vis3[256];         // bit 3 k: food k within sight of cell x | y << 4 (the level bits' positions in w1)
+  // normalised rewards (double)(level * food_level) / (double)(loaders' level sum * total level spawned), every
+  // quotient the state can ask for, divided once on the host (IEEE, the oracle's float division): DEVICE pointer
+  // to REWARD_DEN x REWARD_NUM doubles in global memory (a load rarely executed instead of a ~50-instruction
+  // division the whole warp waits for); NULL on the host copy
+  const double* reward_div;
+  uint64_t pad2_;
 };
+constexpr int REWARD_NUM = 3 * 7 + 1, REWARD_DEN = 6 * 63 + 1;
 static_assert(sizeof(Blob) % 16 == 0, "blob must be a multiple of 16 B");
 
 // host side: fill the tables from food_xy / size / sight
@@ -108,7 +115,7 @@ __device__ __forceinline__ bool transition(const Blob& B, uint32_t& w0, uint32_t
   w0 = (w0 & 0xFFF00000u) | cell[0] | (lvl[0] << 8) | ((cell[1] | (lvl[1] << 8)) << 10);
   rew[0] = 0.0; rew[1] = 0.0;
   if (load_sh[0] != 24u || load_sh[1] != 24u) {   // somebody loads
-    const double spawned = (double)((w0 >> 20) & 63u);
+    const uint32_t spawned = (w0 >> 20) & 63u;
     bool pending[NPL] = {load_sh[0] != 24u, load_sh[1] != 24u};
     // loading, in player index order; a group = the pending loaders adjacent to the same food
 #pragma unroll
@@ -136,7 +143,7 @@ __device__ __forceinline__ bool transition(const Blob& B, uint32_t& w0, uint32_t
       for (int j = 0; j < NPL; ++j) {
         if (!in_group[j]) continue;
         double r = (double)(lvl[j] * flevel);
-        if (B.normalize_reward) r = __ddiv_rn(r, __dmul_rn((double)level_sum, spawned));
+        if (B.normalize_reward) r = __ldg(B.reward_div + (level_sum * spawned) * (uint32_t)REWARD_NUM + lvl[j] * flevel);
         rew[j] = __dadd_rn(rew[j], r);
       }
       w1 &= ~(7u << sh);

@@ -150,9 +150,20 @@ int posg_lbf_create(int size, int num_agents, int max_agent_level, int max_food,
   posg_model* m = new posg_model();
   m->kind = KIND_LBF; m->num_agents = num_agents; m->blob_bytes = (int)sizeof(lbf::Blob);
   m->h_blob = h; m->d_blob = nullptr;
+  // the reward quotient table follows the staged blob in the same allocation (only the blob is staged into shared
+  // memory; the table stays in global memory)
+  std::vector<double> div((size_t)lbf::REWARD_DEN * lbf::REWARD_NUM, 0.0);
+  for (int d = 1; d < lbf::REWARD_DEN; ++d)
+    for (int n = 0; n < lbf::REWARD_NUM; ++n) div[(size_t)d * lbf::REWARD_NUM + n] = (double)n / (double)d;
   cudaError_t e = cudaGetDevice(&m->device);
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, sizeof(lbf::Blob));
-  if (e == cudaSuccess) e = cudaMemcpy(m->d_blob, h, sizeof(lbf::Blob), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_blob, sizeof(lbf::Blob) + div.size() * sizeof(double));
+  if (e == cudaSuccess) {
+    lbf::Blob up = *h;
+    up.reward_div = (const double*)((const unsigned char*)m->d_blob + sizeof(lbf::Blob));
+    e = cudaMemcpy(m->d_blob, &up, sizeof(lbf::Blob), cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpy((unsigned char*)m->d_blob + sizeof(lbf::Blob), div.data(), div.size() * sizeof(double), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { int rc = cuda_fail(e, "model upload"); posg_model_destroy(m); return rc; }
   *out = m;
   return POSG_OK;
