@@ -24,7 +24,8 @@ struct alignas(16) Blob {
   uint8_t player_xy[4];       // start cells
   uint8_t size, sight, max_agent_level, force_coop, normalize_reward;
   uint8_t vis_max;            // most foods any cell can see (build_tables); <= 7: the observation stream fits 64 bits
-  uint8_t pad_[2];
+  uint8_t adj_fast;           // 1: N, S, W, E order of a cell's adjacent foods = ascending food index (adj3 + ffs)
+  uint8_t pad_[1];
   int8_t move_delta[8];       // cell-index delta (x | y << 4 arithmetic) of NONE, N, S, W, E, LOAD
   // 3 * k of the food whose cell is x | y << 4, 24 if there is none: level = (w1 >> shift) & 7
   // (w1 holds 24 level bits, so shift 24 reads 0)
@@ -35,6 +36,7 @@ struct alignas(16) Blob {
   // bits 8 + 6 k .. 13 + 6 k: (dx + sight + 1) | (dy + sight + 1) << 3 of food k
   unsigned long long vis[256];
   uint32_t vis3[256];         // bit 3 k: food k within sight of cell x | y << 4 (the level bits' positions in w1)
+  uint32_t adj3[256];         // bit 3 k: food k is the N, S, W or E neighbour of cell x | y << 4; bit 24 always set
   // normalised rewards (double)(level * food_level) / (double)(loaders' level sum * total level spawned), every
   // quotient the state can ask for, divided once on the host (IEEE, the oracle's float division): DEVICE pointer
   // to REWARD_DEN x REWARD_NUM doubles in global memory (a load rarely executed instead of a ~50-instruction
@@ -76,10 +78,32 @@ inline void build_tables(Blob* b) {
       if (x < size && y < size && seen > vis_max) vis_max = seen;
     }
   b->vis_max = (uint8_t)vis_max;
+  // adjacent foods as a mask over the level bits of w1; the lowest set bit is the N, S, W, E choice when the foods
+  // next to every cell come in ascending index order (true for the lattice layouts: two foods are never
+  // adjacent to one cell across a corner)
+  bool ordered = true;
+  for (int c = 0; c < 256; ++c) {
+    const uint32_t a = b->adj_sh[c];
+    const uint32_t in_order[4] = {a & 255u, (a >> 8) & 255u, (a >> 16) & 255u, a >> 24};   // N, S, W, E
+    uint32_t m = 1u << 24, last = 0;
+    bool first = true;
+    for (int q = 0; q < 4; ++q) {
+      if (in_order[q] == 24u) continue;
+      m |= 1u << in_order[q];
+      if (!first && in_order[q] < last) ordered = false;
+      last = in_order[q]; first = false;
+    }
+    b->adj3[c] = m;
+  }
+  b->adj_fast = ordered ? 1 : 0;
 }
 
 // shift (3 * food index) of the first uncollected food next to `cell` in the order N, S, W, E; 24 if none
 __device__ __forceinline__ uint32_t adjacent_food(const Blob& B, uint32_t w1, uint32_t cell) {
+  if (B.adj_fast) {   // (uniform) bit 3 k of nz: food k still has a level; bit 24 of adj3 yields "none"
+    const uint32_t nz = w1 | (w1 >> 1) | (w1 >> 2) | (1u << 24);
+    return (uint32_t)__ffs((int)(B.adj3[cell] & nz & 0x1249249u)) - 1u;
+  }
   const uint32_t a = B.adj_sh[cell];
   const uint32_t sn = a & 255u, ss = (a >> 8) & 255u, sw = (a >> 16) & 255u, se = a >> 24;
   uint32_t sh = ((w1 >> se) & 7u) ? se : 24u;
