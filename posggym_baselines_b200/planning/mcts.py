@@ -85,6 +85,8 @@ class MCTS:
     #: largest wave as a fraction of the root's visits for which the wave-parallel search reproduces the
     #: reference planner's root statistics at large budgets (tests/test_pomcp_gpu.py)
     WAVE_GROWTH = 1.0 / 2048.0
+    #: smallest wave by root visits: (visits from which it applies, wave size), ascending
+    WAVE_FLOORS = ((0, 32), (8192, 64))
     #: host threads that run the per-tree updates of a forest (trees_per_gpu >= 4)
     UPDATE_THREADS = 8
 
@@ -487,8 +489,10 @@ class MCTS:
                         wave = min(wave, 1024)   # one CTA per tree
                 waves = chunk
                 if not self.wave_size:   # stay on this wave size only while the schedule allows it
-                    grow_at = 8192 if root_visits < 8192 else (
-                        int((wave + 32) / self.wave_growth) + 1 if wave < self.max_wave else 1 << 62)
+                    grow_at = int((wave + 32) / self.wave_growth) + 1 if wave < self.max_wave else 1 << 62
+                    for visits, _ in self.WAVE_FLOORS:   # the next floor of the schedule, if it comes first
+                        if root_visits < visits < grow_at:
+                            grow_at = visits
                     waves = max(1, min(chunk, (grow_at - root_visits + wave - 1) // wave))
                 if self.max_sims is not None:
                     left = self.max_sims - n_sims
@@ -584,7 +588,10 @@ class MCTS:
         """Simulations per wave for a root with ``root_visits`` visits: one warp while the tree is young, two
         warps from 8 192 visits on, then ``wave_growth`` (1/2048) of the visits -- the sizes for which the
         search reproduces the reference planner's root statistics at 65 536 and 262 144 simulations."""
-        floor = 32 if root_visits < 8192 else 64
+        floor = 32
+        for visits, wave in self.WAVE_FLOORS:
+            if root_visits >= visits:
+                floor = wave
         return max(floor, min(self.max_wave, (int(root_visits * self.wave_growth) // 32) * 32))
 
     _respect_time = False  # with max_sims set, the time limit only applies when asked for
