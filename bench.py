@@ -441,7 +441,7 @@ def bench_collector(dev, rank, world, seed, barrier):
     lstm = nn.LSTM(64, 64)
     for k, v in lstm.state_dict().items():
         sd["lstm." + k] = v
-    out = {"rollout_steps": 64, "launches_per_step": 3,
+    out = {"rollout_steps": 64, "launches_per_step": 2,
            "network": "PPOLSTMModel trunk [64, 64], LSTM 64, heads [64], random init; fp16 tensor-core operands, fp32 accumulate"}
     for label, nv in (("envs_8192_per_gpu", 8192), ("envs_131072_per_gpu", 131072)):
         col = DeviceCollector(LBFModel(device=dev), sd, nv, rollout_length=64, seed=seed, env_offset=rank * nv)

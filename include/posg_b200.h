@@ -392,6 +392,17 @@ int posg_vec_step(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_
 int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const float* wT, const float* bias,
                    int hidden, int apply_tanh, float* out, void* stream);
 
+/* envs.step FUSED with posg_vec_embed of the observations it returns (the collector's loop, worker.py:143-178:
+ * the rows envs.step returns are only ever fed to trunk layer 0): posg_vec_step's step (no one-hot rows, no wall
+ * clock) and, in the same launch, x_out [n * A, 64] = act(bias + sum of weight rows) for the NEXT policy step;
+ * state_copy_out (optional) also receives the new packed state (the rollout storage's row).  hidden must be 64. */
+int posg_vec_step_embed(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_t, double* ep_ret,
+                        uint32_t* ep_count, const int64_t* actions, uint64_t seed, uint32_t global_step,
+                        uint64_t env_offset, int max_episode_steps, float* rew_out, uint8_t* term_out,
+                        uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int32_t* stat_l, uint32_t* step_counter,
+                        const float* wT, const float* bias, int hidden, int apply_tanh, float* x_out,
+                        uint32_t* state_copy_out, void* stream);
+
 /* The rest of the collector's policy step: PPOLSTMModel.get_action_and_value
  * (ppo/network.py:212-268,305-330) after trunk[0:2] for trunk_sizes [64, 64], lstm_size 64, one LSTM layer,
  * head_sizes [64] (baseline_exps/exp_utils.py:101-104), fused into one tcgen05 tensor-core kernel

@@ -68,6 +68,8 @@ SIGNATURES = {
     "posg_vec_step": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _int, _int, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp]),
     "posg_vec_embed": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp]),
+    "posg_vec_step_embed": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u64, _int, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "posg_policy_create": (_int, [_int, _int] + [_vp] * 14 + [C.POINTER(_vp)]),
     "posg_policy_destroy": (_int, [_vp]),
     "posg_policy_step": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp,

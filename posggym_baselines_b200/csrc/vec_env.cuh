@@ -52,40 +52,19 @@ __device__ __forceinline__ void field_bytes(const unsigned long long (&obs)[M::O
   }
 }
 
-template <class M, int EPC, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
-                uint32_t* __restrict__ state, uint16_t* __restrict__ ep_t, double* __restrict__ ep_ret,
-                uint32_t* __restrict__ ep_count, const long long* __restrict__ actions,
-                const Quad* __restrict__ desc, int flat_dim, uint64_t seed, uint32_t global_step,
-                uint64_t env_offset, int max_episode_steps, int reset_only,
-                float* __restrict__ obs_out, float* __restrict__ rew_out, uint8_t* __restrict__ term_out,
-                uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out, float* __restrict__ stat_r,
-                int* __restrict__ stat_l, double now, double* __restrict__ ep_t0, double* __restrict__ stat_t,
-                uint32_t* __restrict__ step_counter) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ alignas(8) uint64_t mbar;
-  constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
-  static_assert(M::NFIELD <= MAX_FIELDS, "too many observation fields");
-  __shared__ uint32_t s_fields[EPC * NAG * ROW_WORDS];
-  __shared__ Quad s_desc[MAX_FLAT / 4];
-  const int Q = flat_dim >> 2;                 // float4s per row
-  for (int p = threadIdx.x; p < Q; p += NT) s_desc[p] = desc[p];
-  stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
-  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
-  // CUDA-graph replays bake the scalar arguments: the step index then comes from device memory,
-  // step_counter[0] + 1; the last CTA to finish publishes it for the next replay (every CTA has read
-  // the counter before it can finish; step_counter[1] counts the finished CTAs)
-  if (step_counter != nullptr) global_step = *((volatile uint32_t*)step_counter) + 1u;
-  const int tid = threadIdx.x;
-  const int row0 = tid / Q, q0 = tid - row0 * Q;      // this thread's first float4 of a chunk
-  const int dr = NT / Q, dq = NT - dr * Q;  // and its stride
-
-  for (int64_t base = (int64_t)blockIdx.x * EPC; base < n; base += (int64_t)gridDim.x * EPC) {
-    const int64_t i = base + tid;
-    if (tid < EPC && i < n) {
+// envs.step / envs.reset of ONE env (ppo/worker.py:176-216 through the wrapper stack of ppo/config.py:223-232): model
+// step, TimeLimit, RecordEpisodeStatistics, auto-reset; leaves the observations the call returns in `obs`.
+template <class M>
+__device__ __forceinline__ void step_one_env(
+    const typename M::Blob& B, int64_t i, uint32_t* __restrict__ state, uint16_t* __restrict__ ep_t,
+    double* __restrict__ ep_ret, uint32_t* __restrict__ ep_count, const long long* __restrict__ actions, uint64_t seed,
+    uint32_t global_step, uint64_t env_offset, int max_episode_steps, int reset_only, float* __restrict__ rew_out,
+    uint8_t* __restrict__ term_out, uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out,
+    float* __restrict__ stat_r, int* __restrict__ stat_l, double now, double* __restrict__ ep_t0,
+    double* __restrict__ stat_t, unsigned long long (&obs)[M::NAG][M::OW]) {
+  constexpr int SW = M::SW, NAG = M::NAG, NW = M::NW;
+  {
       typename M::State s;
-      unsigned long long obs[NAG][OW];
       const uint64_t env = env_offset + (uint64_t)i;
       if (reset_only) {
         // envs.reset(): fresh episode for every env
@@ -139,6 +118,44 @@ vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, 
       }
 #pragma unroll
       for (int k = 0; k < SW; ++k) state[i * SW + k] = s.w[k];
+  }
+}
+
+template <class M, int EPC, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+vec_step_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+                uint32_t* __restrict__ state, uint16_t* __restrict__ ep_t, double* __restrict__ ep_ret,
+                uint32_t* __restrict__ ep_count, const long long* __restrict__ actions,
+                const Quad* __restrict__ desc, int flat_dim, uint64_t seed, uint32_t global_step,
+                uint64_t env_offset, int max_episode_steps, int reset_only,
+                float* __restrict__ obs_out, float* __restrict__ rew_out, uint8_t* __restrict__ term_out,
+                uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out, float* __restrict__ stat_r,
+                int* __restrict__ stat_l, double now, double* __restrict__ ep_t0, double* __restrict__ stat_t,
+                uint32_t* __restrict__ step_counter) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NW = M::NW;
+  static_assert(M::NFIELD <= MAX_FIELDS, "too many observation fields");
+  __shared__ uint32_t s_fields[EPC * NAG * ROW_WORDS];
+  __shared__ Quad s_desc[MAX_FLAT / 4];
+  const int Q = flat_dim >> 2;                 // float4s per row
+  for (int p = threadIdx.x; p < Q; p += NT) s_desc[p] = desc[p];
+  stage_blob(smem_raw, gblob, blob_size, &mbar);  // contains a __syncthreads()
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  // CUDA-graph replays bake the scalar arguments: the step index then comes from device memory,
+  // step_counter[0] + 1; the last CTA to finish publishes it for the next replay (every CTA has read
+  // the counter before it can finish; step_counter[1] counts the finished CTAs)
+  if (step_counter != nullptr) global_step = *((volatile uint32_t*)step_counter) + 1u;
+  const int tid = threadIdx.x;
+  const int row0 = tid / Q, q0 = tid - row0 * Q;      // this thread's first float4 of a chunk
+  const int dr = NT / Q, dq = NT - dr * Q;  // and its stride
+
+  for (int64_t base = (int64_t)blockIdx.x * EPC; base < n; base += (int64_t)gridDim.x * EPC) {
+    const int64_t i = base + tid;
+    if (tid < EPC && i < n) {
+      unsigned long long obs[NAG][OW];
+      step_one_env<M>(B, i, state, ep_t, ep_ret, ep_count, actions, seed, global_step, env_offset, max_episode_steps,
+                      reset_only, rew_out, term_out, trunc_out, done_out, stat_r, stat_l, now, ep_t0, stat_t, obs);
 #pragma unroll
       for (int a = 0; a < NAG; ++a) {
         uint32_t fw[MAX_FIELDS / 4];
@@ -268,6 +285,83 @@ vec_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size,
       }
     }
     __syncthreads();
+  }
+}
+
+// envs.step FUSED with the next policy step's trunk layer 0 (the collector's loop: worker.py:143-178): phase 1 is
+// vec_step_kernel's (step_one_env), phase 2 is vec_embed_kernel's embedding-sum on the observations the step just
+// produced -- no one-hot rows, no second kernel that recomputes the observation from the state, and the new state is
+// also written to `state_copy` (the rollout storage's row for the next step) when that is not NULL.  H = 4 * LPR.
+template <class M, int LPR, int EPC>
+__global__ void __launch_bounds__(EMB_THREADS)
+vec_step_embed_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
+                      uint32_t* __restrict__ state, uint16_t* __restrict__ ep_t, double* __restrict__ ep_ret,
+                      uint32_t* __restrict__ ep_count, const long long* __restrict__ actions, uint64_t seed,
+                      uint32_t global_step, uint64_t env_offset, int max_episode_steps, float* __restrict__ rew_out,
+                      uint8_t* __restrict__ term_out, uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ done_out,
+                      float* __restrict__ stat_r, int* __restrict__ stat_l, uint32_t* __restrict__ step_counter,
+                      const uint16_t* __restrict__ field_offset, const float* __restrict__ wT,
+                      const float* __restrict__ bias, int apply_tanh, float* __restrict__ x_out,
+                      uint32_t* __restrict__ state_copy) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ alignas(8) uint64_t mbar;
+  constexpr int SW = M::SW, OW = M::OW, NAG = M::NAG, NF = M::NFIELD;
+  __shared__ uint16_t s_idx[EPC * NAG][MAX_FIELDS + 2];
+  __shared__ uint16_t s_off[MAX_FIELDS];
+  if (threadIdx.x < MAX_FIELDS) s_off[threadIdx.x] = threadIdx.x < NF ? field_offset[threadIdx.x] : 0;
+  stage_blob(smem_raw, gblob, blob_size, &mbar);
+  const typename M::Blob& B = *reinterpret_cast<const typename M::Blob*>(smem_raw);
+  if (step_counter != nullptr) global_step = *((volatile uint32_t*)step_counter) + 1u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * EPC; base < n; base += (int64_t)gridDim.x * EPC) {
+    const int64_t i = base + tid;
+    if (tid < EPC && i < n) {
+      unsigned long long obs[NAG][OW];
+      step_one_env<M>(B, i, state, ep_t, ep_ret, ep_count, actions, seed, global_step, env_offset, max_episode_steps, 0,
+                      rew_out, term_out, trunc_out, done_out, stat_r, stat_l, 0.0, nullptr, nullptr, obs);
+      if (state_copy != nullptr) {
+#pragma unroll
+        for (int k = 0; k < SW; ++k) state_copy[i * SW + k] = state[i * SW + k];
+      }
+#pragma unroll
+      for (int a = 0; a < NAG; ++a) {
+        uint32_t fw[MAX_FIELDS / 4];
+        field_bytes<M>(obs[a], fw);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_idx[tid * NAG + a][0]);
+#pragma unroll
+        for (int f = 0; f < NF; f += 2) {
+          const uint32_t v0 = (fw[f >> 2] >> (8 * (f & 3))) & 255u;
+          const uint32_t v1 = f + 1 < NF ? (fw[(f + 1) >> 2] >> (8 * ((f + 1) & 3))) & 255u : 0u;
+          dst[f >> 1] = (v0 + s_off[f]) | ((v1 + (f + 1 < NF ? s_off[f + 1] : 0u)) << 16);
+        }
+      }
+    }
+    __syncthreads();
+    const int64_t left = n - base;
+    const int rows = (int)(left < EPC ? left : EPC) * NAG;
+    constexpr int RPW = 32 / LPR;
+    const int sub = lane / LPR, col = (lane % LPR) * 4;
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+    for (int row = warp * RPW + sub; row < rows; row += (EMB_THREADS / 32) * RPW) {
+      float4 acc = b4;
+#pragma unroll
+      for (int f = 0; f < NF; ++f) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wT + (int)s_idx[row][f] * (4 * LPR) + col));
+        acc.x = __fadd_rn(acc.x, w.x); acc.y = __fadd_rn(acc.y, w.y);
+        acc.z = __fadd_rn(acc.z, w.z); acc.w = __fadd_rn(acc.w, w.w);
+      }
+      if (apply_tanh) { acc.x = tanhf(acc.x); acc.y = tanhf(acc.y); acc.z = tanhf(acc.z); acc.w = tanhf(acc.w); }
+      *reinterpret_cast<float4*>(x_out + (base * NAG + row) * (4 * LPR) + col) = acc;
+    }
+    __syncthreads();
+  }
+  if (step_counter != nullptr && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(step_counter + 1, 1u) == gridDim.x - 1u) {
+      step_counter[1] = 0u;
+      step_counter[0] = global_step;
+      __threadfence();
+    }
   }
 }
 

@@ -137,6 +137,32 @@ static int launch_vec(posg_model* m, int64_t n, Args... args) {
   return launch_vec_epc<M, 256, 256, 4>(m, n, args...);
 }
 
+// envs.step + the next policy step's trunk layer 0 in one launch (vec_step_embed_kernel); H = 64 (the reference's
+// trunk size, baseline_exps/exp_utils.py:101-104).  32 envs per CTA at collector-scale batches, 128 above.
+template <class M>
+static int launch_step_embed(posg_model* m, int64_t n, uint32_t* state, uint16_t* ep_t, double* ep_ret,
+                             uint32_t* ep_count, const long long* actions, uint64_t seed, uint32_t global_step,
+                             uint64_t env_offset, int max_steps, float* rew_out, uint8_t* term_out, uint8_t* trunc_out,
+                             uint8_t* done_out, float* stat_r, int* stat_l, uint32_t* step_counter, const float* wT,
+                             const float* bias, int apply_tanh, float* x_out, uint32_t* state_copy, cudaStream_t s) {
+  const uint16_t* off = (const uint16_t*)((const char*)m->d_flat_desc + (size_t)(m->flat_dim / 4) * sizeof(vec::Quad));
+#define POSG_STEP_EMBED(EPC)                                                                                        \
+  do {                                                                                                              \
+    smem_optin(vec::vec_step_embed_kernel<M, 16, EPC>, m->blob_bytes);                                             \
+    const int64_t need = (n + EPC - 1) / EPC;                                                                       \
+    vec::vec_step_embed_kernel<M, 16, EPC><<<(int)(need < (1 << 30) ? need : (1 << 30)), vec::EMB_THREADS,          \
+                                             m->blob_bytes, s>>>(                                                   \
+        (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state, ep_t, ep_ret, ep_count, actions, seed, \
+        global_step, env_offset, max_steps, rew_out, term_out, trunc_out, done_out, stat_r, stat_l, step_counter, off, \
+        wT, bias, apply_tanh, x_out, state_copy);                                                                   \
+  } while (0)
+  if (n < (int64_t)sm_count() * 2 * vec::EMB_EPC) POSG_STEP_EMBED(32);
+  else POSG_STEP_EMBED(128);
+#undef POSG_STEP_EMBED
+  POSG_CUDA(cudaGetLastError());
+  return POSG_OK;
+}
+
 // Generalised advantage estimation of the PPO learner (ppo/core.py:226-244) for a whole rollout
 // batch in one launch: one thread per (env, agent) column scans the T steps backwards.  The
 // float32 operations and their order are those of the reference's tensor expressions (the Python
@@ -222,6 +248,37 @@ int posg_vec_embed(posg_model_t m, int64_t n_envs, const uint32_t* state, const 
     case KIND_PREDATOR_PREY: return launch_embed<PPSim>(m, n_envs, state, wT, bias, hidden, apply_tanh, out, s);
     default: set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED;
   }
+}
+
+int posg_vec_step_embed(posg_model_t m, int64_t n_envs, uint32_t* state, uint16_t* ep_t, double* ep_ret,
+                        uint32_t* ep_count, const int64_t* actions, uint64_t seed, uint32_t global_step,
+                        uint64_t env_offset, int max_episode_steps, float* rew_out, uint8_t* term_out,
+                        uint8_t* trunc_out, uint8_t* done_out, float* stat_r, int32_t* stat_l, uint32_t* step_counter,
+                        const float* wT, const float* bias, int hidden, int apply_tanh, float* x_out,
+                        uint32_t* state_copy_out, void* stream) {
+  POSG_REQUIRE(m, "null model");
+  int rc = ensure_desc(m); if (rc) return rc;
+  if (n_envs == 0) return POSG_OK;
+  POSG_REQUIRE(n_envs > 0 && state && ep_t && ep_ret && ep_count && actions && rew_out && term_out && trunc_out &&
+               done_out && stat_r && stat_l && wT && bias && x_out, "bad arguments");
+  POSG_REQUIRE(max_episode_steps > 0 && max_episode_steps < 65535, "bad max_episode_steps");
+  if (hidden != 64 || ((((uintptr_t)wT | (uintptr_t)bias | (uintptr_t)x_out) & 15u) != 0)) {
+    set_error("posg_vec_step_embed: hidden size 64 and 16-byte aligned weights / output (use posg_vec_step + posg_vec_embed)");
+    return POSG_E_UNSUPPORTED;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+#define POSG_SE(MODEL)                                                                                            \
+  return launch_step_embed<MODEL>(m, n_envs, state, ep_t, ep_ret, ep_count, (const long long*)actions, seed,      \
+                                  global_step, env_offset, max_episode_steps, rew_out, term_out, trunc_out,       \
+                                  done_out, stat_r, stat_l, step_counter, wT, bias, apply_tanh, x_out,            \
+                                  state_copy_out, s)
+  switch (m->kind) {
+    case KIND_DRIVING: POSG_SE(DrivingSim);
+    case KIND_LBF: POSG_SE(LBFSim);
+    case KIND_PREDATOR_PREY: POSG_SE(PPSim);
+    default: set_error("model kind has no vector-env support"); return POSG_E_UNSUPPORTED;
+  }
+#undef POSG_SE
 }
 
 int posg_gae(int T, int64_t n_cols, const float* rewards, const float* dones, const float* values, double gamma,

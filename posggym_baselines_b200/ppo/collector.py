@@ -1,8 +1,9 @@
 """The rollout collector's inner loop on the device (ppo/worker.py:135-224 of the reference): per step
 ``policy.get_action_and_value`` on the current observations, ``envs.step`` with the sampled actions, store
-reward / done / value / log-prob.  Three kernels of the library per step -- ``posg_vec_embed`` (trunk layer 0 on the packed
-observation), ``posg_policy_step`` (the rest of the network on the tensor cores, samples the actions),
-``posg_vec_step`` (env step, TimeLimit, statistics, auto-reset; no one-hot rows) -- and the whole
+reward / done / value / log-prob.  TWO launches per step -- ``posg_policy_step`` (the network after trunk layer 0 on
+the tensor cores, samples the actions) and ``posg_vec_step_embed`` (env step, TimeLimit, statistics, auto-reset, AND
+trunk layer 0 of the next step on the observations it returns: no one-hot rows, nothing recomputed; rewards,
+terminated / truncated and the packed states go straight into the rollout storage) -- and the whole
 ``rollout_length``-step loop is captured in ONE CUDA graph: the step index of every Philox counter lives in
 device memory, so a replay is a fresh rollout."""
 from __future__ import annotations
@@ -37,19 +38,21 @@ class DeviceCollector:
         self.terms = torch.zeros((T + 1, R), dtype=torch.uint8, device=dev)
         self.truncs = torch.zeros((T + 1, R), dtype=torch.uint8, device=dev)
         self.dones = torch.zeros((T + 1, R), dtype=torch.uint8, device=dev)
-        self.states = torch.zeros((T, num_envs, self.envs._state.shape[1]), dtype=torch.int32, device=dev)
+        self.states = torch.zeros((T + 1, num_envs, self.envs._state.shape[1]), dtype=torch.int32, device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self.envs.reset()
         self.envs.enable_device_counter()
+        self.states[T].copy_(self.envs._state)
+        self._embed()          # x0 of the first step; afterwards every env step leaves the next x0 behind
 
     def _step(self, t: int):
         e, p = self.envs, self.policy
-        self.states[t].copy_(e._state)                       # packed observations' source (the learner re-embeds it)
-        self._embed()
         out = {"action": self.actions[t], "logprob": self.logprobs[t], "entropy": self.entropies[t], "value": self.values[t]}
         p.step(self.x0, (self.h, self.c), None, terminated=self.terms[t], truncated=self.truncs[t], seed=self.seed,
                row_offset=self.env_offset * e.num_agents, step_device=e._step_ctr, out=out)
-        e.step_device(self.actions[t], outs=(self.rewards[t], self.terms[t + 1], self.truncs[t + 1]))
+        # states[t + 1] = the packed observations' source of the next step (the learner re-embeds it)
+        e.step_embed_device(self.actions[t], p.w0_t, p.b0, self.x0,
+                            outs=(self.rewards[t], self.terms[t + 1], self.truncs[t + 1]), state_copy=self.states[t + 1])
 
     def _embed(self):
         from posggym_baselines_b200 import _lib
@@ -62,6 +65,7 @@ class DeviceCollector:
     def rollout_eager(self):
         self.terms[0].copy_(self.terms[self.T])      # next_done of the previous rollout (zeros after reset)
         self.truncs[0].copy_(self.truncs[self.T])
+        self.states[0].copy_(self.states[self.T])
         for t in range(self.T):
             self._step(t)
         torch.bitwise_or(self.terms, self.truncs, out=self.dones)
@@ -82,4 +86,4 @@ class DeviceCollector:
         else:
             self._graph.replay()
         return {"actions": self.actions, "logprobs": self.logprobs, "values": self.values, "entropies": self.entropies,
-                "rewards": self.rewards, "dones": self.dones, "states": self.states}
+                "rewards": self.rewards, "dones": self.dones, "states": self.states[:self.T]}

@@ -183,6 +183,27 @@ class BatchedVecEnv:
         self._launch(actions, 0, graphed=capturing, outs=outs)
         return self.step(None, _replay_only=True)
 
+    def step_embed_device(self, actions: torch.Tensor, w_t: torch.Tensor, bias: torch.Tensor, x_out: torch.Tensor,
+                          outs=None, state_copy: Optional[torch.Tensor] = None, tanh: bool = True):
+        """``step_device`` FUSED with ``embed`` of the observations the step returns (posg_vec_step_embed): one
+        launch steps the envs and writes ``x_out`` = trunk layer 0 of the policy for the NEXT step (and the new
+        packed state into ``state_copy``).  ``w_t`` = ``trunk.0.weight`` transposed ``[obs_dim, 64]``.  ``outs`` =
+        ``(rewards, terminated, truncated)`` rows of the rollout storage (default: the env's own buffers)."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.enable_device_counter()
+        assert self._device_counter, "call enable_device_counter() before capturing"
+        self._global_step += 1
+        rew, term, trunc = outs if outs is not None else (self._rew, self._term, self._trunc)
+        with torch.cuda.device(self._b.device):
+            _lib.check(_lib.lib().posg_vec_step_embed(
+                self._b._handle, self.num_envs, _lib.ptr(self._state), _lib.ptr(self._ep_t), _lib.ptr(self._ep_ret),
+                _lib.ptr(self._ep_count), actions.data_ptr(), self.seed, self._global_step, self.env_offset,
+                self.max_episode_steps, _lib.ptr(rew), _lib.ptr(term), _lib.ptr(trunc), _lib.ptr(self._done),
+                _lib.ptr(self._stat_r), _lib.ptr(self._stat_l), self._step_ctr.data_ptr(), _lib.ptr(w_t), _lib.ptr(bias),
+                int(w_t.shape[1]), int(tanh), _lib.ptr(x_out), None if state_copy is None else _lib.ptr(state_copy),
+                _lib.stream_ptr()))
+
     def capture_step(self):
         """Capture one ``envs.step`` in a CUDA graph.  Returns ``(actions, replay)``: write the step's
         actions into the static int64 tensor ``actions``, call ``replay()`` -- it returns the same

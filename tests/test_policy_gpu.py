@@ -144,7 +144,7 @@ def test_device_collector_graph_replays_are_fresh_rollouts():
     b.rollout_eager()                                         # second rollout: eager
     torch.cuda.synchronize()
     for k in ("actions", "rewards", "dones", "states"):
-        assert torch.equal(r1[k], getattr(b, k)), k
+        assert torch.equal(r1[k], getattr(b, k)[:r1[k].shape[0]]), k   # (states keeps one more row: the next rollout's first)
     r2 = a.rollout()
     torch.cuda.synchronize()
     assert not torch.equal(r1["actions"], r2["actions"])      # a replay continues the envs with new draws
