@@ -411,10 +411,30 @@ def bench_particle_sweep(env, dev, rank, seed, barrier):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        out.append({"particles": n, "ms_per_sweep": ms, "us_per_launch": 1e3 * ms / DEPTH,
-                    "padded_env_steps_per_s": n * DEPTH / (ms / 1e3),
-                    "algorithmic_gbs": BYTES_PER_ENV_STEP * n * DEPTH / (ms / 1e3) / 1e9,
-                    "working_set_mb": n * BYTES_PER_ENV_STEP / 1e6})
+        row = {"particles": n, "ms_per_sweep": ms, "us_per_launch": 1e3 * ms / DEPTH,
+               "padded_env_steps_per_s": n * DEPTH / (ms / 1e3),
+               "algorithmic_gbs": BYTES_PER_ENV_STEP * n * DEPTH / (ms / 1e3) / 1e9,
+               "working_set_mb": n * BYTES_PER_ENV_STEP / 1e6}
+        if n <= (1 << 20):
+            # small batches are bound by the host's launch rate (Python -> ctypes -> cudaLaunchKernel, ~12 us): the
+            # same 50 launches captured once in a CUDA graph show what the device needs
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sweep()
+                g.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                gms = e0.elapsed_time(e1) / reps
+                row["cuda_graph"] = {"us_per_launch": 1e3 * gms / DEPTH, "padded_env_steps_per_s": n * DEPTH / (gms / 1e3)}
+                del g
+            except Exception as ex:   # pragma: no cover
+                row["cuda_graph"] = {"error": repr(ex)}
+        out.append(row)
         del bufs, st0
     return out
 
@@ -423,7 +443,7 @@ def bench_collector(dev, rank, world, seed, barrier):
     """BASELINE.json configs[4] with the policy in the loop: the rollout worker's step --
     policy.get_action_and_value on the current observations, envs.step with the sampled actions, store
     reward / done / value / log-prob (ppo/worker.py:135-224) -- for LevelBasedForaging-v3, 8 192 envs per GPU, 64
-    steps: three launches per step (posg_vec_embed, posg_policy_step on the tensor cores, posg_vec_step) and the
+    steps: two launches per step (posg_policy_step on the tensor cores, posg_vec_step_embed) and the
     whole 64-step rollout captured in ONE CUDA graph.  Random-init network of the experiments' shape
     (trunk [64, 64], LSTM 64, heads [64]; exp_utils.py:101-104)."""
     import torch

@@ -260,7 +260,7 @@ int posg_tree_update(posg_model_t m, void* arena, void* spare_arena, int64_t cap
                      int32_t* reroot_scratch, int64_t* result_host, void* stream);
 /* Root parallelisation inside one GPU: n_trees independent searches in ONE launch, CTA k on the tree
  * entries_dev[k] (a DEVICE array; all trees share cap_nodes / cap_log / root_t and the Philox key, tree k uses the
- * counters sim_id0 + (k << 32) + ...).  Each tree runs posg_search_waves' loop -- the reference's MCTS.get_action
+ * counters sim_id0 + (k << 32) + w * wave_size + thread; wave_size = the largest wave of the launch).  Each tree runs posg_search_waves' loop -- the reference's MCTS.get_action
  * loop body (mcts.py:285-290) on its own tree; the caller sums the roots' visits / total values afterwards, the
  * same merge as root-parallel POMCP across GPUs. */
 typedef struct posg_forest_entry {
@@ -268,7 +268,8 @@ typedef struct posg_forest_entry {
   const uint32_t* particles; /* its root belief: n_particles packed states */
   int64_t n_particles;
   int32_t root;              /* its root node */
-  int32_t pad_;
+  int32_t wave;              /* simulations per wave of this tree, <= wave_size (0: wave_size): a tree whose root has
+                                more visits may run larger waves than its neighbours */
 } posg_forest_entry;
 int posg_search_forest(posg_model_t m, const posg_forest_entry* entries_dev, int n_trees, int64_t cap_nodes,
                        int64_t cap_log, int root_t, int wave_size, int n_waves, uint64_t sim_id0,

@@ -74,7 +74,7 @@ struct ForestEntry {
   const uint32_t* particles;
   long long n_particles;
   int root;
-  int pad;
+  int wave;   // simulations per wave of THIS tree (0: the launch's wave_size) -- every tree follows its own schedule
 };
 static_assert(sizeof(ForestEntry) == sizeof(posg_forest_entry), "posg_forest_entry layout");
 
@@ -93,10 +93,12 @@ search_forest_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_s
   search::layout(&T, en.arena, cap_nodes, cap_log, M::A, M::OW, M::SW);
   const search::RootSelect sel = {nullptr, nullptr, nullptr, 0};
   const unsigned long long base = sim_id0 + ((unsigned long long)blockIdx.x << 32);
+  const int wave = en.wave > 0 ? (en.wave < wave_size ? en.wave : wave_size) : wave_size;
   for (int w = 0; w < n_waves; ++w) {
+    // (counters advance by the launch's wave_size, the largest wave of the forest: unique whatever `wave` is)
     search::simulate<M>(B, ctx, T, P, en.root, root_t, en.particles, en.n_particles, sel,
                         base + (unsigned long long)w * (unsigned long long)wave_size + threadIdx.x,
-                        (int)threadIdx.x < wave_size);
+                        (int)threadIdx.x < wave);
     __threadfence();
     __syncthreads();
   }

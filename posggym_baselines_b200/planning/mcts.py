@@ -471,24 +471,40 @@ class MCTS:
         # start with larger waves.  Consecutive waves are chained inside one launch (posg_search_waves; with
         # trees_per_gpu > 1 posg_search_forest runs the same chain on every tree at once); the clock is read
         # between chunks of waves sized for ~2 ms.
+        tree_visits = tree_sims = None
         if self.wave_size:
             root_visits = 0
         elif forest:
-            root_visits = int(self._forest_stats(entries, len(trees))[:, 3 * A].min())
+            # every tree follows the schedule with its OWN root visits (after a re-root the trees kept different
+            # numbers of visits); the launch is sized for the largest wave
+            tree_visits = self._forest_stats(entries, len(trees))[:, 3 * A].astype(np.int64)
+            tree_sims = np.zeros(len(trees), np.int64)
+            root_visits = int(tree_visits.min())
         else:
             root_visits = int(self._stats()["node_visits"])
+        per_tree = forest and tree_visits is not None and self.max_sims is None
+        if per_tree:
+            tree_room = [max(32, ((self._cap_nodes - t._nodes_bound) // 2048) // 32 * 32) for t in trees]
         chunk = 8          # waves per launch, adapted to ~2 ms per chunk
         with torch.cuda.device(b.device):
             stream = self._stream()
             while True:
                 if self.wave_size:
                     wave = self.wave_size
+                elif per_tree:
+                    # (every simulation reserves a node id: a tree's wave is also held to what its arena can take in
+                    # a decision of ~2 000 waves, so that no tree runs out of ids before the budget ends)
+                    tree_waves = np.array([min(1024, room, self._scheduled_wave(int(v)))
+                                           for v, room in zip(tree_visits, tree_room)], np.int64)
+                    wave = int(tree_waves.max())   # one CTA per tree
+                    tab[:, 3] = tab[:, 3] & 0xFFFFFFFF | (tree_waves << 32)
+                    entries.copy_(torch.from_numpy(tab), non_blocking=False)
                 else:
                     wave = self._scheduled_wave(root_visits)
                     if forest:
                         wave = min(wave, 1024)   # one CTA per tree
                 waves = chunk
-                if not self.wave_size:   # stay on this wave size only while the schedule allows it
+                if not self.wave_size and not per_tree:   # stay on this wave size only while the schedule allows it
                     grow_at = int((wave + 32) / self.wave_growth) + 1 if wave < self.max_wave else 1 << 62
                     for visits, _ in self.WAVE_FLOORS:   # the next floor of the schedule, if it comes first
                         if root_visits < visits < grow_at:
@@ -520,6 +536,9 @@ class MCTS:
                 n_sims += wave * waves
                 n_waves += waves
                 root_visits += wave * waves
+                if per_tree:
+                    tree_sims += tree_waves * waves
+                    tree_visits += tree_waves * waves
                 torch.cuda.current_stream().synchronize()
                 now = time.time()
                 if self.max_sims is None and now - start >= cfg.search_time_limit:
@@ -544,7 +563,9 @@ class MCTS:
             t._min_value, t._max_value = st_k["min_value"], st_k["max_value"]
             t._last_root_stats = st_k
         st = sts[0]
-        n_total = n_sims * len(trees)
+        n_total = int(tree_sims.sum()) if per_tree else n_sims * len(trees)
+        if per_tree:
+            n_sims = int(tree_sims.mean())
         self._min_value = min(s_["min_value"] for s_ in sts)
         self._max_value = max(s_["max_value"] for s_ in sts)
         self.step_statistics["search_time"] = time.time() - start
