@@ -246,13 +246,18 @@ int posg_search(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log,
 int posg_search_waves(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
                       const uint32_t* particles, int64_t n_particles, int64_t wave_size, int n_waves, uint64_t sim_id0,
                       const posg_search_params* p, void* stream);
+/* Loads the kernels of the search / update path for this model now instead of at their first launch (a lazily
+ * loaded kernel is loaded under a process-wide lock; a forest updating from several host threads should not meet
+ * that in the middle of a decision). */
+int posg_search_warmup(posg_model_t m);
 /* MCTS._update (mcts.py:229-263) for one tree in one call: posg_tree_advance (creating the child if the searches
  * never reached it), posg_tree_gather_belief into belief_out (capacity >= log_bound + target rows; log_bound = an
  * upper bound of the tree's particle-log length), posg_belief_reinvigorate from parent_particles for the particles
  * still missing to `target` (at most sample_limit_factor * missing attempts, Philox draws from draw_id), then
  * posg_tree_reroot into spare_arena.  result_host[8]: child's old node id (-1: arena full, nothing else done),
  * its flags (bit 1 = absorbing: no belief is built), particles now in belief_out, nodes kept, log entries kept,
- * draw counters consumed, 1 if reinvigoration ran, 0. */
+ * draw counters consumed, 1 if reinvigoration ran, host microseconds / 16 spent in the four steps (16 bits each:
+ * advance, gather, reinvigorate, re-root; diagnostics). */
 int posg_tree_update(posg_model_t m, void* arena, void* spare_arena, int64_t cap_nodes, int64_t cap_log, int root,
                      int action, const uint64_t* obs_host, int ego_agent, const uint32_t* parent_particles,
                      int64_t n_parent, uint32_t* belief_out, int64_t belief_capacity, int64_t log_bound, int64_t target,

@@ -82,6 +82,7 @@ SIGNATURES = {
     "posg_tree_reset": (_int, [_vp, _vp, _i64, _i64, _int, _dbl, _dbl, _vp]),
     "posg_search": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _u64, _vp, _vp]),
     "posg_search_waves": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _i64, _i64, _int, _u64, _vp, _vp]),
+    "posg_search_warmup": (_int, [_vp]),
     "posg_tree_update": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _int, _vp, _i64, _vp, _i64, _i64, _i64, _dbl,
                                 _u64, _u64, _vp, _vp, _vp, _vp]),
     "posg_search_forest": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, _u64, _vp, _vp]),

@@ -1,5 +1,6 @@
 // Search-tree and particle-belief entry points of the C-ABI (model-generic; dispatched
 // on the model kind).  See search.cuh / belief.cuh for the algorithms.
+#include <chrono>
 #include <cooperative_groups.h>
 
 #include <cmath>
@@ -217,6 +218,47 @@ reroot_bfs_kernel(search::Tree S, int n_actions, int new_root, int* __restrict__
     lo = hi;
     hi = *((volatile unsigned int*)&counters[0]);
     grid.sync();   // every thread has read the level's end before the next level appends
+  }
+}
+
+// the same walk by ONE CTA (block barrier between levels) for small trees -- the trees of a forest: a plain launch,
+// so the re-roots that several host threads issue on their own streams run side by side (cooperative launches from
+// several streams were seen to stall each other, and every other CUDA call of the process, for tens of milliseconds)
+__global__ void __launch_bounds__(1024)
+reroot_bfs_cta_kernel(search::Tree S, int n_actions, int new_root, int* __restrict__ mark, int* __restrict__ order,
+                      unsigned int* __restrict__ counters /* [0] nodes kept */) {
+  __shared__ unsigned s_hi;
+  const unsigned lane = threadIdx.x & 31u;
+  const long long tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0) { order[0] = new_root; mark[new_root] = 0; counters[0] = 1u; }
+  __syncthreads();
+  unsigned lo = 0, hi = 1;
+  while (lo < hi) {
+    const long long work = (long long)(hi - lo) * n_actions;
+    for (long long i0 = tid - lane; i0 < work; i0 += nthr) {
+      const long long i = i0 + lane;
+      int c = -1;
+      if (i < work) c = S.an_first[(long long)order[lo + i / n_actions] * n_actions + (int)(i % n_actions)];
+      while (true) {
+        const unsigned has = __ballot_sync(0xffffffffu, c >= 0);
+        if (!has) break;
+        unsigned base = 0;
+        const int leader = __ffs(has) - 1;
+        if ((int)lane == leader) base = atomicAdd(&counters[0], (unsigned)__popc(has));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (c >= 0) {
+          const unsigned id = base + __popc(has & ((1u << lane) - 1u));
+          order[id] = c;
+          mark[c] = (int)id;
+          c = S.node_next[c];
+        }
+      }
+    }
+    __syncthreads();            // (block-scope barrier: the CTA's global writes above are visible to the CTA)
+    if (tid == 0) s_hi = *((volatile unsigned int*)&counters[0]);
+    __syncthreads();
+    lo = hi;
+    hi = s_hi;
   }
 }
 
@@ -504,7 +546,12 @@ int posg_tree_reroot(posg_model_t m, void* src_arena, void* dst_arena, int64_t c
     long long want = (n_old + 2047) / 2048;
     if (want < 8) want = 8;
     const int grid = (int)(want < (long long)bfs_grid[dev] ? want : (long long)bfs_grid[dev]);
-    POSG_CUDA(cudaLaunchCooperativeKernel((const void*)reroot_bfs_kernel, dim3(grid), dim3(256), args, 0, s));
+    if (n_old <= (1LL << 19)) {
+      reroot_bfs_cta_kernel<<<1, 1024, 0, s>>>(S, na, new_root, mark, order, counters);
+      POSG_CUDA(cudaGetLastError());
+    } else {
+      POSG_CUDA(cudaLaunchCooperativeKernel((const void*)reroot_bfs_kernel, dim3(grid), dim3(256), args, 0, s));
+    }
   }
   reroot_copy_kernel<<<sm_count() * 8, 256, 0, s>>>(S, D, k.n_actions, k.obs_words, mark, order, counters);
   POSG_CUDA(cudaGetLastError());
@@ -574,6 +621,16 @@ static void launch_forest(const posg_model* m, const ForestEntry* entries, int n
   search_forest_kernel<M><<<n_trees, threads, m->blob_bytes, s>>>(
       (const typename M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, entries, cap_nodes, cap_log, P, NoCtx{}, root_t,
       wave_size, n_waves, sim_id0);
+}
+
+template <class M>
+static void warm_model_kernels() {
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, search_kernel<M>);
+  cudaFuncGetAttributes(&a, search_waves_kernel<M>);
+  cudaFuncGetAttributes(&a, search_forest_kernel<M>);
+  cudaFuncGetAttributes(&a, reinvigorate_kernel<M>);
+  cudaFuncGetAttributes(&a, initial_belief_kernel<M>);
 }
 
 static int search_common(posg_model_t m, void* arena, int64_t cap_nodes, int64_t cap_log, int root, int root_t,
@@ -976,7 +1033,10 @@ int posg_tree_update(posg_model_t m, void* arena, void* spare_arena, int64_t cap
                "bad arguments");
   for (int i = 0; i < 8; ++i) result_host[i] = 0;
   int out4[4] = {0, 0, 0, 0};
+  auto now_us = []() { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  long long t0 = now_us(), t_adv = 0, t_gat = 0, t_rei = 0;
   int rc = posg_tree_advance(m, arena, cap_nodes, cap_log, root, action, obs_host, 1, out4, stream); if (rc) return rc;
+  t_adv = now_us() - t0; t0 = now_us();
   const int child = out4[0], flags = out4[2];
   result_host[0] = child; result_host[1] = flags;
   if (child < 0) return POSG_OK;   // arena full: the caller reports it
@@ -984,6 +1044,7 @@ int posg_tree_update(posg_model_t m, void* arena, void* spare_arena, int64_t cap
   if (!(flags & 2)) {
     rc = posg_tree_gather_belief(m, arena, cap_nodes, cap_log, child, belief_out, log_bound, &have, stream); if (rc) return rc;
     if (have > log_bound) have = log_bound;
+    t_gat = now_us() - t0; t0 = now_us();
     const int64_t need = target - have;
     if (need > 0) {
       const int64_t limit = (int64_t)(sample_limit_factor * (double)need);
@@ -999,9 +1060,44 @@ int posg_tree_update(posg_model_t m, void* arena, void* spare_arena, int64_t cap
     }
   }
   result_host[2] = have;
+  t_rei = now_us() - t0; t0 = now_us();
   int64_t rr[2] = {0, 0};
   rc = posg_tree_reroot(m, arena, spare_arena, cap_nodes, cap_log, child, reroot_scratch, rr, stream); if (rc) return rc;
   result_host[3] = rr[0]; result_host[4] = rr[1];
+  // diagnostics: microseconds spent in advance / gather / reinvigorate / re-root, 16 bits each (saturating)
+  auto sat = [](long long v) { return (unsigned long long)(v < 0 ? 0 : v > 65535 * 16 ? 65535 : v / 16); };
+  result_host[7] = (int64_t)(sat(t_adv) | (sat(t_gat) << 16) | (sat(t_rei) << 32) | (sat(now_us() - t0) << 48));
+  return POSG_OK;
+}
+
+// Loads every kernel of the planner's search / update path for this model NOW (the CUDA runtime loads a kernel
+// lazily at its first launch, under a process-wide lock: a forest that updates its trees from several host threads
+// otherwise meets those loads in the middle of a decision, all threads at once -- stalls of 0.1-2 s were measured).
+int posg_search_warmup(posg_model_t m) {
+  KindInfo k;
+  if (!kind_info(m, &k)) { set_error("model kind has no search support"); return POSG_E_UNSUPPORTED; }
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, forest_stats_kernel);
+  cudaFuncGetAttributes(&a, tree_init_kernel);
+  cudaFuncGetAttributes(&a, reroot_bfs_kernel);
+  cudaFuncGetAttributes(&a, reroot_bfs_cta_kernel);
+  cudaFuncGetAttributes(&a, reroot_copy_kernel);
+  cudaFuncGetAttributes(&a, reroot_clear_kernel);
+  cudaFuncGetAttributes(&a, reroot_log_kernel);
+  cudaFuncGetAttributes(&a, reroot_finish_kernel);
+  cudaFuncGetAttributes(&a, root_stats_kernel);
+  cudaFuncGetAttributes(&a, gather_belief_kernel);
+  if (k.obs_words == 1) cudaFuncGetAttributes(&a, tree_advance_kernel<1>);
+  else cudaFuncGetAttributes(&a, tree_advance_kernel<2>);
+  switch (m->kind) {
+    case KIND_DRIVING: warm_model_kernels<DrivingSim>(); break;
+    case KIND_PREDATOR_PREY:
+      if (((const pp::Blob*)m->h_blob)->lut_ok) warm_model_kernels<PPSimLut>(); else warm_model_kernels<PPSim>();
+      break;
+    case KIND_LBF: warm_model_kernels<LBFSim>(); break;
+    default: break;
+  }
+  cudaGetLastError();
   return POSG_OK;
 }
 

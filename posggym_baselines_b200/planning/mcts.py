@@ -201,6 +201,8 @@ class MCTS:
                 for k in range(1, trees_per_gpu)]
             for sib in self._siblings:
                 sib._seed, sib._params.seed = self._seed, self._params.seed   # one Philox key, disjoint counters
+            with torch.cuda.device(self._b.device):
+                _lib.check(lib.posg_search_warmup(self._b._handle))   # no lazy kernel loads in the threaded update
         self._host = None
         if self._host_mode:
             from posggym_baselines_b200.planning.host_search import HostSearch
@@ -255,9 +257,10 @@ class MCTS:
                 _lib.check(lib.posg_tree_reset(self._b._handle, _lib.ptr(self._arena_spare), self._cap_nodes,
                                                self._cap_log, 0, 1.0, 0.0, self._stream()))
             self._reroot_scratch = torch.empty(3 * self._cap_nodes, dtype=torch.int32, device=self._b.device)
-            # belief buffers of the update, sized for a typical decision's particle log up front: an allocation
-            # during the update (cudaMalloc behind the caching allocator) stalls every stream of a forest's update
-            rows = min(self._cap_log, 1 << 19) + self.config.num_particles + self.config.extra_particles
+            # belief buffers of the update, sized for the whole particle log up front: an allocation during the
+            # update (cudaMalloc behind the caching allocator, ~0.1 s with tens of GB of arenas mapped) was the
+            # source of every update-time spike measured
+            rows = min(self._cap_log, 1 << 26) + self.config.num_particles + self.config.extra_particles
             cap = 1 << max(12, int(rows - 1).bit_length())
             self._bbuf = [torch.empty((cap, self._SW), dtype=torch.int32, device=self._b.device) for _ in range(2)]
             self._rej = torch.empty((max(1, self.config.num_particles + self.config.extra_particles), self._SW),
@@ -367,7 +370,7 @@ class MCTS:
                     for tree in trees[w::n]:
                         t_tree = time.time()
                         update_tree(tree)
-                        self._update_trace.append((tree._forest_index, w, t_tree - start, time.time() - t_tree))
+                        self._update_trace.append((tree._forest_index, w, t_tree - start, time.time() - t_tree, getattr(tree, '_update_steps_us', None)))
                     torch.cuda.current_stream().synchronize()
 
             for f in [self._update_pool.submit(work, w) for w in range(n)]:
@@ -427,6 +430,7 @@ class MCTS:
                 self._draw_base + self._draw_counter, _lib.ptr(self._rej), _lib.ptr(self._reroot_scratch),
                 _lib.ptr(res), self._stream()))
         child, flags = int(res[0]), int(res[1])
+        self._update_steps_us = [16 * ((int(res[7]) >> sh) & 0xFFFF) for sh in (0, 16, 32, 48)]   # advance, gather, reinvigorate, re-root
         if child < 0:
             raise RuntimeError("search tree arena is full; raise node_capacity")
         self._draw_counter += int(res[5])
