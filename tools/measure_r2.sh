@@ -15,8 +15,7 @@ cap r2_step_fast_lbf "step_fast_kernel" 5 python tools/model_one.py lbf 4194304
 cap r2_rollout_driving "rollout_kernel" 1 python tools/rollout_one.py 4194304
 cap r2_search_waves "search_waves" 6 python tools/waves_one.py 32768
 cap r2_policy_step "policy_step" 10 python tools/policy_one.py 8192
-cap r2_vec_embed_8192 "vec_embed" 10 python tools/policy_one.py 8192
-cap r2_vec_step_8192 "vec_step" 10 python tools/policy_one.py 8192
+cap r2_vec_step_embed_8192 "vec_step_embed" 10 python tools/policy_one.py 8192
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/r2_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --only-sweep > $out/r2_ncu_launches.log 2>&1
 echo "launch list rc=$?"
