@@ -205,3 +205,35 @@ def test_captured_step_equals_eager_step(env_id, nact):
     a, b = eager.step(acts[0]), graphed.step(acts[0])
     for k in range(5):
         assert torch.equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("env_id,nact", [("LevelBasedForaging-v3", 6), ("Driving-v1", 5), ("PredatorPrey-v0", 5)])
+def test_fused_step_embed_equals_step_then_embed(env_id, nact):
+    """posg_vec_step_embed (the collector's second launch) == envs.step followed by posg_vec_embed, bit for bit:
+    rewards, terminated / truncated, the carried state, the copy of the state for the rollout storage and the
+    embedding of the observations the step returned -- over enough steps for episodes to end and auto-reset."""
+    from posggym_baselines_b200.vector import load_vec_env
+
+    n, hidden = 2048 + 37, 64
+    a = load_vec_env(env_id, num_envs=n, seed=13)
+    b = load_vec_env(env_id, num_envs=n, seed=13)
+    for e in (a, b):
+        e.write_obs, e._obs, e._args = False, None, None
+        e.reset()
+        e.enable_device_counter()
+    g = torch.Generator().manual_seed(4)
+    w = (torch.randn(hidden, a.flat_dim, generator=g) * 0.3).cuda()
+    w_t, bias = w.t().contiguous(), (torch.randn(hidden, generator=g) * 0.1).cuda()
+    x = torch.empty((2 * n, hidden), dtype=torch.float32, device="cuda")
+    rew, term, trunc = (torch.empty(2 * n, dtype=dt, device="cuda") for dt in (torch.float32, torch.uint8, torch.uint8))
+    copy = torch.empty_like(b._state)
+    for step in range(70):
+        act = torch.randint(0, nact, (2 * n,), generator=g).cuda()
+        a.step_device(act)
+        ref_x = a.embed(w, bias)
+        b.step_embed_device(act, w_t, bias, x, outs=(rew, term, trunc), state_copy=copy)
+        assert torch.equal(a._state, b._state) and torch.equal(copy, b._state), step
+        assert torch.equal(a._rew, rew) and torch.equal(a._term, term) and torch.equal(a._trunc, trunc), step
+        assert torch.equal(a._done, b._done) and torch.equal(a._stat_r, b._stat_r) and torch.equal(a._stat_l, b._stat_l)
+        assert torch.equal(ref_x, x), (step, (ref_x - x).abs().max().item())
+    assert int(a._ep_count.sum()) > 0      # episodes ended and were reset on the way
