@@ -257,7 +257,8 @@ __host__ __device__ __forceinline__ void decode_step_noise(uint32_t word, int& a
   a1 = (int)(r / 5u);
   a0 = (int)(r - 5u * (uint32_t)a1);
 }
-__device__ __forceinline__ void sample_step_noise(uint64_t seed, uint64_t particle, uint32_t step,
+template <class Seed>   // uint64_t seed or the PhiloxKeys of one
+__device__ __forceinline__ void sample_step_noise(const Seed& seed, uint64_t particle, uint32_t step,
                                                   int& a0, int& a1, int& order_idx) {
   const uint4 blk = philox_block(seed, particle >> 2, step, STREAM_STEP);
   decode_step_noise(pick_word(blk, (unsigned)(particle & 3ULL)), a0, a1, order_idx);

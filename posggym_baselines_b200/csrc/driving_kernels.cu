@@ -182,7 +182,8 @@ constexpr int WARP_ENVS = 128;
 template <bool WRITE_ACTIONS, bool COUNT_LIVE, bool REWARD_CODE = false>
 __global__ void __launch_bounds__(THREADS, STEP_FAST_MIN_CTAS)
 step_fast_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nblocks,
-                 const uint2* __restrict__ state_in, uint64_t seed, uint32_t step_idx, uint64_t group_offset,
+                 const uint2* __restrict__ state_in, const __grid_constant__ PhiloxKeys seed, uint32_t step_idx,
+                 uint64_t group_offset,
                  uint2* __restrict__ state_out, ulonglong2* __restrict__ obs_out, double2* __restrict__ rewards_out,
                  uint8_t* __restrict__ flags_out, uchar2* __restrict__ actions_out,
                  unsigned long long* __restrict__ live_count, uint8_t* __restrict__ reward_code_out = nullptr) {
@@ -319,7 +320,7 @@ struct DiscountTable { double v[256]; };
 __global__ void __launch_bounds__(THREADS)
 rollout_kernel(const Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
                const uint32_t* __restrict__ state_in, int ego, int max_steps,
-               const __grid_constant__ DiscountTable dtab, uint64_t seed, uint32_t step0,
+               const __grid_constant__ DiscountTable dtab, const __grid_constant__ PhiloxKeys seed, uint32_t step0,
                uint64_t particle_offset, double* __restrict__ returns_out,
                uint8_t* __restrict__ steps_out, uint32_t* __restrict__ state_out,
                unsigned long long* __restrict__ work_counter,
@@ -591,8 +592,9 @@ static int step_fast_coded(posg_model_t m, int64_t n, const uint32_t* state_in, 
   const uint32_t nb = (uint32_t)(n / WARP_ENVS);
   step_fast_kernel<true, true, true><<<grid_for(step_fast_kernel<true, true, true>, m->blob_bytes, (int64_t)nb * 32), THREADS,
                                         m->blob_bytes, s>>>(
-      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, seed, step_idx, particle_offset >> 2,
-      (uint2*)state_out, (ulonglong2*)obs_out, nullptr, flags_out, (uchar2*)actions_out, live_count, code_out);
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, PhiloxKeys(seed), step_idx,
+      particle_offset >> 2, (uint2*)state_out, (ulonglong2*)obs_out, nullptr, flags_out, (uchar2*)actions_out, live_count,
+      code_out);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;
 }
@@ -698,7 +700,7 @@ int posg_driving_step(posg_model_t m, int64_t n, const uint32_t* state_in, const
     const int64_t items = (int64_t)nb * 32;   // threads needed
 #define POSG_STEP_FAST(WA, CL)                                                                                      \
     step_fast_kernel<WA, CL><<<grid_for(step_fast_kernel<WA, CL>, m->blob_bytes, items), THREADS, m->blob_bytes, s>>>( \
-        blob, bb, nb, (const uint2*)state_in, seed, step_idx, particle_offset >> 2, (uint2*)state_out,               \
+        blob, bb, nb, (const uint2*)state_in, PhiloxKeys(seed), step_idx, particle_offset >> 2, (uint2*)state_out,   \
         (ulonglong2*)obs_out, (double2*)rewards_out, flags_out, (uchar2*)actions_out, live_count)
     if (actions_out && live_count) POSG_STEP_FAST(true, true);
     else if (actions_out) POSG_STEP_FAST(true, false);
@@ -728,7 +730,7 @@ static int rollout_launch(posg_model_t m, int64_t n, const uint32_t* state_in, i
   DiscountTable dtab;
   for (int k = 0; k < 256; ++k) dtab.v[k] = pow(discount, (double)k);
   rollout_kernel<<<grid_for(rollout_kernel, m->blob_bytes, n), THREADS, m->blob_bytes, stream>>>(
-      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, ego, max_steps, dtab, seed, step0,
+      (const Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, ego, max_steps, dtab, PhiloxKeys(seed), step0,
       particle_offset, returns_out, steps_out, state_out, work_counter, live_count);
   POSG_CUDA(cudaGetLastError());
   return POSG_OK;

@@ -40,7 +40,8 @@ struct DrivingSim {
     const uint32_t t0 = driving::vdone(s.w[0]) ? 1u : 0u, t1 = driving::vdone(s.w[1]) ? 1u : 0u;
     flags = t0 | (t1 << 1) | ((t0 & t1) ? 0x80u : 0u);
   }
-  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
+  template <class Seed>   // uint64_t seed or the PhiloxKeys of one
+  __device__ static __forceinline__ void noise_from_philox(const Seed& seed, uint64_t particle, uint32_t step,
                                                            int (&act)[NAG], uint32_t (&noise)[NW]) {
     int order;
     driving::sample_step_noise(seed, particle, step, act[0], act[1], order);

@@ -99,7 +99,8 @@ constexpr int FAST_WARP_ENVS = 128, FAST_EPT = 4;
 template <class M, bool WRITE_ACTIONS, bool COUNT_LIVE>
 __global__ void __launch_bounds__(THREADS, GENERIC_FAST_MIN_CTAS)
 step_fast_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, uint32_t nblocks,
-                 const uint2* __restrict__ state_in, uint64_t seed, uint32_t step_idx, uint64_t group_offset,
+                 const uint2* __restrict__ state_in, const __grid_constant__ PhiloxKeys seed, uint32_t step_idx,
+                 uint64_t group_offset,
                  uint2* __restrict__ state_out, ulonglong2* __restrict__ obs_out, double2* __restrict__ rewards_out,
                  uint8_t* __restrict__ flags_out, uchar2* __restrict__ actions_out,
                  unsigned long long* __restrict__ live_count) {
@@ -241,7 +242,7 @@ template <class M>
 __global__ void __launch_bounds__(THREADS)
 rollout_kernel(const typename M::Blob* __restrict__ gblob, uint32_t blob_size, int64_t n,
                const uint32_t* __restrict__ state_in, int ego, int max_steps,
-               const __grid_constant__ DiscountTable dtab, uint64_t seed, uint32_t step0,
+               const __grid_constant__ DiscountTable dtab, const __grid_constant__ PhiloxKeys seed, uint32_t step0,
                uint64_t particle_offset, double* __restrict__ returns_out, uint8_t* __restrict__ steps_out,
                uint32_t* __restrict__ state_out, unsigned long long* __restrict__ work_counter,
                unsigned long long* __restrict__ live_count) {

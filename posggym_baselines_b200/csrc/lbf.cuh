@@ -288,7 +288,8 @@ struct LBFSim {
     act[1] = (int)(idx / 6u);
     act[0] = (int)(idx - 6u * (uint32_t)act[1]);
   }
-  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
+  template <class Seed>   // uint64_t seed or the PhiloxKeys of one
+  __device__ static __forceinline__ void noise_from_philox(const Seed& seed, uint64_t particle, uint32_t step,
                                                            int (&act)[NAG], uint32_t (&noise)[NW]) {
     // one 32-bit word per env-step: block (particle >> 2, step), word particle & 3 (four consecutive
     // envs share a block; generic::step_fast_kernel computes it once for the four)

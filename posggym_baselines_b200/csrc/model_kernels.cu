@@ -214,7 +214,7 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
 #define POSG_FAST(WA, CL)                                                                                        \
     generic::step_fast_kernel<M, WA, CL><<<persistent_grid(generic::step_fast_kernel<M, WA, CL>, m->blob_bytes,   \
                                                            (int64_t)nb * 32), generic::THREADS, m->blob_bytes, s>>>( \
-        (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, seed, step_idx,           \
+        (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, nb, (const uint2*)state_in, PhiloxKeys(seed), step_idx, \
         particle_offset >> 2, (uint2*)state_out, (ulonglong2*)obs_out, (double2*)rewards_out, flags_out,          \
         (uchar2*)actions_out, live_count)
 #define POSG_FAST_ALL()                                 \
@@ -269,8 +269,8 @@ int posg_model_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, int 
   for (int k = 0; k < 256; ++k) dtab.v[k] = pow(discount, (double)k);
   MODEL_DISPATCH(m, (generic::rollout_kernel<M><<<persistent_grid(generic::rollout_kernel<M>, m->blob_bytes, n),
                      generic::THREADS, m->blob_bytes, s>>>(
-                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, ego_agent, max_steps, dtab, seed,
-                     step0, particle_offset, returns_out, steps_out, state_out, counter, live_count)));
+                     (const M::Blob*)m->d_blob, (uint32_t)m->blob_bytes, n, state_in, ego_agent, max_steps, dtab,
+                     PhiloxKeys(seed), step0, particle_offset, returns_out, steps_out, state_out, counter, live_count)));
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(counter, s);
   POSG_CUDA(e);

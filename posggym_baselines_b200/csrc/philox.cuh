@@ -48,6 +48,32 @@ __host__ __device__ __forceinline__ uint4 philox_block(uint64_t seed, uint64_t p
                        (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
+// The ten round keys of one seed, computed once on the host and passed as a (__grid_constant__) kernel parameter:
+// the key schedule is the same for every block of a launch, and as constant-bank operands the keys cost the
+// integer ALU pipe nothing (two additions per round and block otherwise).
+struct PhiloxKeys {
+  uint32_t k0[10], k1[10];
+  PhiloxKeys() = default;
+  __host__ __device__ explicit PhiloxKeys(uint64_t seed) {
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { k0[r] = a; k1[r] = b; a += PHILOX_W0; b += PHILOX_W1; }
+  }
+};
+
+__device__ __forceinline__ uint4 philox_block(const PhiloxKeys& K, uint64_t particle, uint32_t step, uint32_t stream) {
+  uint32_t c0 = (uint32_t)particle, c1 = (uint32_t)(particle >> 32), c2 = step, c3 = stream;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+    const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ K.k0[r];
+    const uint32_t n2 = hi0 ^ c3 ^ K.k1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  uint4 out; out.x = c0; out.y = c1; out.z = c2; out.w = c3;
+  return out;
+}
+
 // uniform integer in [0, n) by multiply-shift (bias < n / 2^32)
 __host__ __device__ __forceinline__ uint32_t uniform_below(uint32_t word, uint32_t n) {
 #ifdef __CUDA_ARCH__

@@ -574,7 +574,8 @@ struct PPSimT {
     act[1] = (int)(idx / 5u);
     act[0] = (int)(idx - 5u * (uint32_t)act[1]);
   }
-  __device__ static __forceinline__ void noise_from_philox(uint64_t seed, uint64_t particle, uint32_t step,
+  template <class Seed>   // uint64_t seed or the PhiloxKeys of one
+  __device__ static __forceinline__ void noise_from_philox(const Seed& seed, uint64_t particle, uint32_t step,
                                                            int (&act)[NAG], uint32_t (&noise)[NW]) {
     const uint4 w = philox_block(seed, noise_counter(particle), step, STREAM_STEP);
     const bool hi = (particle >> 5) & 1u;
