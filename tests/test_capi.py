@@ -50,6 +50,18 @@ def test_tma_bulk_copy_in_sass(built_lib):
     assert "UBLKCP" in out and "SYNCS" in out
 
 
+def test_policy_kernel_runs_on_tcgen05(built_lib):
+    """The collector's policy step is a tcgen05 kernel: its SASS has the fifth-generation tensor-core MMA
+    (UTCHMMA), accumulator loads from tensor memory (LDTM) and the MMA-completion barrier arrive (UTCBAR) -- and
+    no warp-level HMMA fallback."""
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", "policy_step_kernel", built_lib], capture_output=True, text=True).stdout
+    if "UTCHMMA" not in out:   # (-fun wants the mangled name on some toolkits: fall back to the whole library)
+        out = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out and "LDTM" in out and "UTCBAR" in out
+    kernel = out[out.find("policy_step_kernel"):] if "policy_step_kernel" in out else out
+    assert "HMMA.16816" not in kernel.split("Function :")[0]
+
+
 def test_no_gpu_fails_loudly(built_lib):
     import torch
 
