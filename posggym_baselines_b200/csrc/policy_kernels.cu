@@ -29,6 +29,12 @@
 
 namespace posg {
 namespace policy {
+#ifdef POSG_POLICY_TRACE
+__device__ unsigned long long g_policy_trace[16];
+#define PTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_policy_trace[i] = t_; } } while (0)
+#else
+#define PTRACE(i) do {} while (0)
+#endif
 
 constexpr int TILE = 128;   // rows per CTA = TMEM lanes
 constexpr int THREADS = 256; // two threads per row: warp w and warp w + 4 read the same 32 TMEM lanes and split the columns
@@ -143,6 +149,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
   const Weights& W = *reinterpret_cast<const Weights*>(smem);
   const uint32_t sbase = smem_u32(smem), bar = smem_u32(&mma_bar);
 
+  PTRACE(0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"(TM_COLS) : "memory");
@@ -175,6 +182,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     for (int q = 0; q < 8; ++q)
       cprev[q] = live ? *reinterpret_cast<const float4*>(c_in + row * H + half * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+    PTRACE(1);
     // ---- x0 -> A0, (1 - done) * h -> AL[:, 64:128): coalesced float4 loads, fp16 core-matrix stores
 #pragma unroll
     for (int it = 0; it < (TILE * H) / (4 * THREADS); ++it) {
@@ -193,11 +201,14 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
           make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     }
     publish_smem();
+    PTRACE(2);
     if (!weights_ready) { stage_blob_wait(&stage_bar); weights_ready = true; }
+    PTRACE(3);
 
     // ---- trunk[2:4]: x1 = tanh(x0 W1^T + b1) -> AL[:, 0:64)
     if (tid == 0) gemm(tmem + TM_D1, sbase + SM_A0, sbase + (uint32_t)offsetof(Weights, w1), H, H, bar);
     mbar_wait(bar, parity); parity ^= 1u;
+    PTRACE(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int jj = 0; jj < H / 32; ++jj) {
@@ -211,10 +222,12 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     }
     publish_smem();
 
+    PTRACE(5);
     // ---- LSTM cell: gates = [x1 | h] [W_ih | W_hh]^T + b (i, f, g, o)
     if (tid == 0) gemm(tmem + TM_G, sbase + SM_AL, sbase + (uint32_t)offsetof(Weights, wl), 2 * H, 4 * H, bar);
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    PTRACE(6);
     {
       const float keep = s_keep[r_];
 #pragma unroll
@@ -248,6 +261,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     }
     publish_smem();
 
+    PTRACE(7);
     // ---- heads, first layer: [ha | hc] = tanh(h' [Wa1; Wc1]^T + b) -> AF
     if (tid == 0) gemm(tmem + TM_HD, sbase + SM_AH, sbase + (uint32_t)offsetof(Weights, wh), H, 2 * H, bar);
     mbar_wait(bar, parity); parity ^= 1u;
@@ -264,10 +278,12 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     }
     publish_smem();
 
+    PTRACE(8);
     // ---- final layer (block diagonal): logits and value, then Categorical
     if (tid == 0) gemm(tmem + TM_F, sbase + SM_AF, sbase + (uint32_t)offsetof(Weights, wf), 2 * H, NF, bar);
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    PTRACE(9);
     if (half == 0) {
       float v[16];
       tmem_ld16(trow + TM_F, v);
@@ -312,6 +328,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
           for (int a = 0; a < n_actions; ++a) logits_out[row * n_actions + a] = v[a];
       }
     }
+    PTRACE(10);
     // the next tile overwrites shared memory and TMEM the tensor core may still be reading: all accumulator
     // loads of this tile are complete (tcgen05.wait::ld), order them before the next tile's MMAs
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -332,6 +349,12 @@ struct posg_policy {
   policy::Weights* d_w;
   int n_actions, device;
 };
+
+#ifdef POSG_POLICY_TRACE
+extern "C" int posg_policy_trace(unsigned long long* out_host) {
+  return (int)cudaMemcpyFromSymbol(out_host, posg::policy::g_policy_trace, 16 * 8);
+}
+#endif
 
 extern "C" {
 
