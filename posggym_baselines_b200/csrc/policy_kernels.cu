@@ -37,7 +37,12 @@ __device__ unsigned long long g_policy_trace[16];
 #endif
 
 constexpr int TILE = 128;   // rows per CTA = TMEM lanes
-constexpr int THREADS = 256; // two threads per row: warp w and warp w + 4 read the same 32 TMEM lanes and split the columns
+#ifndef POSG_POLICY_THREADS
+#define POSG_POLICY_THREADS 256
+#endif
+constexpr int THREADS = POSG_POLICY_THREADS;   // NPART threads per row: warps w, w + 4, ... read the same 32 TMEM lanes and split the columns
+constexpr int NPART = THREADS / TILE;          // (two or four: more warps hide the epilogues' MUFU / TMEM-load latency)
+static_assert(NPART == 2 || NPART == 4, "two or four threads per row");
 constexpr int H = 64;       // trunk / LSTM / head width (baseline_exps/exp_utils.py:101-104)
 constexpr int NF = 16;      // final layer: logits in columns 0..A-1 (A <= 8), value in column VCOL
 constexpr int VCOL = 8;
@@ -145,7 +150,7 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
   __shared__ float s_keep[TILE];   // 1 - done per row
   const int tid = threadIdx.x, warp = tid >> 5;
   const int r_ = ((warp & 3) << 5) | (tid & 31);   // this thread's row of the tile (= TMEM lane)
-  const int half = warp >> 2;                       // which half of the columns it owns
+  const int half = warp >> 2;                       // which part (of NPART) of the columns it owns
   const Weights& W = *reinterpret_cast<const Weights*>(smem);
   const uint32_t sbase = smem_u32(smem), bar = smem_u32(&mma_bar);
 
@@ -177,10 +182,10 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     if (half == 0)
       s_keep[r_] = !live ? 0.0f : (done != nullptr ? 1.0f - done[row] : ((term[row] | trunc[row]) ? 0.0f : 1.0f));
     // this thread's 32 cell-state values: requested now, needed after the second MMA group
-    float4 cprev[8];
+    float4 cprev[H / NPART / 4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      cprev[q] = live ? *reinterpret_cast<const float4*>(c_in + row * H + half * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < H / NPART / 4; ++q)
+      cprev[q] = live ? *reinterpret_cast<const float4*>(c_in + row * H + half * (H / NPART) + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     PTRACE(1);
     // ---- x0 -> A0, (1 - done) * h -> AL[:, 64:128): coalesced float4 loads, fp16 core-matrix stores
@@ -211,8 +216,8 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     PTRACE(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int jj = 0; jj < H / 32; ++jj) {
-      const int jc = half * (H / 32) + jj;
+    for (int jj = 0; jj < H / NPART / 16; ++jj) {
+      const int jc = half * (H / NPART / 16) + jj;
       float v[16];
       tmem_ld16(trow + TM_D1 + jc * 16, v);
 #pragma unroll
@@ -231,8 +236,8 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     {
       const float keep = s_keep[r_];
 #pragma unroll
-      for (int jj = 0; jj < H / 32; ++jj) {
-        const int jc = half * (H / 32) + jj;
+      for (int jj = 0; jj < H / NPART / 16; ++jj) {
+        const int jc = half * (H / NPART / 16) + jj;
         float gi[16], gf[16], gg[16], go[16], hn[16], cn[16];
         tmem_ld16(trow + TM_G + 0 * H + jc * 16, gi);
         tmem_ld16(trow + TM_G + 1 * H + jc * 16, gf);
@@ -267,8 +272,8 @@ policy_step_kernel(const Weights* __restrict__ gw, long long n_rows, const float
     mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int jj = 0; jj < 2 * H / 32; ++jj) {
-      const int jc = half * (2 * H / 32) + jj;
+    for (int jj = 0; jj < 2 * H / NPART / 16; ++jj) {
+      const int jc = half * (2 * H / NPART / 16) + jj;
       float v[16];
       tmem_ld16(trow + TM_HD + jc * 16, v);
 #pragma unroll
