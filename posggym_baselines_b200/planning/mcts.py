@@ -487,8 +487,9 @@ class MCTS:
         else:
             root_visits = int(self._stats()["node_visits"])
         per_tree = forest and tree_visits is not None and self.max_sims is None
+        tree_waves = None
         if per_tree:
-            tree_room = [max(32, ((self._cap_nodes - t._nodes_bound) // 2048) // 32 * 32) for t in trees]
+            tree_room = np.array([max(32, ((self._cap_nodes - t._nodes_bound) // 2048) // 32 * 32) for t in trees], np.int64)
         chunk = 8          # waves per launch, adapted to ~2 ms per chunk
         with torch.cuda.device(b.device):
             stream = self._stream()
@@ -498,11 +499,12 @@ class MCTS:
                 elif per_tree:
                     # (every simulation reserves a node id: a tree's wave is also held to what its arena can take in
                     # a decision of ~2 000 waves, so that no tree runs out of ids before the budget ends)
-                    tree_waves = np.array([min(1024, room, self._scheduled_wave(int(v)))
-                                           for v, room in zip(tree_visits, tree_room)], np.int64)
+                    new_waves = np.minimum(np.minimum(self._scheduled_waves(tree_visits), tree_room), 1024)
+                    if tree_waves is None or not np.array_equal(new_waves, tree_waves):   # (rarely changes)
+                        tree_waves = new_waves
+                        tab[:, 3] = tab[:, 3] & 0xFFFFFFFF | (tree_waves << 32)
+                        entries.copy_(torch.from_numpy(tab), non_blocking=False)
                     wave = int(tree_waves.max())   # one CTA per tree
-                    tab[:, 3] = tab[:, 3] & 0xFFFFFFFF | (tree_waves << 32)
-                    entries.copy_(torch.from_numpy(tab), non_blocking=False)
                 else:
                     wave = self._scheduled_wave(root_visits)
                     if forest:
@@ -618,6 +620,14 @@ class MCTS:
             if root_visits >= visits:
                 floor = wave
         return max(floor, min(self.max_wave, (int(root_visits * self.wave_growth) // 32) * 32))
+
+    def _scheduled_waves(self, root_visits: np.ndarray) -> np.ndarray:
+        """``_scheduled_wave`` for an array of root visit counts (the trees of a forest)."""
+        floors = np.full(root_visits.shape, 32, np.int64)
+        for visits, wave in self.WAVE_FLOORS:
+            floors = np.where(root_visits >= visits, wave, floors)
+        grown = (root_visits * self.wave_growth).astype(np.int64) // 32 * 32
+        return np.maximum(floors, np.minimum(self.max_wave, grown))
 
     _respect_time = False  # with max_sims set, the time limit only applies when asked for
 
