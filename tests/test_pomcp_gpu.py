@@ -179,6 +179,40 @@ def test_forest_episode_and_throughput(model, gold):
     planner.close()
 
 
+def test_forest_episodes_not_worse_than_one_tree(model):
+    """Episode outcomes with 8 trees per GPU against one tree at the same time budget (0.02 s per decision, the
+    planner's own wave schedule in both): merging independent searches at the root must not play worse -- success
+    rate not lower by more than 3 binomial standard errors + 0.05, returns not told apart by a KS test at p > 0.001."""
+    from posggym_baselines_b200.envs.env import Env
+
+    env = Env(model)
+
+    def play(n, **opts):
+        wins, rets = 0, []
+        for ep in range(n):
+            planner = make_planner(model, seed=ep, search_time_limit=0.02, node_capacity=1 << 24, log_capacity=1 << 26, **opts)
+            rng = random.Random(30_000 + ep)
+            obs, _ = env.reset(seed=2000 + ep)
+            planner.reset()
+            done, R = False, 0.0
+            while not done:
+                a = planner.step(obs["0"])
+                obs, rew, term, trunc, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+                R += rew["0"]
+            wins += env.state[0].dest_reached
+            rets.append(R)
+            planner.close()
+        return wins / n, np.array(rets)
+
+    n = 24
+    p_one, r_one = play(n)
+    p_forest, r_forest = play(n, trees_per_gpu=8)
+    se = math.sqrt(p_one * (1 - p_one) / n + p_forest * (1 - p_forest) / n)
+    assert p_forest > p_one - 3 * se - 0.05, (p_forest, p_one)
+    d, pv = ks_2samp(r_forest, r_one)
+    assert pv > 0.001, (d, pv, r_forest.mean(), r_one.mean())
+
+
 def ks_2samp(a, b):
     a, b = np.sort(a), np.sort(b)
     allv = np.concatenate([a, b])
