@@ -145,12 +145,31 @@ class HostSearch:
                 out[i] = self.other_agent_policies[i].sample_action(hps.policy_state[i])
         return out
 
-    def _add_obs_node(self, parent: _ActionNode, obs, init_visits=0) -> _ObsNode:
+    def _add_obs_node(self, parent: _ActionNode, obs, init_visits=0, sim_policy=None) -> _ObsNode:
+        """``sim_policy`` is the search policy of the simulation that creates the node; None on the update path."""
         sp_state = self._policy_next(parent.action, obs, self.search_policy, parent.parent.search_policy_state)
-        node = _ObsNode(parent, obs, parent.parent.t + 1, _Belief(self._rng), self.search_policy.get_pi(sp_state),
+        node = _ObsNode(parent, obs, parent.parent.t + 1, _Belief(self._rng), self._node_prior(sp_state, sim_policy),
                         sp_state, init_visits)
         parent.children[obs] = node
         return node
+
+    # -- the places where a typed planner (planning/potmmcp.py) differs from MCTS
+    def _sim_policy(self, hps: HPS):
+        """Search policy of one simulation (mcts.py:285-290: the planner's own)."""
+        return self.search_policy
+
+    def _node_prior(self, sp_state, sim_policy):
+        return self.search_policy.get_pi(sp_state)
+
+    def _leaf_state(self, node: _ObsNode, sim_policy):
+        return node.search_policy_state
+
+    def _revisit(self, node: _ObsNode, child: _ObsNode, sim_policy):
+        """An existing child is reached again: moving average of the prior (mcts.py:359-366)."""
+        child.visits += 1
+        pi = sim_policy.get_pi(child.search_policy_state)
+        for a, pr in pi.items():
+            child.action_probs[a] += (pr - child.action_probs[a]) / child.visits
 
     def _advance(self, hps: HPS, joint_action, ts) -> HPS:
         if self.config.state_belief_only:
@@ -255,7 +274,7 @@ class HostSearch:
         max_sims = self.p.max_sims
         while (time.time() - start < cfg.search_time_limit) if max_sims is None else (n_sims < max_sims):
             hps = self.root.belief.sample()
-            _, depth = self._simulate(hps, self.root, 0)
+            _, depth = self._simulate(hps, self.root, 0, self._sim_policy(hps))
             self.root.visits += 1
             max_depth = max(max_depth, depth)
             n_sims += 1
@@ -265,14 +284,14 @@ class HostSearch:
             return self._max_visit(self.root)
         return self._max_value(self.root)
 
-    def _simulate(self, hps: HPS, node: _ObsNode, depth: int):
+    def _simulate(self, hps: HPS, node: _ObsNode, depth: int, sim_policy):
         cfg = self.config
         if depth > cfg.depth_limit or node.t > self.step_limit:
             return 0.0, depth
         if not node.children:
             for a in self.action_space:
                 node.add_child(a)
-            return self._evaluate(hps, depth, node.search_policy_state), depth
+            return self._evaluate(hps, depth, sim_policy, self._leaf_state(node, sim_policy)), depth
         ego_action = self._select(node)
         joint_action = self._joint_action(hps, ego_action)
         ts = self.model.step(hps.state, joint_action)
@@ -283,48 +302,45 @@ class HostSearch:
         anode = node.children[ego_action]
         child = anode.children.get(ego_obs)
         if child is not None:
-            child.visits += 1
-            pi = self.search_policy.get_pi(child.search_policy_state)
-            for a, pr in pi.items():                      # moving average of the prior (mcts.py:359-366)
-                child.action_probs[a] += (pr - child.action_probs[a]) / child.visits
+            self._revisit(node, child, sim_policy)
         else:
-            child = self._add_obs_node(anode, ego_obs, 1)
+            child = self._add_obs_node(anode, ego_obs, 1, sim_policy)
         child.is_absorbing = done
         child.belief.add_particle(nxt)
         max_depth = depth
         if not done:
-            future, max_depth = self._simulate(nxt, child, depth + 1)
+            future, max_depth = self._simulate(nxt, child, depth + 1, sim_policy)
             ret += cfg.discount * future
         anode.update(ret)
         self.min_max.update(anode.value)
         return ret, max_depth
 
-    def _evaluate(self, hps: HPS, depth: int, sp_state) -> float:
+    def _evaluate(self, hps: HPS, depth: int, policy, sp_state) -> float:
         t0 = time.time()
         cfg = self.config
         if cfg.truncated:
             try:
-                v = self.search_policy.get_value(sp_state)
+                v = policy.get_value(sp_state)
             except NotImplementedError:
                 if not cfg.use_rollout_if_no_value:
                     raise
-                v = self._rollout(hps, depth, sp_state)
+                v = self._rollout(hps, depth, policy, sp_state)
         else:
-            v = self._rollout(hps, depth, sp_state)
+            v = self._rollout(hps, depth, policy, sp_state)
         self.stats["evaluation_time"] += time.time() - t0
         return v
 
-    def _rollout(self, hps: HPS, depth: int, sp_state) -> float:
+    def _rollout(self, hps: HPS, depth: int, policy, sp_state) -> float:
         cfg, ret, k = self.config, 0, 0
         while depth <= cfg.depth_limit and hps.t <= self.step_limit:
-            ego_action = self.search_policy.sample_action(sp_state)
+            ego_action = policy.sample_action(sp_state)
             joint_action = self._joint_action(hps, ego_action)
             ts = self.model.step(hps.state, joint_action)
             ret += cfg.discount**k * ts.rewards[self.agent_id]
             if ts.terminations[self.agent_id] or ts.truncations[self.agent_id] or ts.all_done:
                 break
             hps = self._advance(hps, joint_action, ts)
-            sp_state = self._policy_next(ego_action, ts.observations[self.agent_id], self.search_policy, sp_state)
+            sp_state = self._policy_next(ego_action, ts.observations[self.agent_id], policy, sp_state)
             depth += 1
             k += 1
         return ret

@@ -205,11 +205,15 @@ class MCTS:
                 _lib.check(lib.posg_search_warmup(self._b._handle))   # no lazy kernel loads in the threaded update
         self._host = None
         if self._host_mode:
-            from posggym_baselines_b200.planning.host_search import HostSearch
-
             self._reset_step_statistics_host()
-            self._host = HostSearch(self)
+            self._host = self._host_engine()(self)
         self.reset()
+
+    def _host_engine(self):
+        """Engine class of the plugin path (typed planners substitute their own)."""
+        from posggym_baselines_b200.planning.host_search import HostSearch
+
+        return HostSearch
 
     @property
     def root(self):

@@ -73,6 +73,44 @@ class RandomSearchPolicy(SearchPolicy):
         raise NotImplementedError("RandomSearchPolicy does not support value estimates.")
 
 
+class SearchPolicyWrapper(SearchPolicy):
+    """A ``posggym.agents`` ``Policy`` object as a ``SearchPolicy`` (search_policy.py:188-232): same calls
+    forwarded, ``get_pi`` unwrapped from the action distribution and padded to every action."""
+
+    def __init__(self, policy):
+        super().__init__(policy.model, policy.agent_id, policy.policy_id)
+        self.policy = policy
+        self.action_space = list(range(policy.model.action_spaces[policy.agent_id].n))
+
+    def get_initial_state(self) -> PolicyState:
+        return self.policy.get_initial_state()
+
+    def get_next_state(self, action: Optional[Any], obs, state: PolicyState) -> PolicyState:
+        return self.policy.get_next_state(action, obs, state)
+
+    def sample_action(self, state: PolicyState):
+        return self.policy.sample_action(state)
+
+    def get_pi(self, state: PolicyState) -> Dict[Any, float]:
+        probs = self.policy.get_pi(state).probs
+        if len(probs) != len(self.action_space):
+            for a in self.action_space:
+                probs.setdefault(a, 0.0)
+        return probs
+
+    def get_value(self, state: PolicyState) -> float:
+        return self.policy.get_value(state)
+
+    def close(self):
+        self.policy.close()
+
+
+def load_posggym_agents_search_policy(model, agent_id: str, policy_id: str) -> SearchPolicyWrapper:
+    import posggym.agents as pga   # only where the real posggym.agents registry is installed
+
+    return SearchPolicyWrapper(pga.make(policy_id, model, agent_id))
+
+
 def _flat_index_layout(space):
     """(offset, start) of every Discrete leaf of a (nested) Tuple space in gymnasium's ``flatten`` order, and the
     flattened width -- the one-hot layout ``processors.FlattenProcessor`` produces for the reference's policies."""

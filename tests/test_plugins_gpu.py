@@ -346,3 +346,95 @@ def test_ppo_lstm_search_policy_combined_planner():
     assert min(sims) >= 5, sims        # the reference's COMBINED planner does ~37 simulations per 0.1 s on Driving
     print("COMBINED planner simulations per 0.1 s decision:", sims)
     planner.close()
+
+
+def _driving_obs(f):
+    return (tuple(f[:15]), f[15], (f[16], f[17]), (f[18], f[19]), f[20], f[21])
+
+
+@pytest.mark.parametrize("truncated", [False, True])
+def test_potmmcp_matches_the_unmodified_reference_planner(truncated):
+    """POTMMCP (typed other agent = ``OtherAgentMixturePolicy``, meta-policy over the planning
+    agent's policies) through the host engine with the model on the device.  tests/golden/potmmcp_driving.json
+    holds root statistics of the UNMODIFIED reference POTMMCP with the same policy objects
+    (tests/potmmcp_policies.py) over 64 repetitions, for the first decision and for the one after
+    ``update(action, obs)``; action values, visit shares, the root prior after the search's moving-average updates
+    and the share of 'pusher' particles in the updated belief agree within 4 standard errors plus a small margin."""
+    import json
+
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.planning import POTMMCP, MCTSConfig, OtherAgentMixturePolicy, POTMMCPMetaPolicy
+    from tests.conftest import GOLDEN
+    from tests.potmmcp_policies import META_POLICY, ego_policies, other_agent_types
+
+    gold = json.load(open(os.path.join(GOLDEN, "potmmcp_driving.json")))
+    scen = next(s for s in gold["scenarios"] if s["truncated"] == truncated)
+    obs0, obs1 = _driving_obs(scen["obs0"]), _driving_obs(scen["obs1"])
+    model = DrivingModel()
+    reps = 8
+    rows = {"first": [], "second": []}
+    shares = []
+    for rep in range(reps):
+        random.seed(1000 + rep)
+        model.seed(7000 + rep)
+        cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.25, truncated=truncated, action_selection="pucb",
+                         pucb_exploration_fraction=0.5, state_belief_only=False, seed=rep)
+        ego = ego_policies(model)
+        for pi in ego.values():
+            pi.value = 0.05 if truncated else None
+        planner = POTMMCP(model, "0", cfg, {"1": OtherAgentMixturePolicy(model, "1", other_agent_types(model))},
+                          POTMMCPMetaPolicy(model, "0", ego, META_POLICY), max_sims=scen["n_sims"])
+        planner.reset()
+        planner.update(None, obs0)
+        for which, nxt in (("first", obs1), ("second", None)):
+            assert planner.get_action() in range(5)
+            root = planner.root
+            assert planner.step_statistics["num_sims"] == scen["n_sims"] and root.visits >= scen["n_sims"]
+            vis = np.array([root.children[a].visits for a in range(5)], dtype=float)
+            rows[which].append(([root.children[a].value for a in range(5)], vis / vis.sum(),
+                                [root.action_probs[a] for a in range(5)]))
+            if nxt is not None:
+                planner.update(scen["ego_action"], nxt)
+                parts = planner.root.belief.particles
+                assert len(parts) >= cfg.num_particles + cfg.extra_particles
+                assert all(len(p.history) == 2 and p.t == 2 for p in parts)
+                shares.append(np.mean([p.policy_state["1"]["policy_id"] == "pusher" for p in parts]))
+        planner.close()
+    for which in ("first", "second"):
+        g = scen[which]
+        vals, frac, prior = (np.array(x) for x in zip(*rows[which]))
+        for got, key, margin in ((vals, "value", 0.03), (frac, "visit_frac", 0.05), (prior, "prior", 0.02)):
+            mean, std = np.array(g[key + "_mean"]), np.array(g[key + "_std"])
+            se = np.sqrt(std**2 / scen["reps"] + got.std(0) ** 2 / reps)
+            assert (np.abs(got.mean(0) - mean) < 4 * se + margin).all(), (which, key, got.mean(0), mean, se)
+    se = math.sqrt(scen["pusher_share_std"] ** 2 / scen["reps"] + np.std(shares) ** 2 / reps)
+    assert abs(np.mean(shares) - scen["pusher_share_mean"]) < 4 * se + 0.05, (np.mean(shares), scen["pusher_share_mean"])
+
+
+def test_ipomcp_with_typed_other_agent_plays_an_episode():
+    """IPOMCP (planning/ipomcp.py) = MCTS over history / policy-state particles: with a mixture of other-agent types
+    and a wrapped ``posggym.agents``-style search policy it runs an episode through the host engine."""
+    from posggym_baselines_b200.envs.driving import DrivingModel
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.planning import IPOMCP, MCTSConfig, OtherAgentMixturePolicy, SearchPolicyWrapper
+    from tests.potmmcp_policies import BiasedPolicy, other_agent_types
+
+    model = DrivingModel()
+    env = Env(model)
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.05, c=1.25, truncated=True, action_selection="pucb",
+                     state_belief_only=False, seed=4)
+    planner = IPOMCP(model, "0", cfg, {"1": OtherAgentMixturePolicy(model, "1", other_agent_types(model))},
+                     SearchPolicyWrapper(BiasedPolicy(model, "0", "fast", 1, 4.0, value=0.1)), max_sims=64)
+    assert planner._host is not None
+    obs, _ = env.reset(seed=4)
+    planner.reset()
+    rng = random.Random(4)
+    for step in range(5):
+        a = planner.step(obs["0"])
+        assert a in range(5) and planner.step_statistics["num_sims"] == 64
+        ids = {p.policy_state["1"]["policy_id"] for p in planner.root.belief.particles}
+        assert ids <= {"pusher", "idler"} and ids
+        obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+        if done:
+            break
+    planner.close()
