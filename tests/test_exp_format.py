@@ -86,3 +86,227 @@ def test_pomcp_episodes_to_csv(tmp_path):
     assert len(got) == 2 and list(got[0].keys()) == EXPECTED
     assert all(1 <= int(r["len"]) <= 50 and float(r["num_sims"]) == 64.0 for r in got)
     assert rows[0]["len"] == int(got[0]["len"])
+
+
+# ---------------------------------------------------------------- belief statistics (planning/utils.py:147-339)
+class _FakeEnv:
+    """What BeliefStatTracker reads of the agent-folding env wrapper."""
+
+    class spec:
+        max_episode_steps = 6
+
+    def __init__(self):
+        self.policies, self.last_actions, self.last_obs, self.state = {}, {}, {}, None
+
+
+def _belief_episode_script(rng, n_steps, n_particles):
+    """Per step: the true (state, other action, other obs, other policy id) and the particle data."""
+    script = []
+    for t in range(n_steps):
+        parts = []
+        for _ in range(0 if (t == 2 and n_steps > 4) else n_particles):
+            hist = tuple(({"0": rng.randrange(2), "1": (None if k == 0 else rng.randrange(2))},
+                          {"0": rng.randrange(2), "1": rng.randrange(2)}) for k in range(t + 1))
+            if t == 0:
+                hist = (({"0": None, "1": None}, {"0": rng.randrange(2), "1": rng.randrange(2)}),)
+            parts.append((rng.randrange(3), hist, {"1": {"policy_id": rng.choice(["A", "B"]), "k": rng.randrange(3)}}, t + 1))
+        script.append({"state": rng.randrange(3), "action": rng.randrange(2), "obs": rng.randrange(2), "particles": parts})
+    return script
+
+
+def _run_tracker(world, script_eps, stats, per_step):
+    """``world`` builds particles / policies in the reference's or this repo's representation."""
+    env = _FakeEnv()
+    planner = world["planner"]()
+    tracker = world["tracker"](planner, env, track_per_step=per_step, stats_to_track=list(stats))
+    out = []
+    for true_pid, obs0, state0, script in script_eps:
+        env.policies = {"1": type("P", (), {"policy_id": true_pid})()}
+        env.last_actions, env.last_obs, env.state = {"1": None}, {"1": obs0}, state0
+        tracker.reset_episode()
+        for step in script:
+            planner.root.belief.particles = [world["particle"](*p) for p in step["particles"]]
+            env.last_actions, env.last_obs, env.state = {"1": step["action"]}, {"1": step["obs"]}, step["state"]
+            tracker.step(env)
+        out.append(tracker.get_episode())
+    return out
+
+
+def _worlds():
+    import posggym_baselines.planning.belief as RB
+    from posggym.utils.history import AgentHistory, JointHistory
+    from posggym_baselines.planning.other_policy import OtherAgentPolicy as RefOther
+    from posggym_baselines.planning.utils import BeliefStatTracker as RefTracker
+    from posggym_baselines_b200.planning.host_search import HPS
+    from posggym_baselines_b200.planning.other_policy import OtherAgentPolicy as NewOther
+    from posggym_baselines_b200.planning.utils import BeliefStatTracker as NewTracker
+
+    def other_cls(base):
+        class Typed(base):
+            def __init__(self):
+                pass
+
+            def sample_initial_state(self):
+                return {}
+
+            def get_next_state(self, action, obs, state):
+                return state
+
+            def sample_action(self, state):
+                return 0
+
+            def get_pi(self, state):
+                p = 0.2 + 0.3 * state["k"] if state["policy_id"] == "A" else 0.5
+                return {0: p, 1: 1.0 - p}
+
+        return Typed
+
+    def planner_cls(other):
+        class Belief:
+            particles = []
+
+            def size(self):
+                return len(self.particles)
+
+        class Planner:
+            agent_id = "0"
+
+            class model:
+                possible_agents = ("0", "1")
+
+            def __init__(self):
+                self.other_agent_policies = {"1": other()}
+                self.root = type("R", (), {})()
+                self.root.belief = Belief()
+
+        return Planner
+
+    def ref_particle(state, hist, pstate, t):
+        jh = JointHistory({i: AgentHistory(tuple((ja[i], jo[i]) for ja, jo in hist)) for i in ("0", "1")})
+        return RB.HistoryPolicyState(state, jh, pstate, t)
+
+    return ({"planner": planner_cls(other_cls(RefOther)), "tracker": RefTracker, "particle": ref_particle},
+            {"planner": planner_cls(other_cls(NewOther)), "tracker": NewTracker, "particle": lambda s, h, p, t: HPS(s, h, p, t)})
+
+
+@pytest.mark.parametrize("per_step", [False, True])
+def test_belief_stat_tracker_matches_reference(oracle_env, per_step):
+    """Same particles, same environment trace -> the same ``belief_*_acc`` values (nan where the reference has nan),
+    including an empty-belief step and the first-step-only history accuracy."""
+    if not oracle_env["have_reference"]:
+        pytest.skip("needs the reference tree (build container)")
+    import random
+
+    rng = random.Random(3)
+    eps = [(rng.choice(["A", "B"]), rng.randrange(2), rng.randrange(3), _belief_episode_script(rng, n, 12)) for n in (6, 3, 5)]
+    # make the first step of the first episode a history hit for some particles
+    first = eps[0][3][0]["particles"]
+    eps[0][3][0]["particles"] = [(s, (({"0": None, "1": None}, {"0": h[0][1]["0"], "1": eps[0][1]}),), p, t) for s, h, p, t in first[:6]] + first[6:]
+    stats = ["policy", "action", "state", "history"]
+    ref_world, new_world = _worlds()
+    ref, new = _run_tracker(ref_world, eps, stats, per_step), _run_tracker(new_world, eps, stats, per_step)
+    assert [list(r) for r in ref] == [list(r) for r in new]
+    for r, n in zip(ref, new):
+        for k in r:
+            assert (np.isnan(r[k]) and np.isnan(n[k])) or r[k] == n[k], (k, r[k], n[k])
+    assert ref[0]["belief_history_acc"] > 0 and 0 < ref[0]["belief_policy_acc"] < 1
+    from posggym_baselines.planning.utils import BeliefStatTracker as RefTracker
+    from posggym_baselines_b200.planning.utils import BeliefStatTracker as NewTracker
+
+    for args in ((stats, False, None), (stats, True, 6), (["state"], True, 50)):
+        assert NewTracker.get_stat_keys(*args) == RefTracker.get_stat_keys(*args)
+
+
+def test_belief_stat_tracker_on_state_only_particles():
+    """The device search's root belief is packed states only: the state measure counts them, the others are 0."""
+    from posggym_baselines_b200.planning.utils import BeliefStatTracker
+
+    class Belief:
+        particles = ["s1", "s2", "s1", "s1"]
+
+        def size(self):
+            return 4
+
+    planner = type("P", (), {"agent_id": "0", "other_agent_policies": {}, "model": type("M", (), {"possible_agents": ("0", "1")})})()
+    planner.root = type("R", (), {"belief": Belief()})()
+    env = _FakeEnv()
+    env.last_actions, env.last_obs, env.state = {"1": None}, {"1": 0}, "s1"
+    tr = BeliefStatTracker(planner, env, stats_to_track=["state", "history"])
+    env.last_actions, env.state = {"1": 1}, "s2"
+    tr.step(env)
+    tr.step(env)
+    assert tr.get_episode() == {"belief_state_acc": (0.75 + 0.25) / 2, "belief_history_acc": 0.0}
+
+
+def test_agent_env_wrapper_and_belief_columns(tmp_path):
+    """The experiment loop with the other agent folded into the env and belief columns after the planner's."""
+    import random
+
+    from posggym_baselines_b200.envs.agent_env import AgentEnvWrapper, UniformOtherAgentFn
+    from posggym_baselines_b200.exp import run_planning_exp
+    from posggym_baselines_b200.planning.utils import PlanningStatTracker
+    from tests.potmmcp_policies import BiasedPolicy
+
+    class Model:
+        possible_agents = ("0", "1")
+        rng = random.Random(0)
+        spec = type("S", (), {"max_episode_steps": 4})()
+        action_spaces = {"0": type("A", (), {"n": 5})(), "1": type("A", (), {"n": 5})()}
+
+    class Env:
+        model = Model()
+        state = None
+
+        def reset(self, seed=None):
+            self.t, self.state = 0, ("s", 0)
+            return {"0": 0, "1": 10}, {}
+
+        def step(self, a):
+            assert set(a) == {"0", "1"} and a["1"] in range(5)
+            self.t += 1
+            self.state = ("s", self.t)
+            done = self.t >= 4
+            return {"0": self.t, "1": 10 + self.t}, {"0": 1.0, "1": 0.0}, {"0": done, "1": done}, {"0": False, "1": False}, done, {}
+
+        def close(self):
+            pass
+
+    made = []
+
+    def make(pid, model, agent_id):
+        made.append(pid)
+        return BiasedPolicy(model, agent_id, pid, 1, 3.0)
+
+    env = AgentEnvWrapper(Env(), UniformOtherAgentFn({"1": ["pusher", "idler"]}, make))
+
+    class Planner:
+        agent_id, model, other_agent_policies = "0", Model, {}
+
+        class config:
+            discount = 1.0
+
+        def __init__(self):
+            self.step_statistics = {}
+            self.stat_tracker = PlanningStatTracker(self)
+            self.root = type("R", (), {})()
+            self.root.belief = type("B", (), {"particles": [], "size": lambda self: len(self.particles)})()
+
+        def reset(self):
+            self.stat_tracker.reset_episode()
+
+        def step(self, obs):
+            self.step_statistics = {k: 0.0 for k in PlanningStatTracker.STAT_KEYS}
+            self.stat_tracker.step()
+            self.root.belief.particles = [("s", obs), ("s", obs), ("s", 99), ("s", obs)]    # 3 of 4 hold the true state
+            return 2
+
+    out = tmp_path / "episode_results.csv"
+    rows = run_planning_exp(env, Planner(), "0", None, 3, str(out), belief_stats_to_track=["state"],
+                            track_per_step_belief_stats=True)
+    with open(out) as f:
+        got = list(csv.DictReader(f))
+    assert list(got[0].keys()) == EXPECTED + ["belief_state_acc"] + [f"belief_state_acc_{t}" for t in range(4)]
+    assert all(float(r["belief_state_acc"]) == 0.75 and float(r["belief_state_acc_3"]) == 0.75 for r in got)
+    assert len(rows) == 3 and set(made) <= {"pusher", "idler"} and len(made) == len(set(made))
+    assert env.last_actions["1"] in range(5) and env.last_obs == {"1": 14}
+    env.close()
