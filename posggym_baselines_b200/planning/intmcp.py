@@ -53,9 +53,11 @@ class INTMCP:
                  node_capacity: int = 1 << 25, log_capacity: int = 1 << 27, belief_cap: int = 4096,
                  max_histories: int = 64, history_belief_cap: int = 256):
         if nesting_level != 1 or len(model.possible_agents) != 2:
-            raise NotImplementedError("the B200 I-NTMCP supports nesting_level=1 with two agents")
+            raise NotImplementedError("the device I-NTMCP is nesting_level=1 with two agents; INTMCP.initialize(...) "
+                                      "builds any other hierarchy on the plugin path (planning/host_intmcp.py)")
         if not all(isinstance(p, RandomSearchPolicy) for p in search_policies.values()):
-            raise NotImplementedError("only RandomSearchPolicy search policies run in-kernel")
+            raise NotImplementedError("only RandomSearchPolicy search policies run in-kernel; INTMCP.initialize(...) "
+                                      "routes plugin search policies to planning/host_intmcp.py")
         if config.state_belief_only:
             raise ValueError("I-NTMCP needs history beliefs: state_belief_only must be False")
         if not hasattr(model, "batched"):
@@ -116,10 +118,20 @@ class INTMCP:
     @classmethod
     def initialize(cls, model, ego_agent_id: str, config: MCTSConfig, nesting_level: int,
                    search_policies: Optional[Dict[int, Dict[str, SearchPolicy]]] = None, **b200_options) -> "INTMCP":
-        """Reference signature (intmcp.py:949-994); ``search_policies=None`` -> RandomSearchPolicy."""
+        """Reference signature (intmcp.py:949-994); ``search_policies=None`` -> RandomSearchPolicy.  Nesting level 1
+        with two agents and random search policies is the device planner (this class); any other hierarchy -- deeper
+        nesting, more agents, plugin search policies -- is built by planning/host_intmcp.py (host trees, model on the
+        device), which has the same surface."""
         if search_policies is None:
             search_policies = {lvl: {i: RandomSearchPolicy(model, i) for i in model.possible_agents}
                                for lvl in range(nesting_level + 1)}
+        in_kernel = (nesting_level == 1 and len(model.possible_agents) == 2 and all(
+            type(p) is RandomSearchPolicy for lvl in range(nesting_level + 1) for p in search_policies[lvl].values()))
+        if not in_kernel:
+            from posggym_baselines_b200.planning.host_intmcp import HostINTMCP
+
+            return HostINTMCP.initialize(model, ego_agent_id, config, nesting_level, search_policies,
+                                         max_sims_per_level=b200_options.get("max_sims_per_level"))
         return cls(model, ego_agent_id, config, nesting_level, None, search_policies[nesting_level], **b200_options)
 
     # ------------------------------------------------------------------ plumbing

@@ -111,3 +111,53 @@ def test_episode_outcomes_match_reference(model, gold):
     p = wins / n
     se = math.sqrt(p_ref * (1 - p_ref) / ref["n_episodes"] + p * (1 - p) / n)
     assert abs(p - p_ref) < 3 * se + 0.07, (p, p_ref)
+
+
+@pytest.mark.parametrize("name", ["level2_random", "level1_plugins"])
+def test_general_hierarchies_match_reference(model, name):
+    """Beyond BASELINE's configuration -- nesting level 2, and plugin search policies at nesting level 1 --
+    ``INTMCP.initialize`` builds the hierarchy on the plugin path (planning/host_intmcp.py: host trees, initial
+    beliefs / reinvigoration rounds / model steps on the device).  Root values and visit shares of two consecutive
+    decisions and the number of nested histories match a golden of the UNMODIFIED reference INTMCP
+    (tests/golden/make_intmcp_deep_golden.py) within 4 standard errors plus a small margin."""
+    from posggym_baselines_b200.planning import INTMCP, MCTSConfig, SearchPolicyWrapper
+    from posggym_baselines_b200.planning.host_intmcp import HostINTMCP
+    from tests.potmmcp_policies import BiasedPolicy
+
+    with open(os.path.join(GOLDEN, "intmcp_deep_driving.json")) as f:
+        scen = next(s for s in json.load(f)["scenarios"] if s["name"] == name)
+    obs0, obs1 = fields_to_obs(scen["obs0"]), fields_to_obs(scen["obs1"])
+    level, reps = scen["nesting_level"], 6
+    rows, nested = {"first": [], "second": []}, []
+    for rep in range(reps):
+        random.seed(4000 + rep)
+        model.seed(9700 + rep)
+        cfg = MCTSConfig(discount=0.95, search_time_limit=0.2, c=math.sqrt(2), truncated=False, action_selection="ucb",
+                         state_belief_only=False, seed=rep)
+        sp = None
+        if scen["plugins"]:      # the policies of make_intmcp_deep_golden.plugin_policies_for
+            sp = {lvl: {i: SearchPolicyWrapper(BiasedPolicy(model, i, f"L{lvl}_{i}", 1 if i == "0" else 2, 2.0 + 2.0 * lvl))
+                        for i in model.possible_agents} for lvl in range(level + 1)}
+        planner = INTMCP.initialize(model, "0", cfg, level, sp, max_sims_per_level=scen["n_sims_per_level"])
+        assert isinstance(planner, HostINTMCP)
+        planner.reset()
+        planner.update(None, obs0)
+        for which in ("first", "second"):
+            assert planner.get_action() in range(5)
+            assert planner.step_statistics["num_sims"] == scen["n_sims_per_level"] * (level + 1)
+            root = planner.traverse(planner.history)
+            vis = np.array([root.children[a].visits for a in range(5)], dtype=float)
+            rows[which].append(([root.children[a].value for a in range(5)], vis / vis.sum()))
+            if which == "first":
+                planner.update(scen["ego_action"], obs1)
+                assert root.belief.size() == 22 and planner.traverse(planner.history).belief.size() >= 22
+                nested.append(len(planner.get_nested_history_dist({planner.history: 1.0})["1"]))
+        planner.close()
+    for which in ("first", "second"):
+        vals, frac = (np.array(x) for x in zip(*rows[which]))
+        for got, key, margin in ((vals, "value", 0.015), (frac, "visit_frac", 0.04)):
+            mean, std = np.array(scen[which][key + "_mean"]), np.array(scen[which][key + "_std"])
+            se = np.sqrt(std**2 / scen["reps"] + got.std(0) ** 2 / reps)
+            assert (np.abs(got.mean(0) - mean) < 4 * se + margin).all(), (which, key, got.mean(0), mean, se)
+    se = math.sqrt(scen["nested_histories_std"] ** 2 / scen["reps"] + np.std(nested) ** 2 / reps)
+    assert abs(np.mean(nested) - scen["nested_histories_mean"]) < 4 * se + 0.75

@@ -407,6 +407,7 @@ def test_potmmcp_matches_the_unmodified_reference_planner(truncated):
             mean, std = np.array(g[key + "_mean"]), np.array(g[key + "_std"])
             se = np.sqrt(std**2 / scen["reps"] + got.std(0) ** 2 / reps)
             assert (np.abs(got.mean(0) - mean) < 4 * se + margin).all(), (which, key, got.mean(0), mean, se)
+        assert prior[:, 1].std() > 0.4 * g["prior_std"][1]      # the root prior moves with the search, as in the reference
     se = math.sqrt(scen["pusher_share_std"] ** 2 / scen["reps"] + np.std(shares) ** 2 / reps)
     assert abs(np.mean(shares) - scen["pusher_share_mean"]) < 4 * se + 0.05, (np.mean(shares), scen["pusher_share_mean"])
 
