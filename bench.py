@@ -15,6 +15,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import random
 import statistics
 import subprocess
 import sys
@@ -298,6 +299,8 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
             "reference_source": "unmodified reference INTMCP on the CPU oracle, 1 core, tests/golden/make_intmcp_golden.py"}
     except Exception as ex:
         out["intmcp_level1"] = {"error": repr(ex)}
+    if rank == 0:
+        out["plugin_path"] = bench_plugin_path(model, env)
     if cpu:
         from oracle import shims
 
@@ -325,6 +328,78 @@ def bench_pomcp(dev, rank, world, cpu: bool, decisions: int = 8):
         out["cpu_reference_sims_per_decision"] = sum(c_sims) / max(1, len(c_sims))
         out["cpu_reference"] = "oracle/pomcp.py (restated reference planner, pure Python, 1 core), same config"
         out["ratio"] = out["sims_per_decision_per_gpu"] / max(1e-9, out["cpu_reference_sims_per_decision"])
+    return out
+
+
+class _TiltedPolicy:
+    """A ``posggym.agents``-style policy object for the plugin-path section: prefers one action, has a value."""
+
+    def __init__(self, model, agent_id, policy_id, favourite):
+        self.model, self.agent_id, self.policy_id, self.favourite = model, agent_id, policy_id, favourite
+        self.n = model.action_spaces[agent_id].n
+
+    def get_initial_state(self):
+        return {"k": 0}
+
+    def get_next_state(self, action, obs, state):
+        return {"k": state["k"] + 1}
+
+    def get_pi(self, state):
+        w = [1.0] * self.n
+        w[self.favourite] += 4.0
+        return type("D", (), {"probs": {a: w[a] / sum(w) for a in range(self.n)}})()
+
+    def sample_action(self, state):
+        pi = self.get_pi(state).probs
+        return random.choices(list(pi), weights=list(pi.values()), k=1)[0]
+
+    def get_value(self, state):
+        return 0.05
+
+    def close(self):
+        pass
+
+
+def bench_plugin_path(model, env, decisions: int = 4):
+    """Planners whose policies are Python plugins (typed planners; general I-NTMCP): the tree descent
+    and the plugin calls run on the host (planning/host_search.py, potmmcp.py, host_intmcp.py), the model on the
+    device -- host speed by construction, reported so that nobody mistakes it for the device search's rate."""
+    from posggym_baselines_b200.planning import (INTMCP, POTMMCP, MCTSConfig, OtherAgentMixturePolicy,
+                                                 POTMMCPMetaPolicy)
+
+    out = {}
+
+    def episode(planner, key):
+        rng = random.Random(7)
+        obs, _ = env.reset(seed=300)
+        planner.reset()
+        sims = []
+        for _ in range(decisions):
+            a = planner.step(obs["0"])
+            if planner.step_statistics["num_sims"] == planner.step_statistics["num_sims"]:
+                sims.append(planner.step_statistics["num_sims"])
+            obs, _, _, _, done, _ = env.step({"0": a, "1": rng.randrange(5)})
+            if done:
+                break
+        planner.close()
+        out[key] = sum(sims) / max(1, len(sims))
+
+    try:
+        cfg = MCTSConfig(discount=0.99, search_time_limit=0.1, c=1.25, truncated=True, action_selection="pucb",
+                         state_belief_only=False, seed=0)
+        types = {k: _TiltedPolicy(model, "1", k, f) for k, f in (("pusher", 1), ("idler", 0))}
+        ego = {k: _TiltedPolicy(model, "0", k, f) for k, f in (("fast", 1), ("careful", 2))}
+        meta = POTMMCPMetaPolicy.get_uniform_meta_policy({e: {o: 0.0 for o in types} for e in ego})
+        episode(POTMMCP(model, "0", cfg, {"1": OtherAgentMixturePolicy(model, "1", types)},
+                        POTMMCPMetaPolicy(model, "0", ego, meta)), "potmmcp_sims_per_decision")
+        out["potmmcp_config"] = "Driving-v1, 2 other-agent types x 2 ego policies, value leaves, pucb, 0.1 s"
+        icfg = MCTSConfig(discount=0.95, search_time_limit=0.2, c=1.414, truncated=False, action_selection="ucb",
+                          state_belief_only=False, seed=0)
+        episode(INTMCP.initialize(model, "0", icfg, nesting_level=2, search_policies=None),
+                "intmcp_level2_sims_per_decision")
+        out["intmcp_level2_config"] = "Driving-v1, nesting_level 2 (three trees deep), random search policies, ucb, 0.2 s"
+    except Exception as ex:
+        out["error"] = repr(ex)
     return out
 
 
