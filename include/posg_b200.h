@@ -184,6 +184,16 @@ int posg_model_step(posg_model_t m, int64_t n, const uint32_t* state_in, const u
                     uint64_t particle_offset, uint32_t* state_out, uint64_t* obs_out,
                     double* rewards_out, uint8_t* flags_out, uint8_t* actions_out,
                     unsigned long long* live_count, void* stream);
+/* model.step for a handful of rows in HOST memory, any model kind (Driving included): the scalar call of a
+ * planner whose policies are Python plugins -- planning/mcts.py:333,418 and planning/intmcp.py:468,562 reached
+ * through planning/host_search.py / host_intmcp.py, one call per tree level of a simulation.  Explicit actions
+ * [n][A] and explicit noise [n][noise_row_bytes] (Driving: 1 byte, the processing-order index; other models:
+ * 4 bytes per noise word).  One staged copy in, the model's step kernel, one copy out, one synchronisation on a
+ * stream the handle owns; one call per handle at a time. */
+int posg_model_step_host(posg_model_t m, int64_t n, const uint32_t* state_in_host,
+                         const uint8_t* actions_host, const void* noise_host, int noise_row_bytes,
+                         uint32_t* state_out_host, uint64_t* obs_out_host, double* rewards_out_host,
+                         uint8_t* flags_out_host);
 /* MCTS._rollout with uniform-random policies (mcts.py:405-452), see posg_driving_rollout. */
 int posg_model_rollout(posg_model_t m, int64_t n, const uint32_t* state_in, int ego_agent,
                        int max_steps, double discount, uint64_t seed, uint32_t step0,

@@ -53,6 +53,7 @@ SIGNATURES = {
     "posg_model_observe": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "posg_model_step": (
         _int, [_vp, _i64, _vp, _vp, _vp, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "posg_model_step_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "posg_model_rollout": (
         _int, [_vp, _i64, _vp, _int, _int, _dbl, _u64, _u32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "posg_trace_hash": (_int, [_i64, _vp, _int, _u64, _vp, _int, _vp, _int, _vp, _int, _vp, _vp, _vp]),

@@ -137,6 +137,7 @@ int posg_model_destroy(posg_model_t m) {
   }
   if (m->d_flat_desc) cudaFree(m->d_flat_desc);
   if (m->host_stage && m->host_stage_free) m->host_stage_free(m->host_stage);
+  if (m->step_stage && m->step_stage_free) m->step_stage_free(m->step_stage);
   delete m;
   return POSG_OK;
 }

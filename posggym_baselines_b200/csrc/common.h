@@ -61,4 +61,7 @@ struct posg_model {
   // reused by later calls (guarded by a mutex: one host-buffer call per handle at a time)
   void* host_stage = nullptr;
   void (*host_stage_free)(void*) = nullptr;
+  // staging of posg_model_step_host (small batches from host memory: one pinned block, one device block, one stream)
+  void* step_stage = nullptr;
+  void (*step_stage_free)(void*) = nullptr;
 };

@@ -116,6 +116,20 @@ class BatchedModel:
                 _lib.ptr(out.flags), _lib.ptr(out.actions), _lib.ptr(live_count), _lib.stream_ptr()))
         return out
 
+    def step_host(self, state: np.ndarray, actions: np.ndarray, noise: np.ndarray):
+        """``model.step`` for a few rows in host memory (``posg_model_step_host``): numpy in, numpy out --
+        ``(state [n, state_words] int32, obs [n, A, obs_words] int64, rewards [n, A] float64, flags [n] uint8)``.
+        The scalar facade and the planners' plugin path step through this."""
+        n, a = state.shape[0], self.num_agents
+        state = np.ascontiguousarray(state, dtype=np.int32)
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        noise = np.ascontiguousarray(noise, dtype=np.uint32).reshape(n, self.noise_words)
+        out = (np.empty((n, self.state_words), np.int32), np.empty((n, a, self.obs_words), np.int64),
+               np.empty((n, a), np.float64), np.empty((n,), np.uint8))
+        _lib.check(_lib.lib().posg_model_step_host(self._handle, n, _lib.ptr(state), _lib.ptr(actions), _lib.ptr(noise),
+                                                   4 * self.noise_words, *(_lib.ptr(o) for o in out)))
+        return out
+
     def rollout(self, state, ego_agent: int, max_steps: int, discount: float, seed: int = 0, step0: int = 0,
                 particle_offset: int = 0, want_state: bool = False, live_count=None):
         n = state.shape[0]
@@ -170,24 +184,26 @@ class ModelFacade:
     def sample_agent_initial_state(self, agent_id: str, obs):
         raise NotImplementedError
 
+    def host_step_noise(self, n: int) -> np.ndarray:
+        """Explicit noise for ``n`` rows of ``batched.step_host`` / ``batched.step``: what ``step`` draws from
+        ``self.rng``, n times (uint32 [n, noise_words])."""
+        b = self.batched
+        if getattr(b, "noise_is_dummy", False):     # deterministic transition: nothing is drawn
+            return np.zeros((n, b.noise_words), np.uint32)
+        return np.array([[self._rng.getrandbits(32) for _ in range(b.noise_words)] for _ in range(n)],
+                        dtype=np.uint32).reshape(n, b.noise_words)
+
     def batched_step_noise(self, n: int):
-        """Explicit noise for ``n`` rows of ``batched.step``: what ``step`` draws from ``self.rng``, n times."""
-        if getattr(self.batched, "noise_is_dummy", False):     # deterministic transition: nothing is drawn
-            noise = np.zeros((n, self.batched.noise_words), np.uint32)
-        else:
-            noise = np.array([[self._rng.getrandbits(32) for _ in range(self.batched.noise_words)] for _ in range(n)],
-                             dtype=np.uint32).reshape(n, self.batched.noise_words)
-        return torch.from_numpy(noise.view(np.int32)).to(self.batched.device)
+        return torch.from_numpy(self.host_step_noise(n).view(np.int32)).to(self.batched.device)
 
     def step(self, state, actions: Dict[str, int]) -> JointTimestep:
         b = self.batched
-        packed = torch.from_numpy(b.pack_state([state])).to(b.device)
-        act = torch.tensor([[int(actions[i]) for i in self.possible_agents]], dtype=torch.uint8, device=b.device)
-        out = b.step(packed, act, self.batched_step_noise(1))
-        nstate = b.unpack_state(out.state)[0]
-        obs = b.unpack_obs(out.obs)[0]
-        rew = out.rewards.cpu().numpy()[0]
-        flags = int(out.flags.cpu()[0])
+        act = np.array([[int(actions[i]) for i in self.possible_agents]], dtype=np.uint8)
+        st, ob, rw, fl = b.step_host(b.pack_state([state]), act, self.host_step_noise(1))
+        nstate = b.unpack_state(st)[0]
+        obs = b.unpack_obs(ob)[0]
+        rew = rw[0]
+        flags = int(fl[0])
         ids = self.possible_agents
         return JointTimestep(
             nstate, {i: obs[k] for k, i in enumerate(ids)}, {i: float(rew[k]) for k, i in enumerate(ids)},

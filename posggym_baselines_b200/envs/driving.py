@@ -183,6 +183,20 @@ class BatchedDriving:
                 _lib.ptr(out.flags), _lib.ptr(out.actions), _lib.ptr(live_count), _lib.stream_ptr()))
         return out
 
+    def step_host(self, state: np.ndarray, actions: np.ndarray, order: np.ndarray):
+        """``model.step`` for a few rows in host memory (``posg_model_step_host``): numpy in, numpy out --
+        ``(state [n, A] int32, obs [n, A] int64, rewards [n, A] float64, flags [n] uint8)``.  The scalar facade and
+        the planners' plugin path step through this."""
+        n, a = state.shape[0], self.num_agents
+        state = np.ascontiguousarray(state, dtype=np.int32)
+        actions = np.ascontiguousarray(actions, dtype=np.uint8)
+        order = np.ascontiguousarray(order, dtype=np.uint8).reshape(n)
+        out = (np.empty((n, a), np.int32), np.empty((n, a), np.int64), np.empty((n, a), np.float64),
+               np.empty((n,), np.uint8))
+        _lib.check(_lib.lib().posg_model_step_host(self._handle, n, _lib.ptr(state), _lib.ptr(actions), _lib.ptr(order),
+                                                   1, *(_lib.ptr(o) for o in out)))
+        return out
+
     def rollout(self, state: torch.Tensor, ego_agent: int, max_steps: int, discount: float,
                 seed: int = 0, step0: int = 0, particle_offset: int = 0, want_state: bool = False,
                 live_count: Optional[torch.Tensor] = None):
@@ -381,22 +395,25 @@ class DrivingModel:
     def sample_agent_initial_state(self, agent_id: str, obs):
         raise NotImplementedError
 
-    def batched_step_noise(self, n: int):
-        """Explicit noise for ``n`` rows of ``batched.step``: the processing-order draw of ``step``, n times."""
+    def host_step_noise(self, n: int) -> np.ndarray:
+        """Explicit noise for ``n`` rows of ``batched.step_host`` / ``batched.step``: the processing-order draw of
+        ``step``, n times (uint8 [n])."""
         import math
 
         k = math.factorial(len(self.possible_agents))
-        return torch.tensor([self._rng.randrange(k) for _ in range(n)], dtype=torch.uint8, device=self.batched.device)
+        return np.array([self._rng.randrange(k) for _ in range(n)], dtype=np.uint8)
+
+    def batched_step_noise(self, n: int):
+        return torch.from_numpy(self.host_step_noise(n)).to(self.batched.device)
 
     def step(self, state, actions: Dict[str, int]) -> JointTimestep:
         b = self.batched
-        packed = torch.from_numpy(b.pack_state([state])).to(b.device)
-        act = torch.tensor([[int(actions[i]) for i in self.possible_agents]], dtype=torch.uint8, device=b.device)
-        out = b.step(packed, act, self.batched_step_noise(1))
-        nstate = b.unpack_state(out.state)[0]
-        obs = b.unpack_obs(out.obs)[0]
-        rew = out.rewards.cpu().numpy()[0]
-        flags = int(out.flags.cpu()[0])
+        act = np.array([[int(actions[i]) for i in self.possible_agents]], dtype=np.uint8)
+        st, ob, rw, fl = b.step_host(b.pack_state([state]), act, self.host_step_noise(1))
+        nstate = b.unpack_state(st)[0]
+        obs = b.unpack_obs(ob)[0]
+        rew = rw[0]
+        flags = int(fl[0])
         ids = self.possible_agents
         return JointTimestep(
             nstate,

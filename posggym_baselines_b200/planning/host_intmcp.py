@@ -440,12 +440,11 @@ class HostINTMCP:
                 n = int(min(math.ceil(limit - attempts), max(32, 2 * (need - len(accepted)))))
                 parents = [parent.sample() for _ in range(n)]
                 actions = [self._get_joint_action(h, action) for h in parents]
-                st = torch.from_numpy(b.pack_state([h.state for h in parents])).to(b.device)
-                act = torch.tensor([[int(a[i]) for i in ids] for a in actions], dtype=torch.uint8, device=b.device)
-                out = b.step(st, act, self.model.batched_step_noise(n))
-                keys = out.obs.reshape(n, len(ids), -1)[:, self._ego, :].cpu().numpy().view(np.uint64)
+                act = np.array([[int(a[i]) for i in ids] for a in actions], dtype=np.uint8)
+                nst, nob, _, _ = b.step_host(b.pack_state([h.state for h in parents]), act, self.model.host_step_noise(n))
+                keys = np.ascontiguousarray(nob.reshape(n, len(ids), -1)[:, self._ego, :]).view(np.uint64)
                 match = (keys == want.reshape(1, -1)).all(axis=1)
-                nstates, nobs = b.unpack_state(out.state), b.unpack_obs(out.obs)
+                nstates, nobs = b.unpack_state(nst), b.unpack_obs(nob)
                 for k in range(n):
                     if len(accepted) >= need or attempts >= limit:      # the sequential loop stops here
                         break

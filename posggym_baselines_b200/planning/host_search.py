@@ -14,7 +14,9 @@ it, batched:
 * reinvigoration steps a whole round of rejection-sampling attempts with ONE ``model.step`` launch
   (parents and joint actions chosen on the host, in the order the sequential loop would, so the accepted /
   padded particles are the ones it would produce for the same draws);
-* single model steps inside a simulation go through the facade's batch-of-one ``model.step``.
+* single model steps inside a simulation go through the facade's scalar ``model.step``;
+* both kinds of step are ``posg_model_step_host`` calls: host rows staged through one pinned block, one copy in,
+  the step kernel, one copy out, one synchronisation -- no tensor objects on the way.
 
 Particles carry ``(state, joint history, other agents' policy states, t)`` unless
 ``config.state_belief_only``.
@@ -240,14 +242,12 @@ class HostSearch:
                 n = min(limit - attempts, max(32, 2 * (need - len(accepted))))
                 parents = [parent.sample() for _ in range(n)]
                 actions = [self._joint_action(h, action) for h in parents]
-                st = torch.from_numpy(b.pack_state([h.state for h in parents])).to(b.device)
-                act = torch.tensor([[int(a[i]) for i in ids] for a in actions], dtype=torch.uint8, device=b.device)
-                noise = self.p._facade_noise(n)
-                out = b.step(st, act, noise)
-                keys = out.obs.reshape(n, len(ids), -1)[:, ego, :].cpu().numpy().view(np.uint64)
+                act = np.array([[int(a[i]) for i in ids] for a in actions], dtype=np.uint8)
+                nst, nob, rew, flags = b.step_host(b.pack_state([h.state for h in parents]), act,
+                                                   self.model.host_step_noise(n))
+                keys = np.ascontiguousarray(nob.reshape(n, len(ids), -1)[:, ego, :]).view(np.uint64)
                 match = (keys == want.reshape(1, -1)).all(axis=1)
-                nstates, nobs = b.unpack_state(out.state), b.unpack_obs(out.obs)
-                rew, flags = out.rewards.cpu().numpy(), out.flags.cpu().numpy()
+                nstates, nobs = b.unpack_state(nst), b.unpack_obs(nob)
                 for k in range(n):
                     if len(accepted) >= need:      # the sequential loop stops here: later attempts never happened
                         break

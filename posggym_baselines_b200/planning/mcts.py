@@ -240,11 +240,6 @@ class MCTS:
             raise RuntimeError(f"initial belief: only {res[0]} of {need} particles matched the first observation")
         return out
 
-    def _facade_noise(self, n: int):
-        """Explicit step noise for ``n`` batched ``model.step`` rows, drawn from ``model.rng`` like the facade's
-        scalar ``step`` does."""
-        return self.model.batched_step_noise(n)
-
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
         return _lib.stream_ptr()

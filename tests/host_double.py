@@ -1,6 +1,6 @@
 """A CPU stand-in for the device model facade, for tests of the planners' HOST logic (planning/host_search.py,
 planning/potmmcp.py, planning/host_intmcp.py): the batch interface those engines call (``pack_state`` /
-``unpack_state`` / ``pack_obs`` / ``unpack_obs`` / ``observe`` / ``step``) answered by the CPU oracle model, with
+``unpack_state`` / ``pack_obs`` / ``unpack_obs`` / ``observe`` / ``step_host``) answered by the CPU oracle model, with
 states and observations "packed" as indices into a registry.  Test infrastructure only -- the product planners get
 their facade from posggym_baselines_b200.envs and fail without the CUDA library."""
 from __future__ import annotations
@@ -50,13 +50,11 @@ class RegistryBatched:
     def observe(self, states):
         return self._obs_rows([self.m.sample_initial_obs(s) for s in self.unpack_state(states)])
 
-    def step(self, st, act, noise=None):
+    def step_host(self, st, act, noise=None):
         rows = [self.m.step(s, {i: int(a[k]) for k, i in enumerate(self.ids)}) for s, a in zip(self.unpack_state(st), act)]
         flags = [sum(int(ts.terminations[i]) << k for k, i in enumerate(self.ids)) | (0x80 if ts.all_done else 0) for ts in rows]
-        return SimpleNamespace(state=torch.from_numpy(self.pack_state([ts.state for ts in rows])),
-                               obs=self._obs_rows([ts.observations for ts in rows]),
-                               rewards=torch.tensor([[ts.rewards[i] for i in self.ids] for ts in rows], dtype=torch.float64),
-                               flags=torch.tensor(flags, dtype=torch.uint8))
+        return (self.pack_state([ts.state for ts in rows]), self._obs_rows([ts.observations for ts in rows]).numpy(),
+                np.array([[ts.rewards[i] for i in self.ids] for ts in rows], dtype=np.float64), np.array(flags, dtype=np.uint8))
 
 
 class DoubleDrivingModel(DrivingModel):
@@ -68,7 +66,7 @@ class DoubleDrivingModel(DrivingModel):
             self.spec = SimpleNamespace(max_episode_steps=50, id="Driving-v1")
         self.batched = RegistryBatched(self)
 
-    def batched_step_noise(self, n):
+    def host_step_noise(self, n):
         return None
 
     def initial_belief(self, agent_id, init_obs, need):

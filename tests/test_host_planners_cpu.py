@@ -46,9 +46,6 @@ class _PlannerShell:
     def _device_initial_belief(self, init_obs, need):
         return self.model.initial_belief(self.agent_id, init_obs, need)
 
-    def _facade_noise(self, n):
-        return None
-
 
 @pytest.mark.parametrize("truncated", [False, True])
 def test_potmmcp_engine_matches_reference_golden(double_model, truncated):
