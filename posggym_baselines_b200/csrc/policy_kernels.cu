@@ -353,7 +353,36 @@ using namespace posg;
 struct posg_policy {
   policy::Weights* d_w;
   int n_actions, device;
+  // posg_policy_set_trunk0 / posg_policy_eval_host: trunk layer 0 as an index-row sum, and the host staging
+  float* d_w0t = nullptr;   // [in_dim, H] = trunk.0.weight transposed
+  float* d_b0 = nullptr;    // [H]
+  int in_dim = 0;
+  unsigned char* h_stage = nullptr;   // pinned
+  unsigned char* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t st = nullptr;
 };
+
+namespace posg {
+namespace policy {
+
+// x0[row] = tanh(b0 + sum_k w0t[idx[row][k]]): trunk layer 0 on a one-hot-flattened observation given as the K row
+// indices of its active inputs (ppo/network.py:171-178 on FlattenProcessor's output).  One warp per row.
+__global__ void embed_rows_kernel(const float* __restrict__ w0t, const float* __restrict__ b0,
+                                  const int* __restrict__ idx, int n, int K, int in_dim, float* __restrict__ x0) {
+  const int row = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float a0 = b0[lane], a1 = b0[lane + 32];
+  for (int k = 0; k < K; ++k) {
+    const int r = idx[row * K + k];
+    if (r >= 0 && r < in_dim) { a0 += w0t[r * H + lane]; a1 += w0t[r * H + lane + 32]; }
+  }
+  x0[row * H + lane] = tanhf(a0);
+  x0[row * H + lane + 32] = tanhf(a1);
+}
+
+}  // namespace policy
+}  // namespace posg
 
 #ifdef POSG_POLICY_TRACE
 extern "C" int posg_policy_trace(unsigned long long* out_host) {
@@ -407,8 +436,83 @@ int posg_policy_create(int hidden, int n_actions, const float* trunk1_w, const f
 
 int posg_policy_destroy(posg_policy_t p) {
   if (!p) return POSG_OK;
+  if (p->st) { cudaStreamSynchronize(p->st); cudaStreamDestroy(p->st); }
   cudaFree(p->d_w);
+  cudaFree(p->d_w0t);
+  cudaFree(p->d_b0);
+  cudaFreeHost(p->h_stage);
+  cudaFree(p->d_stage);
   delete p;
+  return POSG_OK;
+}
+
+int posg_policy_set_trunk0(posg_policy_t p, int in_dim, const float* trunk0_w, const float* trunk0_b) {
+  POSG_REQUIRE(p && trunk0_w && trunk0_b && in_dim > 0, "bad arguments");
+  using namespace policy;
+  std::vector<float> wt((size_t)in_dim * H);
+  for (int n = 0; n < H; ++n)
+    for (int k = 0; k < in_dim; ++k) wt[(size_t)k * H + n] = trunk0_w[(size_t)n * in_dim + k];
+  POSG_CUDA(cudaSetDevice(p->device));
+  cudaFree(p->d_w0t); cudaFree(p->d_b0);
+  p->d_w0t = nullptr; p->d_b0 = nullptr; p->in_dim = 0;
+  POSG_CUDA(cudaMalloc((void**)&p->d_w0t, wt.size() * sizeof(float)));
+  POSG_CUDA(cudaMalloc((void**)&p->d_b0, H * sizeof(float)));
+  POSG_CUDA(cudaMemcpy(p->d_w0t, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+  POSG_CUDA(cudaMemcpy(p->d_b0, trunk0_b, H * sizeof(float), cudaMemcpyHostToDevice));
+  p->in_dim = in_dim;
+  return POSG_OK;
+}
+
+int posg_policy_eval_host(posg_policy_t p, int64_t n, int K, const int32_t* obs_index_host, const float* h_in_host,
+                          const float* c_in_host, float* h_out_host, float* c_out_host, float* logits_out_host,
+                          float* value_out_host) {
+  POSG_REQUIRE(p, "null policy");
+  if (n == 0) return POSG_OK;
+  POSG_REQUIRE(p->d_w0t, "posg_policy_set_trunk0 first");
+  POSG_REQUIRE(n > 0 && n <= (1 << 16) && K > 0 && obs_index_host && h_in_host && c_in_host && h_out_host && c_out_host &&
+               logits_out_host && value_out_host, "bad arguments");
+  using namespace policy;
+  const int A = p->n_actions;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  // in:  [idx | h | c]   scratch (device only): [x0 | done | action_in | action | logprob | entropy]   out: [h | c | logits | value]
+  const size_t b_idx = (size_t)n * K * 4, b_hc = (size_t)n * H * 4;
+  const size_t o_h = up(b_idx), o_c = o_h + up(b_hc), o_scr = o_c + up(b_hc);
+  const size_t o_x0 = o_scr, o_done = o_x0 + up(b_hc), o_ain = o_done + up((size_t)n * 4), o_act = o_ain + up((size_t)n * 8);
+  const size_t o_lp = o_act + up((size_t)n * 8), o_ent = o_lp + up((size_t)n * 4), o_out = o_ent + up((size_t)n * 4);
+  const size_t o_ho = o_out, o_co = o_ho + up(b_hc), o_lg = o_co + up(b_hc), o_val = o_lg + up((size_t)n * A * 4);
+  const size_t total = o_val + up((size_t)n * 4);
+  POSG_CUDA(cudaSetDevice(p->device));
+  if (!p->st) POSG_CUDA(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  if (p->stage_bytes < total) {
+    POSG_CUDA(cudaStreamSynchronize(p->st));
+    cudaFreeHost(p->h_stage); cudaFree(p->d_stage);
+    p->h_stage = nullptr; p->d_stage = nullptr; p->stage_bytes = 0;
+    const size_t cap = total < 16384 ? 16384 : total + total / 2;
+    POSG_CUDA(cudaMallocHost((void**)&p->h_stage, cap));
+    POSG_CUDA(cudaMalloc((void**)&p->d_stage, cap));
+    p->stage_bytes = cap;
+  }
+  unsigned char *h = p->h_stage, *d = p->d_stage;
+  memcpy(h, obs_index_host, b_idx);
+  memcpy(h + o_h, h_in_host, b_hc);
+  memcpy(h + o_c, c_in_host, b_hc);
+  POSG_CUDA(cudaMemcpyAsync(d, h, o_scr, cudaMemcpyHostToDevice, p->st));
+  POSG_CUDA(cudaMemsetAsync(d + o_done, 0, o_act - o_done, p->st));        // done = 0, action_in = 0 (nothing sampled)
+  const int warps_per_block = 8;
+  embed_rows_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, p->st>>>(
+      p->d_w0t, p->d_b0, (const int*)d, (int)n, K, p->in_dim, (float*)(d + o_x0));
+  POSG_CUDA(cudaGetLastError());
+  int rc = posg_policy_step(p, n, (const float*)(d + o_x0), (const float*)(d + o_h), (const float*)(d + o_c),
+                            (const float*)(d + o_done), nullptr, nullptr, 0, 0, nullptr, 0, (const int64_t*)(d + o_ain),
+                            (float*)(d + o_ho), (float*)(d + o_co), (int64_t*)(d + o_act), (float*)(d + o_lp),
+                            (float*)(d + o_ent), (float*)(d + o_val), (float*)(d + o_lg), p->st);
+  if (rc) return rc;
+  POSG_CUDA(cudaMemcpyAsync(h + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, p->st));
+  POSG_CUDA(cudaStreamSynchronize(p->st));
+  memcpy(h_out_host, h + o_ho, b_hc);
+  memcpy(c_out_host, h + o_co, b_hc);
+  memcpy(logits_out_host, h + o_lg, (size_t)n * A * 4);
+  memcpy(value_out_host, h + o_val, (size_t)n * 4);
   return POSG_OK;
 }
 

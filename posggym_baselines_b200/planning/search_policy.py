@@ -145,8 +145,9 @@ class PPOLSTMSearchPolicy(SearchPolicy):
     Here the network runs on the GPU: trunk layer 0 as a sum of the weight columns of the observation's one-hot
     inputs, everything else in the tensor-core policy kernel (``posg_policy_step``, ppo/policy.py) -- also for
     the one-row calls of the planner's host path (``get_next_state``), and for whole batches of tree nodes
-    through ``get_next_state_batch``.  ``state_dict`` uses the reference's parameter names
-    (``checkpoint["model"]``); the LSTM state stays on the device."""
+    through ``get_next_state_batch``; either way ONE library call with host rows (``posg_policy_eval_host``).
+    ``state_dict`` uses the reference's parameter names (``checkpoint["model"]``); a policy state's LSTM pair is
+    held as CPU tensors, as in the reference."""
 
     def __init__(self, model, agent_id: str, policy_id: str, state_dict, device=None):
         import torch
@@ -162,31 +163,34 @@ class PPOLSTMSearchPolicy(SearchPolicy):
         self._leaves, width = _flat_index_layout(model.observation_spaces[agent_id])
         if width != self.policy.w0_t.shape[0]:
             raise ValueError(f"the policy expects {self.policy.w0_t.shape[0]} inputs, the observation space flattens to {width}")
-        self._zero_done = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def get_initial_state(self) -> PolicyState:
         t = self._torch
-        z = lambda: t.zeros((1, self.policy.hidden), dtype=t.float32, device=self.device)  # noqa: E731
+        z = lambda: t.zeros((1, self.policy.hidden), dtype=t.float32)  # noqa: E731
         return {"lstm_state": (z(), z()), "pi": None, "value": 0.0}
 
-    def _x0(self, obs_list):
-        t = self._torch
-        idx = t.tensor([[off + v - start for (off, start), v in zip(self._leaves, _flat_values(o))] for o in obs_list],
-                       dtype=t.int64, device=self.device)
-        return t.tanh(self.policy.w0_t[idx].sum(1) + self.policy.b0).contiguous()
+    def _index_rows(self, obs_list):
+        import numpy as np
+
+        return np.array([[off + v - start for (off, start), v in zip(self._leaves, _flat_values(o))] for o in obs_list],
+                        dtype=np.int32)
 
     def get_next_state_batch(self, obs_list, states):
-        """``get_next_state`` for many (observation, policy state) pairs in one launch of the policy kernel."""
+        """``get_next_state`` for many (observation, policy state) pairs in one evaluation of the network
+        (``posg_policy_eval_host``: host rows in, one launch of trunk layer 0 and one of the tensor-core policy
+        kernel, host rows out).  The LSTM state of a policy state is a pair of CPU tensors [1, 64], as in the
+        reference, whose search policy runs its network on the CPU."""
+        import numpy as np
+
         t = self._torch
         n = len(obs_list)
-        h = t.cat([s["lstm_state"][0] for s in states], 0).contiguous()
-        c = t.cat([s["lstm_state"][1] for s in states], 0).contiguous()
-        done = self._zero_done.expand(n).contiguous()
-        out = self.policy.step(self._x0(obs_list), (h, c), done, action=t.zeros(n, dtype=t.int64, device=self.device),
-                               want_logits=True)
-        probs = t.softmax(out["logits"], -1).cpu().numpy()
-        values = out["value"].cpu().numpy()
-        return [{"lstm_state": (h[k:k + 1], c[k:k + 1]),
+        h = np.concatenate([s["lstm_state"][0].numpy() for s in states], 0)
+        c = np.concatenate([s["lstm_state"][1].numpy() for s in states], 0)
+        h2, c2, logits, values = self.policy.eval_host(self._index_rows(obs_list), h, c)
+        z = np.exp(logits.astype(np.float64) - logits.max(1, keepdims=True))
+        probs = z / z.sum(1, keepdims=True)                       # softmax of the actor's logits (search_policy.py:270)
+        h2, c2 = t.from_numpy(h2), t.from_numpy(c2)
+        return [{"lstm_state": (h2[k:k + 1], c2[k:k + 1]),
                  "pi": {a: float(probs[k, a]) for a in self.action_space}, "value": float(values[k])} for k in range(n)]
 
     def get_next_state(self, action, obs, state: PolicyState) -> PolicyState:

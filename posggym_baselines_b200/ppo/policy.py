@@ -37,6 +37,9 @@ class FusedPolicy:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().posg_policy_create(self.hidden, self.num_actions, *[_lib.ptr(a) for a in arrs],
                                                      C.byref(self._handle)))
+            w0 = np.ascontiguousarray(state_dict["trunk.0.weight"].detach().cpu().numpy(), dtype=np.float32)
+            b0 = np.ascontiguousarray(state_dict["trunk.0.bias"].detach().cpu().numpy(), dtype=np.float32)
+            _lib.check(_lib.lib().posg_policy_set_trunk0(self._handle, int(w0.shape[1]), _lib.ptr(w0), _lib.ptr(b0)))
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -46,6 +49,20 @@ class FusedPolicy:
             except Exception:
                 pass
             self._handle = None
+
+    def eval_host(self, obs_index: np.ndarray, h: np.ndarray, c: np.ndarray):
+        """The network for a few rows in host memory (``posg_policy_eval_host``; the planners' plugin path calls it once
+        per node a simulation adds): ``obs_index`` [n, K] int32 = the active inputs of each one-hot-flattened
+        observation, ``h`` / ``c`` [n, 64] float32.  Returns ``(h', c', logits [n, A], value [n])`` as numpy arrays."""
+        obs_index = np.ascontiguousarray(obs_index, dtype=np.int32)
+        n, k = obs_index.shape
+        h = np.ascontiguousarray(h, dtype=np.float32).reshape(n, self.hidden)
+        c = np.ascontiguousarray(c, dtype=np.float32).reshape(n, self.hidden)
+        out = (np.empty((n, self.hidden), np.float32), np.empty((n, self.hidden), np.float32),
+               np.empty((n, self.num_actions), np.float32), np.empty((n,), np.float32))
+        _lib.check(_lib.lib().posg_policy_eval_host(self._handle, n, k, _lib.ptr(obs_index), _lib.ptr(h), _lib.ptr(c),
+                                                    *(_lib.ptr(o) for o in out)))
+        return out
 
     def step(self, x0: torch.Tensor, lstm_state: Tuple[torch.Tensor, torch.Tensor], done: Optional[torch.Tensor],
              action: Optional[torch.Tensor] = None, seed: int = 0, step_idx: int = 0, row_offset: int = 0,

@@ -329,7 +329,7 @@ def test_ppo_lstm_search_policy_combined_planner():
                                                                torch.zeros(1, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
     ref_pi = torch.softmax(logits[0], -1).cpu().numpy()
     assert np.abs(np.array([st["pi"][a] for a in range(5)]) - ref_pi).max() < 5e-3
-    assert abs(st["value"] - val.item()) < 5e-3 and (st["lstm_state"][0] - h1[0]).abs().max().item() < 5e-3
+    assert abs(st["value"] - val.item()) < 5e-3 and (st["lstm_state"][0] - h1[0].cpu()).abs().max().item() < 5e-3
     cfg = MCTSConfig(discount=0.99, search_time_limit=0.1, c=1.25, truncated=True, action_selection="pucb",
                      state_belief_only=False, seed=1)
     planner = MCTS(model, "0", cfg, {"1": RandomOtherAgentPolicy(model, "1")}, sp)

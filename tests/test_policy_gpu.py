@@ -148,3 +148,44 @@ def test_device_collector_graph_replays_are_fresh_rollouts():
     r2 = a.rollout()
     torch.cuda.synchronize()
     assert not torch.equal(r1["actions"], r2["actions"])      # a replay continues the envs with new draws
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000])
+def test_policy_eval_host_matches_fp32_torch(n):
+    """posg_policy_eval_host -- the planners' one-call network evaluation with host rows (trunk layer 0 as an
+    index-row sum, then the tensor-core kernel): new LSTM state, logits and value within 5e-3 of the fp32 module fed
+    the one-hot rows those indices stand for; out-of-range indices contribute nothing."""
+    from posggym_baselines_b200.ppo import FusedPolicy
+
+    torch.manual_seed(100 + n)
+    dev = torch.device("cuda")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = RefNet(124, 5).to(dev)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.5).add_(0.05 * torch.randn_like(p))
+        pol = FusedPolicy(net.state_dict(), device=dev)
+        rng = np.random.default_rng(n)
+        k = 22
+        idx = np.stack([rng.choice(124, size=k, replace=False) for _ in range(n)]).astype(np.int32)
+        x = torch.zeros(n, 124, device=dev)
+        x[torch.arange(n, device=dev).view(-1, 1), torch.from_numpy(idx.astype(np.int64)).to(dev)] = 1.0
+        idx_padded = np.concatenate([idx, np.full((n, 2), -1, np.int32)], 1)
+        idx_padded[:, -1] = 124                                  # both pads are out of range
+        h = (torch.randn(n, 64) * 0.5).numpy()
+        c = torch.randn(n, 64).numpy()
+        with torch.no_grad():
+            logits, _, _, val, (h1, c1) = net.get_action_and_value(
+                x, (torch.from_numpy(h).to(dev).unsqueeze(0), torch.from_numpy(c).to(dev).unsqueeze(0)),
+                torch.zeros(n, device=dev), torch.zeros(n, dtype=torch.int64, device=dev))
+        h2, c2, lg, v = pol.eval_host(idx_padded, h, c)
+        tol = 5e-3
+        assert np.abs(lg - logits.cpu().numpy()).max() < tol and np.abs(v - val.cpu().numpy()).max() < tol
+        assert np.abs(h2 - h1[0].cpu().numpy()).max() < tol and np.abs(c2 - c1[0].cpu().numpy()).max() < tol
+        h3, c3, lg3, v3 = pol.eval_host(idx_padded, h, c)           # the staging is reused: same answer
+        assert np.array_equal(lg, lg3) and np.array_equal(h2, h3) and np.array_equal(v, v3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
