@@ -38,6 +38,48 @@ class JointTimestep(NamedTuple):
     infos: Dict[str, dict]
 
 
+class ScalarCodec:
+    """Memo of the packed words <-> posggym value conversions of the SCALAR facade calls.  A planner's host path steps
+    one state at a time and keeps seeing the same states and observations; the Python codec loops cost more than the
+    device round trip, so their results are remembered by packed bytes / by (hashable) state."""
+
+    LIMIT = 1 << 17
+
+    def __init__(self, batched):
+        self.b = batched
+        self._packed: dict = {}
+        self._state: dict = {}
+        self._obs: dict = {}
+
+    def pack(self, state) -> np.ndarray:
+        row = self._packed.get(state)
+        if row is None:
+            if len(self._packed) >= self.LIMIT:
+                self._packed.clear()
+            row = self._packed[state] = self.b.pack_state([state])
+        return row
+
+    def state(self, packed_row: np.ndarray):
+        key = packed_row.tobytes()
+        st = self._state.get(key)
+        if st is None:
+            if len(self._state) >= self.LIMIT:
+                self._state.clear()
+            st = self._state[key] = self.b.unpack_state(packed_row)[0]
+            self._packed.setdefault(st, packed_row.copy())
+        return st
+
+    def obs(self, obs_row: np.ndarray) -> tuple:
+        """``obs_row``: one env's packed observations [A, ...] -> tuple of per-agent observations."""
+        key = obs_row.tobytes()
+        ob = self._obs.get(key)
+        if ob is None:
+            if len(self._obs) >= self.LIMIT:
+                self._obs.clear()
+            ob = self._obs[key] = self.b.unpack_obs(obs_row[None])[0]
+        return ob
+
+
 def to_numpy(t) -> np.ndarray:
     return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
 
@@ -199,9 +241,10 @@ class ModelFacade:
     def step(self, state, actions: Dict[str, int]) -> JointTimestep:
         b = self.batched
         act = np.array([[int(actions[i]) for i in self.possible_agents]], dtype=np.uint8)
-        st, ob, rw, fl = b.step_host(b.pack_state([state]), act, self.host_step_noise(1))
-        nstate = b.unpack_state(st)[0]
-        obs = b.unpack_obs(ob)[0]
+        codec = self.__dict__.get("_codec") or self.__dict__.setdefault("_codec", ScalarCodec(b))
+        st, ob, rw, fl = b.step_host(codec.pack(state), act, self.host_step_noise(1))
+        nstate = codec.state(st)
+        obs = codec.obs(ob[0])
         rew = rw[0]
         flags = int(fl[0])
         ids = self.possible_agents

@@ -409,9 +409,14 @@ class DrivingModel:
     def step(self, state, actions: Dict[str, int]) -> JointTimestep:
         b = self.batched
         act = np.array([[int(actions[i]) for i in self.possible_agents]], dtype=np.uint8)
-        st, ob, rw, fl = b.step_host(b.pack_state([state]), act, self.host_step_noise(1))
-        nstate = b.unpack_state(st)[0]
-        obs = b.unpack_obs(ob)[0]
+        codec = self.__dict__.get("_codec")
+        if codec is None:
+            from posggym_baselines_b200.envs.base import ScalarCodec
+
+            codec = self._codec = ScalarCodec(b)
+        st, ob, rw, fl = b.step_host(codec.pack(state), act, self.host_step_noise(1))
+        nstate = codec.state(st)
+        obs = codec.obs(ob[0])
         rew = rw[0]
         flags = int(fl[0])
         ids = self.possible_agents
