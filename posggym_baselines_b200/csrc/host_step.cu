@@ -2,9 +2,11 @@
 // plugin path makes once per tree level of a simulation (reference: planning/mcts.py:333,418 `self.model.step(
 // hps.state, joint_action)`; planning/intmcp.py:468,562), where a stateful Python policy decides the next action
 // from the previous step's result, so the rows cannot be batched.  One pinned block and one device block per
-// handle, one copy in, the model's step kernel, one copy out, one stream synchronisation.
+// handle, one copy in, the model's step kernel, one copy out, one stream synchronisation (up to 64 rows: no copies,
+// the kernel works on the pinned block directly).
 #include "common.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -81,8 +83,13 @@ extern "C" int posg_model_step_host(posg_model_t m, int64_t n, const uint32_t* s
   memcpy(ss->h, state_in_host, b_sin);
   memcpy(ss->h + o_act, actions_host, b_act);
   memcpy(ss->h + o_noise, noise_host, b_noise);
-  POSG_CUDA(cudaMemcpyAsync(ss->d, ss->h, o_out, cudaMemcpyHostToDevice, ss->st));
-  unsigned char* d = ss->d;
+  // a handful of rows: the kernel reads and writes the pinned block itself (unified addressing maps it into the
+  // device's address space) -- a few hundred bytes over PCIe inside the launch instead of two copy operations
+  // around it.  POSG_STEP_HOST_STAGED=1 forces the copies (dev A/B switch).
+  static const bool staged_only = getenv("POSG_STEP_HOST_STAGED") != nullptr;
+  const bool direct = !staged_only && n <= 64;
+  if (!direct) POSG_CUDA(cudaMemcpyAsync(ss->d, ss->h, o_out, cudaMemcpyHostToDevice, ss->st));
+  unsigned char* d = direct ? ss->h : ss->d;
   if (driving) {
     rc = posg_driving_step(m, n, (const uint32_t*)d, d + o_act, d + o_noise, 0, 0, 0, (uint32_t*)(d + o_sout),
                            (uint64_t*)(d + o_obs), (double*)(d + o_rew), d + o_flags, nullptr, nullptr, ss->st);
@@ -92,7 +99,7 @@ extern "C" int posg_model_step_host(posg_model_t m, int64_t n, const uint32_t* s
                          nullptr, ss->st);
   }
   if (rc) return rc;
-  POSG_CUDA(cudaMemcpyAsync(ss->h + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, ss->st));
+  if (!direct) POSG_CUDA(cudaMemcpyAsync(ss->h + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, ss->st));
   POSG_CUDA(cudaStreamSynchronize(ss->st));
   memcpy(state_out_host, ss->h + o_sout, b_sin);
   memcpy(obs_out_host, ss->h + o_obs, b_obs);
