@@ -792,6 +792,9 @@ int posg_nested_create(posg_model_t base, posg_model_t* out) {
   m->kind = base->kind | KIND_NESTED;   // same blob (borrowed), one extra state word per particle
   m->borrowed = 1;
   m->d_flat_desc = nullptr; m->flat_dim = 0;
+  // the copy must not share (and later free) the base handle's lazily created staging contexts
+  m->host_stage = nullptr; m->host_stage_free = nullptr;
+  m->step_stage = nullptr; m->step_stage_free = nullptr;
   *out = m;
   return POSG_OK;
 }

@@ -78,3 +78,27 @@ def _plain(x):
     if isinstance(x, (tuple, list)):
         return tuple(_plain(v) for v in x)
     return int(x)
+
+
+def test_nested_handle_does_not_share_the_staging():
+    """posg_nested_create copies the model handle (I-NTMCP's nested search adapter); the copy must not take the base
+    handle's lazily created host staging with it -- closing the planner used to free the block the facade's scalar
+    step still used."""
+    import math
+
+    from posggym_baselines_b200.planning import INTMCP, MCTSConfig
+
+    model = _models()["Driving-v1"]()
+    model.seed(0)
+    s = model.sample_initial_state()
+    ts = model.step(s, {"0": 1, "1": 1})                       # creates the staging of posg_model_step_host
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.05, c=math.sqrt(2), truncated=False, action_selection="ucb",
+                     state_belief_only=False, seed=0)
+    for _ in range(2):
+        planner = INTMCP.initialize(model, "0", cfg, nesting_level=1, search_policies=None, node_capacity=1 << 16,
+                                    log_capacity=1 << 18, max_sims_per_level=64)
+        planner.reset()
+        planner.step(model.sample_initial_obs(s)["0"])
+        planner.close()
+        ts = model.step(ts.state, {"0": 0, "1": 2})
+    assert ts.state is not None
