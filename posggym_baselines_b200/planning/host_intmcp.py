@@ -11,7 +11,9 @@ device:
   ``posg_belief_initial`` launches (one per initial history, the rejection loop of 231-243 inside the kernel);
 * belief reinvigoration (843-892, belief.py:145-194) steps a round of rejection-sampling attempts per
   ``model.step`` launch, parents and joint actions chosen on the host in the sequential loop's order;
-* single steps inside ``_simulate`` / ``_rollout`` go through the facade's scalar ``model.step``.
+* single steps inside ``_simulate`` / ``_rollout`` go through the facade's scalar ``model.step``
+  (``posg_model_step_host``); where every agent's search policy of a level is ``RandomSearchPolicy`` a leaf's whole
+  rollout is ONE launch of the fused rollout kernel instead.
 
 One deviation: the reference's PUCB selection reads ``self.action_space`` (intmcp.py:646), an attribute the class
 never sets, so its I-NTMCP cannot search with ``action_selection="pucb"`` at all; here PUCB works (same formula as
@@ -88,6 +90,9 @@ class HostINTMCP:
         self._final = self._max_visit if config.action_selection == "pucb" else self._max_value
         self.max_sims_per_level = max_sims_per_level
         self._draws = _draws or _Draws(config.seed if config.seed is not None else random.getrandbits(48))
+        # a rollout in which EVERY agent follows RandomSearchPolicy is MCTS._rollout with uniform-random policies:
+        # the fused rollout kernel (posg_*_rollout), one launch instead of one scalar step per rollout step
+        self._device_rollouts = all(type(p) is RandomSearchPolicy for p in search_policies.values())
         self.min_max = _MinMax(config.known_bounds)
         self.step_statistics: Dict[str, float] = {}
         self._reset_step_statistics()
@@ -325,6 +330,8 @@ class HostINTMCP:
         t0, cfg = time.time(), self.config
 
         def rollout():
+            if self._device_rollouts:
+                return self._device_rollout(hps, depth)
             states = dict(hps.policy_state)
             states[self.agent_id] = node.search_policy_state
             return self._rollout(hps, depth, states)
@@ -360,6 +367,23 @@ class HostINTMCP:
             depth += 1
             k += 1
         return ret
+
+    def _device_rollout(self, hps: HPS, depth: int) -> float:
+        """``_rollout`` when all agents act uniformly at random: the loop's bounds (``depth <= depth_limit and
+        t <= step_limit``), discounting and stop rule inside the fused rollout kernel, actions from a Philox
+        sub-sequence of this rollout's own."""
+        cfg, b = self.config, self._b
+        steps = min(cfg.depth_limit - depth + 1, self.step_limit - hps.t + 1, 255)
+        if steps <= 0:
+            return 0
+        st = torch.from_numpy(b.pack_state([hps.state])).to(b.device)
+        ret, done, _ = b.rollout(st, self._ego, int(steps), cfg.discount, seed=self._draws.seed ^ 0x726F6C6C,
+                                 particle_offset=self._draws.take(1))
+        k = int(done.cpu()[0])
+        # the reference advances every agent's (stateless) search-policy state after each step that does not end the
+        # rollout: 2 * agents - 1 counted calls per such step (intmcp.py:574-588)
+        self.step_statistics["policy_calls"] += (2 * len(self._ids) - 1) * max(0, k - 1 if k < steps else k)
+        return float(ret.cpu()[0])
 
     # ------------------------------------------------------------------ policies and joint actions
     def _policy_next(self, action, obs, policy, state):

@@ -57,6 +57,27 @@ class RegistryBatched:
                 np.array([[ts.rewards[i] for i in self.ids] for ts in rows], dtype=np.float64), np.array(flags, dtype=np.uint8))
 
 
+    def rollout(self, st, ego_agent, max_steps, discount, seed=0, step0=0, particle_offset=0):
+        """The fused uniform-random rollout kernel's contract: discounted ego return, stops after the step on which the
+        ego agent terminated or everything is done; (returns, steps executed, None)."""
+        import random as _random
+
+        rng = _random.Random((seed << 20) ^ particle_offset)
+        rets, steps = [], []
+        for s in self.unpack_state(st):
+            ret, k = 0.0, 0
+            while k < max_steps:
+                ts = self.m.step(s, {i: rng.randrange(self.m.action_spaces[i].n) for i in self.ids})
+                ret += discount**k * ts.rewards[self.ids[ego_agent]]
+                k += 1
+                if ts.terminations[self.ids[ego_agent]] or ts.all_done:
+                    break
+                s = ts.state
+            rets.append(ret)
+            steps.append(k)
+        return torch.tensor(rets, dtype=torch.float64), torch.tensor(steps, dtype=torch.uint8), None
+
+
 class DoubleDrivingModel(DrivingModel):
     """The oracle Driving model with a ``.batched`` the host engines can call."""
 
