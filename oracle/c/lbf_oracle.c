@@ -34,17 +34,19 @@ int lbf_init(int size, int sight, int max_agent_level, int force_coop, int norma
   memset(&C, 0, sizeof(C));
   C.size = size; C.sight = sight; C.max_agent_level = max_agent_level; C.force_coop = force_coop;
   C.normalize_reward = normalize_reward;
-  /* static_food_coords: first max_food cells of product(range(1, size - 1, 2), repeat=2) */
+  /* static_food_coords: LAST max_food cells of sorted product(range(1, size - 1, 2), repeat=2) */
+  int lx[64], ly[64], nl = 0;
+  for (int x = 1; x < size - 1; x += 2)
+    for (int y = 1; y < size - 1; y += 2) { lx[nl] = x; ly[nl++] = y; }
   int k = 0;
-  for (int x = 1; x < size - 1 && k < NFOOD; x += 2)
-    for (int y = 1; y < size - 1 && k < NFOOD; y += 2) { C.fx[k] = x; C.fy[k] = y; ++k; }
-  /* static_player_coords: evenly spaced along the border, from the bottom-left corner, walking up
-   * the left side, along the top, down the right side and back along the bottom */
+  for (int j = nl - NFOOD; j < nl; ++j) { C.fx[k] = lx[j]; C.fy[k] = ly[j]; ++k; }
+  /* static_player_coords: evenly spaced along the border, from the top-right corner, walking down
+   * the right side, along the bottom, up the left side and back along the top */
   int bx[64], by[64], nb = 0;
-  for (int y = size - 1; y >= 0; --y) { bx[nb] = 0; by[nb++] = y; }
-  for (int x = 1; x < size; ++x) { bx[nb] = x; by[nb++] = 0; }
-  for (int y = 1; y < size; ++y) { bx[nb] = size - 1; by[nb++] = y; }
-  for (int x = size - 2; x > 0; --x) { bx[nb] = x; by[nb++] = size - 1; }
+  for (int y = 0; y < size; ++y) { bx[nb] = size - 1; by[nb++] = y; }
+  for (int x = size - 2; x >= 0; --x) { bx[nb] = x; by[nb++] = size - 1; }
+  for (int y = size - 2; y >= 0; --y) { bx[nb] = 0; by[nb++] = y; }
+  for (int x = 1; x < size - 1; ++x) { bx[nb] = x; by[nb++] = 0; }
   const double step = (double)nb / (double)NPL;
   for (int i = 0; i < NPL; ++i) { const int j = (int)((double)i * step); C.px[i] = bx[j]; C.py[i] = by[j]; }
   return k * 100 + nb;

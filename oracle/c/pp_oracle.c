@@ -185,12 +185,12 @@ static int pp_step1(const PP* s, const int* act, const uint32_t* words, PP* ns, 
   return ns->caught[0] && ns->caught[1] && ns->caught[2];
 }
 
-/* _get_local_cell_obs: (2 obs_dim + 1)^2 cells in itertools.product(col, row) order */
+/* _get_local_cell_obs: (2 obs_dim + 1)^2 cells, row-major (index = row * w + col, row = y offset) */
 static void observe(const PP* s, int idx, int* out) {
   const int w = 2 * C.obs_dim + 1;
   int k = 0;
-  for (int col = 0; col < w; ++col)
-    for (int row = 0; row < w; ++row) {
+  for (int row = 0; row < w; ++row)
+    for (int col = 0; col < w; ++col) {
       const Cell c = {s->pred[idx].x + col - C.obs_dim, s->pred[idx].y + row - C.obs_dim};
       int code = EMPTY;
       if (!in_bounds(c)) code = WALL;

@@ -23,13 +23,23 @@ in-tree fixtures pin (tests/test_oracle_fixtures.py):
   episode returns are small-denominator rationals in [0, 1] (``br_results.csv``);
 * step limit 50.
 
-NOT pinned (documented guesses, chosen to be consistent with the masks above): the static
-layout -- foods on the first ``max_food`` cells of ``product(range(1, size-1, 2), repeat=2)``
-(two columns x four rows, spacing 2: the mask shows six foods visible only with the agent
-between two columns, rows two apart), players spread evenly along the border starting at
-the bottom-left corner -- and the level sampling (player levels uniform on 1..max_agent_level, food levels
-uniform on 1..sum of player levels).  The order in which simultaneous LOADs are resolved
-follows lb-foraging (player index order, first adjacent food in N, S, W, E order).
+Static layout.  Nothing in the reference tree states it; two fixtures select it:
+
+* the ten shipped best-response checkpoints (``env_data/LevelBasedForaging-v3/br_models``, trained on the real
+  environment) run on this model (tests/test_oracle_policies.py): with the foods on the LAST eight cells of the
+  sorted lattice ``product(range(1, size-1, 2), repeat=2)`` -- x in {5, 7}, y in {1, 3, 5, 7} -- two of them in
+  self-play collect 0.2 - 0.45 each from whatever border cells they start on -- they walk to that half of the
+  field (the reference's ``br_results.csv``: 0.41 with its own partner population); with the first eight cells
+  (x in {1, 3}: this file's first version) the agent that starts on the far side collects 0.00 in every episode,
+  and with every other two-column / two-row / four-by-two / checkerboard placement tried the pair collects less
+  than half as much; swapping the observation's (x, y) order gives ~0 everywhere.  The same runs confirm the observation layout, the action semantics (NORTH = y - 1) and
+  the load rule.  The mask above (six foods visible at once) holds for this placement too;
+* uniform-random play (``div_results.csv``: 0.0597 +- 0.0088 / 0.0158 +- 0.0041 -- agent 0 collects four times as
+  much) puts agent 0 next to the foods, on the right border: see ``static_player_coords``.
+
+Still guesses: which of the two right-hand corners agent 0 starts in, and the level sampling (player levels uniform
+on 1..max_agent_level, food levels uniform on 1..sum of player levels, as in lb-foraging).  The order in which
+simultaneous LOADs are resolved follows lb-foraging (player index order, first adjacent food in N, S, W, E order).
 
 Noise definition: ``step`` is deterministic.  ``sample_initial_state`` takes
 ``num_agents + max_food`` picks: player level - 1, then food level - 1.
@@ -68,18 +78,22 @@ LBFObs = Tuple[int, ...]
 
 
 def static_food_coords(size: int, max_food: int) -> List[Coord]:
+    """The LAST ``max_food`` cells of the sorted spacing-2 interior lattice (size 10, 8 foods: x in {5, 7},
+    y in {1, 3, 5, 7}) -- see the module docstring for what selects it."""
     cells = list(itertools.product(range(1, size - 1, 2), repeat=2))
     assert max_food <= len(cells)
-    return cells[:max_food]
+    return cells[len(cells) - max_food:]
 
 
 def static_player_coords(size: int, num_agents: int) -> List[Coord]:
-    """Evenly spaced along the border, starting at the bottom-left corner and walking up the
-    left side, along the top, down the right side and back along the bottom (two agents:
-    (0, size-1) and (size-1, 0)).  Among the opposite-border pairs this start fits the
-    uniform-random returns of div_results.csv (0.060 / 0.016) best: 0.058 / 0.010."""
-    border = ([(0, y) for y in range(size - 1, -1, -1)] + [(x, 0) for x in range(1, size)]
-              + [(size - 1, y) for y in range(1, size)] + [(x, size - 1) for x in range(size - 2, 0, -1)])
+    """Evenly spaced along the border, starting at the top-right corner and walking down the right side, along
+    the bottom, up the left side and back along the top (two agents: (size-1, 0) and (0, size-1)).  With the foods
+    on the right half this start reproduces the uniform-random returns of div_results.csv (0.060 / 0.016: agent
+    0 collects more): 0.062 / 0.012; the mirrored pair (size-1, size-1) / (0, 0) fits equally (0.051 / 0.016),
+    agent 0 on the left does not (0.013 / 0.060)."""
+    n = size
+    border = ([(n - 1, y) for y in range(n)] + [(x, n - 1) for x in range(n - 2, -1, -1)]
+              + [(0, y) for y in range(n - 2, -1, -1)] + [(x, 0) for x in range(1, n - 1)])
     step = len(border) / num_agents
     return [border[int(i * step)] for i in range(num_agents)]
 

@@ -13,6 +13,12 @@ the in-tree fixtures (tests/test_oracle_fixtures.py):
 * observation = 25 local cells, each EMPTY=0 / WALL=1 / PREDATOR=2 / PREY=3 -- flattened
   width 100 (br_models/*.pt ``trunk.0.weight``); the centre cell (index 12) is always
   PREDATOR and every other one-hot input occurs (Adam ``exp_avg_sq`` masks);
+* cell ORDER and type codes, action semantics and the dynamics as a whole: the ten shipped best-response
+  checkpoints (``env_data/PredatorPrey-v0/br_models``, trained on the real environment) are run on this model
+  (tests/test_oracle_policies.py).  With the window in ROW-major order (index = row * 5 + col, row = y offset)
+  two of them in self-play collect a mean return of 0.89 (the reference's ``br_results.csv``: 0.75 with its own
+  partner population); with the window transposed -- this file's first version, column-major -- or with any other
+  symmetry of the window or permutation of the type codes they collect 0.00 to 0.36;
 * returns live on the lattice {0, 1/3, 2/3, 1} (``br_results.csv``): cooperative reward
   ``n_caught * (1 / num_prey)`` shared by all predators; episodes end when all prey are
   caught; step limit 50;
@@ -298,7 +304,7 @@ class PredatorPreyModel:
         preds = set(state.predator_coords)
         prey = {c for i, c in enumerate(state.prey_coords) if not state.prey_caught[i]}
         cells = []
-        for col, row in itertools.product(range(width), repeat=2):
+        for row, col in itertools.product(range(width), repeat=2):     # row-major: index = row * width + col
             c = (ax + col - self.obs_dim, ay + row - self.obs_dim)
             if not self.grid.coord_in_bounds(c) or c in self.grid.block_coords:
                 cells.append(WALL)

@@ -81,7 +81,7 @@ static pp::Blob* build_pp_blob(int size, const char* blocks, int num_predators, 
         for (int row = 0; row < w; ++row) {
           const int gx = x + col - obs_dim, gy = y + row - obs_dim;
           const bool wall = gx < 0 || gy < 0 || gx >= size || gy >= size || blk[gy][gx];
-          if (wall) cells |= (unsigned long long)pp::WALL << (2 * (col * w + row));
+          if (wall) cells |= (unsigned long long)pp::WALL << (2 * (row * w + col));
         }
       b->obs_base[x | (y << 4)] = cells;
     }

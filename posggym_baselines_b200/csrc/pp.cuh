@@ -4,7 +4,8 @@
 //   state word 0: predator 0 (x | y<<4) | predator 1 << 8 | caught bits << 16
 //   state word 1: prey 0 (x | y<<4) | prey 1 << 8 | prey 2 << 16
 //   observation : 25 cells x 2 bits (EMPTY=0 WALL=1 PREDATOR=2 PREY=3), cell index
-//                 col*5 + row of the 5x5 window centred on the predator
+//                 row*5 + col of the 5x5 window centred on the predator (row = y offset; the order the shipped
+//                 best-response policies were trained on: oracle/predator_prey.py, tests/test_oracle_policies.py)
 #pragma once
 #include <stdint.h>
 
@@ -85,7 +86,7 @@ inline void build_tables(Blob* b) {
       const int i = REL0 + dx + 16 * dy, man = abs(dx) + abs(dy);
       if (man <= od && man > 0) b->rel_thr[i] = (uint8_t)(4 * man + 2);
       if (man == 1) b->rel_nb[i] = (uint8_t)(dy == -1 ? 1 : dx == 1 ? 2 : dy == 1 ? 4 : 8);
-      b->win_obs[(dx + od) + 16 * (dy + od)] = (unsigned long long)PREY << (2 * ((dx + od) * w + (dy + od)));
+      b->win_obs[(dx + od) + 16 * (dy + od)] = (unsigned long long)PREY << (2 * ((dy + od) * w + (dx + od)));
     }
   for (int v = 0; v < 16; ++v) {
     unsigned long long col = (unsigned long long)PREDATOR << (2 * (od * w + od)), row = 0;
@@ -93,8 +94,8 @@ inline void build_tables(Blob* b) {
       const int g = v + k - od;   // grid column (row) shown in window column (row) k
       if (g >= 0 && g < b->size) continue;
       for (int m = 0; m < w; ++m) {
-        col |= (unsigned long long)WALL << (2 * (k * w + m));
-        row |= (unsigned long long)WALL << (2 * (m * w + k));
+        col |= (unsigned long long)WALL << (2 * (m * w + k));   // window column k, every row m
+        row |= (unsigned long long)WALL << (2 * (k * w + m));   // window row k, every column m
       }
     }
     b->win_col[v] = col; b->win_row[v] = row;
@@ -294,11 +295,11 @@ __device__ __forceinline__ bool transition(const Blob& B, Ents& e, const int (&a
   return e.caught == 7u;
 }
 
-// window cell index (col*5 + row) of grid cell c seen from predator at p, or -1
+// window cell index (row*5 + col) of grid cell c seen from predator at p, or -1
 __device__ __forceinline__ int window_cell(int p, int c, int obs_dim) {
   const int col = (c & 15) - (p & 15) + obs_dim, row = (c >> 4) - (p >> 4) + obs_dim;
   const int w = 2 * obs_dim + 1;
-  return ((unsigned)col < (unsigned)w && (unsigned)row < (unsigned)w) ? col * w + row : -1;
+  return ((unsigned)col < (unsigned)w && (unsigned)row < (unsigned)w) ? row * w + col : -1;
 }
 
 __device__ __forceinline__ unsigned long long observe(const Blob& B, const Ents& e, int i) {

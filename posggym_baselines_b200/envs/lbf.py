@@ -38,17 +38,20 @@ class LBFState(NamedTuple):
 
 
 def static_food_coords(size: int, max_food: int) -> List[Tuple[int, int]]:
-    """Static layout: the first ``max_food`` cells of the spacing-2 interior lattice."""
+    """Static layout: the LAST ``max_food`` cells of the sorted spacing-2 interior lattice (size 10, 8 foods:
+    x in {5, 7}, y in {1, 3, 5, 7}) -- the placement the reference's shipped best-response policies were trained
+    on (oracle/lbf.py, tests/test_oracle_policies.py)."""
     cells = list(itertools.product(range(1, size - 1, 2), repeat=2))
     if max_food > len(cells):
         raise ValueError(f"max_food={max_food} does not fit a {size}x{size} static layout")
-    return cells[:max_food]
+    return cells[len(cells) - max_food:]
 
 
 def static_player_coords(size: int, num_agents: int) -> List[Tuple[int, int]]:
-    """Static layout: players evenly spaced along the border, from the bottom-left corner."""
-    border = ([(0, y) for y in range(size - 1, -1, -1)] + [(x, 0) for x in range(1, size)]
-              + [(size - 1, y) for y in range(1, size)] + [(x, size - 1) for x in range(size - 2, 0, -1)])
+    """Static layout: players evenly spaced along the border, from the top-right corner down the right side."""
+    n = size
+    border = ([(n - 1, y) for y in range(n)] + [(x, n - 1) for x in range(n - 2, -1, -1)]
+              + [(0, y) for y in range(n - 2, -1, -1)] + [(x, 0) for x in range(1, n - 1)])
     step = len(border) / num_agents
     return [border[int(i * step)] for i in range(num_agents)]
 

@@ -305,11 +305,12 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, "lbf_step.npz"), **lbf_step_cases())
         np.savez_compressed(os.path.join(HERE, "lbf_init.npz"), **lbf_init_cases())
         np.savez_compressed(os.path.join(HERE, "lbf_rollout.npz"), **lbf_rollout_cases())
+    if not only or "pp" in only:
+        np.savez_compressed(os.path.join(HERE, "pp_step.npz"), **pp_step_cases())
+        np.savez_compressed(os.path.join(HERE, "pp_init.npz"), **pp_init_cases())
+        np.savez_compressed(os.path.join(HERE, "pp_rollout.npz"), **pp_rollout_cases())
     if only:
         sys.exit(0)
-    np.savez_compressed(os.path.join(HERE, "pp_step.npz"), **pp_step_cases())
-    np.savez_compressed(os.path.join(HERE, "pp_init.npz"), **pp_init_cases())
-    np.savez_compressed(os.path.join(HERE, "pp_rollout.npz"), **pp_rollout_cases())
     np.savez_compressed(os.path.join(HERE, "driving_step.npz"), **driving_step_cases())
     np.savez_compressed(os.path.join(HERE, "driving_init.npz"), **driving_init_cases())
     np.savez_compressed(os.path.join(HERE, "driving_rollout.npz"), **driving_rollout_cases())
