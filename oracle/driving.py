@@ -30,6 +30,11 @@ pinned against the in-tree fixtures (tests/test_oracle_fixtures.py):
   statistics selected "a reversing vehicle keeps its facing" over "turn actions
   rotate a reversing vehicle" (16 % crashes, 0.116 progress).
 
+* the shipped best-response checkpoints (``env_data/Driving-v1/br_models``, trained on the real environment)
+  drive on this model: in self-play 95 % of the episodes reach the destination (``br_results.csv``: 88 % with the
+  reference's partner population; uniform-random play: none) -- tests/test_oracle_policies.py.  The same check found
+  defects in the first versions of the other two oracles; it found none here.
+
 Noise definition (the "identical noise" of the bit-exact parity tests):
 
 * ``step``: one integer ``order_idx`` in ``[0, n_agents!)`` -- the lexicographic
