@@ -22,15 +22,9 @@ import posggym  # noqa: E402
 from posggym_baselines.planning import INTMCP, MCTSConfig, SearchPolicyWrapper  # noqa: E402
 
 from tests.golden.make_golden import obs_fields  # noqa: E402
-from tests.potmmcp_policies import BiasedPolicy  # noqa: E402
+from tests.potmmcp_policies import plugin_policies_for  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-
-
-def plugin_policies_for(model, levels, wrapper):
-    """Level l, agent i: prefers ACCELERATE (agent 0) / DECELERATE (agent 1), more strongly at higher levels."""
-    return {lvl: {i: wrapper(BiasedPolicy(model, i, f"L{lvl}_{i}", 1 if i == "0" else 2, 2.0 + 2.0 * lvl))
-                  for i in model.possible_agents} for lvl in range(levels + 1)}
 
 
 def search(planner, n_sims):

@@ -55,3 +55,10 @@ def ego_policies(model, agent_id="0"):
 
 
 META_POLICY = {"pusher": {"fast": 0.25, "careful": 0.75}, "idler": {"fast": 0.9, "careful": 0.1}}
+
+
+def plugin_policies_for(model, levels, wrapper):
+    """Search policies per nesting level and agent for the general I-NTMCP tests: level l, agent i prefers ACCELERATE
+    (agent 0) / DECELERATE (agent 1), more strongly at higher levels."""
+    return {lvl: {i: wrapper(BiasedPolicy(model, i, f"L{lvl}_{i}", 1 if i == "0" else 2, 2.0 + 2.0 * lvl))
+                  for i in model.possible_agents} for lvl in range(levels + 1)}

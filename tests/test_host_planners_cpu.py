@@ -98,7 +98,7 @@ def test_general_intmcp_matches_reference_golden(double_model, name):
     two consecutive decisions, and the number of nested histories the update hands to the tree below."""
     from posggym_baselines_b200.planning import MCTSConfig, SearchPolicyWrapper
     from posggym_baselines_b200.planning.host_intmcp import HostINTMCP
-    from tests.golden.make_intmcp_deep_golden import plugin_policies_for
+    from tests.potmmcp_policies import plugin_policies_for
 
     class OnDouble(HostINTMCP):
         def _device_initial_belief(self, init_obs, need):

@@ -122,7 +122,7 @@ def test_general_hierarchies_match_reference(model, name):
     (tests/golden/make_intmcp_deep_golden.py) within 4 standard errors plus a small margin."""
     from posggym_baselines_b200.planning import INTMCP, MCTSConfig, SearchPolicyWrapper
     from posggym_baselines_b200.planning.host_intmcp import HostINTMCP
-    from tests.potmmcp_policies import BiasedPolicy
+    from tests.potmmcp_policies import plugin_policies_for
 
     with open(os.path.join(GOLDEN, "intmcp_deep_driving.json")) as f:
         scen = next(s for s in json.load(f)["scenarios"] if s["name"] == name)
@@ -134,10 +134,7 @@ def test_general_hierarchies_match_reference(model, name):
         model.seed(9700 + rep)
         cfg = MCTSConfig(discount=0.95, search_time_limit=0.2, c=math.sqrt(2), truncated=False, action_selection="ucb",
                          state_belief_only=False, seed=rep)
-        sp = None
-        if scen["plugins"]:      # the policies of make_intmcp_deep_golden.plugin_policies_for
-            sp = {lvl: {i: SearchPolicyWrapper(BiasedPolicy(model, i, f"L{lvl}_{i}", 1 if i == "0" else 2, 2.0 + 2.0 * lvl))
-                        for i in model.possible_agents} for lvl in range(level + 1)}
+        sp = plugin_policies_for(model, level, SearchPolicyWrapper) if scen["plugins"] else None
         planner = INTMCP.initialize(model, "0", cfg, level, sp, max_sims_per_level=scen["n_sims_per_level"])
         assert isinstance(planner, HostINTMCP)
         planner.reset()
