@@ -174,3 +174,40 @@ def test_general_intmcp_facade(double_model):
                           "0", cfg, 1, None)
     deep = INTMCP.initialize(model, "0", cfg, 3, None, max_sims_per_level=2)
     assert isinstance(deep, HostINTMCP) and deep.other_agent_policies["1"].other_agent_policies["0"].nesting_level == 1
+
+
+@pytest.mark.parametrize("state_belief_only", [True, False])
+def test_host_engine_is_the_reference_planner(double_model, state_belief_only):
+    """The plugin path's engine with the Random pair (as subclasses, so that ``MCTS`` would route them to the host):
+    root action values and visit shares after 192 simulations against the golden of the UNMODIFIED reference POMCP
+    (tests/golden/planner_driving.json), with state-only particles and with history / policy-state particles."""
+    from posggym_baselines_b200.planning import MCTSConfig, RandomOtherAgentPolicy, RandomSearchPolicy
+    from posggym_baselines_b200.planning.host_search import HostSearch
+
+    class MySearch(RandomSearchPolicy):
+        pass
+
+    class MyOther(RandomOtherAgentPolicy):
+        pass
+
+    scen = json.load(open(os.path.join(GOLDEN, "planner_driving.json")))["root_stats"][0]
+    obs = _driving_obs(scen["ego_obs"])
+    model, reps = double_model, 10
+    vals, fracs = [], []
+    for rep in range(reps):
+        random.seed(50 + rep)
+        model.seed(150 + rep)
+        cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.414, truncated=False, action_selection="ucb",
+                         state_belief_only=state_belief_only, seed=rep)
+        shell = _PlannerShell(model, "0", cfg, {"1": MyOther(model, "1")}, MySearch(model, "0"), scen["n_sims"])
+        eng = HostSearch(shell)
+        eng.update(None, obs)
+        assert eng.get_action() in range(5)
+        p0 = eng.root.belief.particles[0]
+        assert (p0.history is None and p0.policy_state is None) if state_belief_only else (len(p0.history) == 1 and p0.policy_state == {"1": {}})
+        vis = np.array([eng.root.children[a].visits for a in range(5)], dtype=float)
+        vals.append([eng.root.children[a].value for a in range(5)])
+        fracs.append(vis / vis.sum())
+    ok, info = _close(vals, scen["value_mean"], scen["value_std"], scen["reps"], 0.015)
+    assert ok, info
+    assert (np.abs(np.mean(fracs, 0) - np.array(scen["visit_frac_mean"])) < 0.05).all()
