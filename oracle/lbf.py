@@ -37,6 +37,14 @@ Static layout.  Nothing in the reference tree states it; two fixtures select it:
 * uniform-random play (``div_results.csv``: 0.0597 +- 0.0088 / 0.0158 +- 0.0041 -- agent 0 collects four times as
   much) puts agent 0 next to the foods, on the right border: see ``static_player_coords``.
 
+Residual inconsistency (LBF stays the least certain of the three oracles): the shipped critics assign their highest
+initial value (0.32 against 0.13 here) to a first observation with NOTHING in sight, and the policies' default motion
+on such observations is EAST -- as if agent 0 started out of sight of the foods, west of them -- while the
+uniform-random returns (and the first point of the training curves, 0.05) put agent 0 two cells from a food.  No
+placement in the families tried (two adjacent columns / rows at every offset, 4 x 2 blocks, checkerboards; every
+border start) satisfies both, so something else in this restatement -- the level sampling, the reward normalisation
+or the visibility rule -- may still differ from upstream.  tools/policy_probe.py reproduces the searches.
+
 Still guesses: which of the two right-hand corners agent 0 starts in, and the level sampling (player levels uniform
 on 1..max_agent_level, food levels uniform on 1..sum of player levels, as in lb-foraging).  The order in which
 simultaneous LOADs are resolved follows lb-foraging (player index order, first adjacent food in N, S, W, E order).
