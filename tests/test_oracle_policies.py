@@ -67,9 +67,9 @@ class _Net(torch.nn.Module):
         return int(torch.distributions.Categorical(logits=logits).sample()), state
 
 
-def _policies(env_id, n_actions):
+def _policies(env_id, n_actions, names=("P0_seed0.pt", "P0_seed1.pt")):
     nets = []
-    for name in ("P0_seed0.pt", "P0_seed1.pt"):
+    for name in names:
         ck = torch.load(os.path.join(DATA, env_id, "br_models", name), map_location="cpu", weights_only=False,
                         pickle_module=_PickleModule)
         net = _Net(ck["model"]["trunk.0.weight"].shape[1], n_actions)
@@ -105,20 +105,25 @@ def _self_play(model, nets, episodes, seed, obs_map=lambda o: o):
     return out
 
 
-def test_driving_policies_reach_their_destinations(oracle_env):
+PAIRS = [("P0_seed0.pt", "P0_seed1.pt"), ("P1_seed2.pt", "P1_seed3.pt")]      # both training populations
+
+
+@pytest.mark.parametrize("names", PAIRS)
+def test_driving_policies_reach_their_destinations(oracle_env, names):
     """br_results.csv: 88 % of the reference's episodes end with return exactly 1 (destination reached); uniform-random
     play never gets there (div_results.csv: 24 crashes, 76 time-outs per 100)."""
     from oracle.driving import DrivingModel
 
-    ret = _self_play(DrivingModel(), _policies("Driving-v1", 5), episodes=24, seed=0)
-    assert (ret[:, 0] > 0.99).mean() >= 0.75, ret[:, 0]
+    ret = _self_play(DrivingModel(), _policies("Driving-v1", 5, names), episodes=24, seed=0)
+    assert (ret[:, 0] > 0.99).mean() >= 0.7, ret[:, 0]
 
 
-def test_predator_prey_policies_hunt_and_pin_the_window_order(oracle_env):
+@pytest.mark.parametrize("names", PAIRS)
+def test_predator_prey_policies_hunt_and_pin_the_window_order(oracle_env, names):
     """br_results.csv: mean return 0.75.  Row-major window: 0.89 here; the transposed (column-major) window: 0.00."""
     from oracle.predator_prey import PredatorPreyModel
 
-    nets = _policies("PredatorPrey-v0", 5)
+    nets = _policies("PredatorPrey-v0", 5, names)
     ret = _self_play(PredatorPreyModel(), nets, episodes=30, seed=5)
     assert ret[:, 0].mean() >= 0.6, ret[:, 0].mean()
     transposed = np.arange(25).reshape(5, 5).T.reshape(-1)
