@@ -445,13 +445,15 @@ int posg_policy_destroy(posg_policy_t p);
  * simulation adds -- as ONE call with HOST buffers: posg_policy_set_trunk0 uploads trunk.0.weight [64, in_dim] /
  * bias [64] (host pointers); posg_policy_eval_host takes, per row, the K indices of the active inputs of the
  * one-hot-flattened observation (FlattenProcessor's layout; out-of-range indices are ignored) and the LSTM state
- * h / c [n, 64], and returns the new h / c, the actor's logits [n, A] and the critic's value [n].  Internally: one
- * staged copy in, the index-row sum + tanh of trunk layer 0, posg_policy_step (done = 0, nothing sampled), one copy
+ * h / c [n, 64], and returns the new h / c, the actor's logits [n, A], their softmax probs [n, A]
+ * (Categorical(logits).probs) and the critic's value [n].  Internally: one
+ * staged copy in, the index-row sum + tanh of trunk layer 0, posg_policy_step (done = 0, nothing sampled), a row
+ * softmax, one copy
  * out, one synchronisation on a stream the handle owns.  One call per handle at a time. */
 int posg_policy_set_trunk0(posg_policy_t p, int in_dim, const float* trunk0_w, const float* trunk0_b);
 int posg_policy_eval_host(posg_policy_t p, int64_t n, int K, const int32_t* obs_index_host, const float* h_in_host,
                           const float* c_in_host, float* h_out_host, float* c_out_host, float* logits_out_host,
-                          float* value_out_host);
+                          float* probs_out_host, float* value_out_host);
 int posg_policy_step(posg_policy_t p, int64_t n_rows, const float* x0, const float* h_in, const float* c_in,
                      const float* done, const uint8_t* terminated, const uint8_t* truncated, uint64_t seed,
                      uint32_t step, const uint32_t* step_device, uint64_t row_offset, const int64_t* action_in,

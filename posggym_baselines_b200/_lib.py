@@ -74,7 +74,7 @@ SIGNATURES = {
     "posg_policy_create": (_int, [_int, _int] + [_vp] * 14 + [C.POINTER(_vp)]),
     "posg_policy_destroy": (_int, [_vp]),
     "posg_policy_set_trunk0": (_int, [_vp, _int, _vp, _vp]),
-    "posg_policy_eval_host": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "posg_policy_eval_host": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "posg_policy_step": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _vp, _u64, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp]),
     "posg_seq_chunks": (_int, [_int, _i64, _vp, _int, _vp, _vp, _vp, _i64, _vp, _vp]),

@@ -381,6 +381,17 @@ __global__ void embed_rows_kernel(const float* __restrict__ w0t, const float* __
   x0[row * H + lane + 32] = tanhf(a1);
 }
 
+// probs[row] = softmax(logits[row]) over A <= 8 actions (Categorical(logits).probs, planning/search_policy.py:270)
+__global__ void softmax_rows_kernel(const float* __restrict__ logits, int n, int A, float* __restrict__ probs) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  float m = -INFINITY;
+  for (int a = 0; a < A; ++a) m = fmaxf(m, logits[row * A + a]);
+  float e[VCOL], z = 0.f;
+  for (int a = 0; a < A; ++a) { e[a] = expf(logits[row * A + a] - m); z += e[a]; }
+  for (int a = 0; a < A; ++a) probs[row * A + a] = e[a] / z;
+}
+
 }  // namespace policy
 }  // namespace posg
 
@@ -465,12 +476,12 @@ int posg_policy_set_trunk0(posg_policy_t p, int in_dim, const float* trunk0_w, c
 
 int posg_policy_eval_host(posg_policy_t p, int64_t n, int K, const int32_t* obs_index_host, const float* h_in_host,
                           const float* c_in_host, float* h_out_host, float* c_out_host, float* logits_out_host,
-                          float* value_out_host) {
+                          float* probs_out_host, float* value_out_host) {
   POSG_REQUIRE(p, "null policy");
   if (n == 0) return POSG_OK;
   POSG_REQUIRE(p->d_w0t, "posg_policy_set_trunk0 first");
   POSG_REQUIRE(n > 0 && n <= (1 << 16) && K > 0 && obs_index_host && h_in_host && c_in_host && h_out_host && c_out_host &&
-               logits_out_host && value_out_host, "bad arguments");
+               logits_out_host && probs_out_host && value_out_host, "bad arguments");
   using namespace policy;
   const int A = p->n_actions;
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -479,7 +490,8 @@ int posg_policy_eval_host(posg_policy_t p, int64_t n, int K, const int32_t* obs_
   const size_t o_h = up(b_idx), o_c = o_h + up(b_hc), o_scr = o_c + up(b_hc);
   const size_t o_x0 = o_scr, o_done = o_x0 + up(b_hc), o_ain = o_done + up((size_t)n * 4), o_act = o_ain + up((size_t)n * 8);
   const size_t o_lp = o_act + up((size_t)n * 8), o_ent = o_lp + up((size_t)n * 4), o_out = o_ent + up((size_t)n * 4);
-  const size_t o_ho = o_out, o_co = o_ho + up(b_hc), o_lg = o_co + up(b_hc), o_val = o_lg + up((size_t)n * A * 4);
+  const size_t o_ho = o_out, o_co = o_ho + up(b_hc), o_lg = o_co + up(b_hc), o_pr = o_lg + up((size_t)n * A * 4);
+  const size_t o_val = o_pr + up((size_t)n * A * 4);
   const size_t total = o_val + up((size_t)n * 4);
   POSG_CUDA(cudaSetDevice(p->device));
   if (!p->st) POSG_CUDA(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
@@ -507,11 +519,14 @@ int posg_policy_eval_host(posg_policy_t p, int64_t n, int K, const int32_t* obs_
                             (float*)(d + o_ho), (float*)(d + o_co), (int64_t*)(d + o_act), (float*)(d + o_lp),
                             (float*)(d + o_ent), (float*)(d + o_val), (float*)(d + o_lg), p->st);
   if (rc) return rc;
+  softmax_rows_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>((const float*)(d + o_lg), (int)n, A, (float*)(d + o_pr));
+  POSG_CUDA(cudaGetLastError());
   POSG_CUDA(cudaMemcpyAsync(h + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, p->st));
   POSG_CUDA(cudaStreamSynchronize(p->st));
   memcpy(h_out_host, h + o_ho, b_hc);
   memcpy(c_out_host, h + o_co, b_hc);
   memcpy(logits_out_host, h + o_lg, (size_t)n * A * 4);
+  memcpy(probs_out_host, h + o_pr, (size_t)n * A * 4);
   memcpy(value_out_host, h + o_val, (size_t)n * 4);
   return POSG_OK;
 }

@@ -186,9 +186,7 @@ class PPOLSTMSearchPolicy(SearchPolicy):
         n = len(obs_list)
         h = np.concatenate([s["lstm_state"][0].numpy() for s in states], 0)
         c = np.concatenate([s["lstm_state"][1].numpy() for s in states], 0)
-        h2, c2, logits, values = self.policy.eval_host(self._index_rows(obs_list), h, c)
-        z = np.exp(logits.astype(np.float64) - logits.max(1, keepdims=True))
-        probs = z / z.sum(1, keepdims=True)                       # softmax of the actor's logits (search_policy.py:270)
+        h2, c2, _, probs, values = self.policy.eval_host(self._index_rows(obs_list), h, c)   # probs: search_policy.py:270
         h2, c2 = t.from_numpy(h2), t.from_numpy(c2)
         return [{"lstm_state": (h2[k:k + 1], c2[k:k + 1]),
                  "pi": {a: float(probs[k, a]) for a in self.action_space}, "value": float(values[k])} for k in range(n)]

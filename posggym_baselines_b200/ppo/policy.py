@@ -53,13 +53,15 @@ class FusedPolicy:
     def eval_host(self, obs_index: np.ndarray, h: np.ndarray, c: np.ndarray):
         """The network for a few rows in host memory (``posg_policy_eval_host``; the planners' plugin path calls it once
         per node a simulation adds): ``obs_index`` [n, K] int32 = the active inputs of each one-hot-flattened
-        observation, ``h`` / ``c`` [n, 64] float32.  Returns ``(h', c', logits [n, A], value [n])`` as numpy arrays."""
+        observation, ``h`` / ``c`` [n, 64] float32.  Returns ``(h', c', logits [n, A], probs [n, A], value [n])`` as
+        numpy arrays (``probs`` = softmax of the logits, computed on the device)."""
         obs_index = np.ascontiguousarray(obs_index, dtype=np.int32)
         n, k = obs_index.shape
         h = np.ascontiguousarray(h, dtype=np.float32).reshape(n, self.hidden)
         c = np.ascontiguousarray(c, dtype=np.float32).reshape(n, self.hidden)
         out = (np.empty((n, self.hidden), np.float32), np.empty((n, self.hidden), np.float32),
-               np.empty((n, self.num_actions), np.float32), np.empty((n,), np.float32))
+               np.empty((n, self.num_actions), np.float32), np.empty((n, self.num_actions), np.float32),
+               np.empty((n,), np.float32))
         _lib.check(_lib.lib().posg_policy_eval_host(self._handle, n, k, _lib.ptr(obs_index), _lib.ptr(h), _lib.ptr(c),
                                                     *(_lib.ptr(o) for o in out)))
         return out
