@@ -182,8 +182,8 @@ def test_policy_eval_host_matches_fp32_torch(n):
                 x, (torch.from_numpy(h).to(dev).unsqueeze(0), torch.from_numpy(c).to(dev).unsqueeze(0)),
                 torch.zeros(n, device=dev), torch.zeros(n, dtype=torch.int64, device=dev))
         h2, c2, lg, pr, v = pol.eval_host(idx_padded, h, c)
-        assert np.abs(pr - torch.softmax(logits, -1).cpu().numpy()).max() < tol and np.abs(pr.sum(1) - 1).max() < 1e-5
         tol = 5e-3
+        assert np.abs(pr - torch.softmax(logits, -1).cpu().numpy()).max() < tol and np.abs(pr.sum(1) - 1).max() < 1e-5
         assert np.abs(lg - logits.cpu().numpy()).max() < tol and np.abs(v - val.cpu().numpy()).max() < tol
         assert np.abs(h2 - h1[0].cpu().numpy()).max() < tol and np.abs(c2 - c1[0].cpu().numpy()).max() < tol
         h3, c3, lg3, _, v3 = pol.eval_host(idx_padded, h, c)        # the staging is reused: same answer
