@@ -178,3 +178,41 @@ def test_typed_planners_need_history_particles():
     cfg = MCTSConfig(discount=0.95, search_time_limit=0.1, c=1.25, truncated=False, state_belief_only=True)
     with pytest.raises(ValueError):
         POTMMCP(_TwoAgentModel(), "0", cfg, {}, None)
+
+
+def test_scalar_codec_memoises_both_directions():
+    """envs/base.py ``ScalarCodec``: the scalar facade step's packed-word <-> value conversions are looked up, not
+    recomputed; a state first seen as device output is fed back with exactly the device's words."""
+    import numpy as np
+
+    from posggym_baselines_b200.envs.base import ScalarCodec
+
+    class FakeBatched:
+        calls = {"pack": 0, "unpack_state": 0, "unpack_obs": 0}
+
+        def pack_state(self, states):
+            self.calls["pack"] += 1
+            return np.array([[s[0] * 10, s[1] * 10] for s in states], dtype=np.int32)
+
+        def unpack_state(self, packed):
+            self.calls["unpack_state"] += 1
+            return [(int(r[0]) // 10, int(r[1]) // 10) for r in np.asarray(packed)]
+
+        def unpack_obs(self, packed):
+            self.calls["unpack_obs"] += 1
+            return [tuple(("o", int(v)) for v in row) for row in np.asarray(packed)]
+
+    b = FakeBatched()
+    codec = ScalarCodec(b)
+    row = codec.pack((1, 2))
+    assert row.tolist() == [[10, 20]] and codec.pack((1, 2)) is row and b.calls["pack"] == 1
+    dev = np.array([[31, 47]], dtype=np.int32)                      # a device word that pack_state would not produce
+    st = codec.state(dev)
+    assert st == (3, 4) and codec.state(dev.copy()) is st and b.calls["unpack_state"] == 1
+    assert codec.pack(st).tolist() == [[31, 47]] and b.calls["pack"] == 1     # fed back as the device wrote it
+    ob = codec.obs(np.array([7, 9], dtype=np.int64))
+    assert ob == (("o", 7), ("o", 9)) and codec.obs(np.array([7, 9], dtype=np.int64)) is ob and b.calls["unpack_obs"] == 1
+    codec.LIMIT = 2                                                  # bounded: the memo is dropped when full
+    for k in range(5):
+        codec.pack((k + 10, k))
+    assert len(codec._packed) <= 2
