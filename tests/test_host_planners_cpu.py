@@ -211,3 +211,60 @@ def test_host_engine_is_the_reference_planner(double_model, state_belief_only):
     ok, info = _close(vals, scen["value_mean"], scen["value_std"], scen["reps"], 0.015)
     assert ok, info
     assert (np.abs(np.mean(fracs, 0) - np.array(scen["visit_frac_mean"])) < 0.05).all()
+
+
+def test_experiment_loop_with_belief_statistics_on_the_host_engine(double_model, tmp_path):
+    """SURVEY 8(f) N3 + N4 together, on CPU: the experiment loop (``run_planning_exp``) over an agent-folding env
+    wrapper, a typed planner (the host engine with ``OtherAgentMixturePolicy`` particles) and ``BeliefStatTracker``
+    reading that planner's root belief -- the row has the reference's columns, the policy / action accuracies are
+    real probabilities and the belief concentrates on the other agent's true type over an episode."""
+    import csv
+
+    from posggym_baselines_b200.envs.agent_env import AgentEnvWrapper, UniformOtherAgentFn
+    from posggym_baselines_b200.envs.env import Env
+    from posggym_baselines_b200.exp import episode_results_heads, run_planning_exp
+    from posggym_baselines_b200.planning import (MCTSConfig, OtherAgentMixturePolicy, PlanningStatTracker,
+                                                 SearchPolicyWrapper)
+    from posggym_baselines_b200.planning.host_search import HostSearch
+    from tests.potmmcp_policies import BiasedPolicy, other_agent_types
+
+    model = double_model
+    cfg = MCTSConfig(discount=0.95, search_time_limit=0.05, c=1.25, truncated=True, action_selection="pucb",
+                     state_belief_only=False, seed=0)
+
+    class HostPlanner(_PlannerShell):
+        """``MCTS`` in host mode (planning/mcts.py: reset / step / root) without the device search around it."""
+
+        def __init__(self):
+            super().__init__(model, "0", cfg, {"1": OtherAgentMixturePolicy(model, "1", other_agent_types(model))},
+                             SearchPolicyWrapper(BiasedPolicy(model, "0", "fast", 1, 4.0, value=0.1)), 48)
+            self.stat_tracker = PlanningStatTracker(self)
+            self.engine = HostSearch(self)
+            self._last = None
+
+        root = property(lambda self: self.engine.root)
+
+        def reset(self):
+            self.stat_tracker.reset_episode()
+            self.engine.reset()
+            self._last = None
+
+        def step(self, obs):
+            self.engine.update(self._last, obs)
+            self._last = self.engine.get_action()
+            self.stat_tracker.step()
+            return self._last
+
+    random.seed(3)
+    model.seed(3)
+    env = AgentEnvWrapper(Env(model), UniformOtherAgentFn({"1": ["pusher"]}, lambda pid, m, i: other_agent_types(m, i)[pid]))
+    stats = ["policy", "action", "state", "history"]
+    out = tmp_path / "episode_results.csv"
+    rows = run_planning_exp(env, HostPlanner(), "0", None, 2, str(out), belief_stats_to_track=stats, seed=5)
+    with open(out) as f:
+        got = list(csv.DictReader(f))
+    assert list(got[0].keys()) == episode_results_heads([f"belief_{k}_acc" for k in stats]) and len(got) == 2
+    for r in rows:
+        assert 0.3 < r["belief_policy_acc"] <= 1.0          # two types, the true one is 'pusher': above chance
+        assert 0.0 < r["belief_action_acc"] <= 1.0 and 0.0 <= r["belief_state_acc"] <= 1.0
+        assert r["belief_history_acc"] * r["len"] <= 1.0 + 1e-9 and r["num_sims"] == 48
