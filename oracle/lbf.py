@@ -38,7 +38,7 @@ Static layout.  Nothing in the reference tree states it; two fixtures select it:
   much) puts agent 0 next to the foods, on the right border: see ``static_player_coords``.
 
 Residual inconsistency (LBF stays the least certain of the three oracles): the shipped critics assign their highest
-initial value (0.32 against 0.13 here) to a first observation with NOTHING in sight, and the policies' default motion
+initial value (0.32 against 0.11 here) to a first observation with NOTHING in sight, and the policies' default motion
 on such observations is EAST -- as if agent 0 started out of sight of the foods, west of them -- while the
 uniform-random returns (and the first point of the training curves, 0.05) put agent 0 two cells from a food.  No
 placement in the families tried (two adjacent columns / rows at every offset, 4 x 2 blocks, checkerboards; every
@@ -46,9 +46,10 @@ border start) satisfies both, so something else in this restatement -- the level
 normalisation -- may still differ from upstream (a diamond-shaped field of view was tried and is worse).  A second
 family fits the uniform-random returns as well as this placement does: agent 0 in the top-left corner (0, 0) with the
 nearest food two moves away (e.g. x in {1, 3}, y in {2, 4, 6, 8}, agent 1 at (9, 9)); there the trained agent 0
-collects 0.25 against a random partner (0.15 here) and its critic starts at 0.27, but a second copy of the policy
+collects 0.29 against a random partner (0.20 here) and its critic starts at 0.26, but a second copy of the policy
 playing agent 1 -- a role it was never trained in -- never finds the food.  The fixtures do not separate the two;
-this placement is kept because both roles work on it.  tools/policy_probe.py reproduces the searches.
+this placement is kept because both roles work on it.  tools/policy_probe.py reproduces the searches (``lbf``,
+``lbf-random``, ``lbf-agent0``).
 
 Still guesses: which of the two right-hand corners agent 0 starts in, and the level sampling (player levels uniform
 on 1..max_agent_level, food levels uniform on 1..sum of player levels, as in lb-foraging).  The order in which

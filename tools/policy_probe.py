@@ -5,6 +5,7 @@ collect in self-play on it.  CPU only, needs /root/reference (build container):
     python tools/policy_probe.py pp          # PredatorPrey: 8 window symmetries x 6 cell-code permutations
     python tools/policy_probe.py lbf         # LevelBasedForaging: food placements, player corners, (x, y) order
     python tools/policy_probe.py lbf-random  # uniform-random returns per placement against div_results.csv
+    python tools/policy_probe.py lbf-agent0  # the trained agent 0 alone: return vs a random partner, critics' V(o0)
 
 Results of the committed oracles are asserted in tests/test_oracle_policies.py; the numbers are in DESIGN.md section 3.
 """
@@ -107,6 +108,48 @@ def probe_lbf_random(episodes=1500):
             print("food columns", cols, "players", players, tot.mean(0).round(4))
 
 
+def probe_lbf_agent0(episodes=80):
+    """The two placement families the fixtures leave open (oracle/lbf.py header), by what the trained AGENT 0 does on
+    them: its return against a uniform-random partner (the role and start it was trained in; no second copy playing a
+    role it never saw) and the critics' value of the first observation, over all ten checkpoints."""
+    from gymnasium import spaces
+
+    names = [f"P{p}_seed{k}.pt" for p in (0, 1) for k in range(5)]
+    nets = [_policies("LevelBasedForaging-v3", 6, (n,))[0] for n in names]
+    even = [2, 4, 6, 8]
+    cands = {"adopted: foods x in {5,7}, agents (9,0) / (0,9)": ([(x, y) for x in (5, 7) for y in LATTICE], [(9, 0), (0, 9)]),
+             "round 1: foods x in {1,3}, agents (0,9) / (9,0)": ([(x, y) for x in (1, 3) for y in LATTICE], [(0, 9), (9, 0)]),
+             "second family: foods x in {1,3}, y even, agents (0,0) / (9,9)": ([(x, y) for x in (1, 3) for y in even], [(0, 0), (9, 9)]),
+             "second family: foods x in {2,4}, agents (0,0) / (9,9)": ([(x, y) for x in (2, 4) for y in LATTICE], [(0, 0), (9, 9)]),
+             "foods out of sight: x in {5,7}, agents (0,9) / (9,0)": ([(x, y) for x in (5, 7) for y in LATTICE], [(0, 9), (9, 0)])}
+    for name, (food, players) in cands.items():
+        m = _lbf(food, players)
+        space = m.observation_spaces["0"]
+        m.seed(0)
+        torch.manual_seed(0)
+        rng = random.Random(0)
+        total, values = 0.0, []
+        with torch.no_grad():
+            for ep in range(episodes):
+                net = nets[ep % 2]                       # the two checkpoints of the tests
+                s = m.sample_initial_state()
+                obs = m.sample_initial_obs(s)
+                x0 = torch.tensor(spaces.flatten(space, obs["0"]), dtype=torch.float32)
+                for critic_net in nets:
+                    out, _ = critic_net.lstm(critic_net.trunk(x0).view(1, 1, -1), (torch.zeros(1, 1, 64), torch.zeros(1, 1, 64)))
+                    values.append(float(critic_net.critic(out.view(1, -1))))
+                hidden = (torch.zeros(1, 1, 64), torch.zeros(1, 1, 64))
+                for _ in range(50):
+                    x = torch.tensor(spaces.flatten(space, obs["0"]), dtype=torch.float32)
+                    a, hidden = net.act(x, hidden)
+                    ts = m.step(s, {"0": a, "1": rng.randrange(6)})
+                    s, obs = ts.state, ts.observations
+                    total += ts.rewards["0"]
+                    if ts.all_done:
+                        break
+        print(f"{name}: agent 0 vs random partner {total / episodes:.3f}, critics' V(first observation) {np.mean(values):.3f}", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "pp"
-    {"pp": probe_pp, "lbf": probe_lbf, "lbf-random": probe_lbf_random}[what]()
+    {"pp": probe_pp, "lbf": probe_lbf, "lbf-random": probe_lbf_random, "lbf-agent0": probe_lbf_agent0}[what]()
